@@ -1,0 +1,1681 @@
+// cqg_api.cu — host side of libcqgpu: the C-ABI of include/cq_gpu.h over the sm_100a kernels
+// of cqg_scan.cuh. Plain CUDA runtime; no torch, no CPU operator fallback: every query either
+// runs on the device or fails with an error code.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <strings.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdarg>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "cq_gpu.h"
+#include "cqg_scan.cuh"
+
+using namespace cqg;
+
+#define CQG_API extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024];
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(CQG_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+CQG_API const char* cqg_last_error(void) { return g_err; }
+CQG_API int cqg_abi_version(void) { return 1; }
+CQG_API int64_t cqg_total_kernel_launches(void) { return g_launches.load(); }
+
+CQG_API int cqg_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        fail(CQG_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return n;
+}
+
+static bool g_pool_ready[64];
+CQG_API int cqg_set_device(int device) {
+    CU(cudaSetDevice(device));
+    if (device >= 0 && device < 64 && !g_pool_ready[device]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        g_pool_ready[device] = true;
+    }
+    return CQG_OK;
+}
+
+static int ensure_device() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(CQG_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64 && !g_pool_ready[dev]) return cqg_set_device(dev);
+    return CQG_OK;
+}
+
+constexpr size_t kDevPad = 4096;
+CQG_API size_t cqg_device_padding(void) { return kDevPad; }
+
+// ------------------------------------------------------------------------------------------
+// device scratch with RAII
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t bytes, cudaStream_t st) {
+        release();
+        s = st;
+        n = bytes ? bytes : 8;
+        return cudaMallocAsync(&p, n, st);
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+// ------------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------------
+struct cqg_table {
+    uint8_t* d_data = nullptr;
+    bool owns_device = false;
+    size_t size = 0;
+    const uint8_t* h_data = nullptr;  // host view of the bytes when there is one
+    void* map = nullptr;              // mmap'ed region (portable_mmap, src/mmap.c:78)
+    size_t map_len = 0;
+    cqg_csv_config_t cfg{};
+    std::vector<std::string> names;
+    size_t data_start = 0;  // where data rows may begin (end of the header line)
+    int shard_index = 0, shard_count = 1;
+    uint64_t global_base = 0;
+    int64_t row_count = -1;
+};
+
+static inline bool host_is_space(unsigned c) { return c == 32u || (c - 9u) <= 4u; }
+
+// parse_line (src/csv_reader.c:285-338) on the host, for the header line only
+static void split_header(const uint8_t* ls, const uint8_t* le, char delim, char quote,
+                         std::vector<std::pair<const uint8_t*, size_t>>& out) {
+    const uint8_t* ptr = ls;
+    while (ptr < le) {
+        while (ptr < le && host_is_space(*ptr)) ptr++;
+        if (ptr >= le) break;
+        const uint8_t* fs = ptr;
+        size_t flen = 0;
+        if (*ptr == (uint8_t)quote) {
+            ptr++;
+            fs = ptr;
+            while (ptr < le) {
+                if (*ptr == (uint8_t)quote) {
+                    if (ptr + 1 < le && ptr[1] == (uint8_t)quote) {
+                        ptr += 2;
+                        flen += 2;
+                    } else {
+                        flen = (size_t)(ptr - fs);
+                        ptr++;
+                        break;
+                    }
+                } else {
+                    ptr++;
+                }
+            }
+            while (ptr < le && *ptr != (uint8_t)delim) ptr++;
+        } else {
+            while (ptr < le && *ptr != (uint8_t)delim) ptr++;
+            flen = (size_t)(ptr - fs);
+        }
+        out.emplace_back(fs, flen);
+        if (ptr < le && *ptr == (uint8_t)delim) ptr++;
+    }
+}
+
+// header handling of csv_load (src/csv_reader.c:341-357, 404-427) given the first bytes of the file
+static bool parse_header_bytes(cqg_table* t, const uint8_t* p, size_t n, bool complete) {
+    size_t i = 0;
+    while (i < n) {
+        size_t ls = i;
+        while (i < n && p[i] != '\n' && p[i] != '\r') i++;
+        size_t le = i;
+        if (le > ls) {
+            if (i == n && !complete) return false;  // line not finished in this prefix
+            std::vector<std::pair<const uint8_t*, size_t>> f;
+            split_header(p + ls, p + le, t->cfg.delimiter, t->cfg.quote, f);
+            t->names.clear();
+            for (size_t c = 0; c < f.size(); c++) {
+                if (t->cfg.has_header && f[c].second > 0) {
+                    std::string s((const char*)f[c].first, f[c].second);
+                    size_t z = s.find('\0');
+                    if (z != std::string::npos) s.resize(z);
+                    size_t a = 0;
+                    while (a < s.size() && host_is_space((unsigned char)s[a])) a++;
+                    s = s.substr(a);
+                    while (s.size() > 1 && host_is_space((unsigned char)s.back())) s.pop_back();
+                    if (s.size() == 1 && host_is_space((unsigned char)s[0]) && false) s.clear();
+                    t->names.push_back(s);
+                } else {
+                    t->names.push_back("$" + std::to_string(c));
+                }
+            }
+            t->data_start = t->cfg.has_header ? le : ls;
+            return true;
+        }
+        while (i < n && (p[i] == '\n' || p[i] == '\r')) i++;
+    }
+    if (!complete) return false;
+    t->names.clear();
+    t->data_start = n;
+    return true;
+}
+
+static int finish_open(cqg_table* t) {
+    if (t->h_data) {
+        parse_header_bytes(t, t->h_data, t->size, true);
+        return CQG_OK;
+    }
+    // device-only bytes: pull prefixes until the header line is complete
+    size_t want = 1 << 16;
+    std::vector<uint8_t> tmp;
+    for (;;) {
+        size_t n = std::min(want, t->size);
+        tmp.resize(n);
+        CU(cudaMemcpy(tmp.data(), t->d_data, n, cudaMemcpyDeviceToHost));
+        if (parse_header_bytes(t, tmp.data(), n, n == t->size)) return CQG_OK;
+        want *= 16;
+    }
+}
+
+static int check_dialect(cqg_csv_config_t cfg) {
+    unsigned d = (unsigned char)cfg.delimiter, q = (unsigned char)cfg.quote;
+    auto bad = [](unsigned c) {
+        return c == 0 || c == '\n' || c == '\r' || (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') ||
+               c == '.' || c == '+' || c == '-';
+    };
+    // strtod / strtoll in the reference read on past the field into a delimiter that looks
+    // numeric (src/csv_reader.c:207-210); such dialects are not reproduced here
+    if (bad(d) || bad(q)) return fail(CQG_ERR_UNSUPPORTED, "delimiter/quote character 0x%02x/0x%02x not supported", d, q);
+    return CQG_OK;
+}
+
+static int stage_to_device(cqg_table* t, const uint8_t* src, size_t size, bool pinned) {
+    CU(cudaMalloc((void**)&t->d_data, size + kDevPad));
+    t->owns_device = true;
+    CU(cudaMemsetAsync(t->d_data + size, '\n', kDevPad, 0));
+    if (pinned) {
+        CU(cudaMemcpyAsync(t->d_data, src, size, cudaMemcpyHostToDevice, 0));
+        CU(cudaStreamSynchronize(0));
+        return CQG_OK;
+    }
+    // pageable / mmap'ed source: double-buffered pinned bounce, copy engine overlapped with the
+    // host memcpy that faults the pages in
+    const size_t chunk = 32u << 20;
+    uint8_t* bounce[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    for (int k = 0; k < 2; k++) {
+        CU(cudaMallocHost((void**)&bounce[k], chunk));
+        CU(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+    }
+    int rc = CQG_OK;
+    size_t off = 0;
+    int k = 0;
+    while (off < size) {
+        size_t n = std::min(chunk, size - off);
+        cudaEventSynchronize(ev[k]);
+        memcpy(bounce[k], src + off, n);
+        cudaError_t e = cudaMemcpyAsync(t->d_data + off, bounce[k], n, cudaMemcpyHostToDevice, 0);
+        if (e != cudaSuccess) {
+            rc = fail(CQG_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+            break;
+        }
+        cudaEventRecord(ev[k], 0);
+        off += n;
+        k ^= 1;
+    }
+    cudaStreamSynchronize(0);
+    for (int j = 0; j < 2; j++) {
+        cudaFreeHost(bounce[j]);
+        cudaEventDestroy(ev[j]);
+    }
+    return rc;
+}
+
+CQG_API int cqg_table_open_buffer(const void* data, size_t size, int pinned, cqg_csv_config_t cfg, cqg_table_t** out) {
+    if (!out) return fail(CQG_ERR_ARG, "null out");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_dialect(cfg))) return rc;
+    cqg_table* t = new cqg_table();
+    t->cfg = cfg;
+    t->size = size;
+    t->h_data = (const uint8_t*)data;
+    rc = stage_to_device(t, (const uint8_t*)data, size, pinned != 0);
+    if (rc == CQG_OK) rc = finish_open(t);
+    if (rc != CQG_OK) {
+        cqg_table_close(t);
+        return rc;
+    }
+    *out = t;
+    return CQG_OK;
+}
+
+CQG_API int cqg_table_open(const char* path, cqg_csv_config_t cfg, cqg_table_t** out) {
+    if (!out || !path) return fail(CQG_ERR_ARG, "null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_dialect(cfg))) return rc;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(CQG_ERR_IO, "%s", strerror(errno));
+    struct stat sb;
+    if (fstat(fd, &sb) < 0 || sb.st_size == 0) {  // src/mmap.c:91-98: an empty file is an error too
+        int e = errno;
+        close(fd);
+        return fail(CQG_ERR_IO, "%s", sb.st_size == 0 ? "empty file" : strerror(e));
+    }
+    void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return fail(CQG_ERR_IO, "mmap: %s", strerror(errno));
+    madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+    cqg_table* t = new cqg_table();
+    t->cfg = cfg;
+    t->size = (size_t)sb.st_size;
+    t->map = m;
+    t->map_len = (size_t)sb.st_size;
+    t->h_data = (const uint8_t*)m;
+    rc = stage_to_device(t, t->h_data, t->size, false);
+    if (rc == CQG_OK) rc = finish_open(t);
+    if (rc != CQG_OK) {
+        cqg_table_close(t);
+        return rc;
+    }
+    *out = t;
+    return CQG_OK;
+}
+
+CQG_API int cqg_table_open_device(uint64_t device_ptr, size_t size, cqg_csv_config_t cfg, cqg_table_t** out) {
+    if (!out || !device_ptr) return fail(CQG_ERR_ARG, "null argument");
+    if (device_ptr & 15ull) return fail(CQG_ERR_ARG, "device pointer must be 16-byte aligned");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_dialect(cfg))) return rc;
+    cqg_table* t = new cqg_table();
+    t->cfg = cfg;
+    t->size = size;
+    t->d_data = (uint8_t*)device_ptr;
+    t->owns_device = false;
+    rc = finish_open(t);
+    if (rc != CQG_OK) {
+        cqg_table_close(t);
+        return rc;
+    }
+    *out = t;
+    return CQG_OK;
+}
+
+CQG_API int cqg_table_set_shard(cqg_table_t* t, int index, int count) {
+    if (!t || count < 1 || index < 0 || index >= count) return fail(CQG_ERR_ARG, "bad shard %d/%d", index, count);
+    t->shard_index = index;
+    t->shard_count = count;
+    t->row_count = -1;
+    return CQG_OK;
+}
+
+CQG_API int cqg_table_set_global_offset(cqg_table_t* t, uint64_t offset) {
+    if (!t) return fail(CQG_ERR_ARG, "null table");
+    t->global_base = offset;
+    return CQG_OK;
+}
+
+CQG_API void cqg_table_close(cqg_table_t* t) {
+    if (!t) return;
+    if (t->owns_device && t->d_data) cudaFree(t->d_data);
+    if (t->map) munmap(t->map, t->map_len);
+    delete t;
+}
+
+CQG_API int cqg_table_column_count(const cqg_table_t* t) { return t ? (int)t->names.size() : 0; }
+CQG_API const char* cqg_table_column_name(const cqg_table_t* t, int col) {
+    return (t && col >= 0 && col < (int)t->names.size()) ? t->names[col].c_str() : nullptr;
+}
+CQG_API int cqg_table_column_index(const cqg_table_t* t, const char* name) {
+    if (!t || !name) return -1;
+    for (size_t i = 0; i < t->names.size(); i++)
+        if (strcasecmp(t->names[i].c_str(), name) == 0) return (int)i;
+    return -1;
+}
+CQG_API size_t cqg_table_size(const cqg_table_t* t) { return t ? t->size : 0; }
+CQG_API uint64_t cqg_table_device_ptr(const cqg_table_t* t) { return t ? (uint64_t)t->d_data : 0; }
+
+// ------------------------------------------------------------------------------------------
+// kernel configuration
+// ------------------------------------------------------------------------------------------
+using ScanGeo = Geo<256, 32768, 2>;
+
+struct LaunchCfg {
+    int sms = 0;
+    int ctas_per_sm = 0;
+    bool ready = false;
+};
+static LaunchCfg g_cfg[64];
+
+static int scan_smem_bytes(int table_bytes) { return ScanGeo::OFF_TABLE + table_bytes; }
+
+static int launch_scan(const DevPlan& P, int table_bytes, cudaStream_t st) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    int smem = scan_smem_bytes(table_bytes);
+    static bool attr_set[64];
+    if (!attr_set[dev & 63]) {
+        CU(cudaFuncSetAttribute(scan_kernel<ScanGeo>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev & 63] = true;
+    }
+    LaunchCfg& c = g_cfg[dev & 63];
+    if (!c.ready) {
+        CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+        c.ready = true;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<ScanGeo>, ScanGeo::THREADS, smem));
+    if (per_sm < 1) return fail(CQG_ERR_CUDA, "scan kernel does not fit: %d bytes of shared memory", smem);
+    if (P.n_tiles <= 0) return CQG_OK;
+    int grid = std::min(P.n_tiles, c.sms * per_sm);
+    scan_kernel<ScanGeo><<<grid, ScanGeo::THREADS, smem, st>>>(P);
+    g_launches++;
+    CU(cudaGetLastError());
+    return CQG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// planning
+// ------------------------------------------------------------------------------------------
+struct HostPlan {
+    DevPlan P{};
+    std::vector<uint8_t> entry_init;
+    DevBuf d_entry_init, d_fcode, d_frefs, d_code, d_consts, d_pool;
+    DevBuf d_scalars;  // errflags, rows_scanned, gcount, sel_count, jrow_count, jclass[2]
+    int table_smem_bytes = 0;
+};
+
+struct ScalarBlock {
+    unsigned errflags;
+    unsigned jclass[2];
+    unsigned pad;
+    unsigned long long rows_scanned, gcount, sel_count, jrow_count;
+};
+
+static void shard_range(const cqg_table* t, uint64_t& lo, uint64_t& hi) {
+    unsigned __int128 sz = t->size;
+    lo = (uint64_t)(sz * (unsigned)t->shard_index / (unsigned)t->shard_count);
+    hi = (uint64_t)(sz * (unsigned)(t->shard_index + 1) / (unsigned)t->shard_count);
+    if (lo < t->data_start) lo = t->data_start;
+    if (hi < lo) hi = lo;
+}
+
+static void set_file(DevPlan& P, const cqg_table* t, bool whole) {
+    P.data = t->d_data;
+    P.size = t->size;
+    uint64_t lo, hi;
+    if (whole) {
+        lo = t->data_start;
+        hi = t->size;
+    } else {
+        shard_range(t, lo, hi);
+    }
+    P.own_lo = lo;
+    P.own_hi = hi;
+    P.global_base = t->global_base;
+    P.delim = (uint8_t)t->cfg.delimiter;
+    P.quote = (uint8_t)t->cfg.quote;
+    // the mask fast path needs: quote below 0x23 (so "careful tile" detection sees it), a
+    // delimiter that is neither blank nor below 0x23, delimiter != quote
+    unsigned d = P.delim, q = P.quote;
+    P.exact_only = (q >= 0x23u || d < 0x23u || d == q || d >= 0x80u) ? 1 : 0;
+    if (hi > lo) {
+        P.first_tile = (int32_t)(lo / ScanGeo::TILE);
+        P.n_tiles = (int32_t)((hi - 1) / ScanGeo::TILE) - P.first_tile + 1;
+    } else {
+        P.first_tile = 0;
+        P.n_tiles = 0;
+    }
+}
+
+// register column `col` of one side in the slot map
+static int want_column(DevPlan& P, int col) {
+    if (col < 0) return CQG_OK;
+    if (col >= kMaxQueryCols) return fail(CQG_ERR_UNSUPPORTED, "column index %d beyond %d", col, kMaxQueryCols);
+    if (col >= P.n_cols_total) return CQG_OK;  // reads as NULL
+    if (P.colslot[col] != -1) return CQG_OK;
+    P.colslot[col] = -2;  // marked, numbered later
+    return CQG_OK;
+}
+
+static int number_slots(DevPlan& P) {
+    P.nwantL = P.nwantR = 0;
+    for (int c = 0; c < P.n_left_cols && c < kMaxQueryCols; c++)
+        if (P.colslot[c] == -2) {
+            if (P.nwantL >= kMaxSlots) return fail(CQG_ERR_UNSUPPORTED, "more than %d columns referenced", kMaxSlots);
+            P.wantL[P.nwantL++] = (int16_t)c;
+        }
+    for (int c = P.n_left_cols; c < P.n_cols_total && c < kMaxQueryCols; c++)
+        if (P.colslot[c] == -2) {
+            if (P.nwantR >= kMaxSlots) return fail(CQG_ERR_UNSUPPORTED, "more than %d columns referenced", kMaxSlots);
+            P.wantR[P.nwantR++] = (int16_t)(c - P.n_left_cols);
+        }
+    for (int k = 0; k < P.nwantL; k++) P.colslot[P.wantL[k]] = (int16_t)k;
+    for (int k = 0; k < P.nwantR; k++) P.colslot[P.n_left_cols + P.wantR[k]] = (int16_t)(P.nwantL + k);
+    return CQG_OK;
+}
+
+// cqg_insn_t postfix -> device program(s)
+static int compile_predicate(HostPlan& hp, const cqg_predicate_t& w, cudaStream_t st) {
+    DevPlan& P = hp.P;
+    P.pred_kind = 0;
+    if (!w.code || w.n_code <= 0) return CQG_OK;
+    // constants + string pool
+    std::vector<DConst> consts((size_t)std::max(w.n_consts, 1));
+    std::vector<uint8_t> pool(8, 0);
+    for (int i = 0; i < w.n_consts; i++) {
+        const cqg_value_t& c = w.consts[i];
+        DConst d{};
+        d.type = c.type;
+        switch (c.type) {
+            case CQG_TYPE_INTEGER: d.bits = c.int_value; break;
+            case CQG_TYPE_DOUBLE: memcpy(&d.bits, &c.double_value, 8); break;
+            case CQG_TYPE_DATE:
+                d.bits = ((long long)c.date_value.year << 16) | ((long long)c.date_value.month << 8) | c.date_value.day;
+                break;
+            case CQG_TYPE_STRING: {
+                const char* s = c.string_value ? c.string_value : "";
+                d.len = (uint32_t)strlen(s);
+                d.bits = (long long)pool.size();
+                pool.insert(pool.end(), s, s + d.len);
+                pool.push_back(0);
+                break;
+            }
+            default: d.type = CQG_TYPE_NULL; break;
+        }
+        consts[(size_t)i] = d;
+    }
+    // validate + collect columns; try the fused form
+    struct Item {
+        bool is_value;
+        int ref;  // simple operand reference, or -1 for a computed value
+    };
+    std::vector<Item> stack;
+    std::vector<FInsn> fcode;
+    std::vector<int16_t> frefs;
+    bool fusable = true;
+    int depth_max = 0;
+    for (int pc = 0; pc < w.n_code; pc++) {
+        const cqg_insn_t in = w.code[pc];
+        auto need = [&](size_t n) { return stack.size() >= n; };
+        switch (in.op) {
+            case CQG_OP_COL: {
+                int rc = want_column(P, in.a);
+                if (rc) return rc;
+                int ref = (in.a < 0 || in.a >= P.n_cols_total) ? kRefNull : in.a;
+                if (in.a >= 0x4000) fusable = false;
+                stack.push_back({true, ref});
+                break;
+            }
+            case CQG_OP_CONST:
+                if (in.a < 0 || in.a >= w.n_consts) return fail(CQG_ERR_ARG, "constant index %d out of range", in.a);
+                stack.push_back({true, kRefConst | in.a});
+                break;
+            case CQG_OP_ADD: case CQG_OP_SUB: case CQG_OP_MUL: case CQG_OP_DIV: case CQG_OP_MOD: case CQG_OP_BAND:
+            case CQG_OP_BOR: case CQG_OP_BXOR: case CQG_OP_ARITH_NULL:
+                if (!need(2)) return fail(CQG_ERR_ARG, "predicate stack underflow at %d", pc);
+                stack.pop_back();
+                stack.back() = {true, -1};
+                fusable = false;
+                break;
+            case CQG_OP_NEG:
+                if (!need(1)) return fail(CQG_ERR_ARG, "predicate stack underflow at %d", pc);
+                stack.back() = {true, -1};
+                fusable = false;
+                break;
+            case CQG_OP_POS:
+                if (!need(1)) return fail(CQG_ERR_ARG, "predicate stack underflow at %d", pc);
+                break;
+            case CQG_OP_EQ: case CQG_OP_NE: case CQG_OP_GT: case CQG_OP_LT: case CQG_OP_GE: case CQG_OP_LE:
+            case CQG_OP_LIKE: case CQG_OP_ILIKE: {
+                if (!need(2)) return fail(CQG_ERR_ARG, "predicate stack underflow at %d", pc);
+                Item r = stack.back();
+                stack.pop_back();
+                Item l = stack.back();
+                stack.pop_back();
+                if (!l.is_value || !r.is_value) return fail(CQG_ERR_ARG, "comparison of a condition at %d", pc);
+                if (l.ref < 0 || r.ref < 0) fusable = false;
+                int fop = in.op == CQG_OP_LIKE ? F_LIKE : in.op == CQG_OP_ILIKE ? F_ILIKE : F_CMP;
+                fcode.push_back({(int16_t)fop, (int16_t)l.ref, (int16_t)r.ref, (int16_t)in.op});
+                stack.push_back({false, -1});
+                break;
+            }
+            case CQG_OP_IN: case CQG_OP_NOT_IN: {
+                if (in.a < 0 || !need((size_t)in.a + 1)) return fail(CQG_ERR_ARG, "IN list underflow at %d", pc);
+                int first = (int)frefs.size();
+                for (int k = 0; k < in.a; k++) {
+                    Item it = stack[stack.size() - (size_t)in.a + (size_t)k];
+                    if (!it.is_value) return fail(CQG_ERR_ARG, "IN item is a condition at %d", pc);
+                    if (it.ref < 0) fusable = false;
+                    frefs.push_back((int16_t)it.ref);
+                }
+                stack.resize(stack.size() - (size_t)in.a);
+                Item l = stack.back();
+                stack.pop_back();
+                if (!l.is_value) return fail(CQG_ERR_ARG, "IN operand is a condition at %d", pc);
+                if (l.ref < 0) fusable = false;
+                fcode.push_back({(int16_t)(in.op == CQG_OP_IN ? F_IN : F_NOT_IN), (int16_t)l.ref, (int16_t)first, (int16_t)in.a});
+                stack.push_back({false, -1});
+                break;
+            }
+            case CQG_OP_AND: case CQG_OP_OR:
+                if (!need(2) || stack.back().is_value || stack[stack.size() - 2].is_value)
+                    return fail(CQG_ERR_ARG, "AND/OR operands at %d", pc);
+                stack.pop_back();
+                fcode.push_back({(int16_t)(in.op == CQG_OP_AND ? F_AND : F_OR), 0, 0, 0});
+                break;
+            case CQG_OP_NOT:
+                if (!need(1) || stack.back().is_value) return fail(CQG_ERR_ARG, "NOT operand at %d", pc);
+                fcode.push_back({F_NOT, 0, 0, 0});
+                break;
+            case CQG_OP_TRUE: case CQG_OP_FALSE:
+                stack.push_back({false, -1});
+                fcode.push_back({(int16_t)(in.op == CQG_OP_TRUE ? F_TRUE : F_FALSE), 0, 0, 0});
+                break;
+            case CQG_OP_POP:
+                if (!need(1)) return fail(CQG_ERR_ARG, "POP underflow at %d", pc);
+                stack.pop_back();
+                fusable = false;
+                break;
+            default: return fail(CQG_ERR_ARG, "unknown opcode %d at %d", in.op, pc);
+        }
+        depth_max = std::max(depth_max, (int)stack.size());
+    }
+    if (stack.size() != 1 || stack.back().is_value) return fail(CQG_ERR_ARG, "predicate does not reduce to one condition");
+    if (depth_max >= kStackMax - 1) return fail(CQG_ERR_UNSUPPORTED, "predicate nesting deeper than %d", kStackMax - 2);
+    if (depth_max > 30) fusable = false;
+
+    CU(hp.d_consts.alloc(consts.size() * sizeof(DConst), st));
+    CU(cudaMemcpyAsync(hp.d_consts.p, consts.data(), consts.size() * sizeof(DConst), cudaMemcpyHostToDevice, st));
+    CU(hp.d_pool.alloc(pool.size(), st));
+    CU(cudaMemcpyAsync(hp.d_pool.p, pool.data(), pool.size(), cudaMemcpyHostToDevice, st));
+    P.pred.consts = hp.d_consts.as<DConst>();
+    P.pred.pool = hp.d_pool.as<uint8_t>();
+    if (fusable) {
+        if (frefs.empty()) frefs.push_back(0);
+        CU(hp.d_fcode.alloc(fcode.size() * sizeof(FInsn), st));
+        CU(cudaMemcpyAsync(hp.d_fcode.p, fcode.data(), fcode.size() * sizeof(FInsn), cudaMemcpyHostToDevice, st));
+        CU(hp.d_frefs.alloc(frefs.size() * sizeof(int16_t), st));
+        CU(cudaMemcpyAsync(hp.d_frefs.p, frefs.data(), frefs.size() * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        P.fcode = hp.d_fcode.as<FInsn>();
+        P.frefs = hp.d_frefs.as<int16_t>();
+        P.n_fcode = (int)fcode.size();
+        P.pred_kind = 1;
+    } else {
+        CU(hp.d_code.alloc((size_t)w.n_code * sizeof(cqg_insn_t), st));
+        CU(cudaMemcpyAsync(hp.d_code.p, w.code, (size_t)w.n_code * sizeof(cqg_insn_t), cudaMemcpyHostToDevice, st));
+        P.pred.code = hp.d_code.as<cqg_insn_t>();
+        P.pred.n_code = w.n_code;
+        P.pred_kind = 2;
+    }
+    // the host vectors must outlive the async copies
+    CU(cudaStreamSynchronize(st));
+    return CQG_OK;
+}
+
+static void layout_entry(HostPlan& hp) {
+    DevPlan& P = hp.P;
+    int off = kOffKeys + 16 * P.ngc;
+    for (int a = 0; a < P.naggs; a++) {
+        AggSpec& s = P.aggs[a];
+        if (s.func == CQG_AGG_COUNT_STAR || s.func == CQG_AGG_COUNT || s.col < 0) {
+            s.off = -1;
+            continue;
+        }
+        s.off = off;
+        off += (s.func == CQG_AGG_SUM || s.func == CQG_AGG_AVG) ? 24 : 40;
+    }
+    P.entry_bytes = (off + 7) / 8 * 8;
+    hp.entry_init.assign((size_t)P.entry_bytes, 0);
+    uint64_t ones = ~0ull;
+    memcpy(hp.entry_init.data() + kOffFirst, &ones, 8);
+    for (int a = 0; a < P.naggs; a++) {
+        const AggSpec& s = P.aggs[a];
+        if (s.off < 0) continue;
+        if (s.func == CQG_AGG_MIN || s.func == CQG_AGG_MAX) {
+            uint64_t* st = (uint64_t*)(hp.entry_init.data() + s.off);
+            st[0] = ~0ull;
+            uint64_t empty = s.func == CQG_AGG_MIN ? ~0ull : 0ull;
+            for (int k = 1; k <= 4; k++) st[k] = empty;
+        }
+    }
+}
+
+// common part of a plan over table t (left) [+ right]
+static int build_plan(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, cudaStream_t st) {
+    DevPlan& P = hp.P;
+    set_file(P, t, false);
+    const cqg_table* rt = q->join.right;
+    P.n_left_cols = (int)t->names.size();
+    P.n_cols_total = P.n_left_cols + (rt ? (int)rt->names.size() : 0);
+    if (P.n_cols_total > kMaxQueryCols) return fail(CQG_ERR_UNSUPPORTED, "more than %d columns", kMaxQueryCols);
+    for (int c = 0; c < kMaxQueryCols; c++) P.colslot[c] = -1;
+    P.mode = q->mode == CQG_MODE_SELECT ? SCAN_SELECT : SCAN_AGG;
+    if (q->n_group_cols < 0 || q->n_group_cols > CQG_MAX_GROUP_COLS || q->n_aggs < 0 || q->n_aggs > CQG_MAX_AGGS ||
+        q->n_out_cols < 0 || q->n_out_cols > CQG_MAX_OUT_COLS)
+        return fail(CQG_ERR_ARG, "query dimensions out of range");
+    int rc;
+    if (rt) {
+        if (rt->cfg.delimiter != t->cfg.delimiter || rt->cfg.quote != t->cfg.quote)
+            return fail(CQG_ERR_ARG, "joined tables must share one CSV dialect");
+        P.join = 1;
+        P.rdata = rt->d_data;
+        P.rsize = rt->size;
+        P.jl_col = q->join.left_col;
+        P.jr_col = q->join.right_col;
+        if (P.jl_col >= P.n_left_cols) P.jl_col = -1;
+        if ((rc = want_column(P, P.jl_col))) return rc;
+    }
+    if ((rc = compile_predicate(hp, q->where, st))) return rc;
+    if (P.mode == SCAN_AGG) {
+        P.ngc = q->n_group_cols;
+        for (int g = 0; g < P.ngc; g++) {
+            P.gcol[g] = (int16_t)q->group_cols[g];
+            if ((rc = want_column(P, q->group_cols[g]))) return rc;
+        }
+        P.naggs = q->n_aggs;
+        for (int a = 0; a < P.naggs; a++) {
+            P.aggs[a].func = q->aggs[a].func;
+            P.aggs[a].col = q->aggs[a].col;
+            if (q->aggs[a].func < CQG_AGG_COUNT_STAR || q->aggs[a].func > CQG_AGG_MAX)
+                return fail(CQG_ERR_ARG, "unknown aggregate %d", q->aggs[a].func);
+            if (P.aggs[a].col >= P.n_cols_total) P.aggs[a].col = -1;
+            if (q->aggs[a].func >= CQG_AGG_SUM && (rc = want_column(P, P.aggs[a].col))) return rc;
+        }
+        layout_entry(hp);
+        P.scalar_regs = (P.ngc == 0 && P.naggs <= 4) ? 1 : 0;
+        // shared-memory table: as many entries as fit a 24 KB budget (one when there is no GROUP BY)
+        int cap = 1;
+        if (P.ngc > 0) {
+            cap = 1024;
+            while (cap > 1 && cap * P.entry_bytes > 24 * 1024) cap >>= 1;
+            if (cap < 8) cap = 0;
+        }
+        P.smem_cap = cap;
+        hp.table_smem_bytes = cap * P.entry_bytes;
+        CU(hp.d_entry_init.alloc(hp.entry_init.size(), st));
+        CU(cudaMemcpyAsync(hp.d_entry_init.p, hp.entry_init.data(), hp.entry_init.size(), cudaMemcpyHostToDevice, st));
+        P.entry_init = hp.d_entry_init.as<uint8_t>();
+    }
+    if ((rc = number_slots(P))) return rc;
+    P.need_right_fields = P.nwantR > 0;
+    CU(hp.d_scalars.alloc(sizeof(ScalarBlock), st));
+    CU(cudaMemsetAsync(hp.d_scalars.p, 0, sizeof(ScalarBlock), st));
+    ScalarBlock* sb = hp.d_scalars.as<ScalarBlock>();
+    P.errflags = &sb->errflags;
+    P.jclass = sb->jclass;
+    P.rows_scanned = &sb->rows_scanned;
+    P.gcount = &sb->gcount;
+    P.sel_count = &sb->sel_count;
+    P.jrow_count = &sb->jrow_count;
+    return CQG_OK;
+}
+
+static const char* flag_text(unsigned f) {
+    if (f & KERR_NUMERIC_RANGE) return "a decimal field has more than 19 significant digits";
+    if (f & KERR_KEY_RANGE) return "a DOUBLE group key is outside the exactly rendered %.6f range";
+    if (f & KERR_MINMAX_TIE) return "MIN/MAX tie between an INTEGER and a DOUBLE of equal value (order dependent in the reference)";
+    if (f & KERR_STACK) return "predicate stack overflow";
+    if (f & KERR_JOIN_MIXED) return "join key columns mix comparison classes (cross-type value_compare)";
+    if (f & KERR_BIGINT) return "INTEGER beyond 2^53 compared as double";
+    if (f & KERR_KEY_TAB) return "composite GROUP BY key contains a tab";
+    if (f & KERR_JOIN_FANOUT) return "a row joins with 65536 or more rows";
+    if (f & KERR_STR_LONG) return "MIN/MAX over a string longer than 256 KiB";
+    if (f & KERR_OFFSET_RANGE) return "file larger than 32 TiB";
+    return "unsupported input";
+}
+
+// ------------------------------------------------------------------------------------------
+// join build
+// ------------------------------------------------------------------------------------------
+struct JoinState {
+    DevBuf slots, row_off, row_next, scalars;
+    uint64_t cap = 0, rows = 0;
+};
+
+static int count_rows_device(const cqg_table* t, bool whole, cudaStream_t st, int64_t* out) {
+    HostPlan hp;
+    DevPlan& P = hp.P;
+    set_file(P, t, whole);
+    P.mode = SCAN_COUNT_ROWS;
+    for (int c = 0; c < kMaxQueryCols; c++) P.colslot[c] = -1;
+    CU(hp.d_scalars.alloc(sizeof(ScalarBlock), st));
+    CU(cudaMemsetAsync(hp.d_scalars.p, 0, sizeof(ScalarBlock), st));
+    ScalarBlock* sb = hp.d_scalars.as<ScalarBlock>();
+    P.errflags = &sb->errflags;
+    P.rows_scanned = &sb->rows_scanned;
+    P.jclass = sb->jclass;
+    P.gcount = &sb->gcount;
+    P.sel_count = &sb->sel_count;
+    P.jrow_count = &sb->jrow_count;
+    int rc = launch_scan(P, 0, st);
+    if (rc) return rc;
+    ScalarBlock h;
+    CU(cudaMemcpyAsync(&h, sb, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out = (int64_t)h.rows_scanned;
+    return CQG_OK;
+}
+
+static int build_join(HostPlan& probe, JoinState& js, const cqg_table* rt, int right_col, cudaStream_t st) {
+    int64_t nrows = 0;
+    int rc = count_rows_device(rt, true, st, &nrows);
+    if (rc) return rc;
+    js.rows = (uint64_t)nrows;
+    uint64_t cap = 1024;
+    while (cap < js.rows * 2) cap <<= 1;
+    js.cap = cap;
+    CU(js.slots.alloc(cap * sizeof(JoinSlot), st));
+    CU(cudaMemsetAsync(js.slots.p, 0, cap * sizeof(JoinSlot), st));
+    CU(js.row_off.alloc((js.rows + 1) * 8, st));
+    CU(js.row_next.alloc((js.rows + 1) * 4, st));
+    HostPlan hp;
+    DevPlan& B = hp.P;
+    set_file(B, rt, true);
+    B.mode = SCAN_JOIN_BUILD;
+    for (int c = 0; c < kMaxQueryCols; c++) B.colslot[c] = -1;
+    B.n_left_cols = (int)rt->names.size();
+    B.n_cols_total = B.n_left_cols;
+    B.jr_col = right_col;
+    if (right_col >= 0 && right_col < B.n_cols_total) {
+        B.wantL[0] = (int16_t)right_col;
+        B.nwantL = 1;
+        B.colslot[right_col] = 0;
+    }
+    // the build shares the probe plan's scalar block so that class masks and flags add up
+    B.errflags = probe.P.errflags;
+    B.jclass = probe.P.jclass;
+    B.rows_scanned = probe.P.jrow_count + 0;  // not used for results; keep a valid address
+    CU(js.scalars.alloc(sizeof(ScalarBlock), st));
+    CU(cudaMemsetAsync(js.scalars.p, 0, sizeof(ScalarBlock), st));
+    ScalarBlock* sb = js.scalars.as<ScalarBlock>();
+    B.rows_scanned = &sb->rows_scanned;
+    B.gcount = &sb->gcount;
+    B.sel_count = &sb->sel_count;
+    B.jrow_count = &sb->jrow_count;
+    B.jslots = js.slots.as<JoinSlot>();
+    B.jcap = cap;
+    B.jrow_off = js.row_off.as<uint64_t>();
+    B.jrow_next = js.row_next.as<uint32_t>();
+    B.jrow_cap = js.rows;
+    if (js.rows >= 0xfffffff0ull) return fail(CQG_ERR_UNSUPPORTED, "right table has too many rows");
+    if (right_col >= 0) {
+        rc = launch_scan(B, 0, st);
+        if (rc) return rc;
+    }
+    DevPlan& P = probe.P;
+    P.jslots = B.jslots;
+    P.jcap = cap;
+    P.jrow_off = B.jrow_off;
+    P.jrow_next = B.jrow_next;
+    P.jrow_cap = js.rows;
+    return CQG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------
+struct Arena {
+    std::vector<void*> blocks;
+    void* alloc(size_t n) {
+        void* p = calloc(1, n ? n : 1);
+        blocks.push_back(p);
+        return p;
+    }
+    ~Arena() {
+        for (void* p : blocks) free(p);
+    }
+};
+
+static cqg_result_t* new_result(Arena** arena_out) {
+    cqg_result_t* r = (cqg_result_t*)calloc(1, sizeof(cqg_result_t));
+    Arena* a = new Arena();
+    r->arena = a;
+    *arena_out = a;
+    return r;
+}
+
+CQG_API void cqg_result_free(cqg_result_t* r) {
+    if (!r) return;
+    delete (Arena*)r->arena;
+    free(r);
+}
+
+// turn OutCells into cqg_value_t, pulling string bytes from the host view when there is one,
+// else gathering them on the device
+static int cells_to_values(const cqg_table* t, const cqg_table* rt, const std::vector<OutCell>& cells, cqg_value_t* out,
+                           Arena* arena, cudaStream_t st) {
+    size_t n = cells.size();
+    std::vector<uint64_t> refs;
+    std::vector<uint32_t> lens;
+    std::vector<uint64_t> offs;
+    std::vector<size_t> which;
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        const OutCell& c = cells[i];
+        cqg_value_t v;
+        memset(&v, 0, sizeof v);
+        v.type = c.type;
+        switch (c.type) {
+            case CQG_TYPE_INTEGER: v.int_value = (long long)c.payload; break;
+            case CQG_TYPE_DOUBLE: memcpy(&v.double_value, &c.payload, 8); break;
+            case CQG_TYPE_DATE:
+                v.date_value.year = (int)(c.payload >> 16);
+                v.date_value.month = (int)((c.payload >> 8) & 0xff);
+                v.date_value.day = (int)(c.payload & 0xff);
+                break;
+            case CQG_TYPE_STRING: {
+                bool right = (c.payload >> 63) != 0;
+                uint64_t off = c.payload & 0x7fffffffffffffffull;
+                const cqg_table* src = right ? rt : t;
+                char* s = (char*)arena->alloc((size_t)c.len + 1);
+                v.string_value = s;
+                if (src && src->h_data) {
+                    memcpy(s, src->h_data + off, c.len);
+                } else {
+                    refs.push_back(c.payload);
+                    lens.push_back(c.len);
+                    offs.push_back(total);
+                    which.push_back(i);
+                    total += c.len;
+                }
+                break;
+            }
+            default: v.type = CQG_TYPE_NULL; break;
+        }
+        out[i] = v;
+    }
+    if (!refs.empty()) {
+        DevBuf d_refs, d_lens, d_offs, d_dst;
+        CU(d_refs.alloc(refs.size() * 8, st));
+        CU(d_lens.alloc(lens.size() * 4, st));
+        CU(d_offs.alloc(offs.size() * 8, st));
+        CU(d_dst.alloc(total + 8, st));
+        CU(cudaMemcpyAsync(d_refs.p, refs.data(), refs.size() * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_lens.p, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_offs.p, offs.data(), offs.size() * 8, cudaMemcpyHostToDevice, st));
+        int grid = (int)std::min<size_t>(refs.size(), 65535);
+        pack_strings_kernel<<<grid, 64, 0, st>>>(t->d_data, rt ? rt->d_data : nullptr, d_refs.as<uint64_t>(), d_lens.as<uint32_t>(),
+                                                 d_offs.as<uint64_t>(), refs.size(), d_dst.as<uint8_t>());
+        g_launches++;
+        CU(cudaGetLastError());
+        std::vector<uint8_t> bytes(total + 8);
+        CU(cudaMemcpyAsync(bytes.data(), d_dst.p, total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (size_t k = 0; k < which.size(); k++) memcpy(out[which[k]].string_value, bytes.data() + offs[k], lens[k]);
+    }
+    return CQG_OK;
+}
+
+static int run_fetch(const cqg_table* t, const cqg_table* rt, const int32_t* cols, int ncols, const std::vector<uint64_t>& loff,
+                     const uint64_t* d_roff, unsigned* d_err, std::vector<OutCell>& cells, cudaStream_t st) {
+    size_t n = loff.size();
+    cells.assign(n * (size_t)ncols, OutCell{});
+    if (n == 0 || ncols == 0) return CQG_OK;
+    DevBuf d_loff, d_cells;
+    CU(d_loff.alloc(n * 8, st));
+    CU(cudaMemcpyAsync(d_loff.p, loff.data(), n * 8, cudaMemcpyHostToDevice, st));
+    CU(d_cells.alloc(cells.size() * sizeof(OutCell), st));
+    FetchParams F{};
+    F.data = t->d_data;
+    F.size = t->size;
+    F.rdata = rt ? rt->d_data : nullptr;
+    F.rsize = rt ? rt->size : 0;
+    F.delim = (uint8_t)t->cfg.delimiter;
+    F.quote = (uint8_t)t->cfg.quote;
+    F.n_left_cols = (int)t->names.size();
+    F.ncols = ncols;
+    int total_cols = F.n_left_cols + (rt ? (int)rt->names.size() : 0);
+    for (int c = 0; c < ncols; c++) F.cols[c] = (int16_t)((cols[c] < 0 || cols[c] >= total_cols) ? -1 : cols[c]);
+    F.loff = d_loff.as<uint64_t>();
+    F.roff = d_roff;
+    F.n = n;
+    F.out = d_cells.as<OutCell>();
+    F.errflags = d_err;
+    size_t total = cells.size();
+    int grid = (int)std::min<size_t>((total + 127) / 128, 148 * 16);
+    fetch_kernel<<<grid, 128, 0, st>>>(F);
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cells.data(), d_cells.p, total * sizeof(OutCell), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return CQG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// aggregate finishing: compact entries -> host values
+// ------------------------------------------------------------------------------------------
+struct GroupTable {
+    DevBuf tab;
+    uint64_t cap = 0;
+};
+
+static int alloc_group_table(HostPlan& hp, GroupTable& gt, uint64_t cap, cudaStream_t st) {
+    DevPlan& P = hp.P;
+    gt.cap = cap;
+    CU(gt.tab.alloc(cap * (uint64_t)P.entry_bytes, st));
+    int grid = (int)std::min<uint64_t>((cap * (uint64_t)(P.entry_bytes / 8) + 255) / 256, 148 * 8);
+    init_table_kernel<<<grid, 256, 0, st>>>(gt.tab.as<uint8_t>(), cap, P.entry_bytes, P.entry_init);
+    g_launches++;
+    CU(cudaGetLastError());
+    P.gtab = gt.tab.as<uint8_t>();
+    P.gcap = cap;
+    CU(cudaMemsetAsync(P.gcount, 0, 8, st));
+    return CQG_OK;
+}
+
+static uint64_t initial_group_cap(const DevPlan& P) {
+    if (P.ngc == 0) return 16;
+    uint64_t bytes = P.own_hi - P.own_lo;
+    uint64_t cap = 1 << 12;
+    while (cap < bytes / 32 && cap < (1ull << 22)) cap <<= 1;
+    return cap;
+}
+
+static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* rt, const cqg_query_t* q, const uint8_t* d_entries,
+                            uint64_t G, bool entries_on_device, int64_t rows_scanned, cqg_result_t** out, cudaStream_t st) {
+    DevPlan& P = hp.P;
+    const int eb = P.entry_bytes;
+    std::vector<uint8_t> ent((size_t)G * eb + 8);
+    if (G) {
+        if (entries_on_device) {
+            CU(cudaMemcpyAsync(ent.data(), d_entries, (size_t)G * eb, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        } else {
+            memcpy(ent.data(), d_entries, (size_t)G * eb);
+        }
+    }
+    // create_groups with an unknown single key column makes no group at all (aggregates.c:114-116)
+    bool zero_groups = q->n_group_cols == 1 && q->group_cols[0] < 0;
+    if (zero_groups) G = 0;
+    // no GROUP BY: one `_all_` group even over zero rows (src/evaluator.c:232-247)
+    bool synth = false;
+    if (q->n_group_cols == 0 && G == 0) {
+        ent.assign(hp.entry_init.begin(), hp.entry_init.end());
+        G = 1;
+        synth = true;
+    }
+    std::vector<uint32_t> order((size_t)G);
+    std::iota(order.begin(), order.end(), 0u);
+    auto first_of = [&](uint32_t i) { return *(const uint64_t*)(ent.data() + (size_t)i * eb + kOffFirst); };
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return first_of(a) < first_of(b); });
+
+    Arena* arena;
+    cqg_result_t* r = new_result(&arena);
+    r->n_groups = (int64_t)G;
+    r->n_aggs = q->n_aggs;
+    r->n_out_cols = q->n_out_cols;
+    r->rows_scanned = rows_scanned;
+    size_t gn = std::max<size_t>(G, 1), an = (size_t)std::max(q->n_aggs, 1), on = (size_t)std::max(q->n_out_cols, 1);
+    r->first_offset = (uint64_t*)arena->alloc(8 * gn);
+    r->count = (int64_t*)arena->alloc(8 * gn);
+    r->sum = (double*)arena->alloc(8 * gn * an);
+    r->ncount = (int64_t*)arena->alloc(8 * gn * an);
+    r->value = (cqg_value_t*)arena->alloc(sizeof(cqg_value_t) * gn * an);
+    r->out = (cqg_value_t*)arena->alloc(sizeof(cqg_value_t) * gn * on);
+
+    std::vector<uint64_t> loff(G);
+    std::vector<OutCell> strcells;  // MIN/MAX string results
+    std::vector<size_t> strdst;
+    unsigned host_flags = 0;
+    for (uint64_t gi = 0; gi < G; gi++) {
+        const uint8_t* e = ent.data() + (size_t)order[gi] * eb;
+        uint64_t first = *(const uint64_t*)(e + kOffFirst);
+        int64_t count = (int64_t) * (const uint64_t*)(e + kOffCount);
+        loff[gi] = first == ~0ull ? ~0ull : (first >> 16) - P.global_base;
+        r->first_offset[gi] = first == ~0ull ? 0 : (first >> 16);
+        r->count[gi] = count;
+        for (int a = 0; a < q->n_aggs; a++) {
+            size_t ix = (size_t)a * G + gi;
+            const AggSpec& sp = P.aggs[a];
+            cqg_value_t v;
+            memset(&v, 0, sizeof v);
+            int f = q->aggs[a].func;
+            if (f == CQG_AGG_COUNT_STAR) {
+                v.type = CQG_TYPE_INTEGER;
+                v.int_value = (int)count;  // `result.int_value = row_count` with an int row_count (:270)
+            } else if (sp.col < 0) {
+                v.type = CQG_TYPE_NULL;
+            } else if (f == CQG_AGG_COUNT) {
+                v.type = CQG_TYPE_INTEGER;
+                v.int_value = (int)count;
+            } else if (f == CQG_AGG_SUM || f == CQG_AGG_AVG) {
+                long long si = *(const long long*)(e + sp.off);
+                double sd = *(const double*)(e + sp.off + 8);
+                int64_t n = (int64_t) * (const uint64_t*)(e + sp.off + 16);
+                double sum = (double)si + sd;
+                r->sum[ix] = sum;
+                r->ncount[ix] = n;
+                v.type = CQG_TYPE_DOUBLE;
+                // `count` is an int in the reference (:288); AVG divides by it
+                v.double_value = f == CQG_AGG_SUM ? sum : ((int)n > 0 ? sum / (double)(int)n : 0.0);
+            } else {
+                const uint64_t* s = (const uint64_t*)(e + sp.off);
+                bool is_min = f == CQG_AGG_MIN;
+                uint64_t empty = is_min ? ~0ull : 0ull;
+                uint32_t cls = s[0] == ~0ull ? 0u : (uint32_t)(s[0] & 3u);
+                if (cls == 1) {
+                    bool hi = s[1] != empty, hd = s[2] != empty;
+                    long long iv = hi ? int_of_img(s[1]) : 0;
+                    double dv = 0;
+                    if (hd) {
+                        uint64_t b = bits_of_img(s[2]);
+                        memcpy(&dv, &b, 8);
+                    }
+                    bool take_int;
+                    if (hi && hd) {
+                        double x = (double)iv;
+                        if (x == dv) host_flags |= KERR_MINMAX_TIE;
+                        take_int = is_min ? x < dv : x > dv;
+                    } else {
+                        take_int = hi;
+                    }
+                    if (take_int) {
+                        v.type = CQG_TYPE_INTEGER;
+                        v.int_value = iv;
+                    } else {
+                        v.type = CQG_TYPE_DOUBLE;
+                        v.double_value = dv;
+                    }
+                } else if (cls == 3) {
+                    uint64_t d = s[3] - 1ull;
+                    v.type = CQG_TYPE_DATE;
+                    v.date_value.year = (int)(d >> 16);
+                    v.date_value.month = (int)((d >> 8) & 0xff);
+                    v.date_value.day = (int)(d & 0xff);
+                } else if (cls == 2) {
+                    OutCell c;
+                    c.type = CQG_TYPE_STRING;
+                    c.len = (uint32_t)(s[4] & 0x3ffffu);
+                    c.payload = (s[4] & (1ull << 63)) | ((s[4] >> 18) & 0x1fffffffffffull);
+                    strcells.push_back(c);
+                    strdst.push_back(ix);
+                    v.type = CQG_TYPE_STRING;
+                }
+            }
+            r->value[ix] = v;
+        }
+    }
+    if (host_flags) {
+        cqg_result_free(r);
+        return fail(CQG_ERR_UNSUPPORTED, "%s", flag_text(host_flags));
+    }
+    int rc = CQG_OK;
+    if (!strcells.empty()) {
+        std::vector<cqg_value_t> sv(strcells.size());
+        rc = cells_to_values(t, rt, strcells, sv.data(), arena, st);
+        if (rc == CQG_OK)
+            for (size_t k = 0; k < sv.size(); k++) r->value[strdst[k]] = sv[k];
+    }
+    // bare columns: the group's first row (evaluator_aggregates.c:679-689)
+    if (rc == CQG_OK && q->n_out_cols > 0 && G > 0 && !synth) {
+        DevBuf d_first, d_roff;
+        const uint64_t* roff_ptr = nullptr;
+        if (rt && P.join) {
+            std::vector<uint64_t> firsts(G);
+            for (uint64_t gi = 0; gi < G; gi++) firsts[gi] = *(const uint64_t*)(ent.data() + (size_t)order[gi] * eb + kOffFirst);
+            CU(d_first.alloc(G * 8, st));
+            CU(d_roff.alloc(G * 8, st));
+            CU(cudaMemcpyAsync(d_first.p, firsts.data(), G * 8, cudaMemcpyHostToDevice, st));
+            int grid = (int)std::min<uint64_t>((G + 127) / 128, 148 * 8);
+            resolve_first_right_kernel<<<grid, 128, 0, st>>>(P, d_first.as<uint64_t>(), G, d_roff.as<uint64_t>());
+            g_launches++;
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(st));
+            roff_ptr = d_roff.as<uint64_t>();
+        }
+        std::vector<OutCell> cells;
+        rc = run_fetch(t, rt, q->out_cols, q->n_out_cols, loff, roff_ptr, P.errflags, cells, st);
+        if (rc == CQG_OK) {
+            // cells are [group][col]; the result wants [col][group]
+            std::vector<OutCell> tr(cells.size());
+            for (uint64_t gi = 0; gi < G; gi++)
+                for (int c = 0; c < q->n_out_cols; c++) tr[(size_t)c * G + gi] = cells[(size_t)gi * q->n_out_cols + c];
+            rc = cells_to_values(t, rt, tr, r->out, arena, st);
+        }
+    }
+    if (rc != CQG_OK) {
+        cqg_result_free(r);
+        return rc;
+    }
+    *out = r;
+    return CQG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// execute
+// ------------------------------------------------------------------------------------------
+static int run_aggregate_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBlock& hs, float* ms_out) {
+    DevPlan& P = hp.P;
+    uint64_t cap = initial_group_cap(P);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    int rc = CQG_OK;
+    for (int attempt = 0; attempt < 12; attempt++) {
+        if ((rc = alloc_group_table(hp, gt, cap, st))) break;
+        cudaMemsetAsync(P.errflags, 0, 4, st);
+        cudaMemsetAsync(P.rows_scanned, 0, 8, st);
+        cudaEventRecord(e0, st);
+        if ((rc = launch_scan(P, hp.table_smem_bytes, st))) break;
+        cudaEventRecord(e1, st);
+        cudaError_t ce = cudaMemcpyAsync(&hs, hp.d_scalars.p, sizeof hs, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) {
+            rc = fail(CQG_ERR_CUDA, "scan kernel: %s", cudaGetErrorString(ce));
+            break;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out += ms;
+        if (hs.errflags & KERR_TABLE_FULL) {
+            cap *= 4;
+            if (cap > (1ull << 32)) {
+                rc = fail(CQG_ERR_NOMEM, "group table beyond 2^32 entries");
+                break;
+            }
+            continue;
+        }
+        break;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+static int check_flags(const ScalarBlock& hs, bool join) {
+    unsigned f = hs.errflags & kFatalMask;
+    if (join) {
+        unsigned classes = (hs.jclass[0] | hs.jclass[1]) & ~1u;  // bit 0 = NULL keys
+        if (classes & (classes - 1)) f |= KERR_JOIN_MIXED;
+    }
+    if (f) return fail(CQG_ERR_UNSUPPORTED, "%s", flag_text(f));
+    return CQG_OK;
+}
+
+static int compact_groups(HostPlan& hp, const GroupTable& gt, int owner, int world, DevBuf& out, uint64_t* n_out, cudaStream_t st) {
+    DevPlan& P = hp.P;
+    unsigned long long occupied = 0;
+    CU(cudaMemcpyAsync(&occupied, P.gcount, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(out.alloc((occupied + 1) * (uint64_t)P.entry_bytes, st));
+    DevBuf cnt;
+    CU(cnt.alloc(8, st));
+    CU(cudaMemsetAsync(cnt.p, 0, 8, st));
+    int grid = (int)std::min<uint64_t>((gt.cap + 255) / 256, 148 * 8);
+    compact_table_kernel<<<grid, 256, 0, st>>>(gt.tab.as<uint8_t>(), gt.cap, P.entry_bytes, out.as<uint8_t>(), occupied + 1,
+                                               cnt.as<unsigned long long>(), owner, world);
+    g_launches++;
+    CU(cudaGetLastError());
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_out = std::min<uint64_t>(n, occupied + 1);
+    return CQG_OK;
+}
+
+static int execute_select(HostPlan& hp, const cqg_table* t, const cqg_table* rt, const cqg_query_t* q, cqg_result_t** out,
+                          cudaStream_t st, float* ms_total) {
+    DevPlan& P = hp.P;
+    uint64_t cap = 1 << 16;
+    ScalarBlock hs{};
+    DevBuf okeys, roffs;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    int rc = CQG_OK;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CU(okeys.alloc(cap * 8, st));
+        if (rt) CU(roffs.alloc(cap * 8, st));
+        P.sel_okey = okeys.as<uint64_t>();
+        P.sel_roff = rt ? roffs.as<uint64_t>() : nullptr;
+        P.sel_cap = cap;
+        cudaMemsetAsync(P.errflags, 0, 4, st);
+        cudaMemsetAsync(P.rows_scanned, 0, 8, st);
+        cudaMemsetAsync(P.sel_count, 0, 8, st);
+        cudaEventRecord(e0, st);
+        if ((rc = launch_scan(P, 0, st))) break;
+        cudaEventRecord(e1, st);
+        cudaError_t ce = cudaMemcpyAsync(&hs, hp.d_scalars.p, sizeof hs, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) {
+            rc = fail(CQG_ERR_CUDA, "scan kernel: %s", cudaGetErrorString(ce));
+            break;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_total += ms;
+        if (hs.sel_count > cap) {
+            cap = hs.sel_count + 16;
+            continue;
+        }
+        break;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    if ((rc = check_flags(hs, P.join != 0))) return rc;
+    uint64_t n = hs.sel_count;
+    std::vector<uint64_t> ok(n), ro(rt ? n : 0);
+    if (n) {
+        CU(cudaMemcpyAsync(ok.data(), okeys.p, n * 8, cudaMemcpyDeviceToHost, st));
+        if (rt) CU(cudaMemcpyAsync(ro.data(), roffs.p, n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ok[a] < ok[b]; });
+    uint64_t nout = n;
+    if (q->max_rows >= 0 && (uint64_t)q->max_rows < nout) nout = (uint64_t)q->max_rows;
+    std::vector<uint64_t> loff(nout), roff_sorted(rt ? nout : 0);
+    for (uint64_t i = 0; i < nout; i++) {
+        loff[i] = (ok[order[i]] >> 16) - P.global_base;
+        if (rt) roff_sorted[i] = ro[order[i]];
+    }
+    Arena* arena;
+    cqg_result_t* r = new_result(&arena);
+    r->n_selected = (int64_t)n;
+    r->n_rows_out = (int64_t)nout;
+    r->rows_scanned = (int64_t)hs.rows_scanned;
+    r->n_aggs = 0;
+    r->n_out_cols = q->n_out_cols;
+    size_t rn = std::max<size_t>(nout, 1), on = (size_t)std::max(q->n_out_cols, 1);
+    r->row_offset = (uint64_t*)arena->alloc(8 * rn);
+    r->row_offset_right = rt ? (uint64_t*)arena->alloc(8 * rn) : nullptr;
+    r->rows = (cqg_value_t*)arena->alloc(sizeof(cqg_value_t) * rn * on);
+    for (uint64_t i = 0; i < nout; i++) {
+        r->row_offset[i] = loff[i] + P.global_base;
+        if (rt) r->row_offset_right[i] = roff_sorted[i];
+    }
+    DevBuf d_roff;
+    const uint64_t* roff_ptr = nullptr;
+    if (rt && nout) {
+        CU(d_roff.alloc(nout * 8, st));
+        CU(cudaMemcpyAsync(d_roff.p, roff_sorted.data(), nout * 8, cudaMemcpyHostToDevice, st));
+        roff_ptr = d_roff.as<uint64_t>();
+    }
+    std::vector<OutCell> cells;
+    rc = run_fetch(t, rt, q->out_cols, q->n_out_cols, loff, roff_ptr, P.errflags, cells, st);
+    if (rc == CQG_OK) rc = cells_to_values(t, rt, cells, r->rows, arena, st);
+    if (rc == CQG_OK) {
+        unsigned f = 0;
+        CU(cudaMemcpy(&f, P.errflags, 4, cudaMemcpyDeviceToHost));
+        if (f & kFatalMask) rc = fail(CQG_ERR_UNSUPPORTED, "%s", flag_text(f & kFatalMask));
+    }
+    if (rc != CQG_OK) {
+        cqg_result_free(r);
+        return rc;
+    }
+    *out = r;
+    return CQG_OK;
+}
+
+CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t** out) {
+    if (!t || !q || !out) return fail(CQG_ERR_ARG, "null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    HostPlan hp;
+    if ((rc = build_plan(hp, t, q, st))) return rc;
+    const cqg_table* rt = q->join.right;
+    JoinState js;
+    float ms = 0;
+    long long launches0 = g_launches.load();
+    if (rt && (rc = build_join(hp, js, rt, q->join.right_col, st))) return rc;
+    if (q->mode == CQG_MODE_SELECT) {
+        rc = execute_select(hp, t, rt, q, out, st, &ms);
+    } else {
+        GroupTable gt;
+        ScalarBlock hs{};
+        if ((rc = run_aggregate_scan(hp, gt, st, hs, &ms))) return rc;
+        if ((rc = check_flags(hs, hp.P.join != 0))) return rc;
+        DevBuf entries;
+        uint64_t G = 0;
+        if ((rc = compact_groups(hp, gt, 0, 1, entries, &G, st))) return rc;
+        rc = finish_aggregate(hp, t, rt, q, entries.as<uint8_t>(), G, true, (int64_t)hs.rows_scanned, out, st);
+        if (rc == CQG_OK) {
+            unsigned f = 0;
+            CU(cudaMemcpy(&f, hp.P.errflags, 4, cudaMemcpyDeviceToHost));
+            if (f & kFatalMask) {
+                cqg_result_free(*out);
+                *out = nullptr;
+                rc = fail(CQG_ERR_UNSUPPORTED, "%s", flag_text(f & kFatalMask));
+            }
+        }
+    }
+    if (rc == CQG_OK) {
+        (*out)->kernel_ms = ms;
+        (*out)->kernel_launches = (int32_t)(g_launches.load() - launches0);
+    }
+    return rc;
+}
+
+CQG_API int cqg_table_row_count(const cqg_table_t* t, int64_t* out) {
+    if (!t || !out) return fail(CQG_ERR_ARG, "null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return count_rows_device(t, false, 0, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// parse_value on the device
+// ------------------------------------------------------------------------------------------
+CQG_API int cqg_parse_value(const char* str, size_t len, cqg_value_t* out) {
+    if (!out || (!str && len)) return fail(CQG_ERR_ARG, "null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (len > (1u << 30)) return fail(CQG_ERR_ARG, "field too long");
+    DevBuf d_s, d_o, d_e;
+    CU(d_s.alloc(len + 64, 0));
+    CU(cudaMemsetAsync(d_s.p, 0, len + 64, 0));
+    if (len) CU(cudaMemcpyAsync(d_s.p, str, len, cudaMemcpyHostToDevice, 0));
+    CU(d_o.alloc(sizeof(OutCell), 0));
+    CU(d_e.alloc(4, 0));
+    CU(cudaMemsetAsync(d_e.p, 0, 4, 0));
+    parse_value_kernel<<<1, 1>>>(d_s.as<uint8_t>(), (uint32_t)len, d_o.as<OutCell>(), d_e.as<unsigned>());
+    g_launches++;
+    CU(cudaGetLastError());
+    OutCell c;
+    unsigned f = 0;
+    CU(cudaMemcpy(&c, d_o.p, sizeof c, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&f, d_e.p, 4, cudaMemcpyDeviceToHost));
+    if (f & kFatalMask) return fail(CQG_ERR_UNSUPPORTED, "%s", flag_text(f & kFatalMask));
+    memset(out, 0, sizeof *out);
+    out->type = c.type;
+    switch (c.type) {
+        case CQG_TYPE_INTEGER: out->int_value = (long long)c.payload; break;
+        case CQG_TYPE_DOUBLE: memcpy(&out->double_value, &c.payload, 8); break;
+        case CQG_TYPE_DATE:
+            out->date_value.year = (int)(c.payload >> 16);
+            out->date_value.month = (int)((c.payload >> 8) & 0xff);
+            out->date_value.day = (int)(c.payload & 0xff);
+            break;
+        case CQG_TYPE_STRING: {
+            char* s = (char*)calloc(1, (size_t)c.len + 1);
+            memcpy(s, str + c.payload, c.len);
+            out->string_value = s;
+            break;
+        }
+        default: break;
+    }
+    return CQG_OK;
+}
+
+CQG_API void cqg_value_release(cqg_value_t* v) {
+    if (v && v->type == CQG_TYPE_STRING) {
+        free(v->string_value);
+        v->string_value = nullptr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU partial aggregates
+// ------------------------------------------------------------------------------------------
+struct cqg_partial {
+    HostPlan hp;
+    GroupTable gt;
+    cqg_query_t q{};
+    int64_t rows_scanned = 0;
+    double kernel_ms = 0;
+};
+
+static bool partial_query_ok(const cqg_query_t* q) {
+    return q->mode == CQG_MODE_AGGREGATE && q->join.right == nullptr;
+}
+
+CQG_API int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_partial_t** out) {
+    if (!t || !q || !out) return fail(CQG_ERR_ARG, "null argument");
+    if (!partial_query_ok(q)) return fail(CQG_ERR_UNSUPPORTED, "partials cover single-table aggregates");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cqg_partial* p = new cqg_partial();
+    p->q = *q;
+    p->q.where.code = nullptr;  // the partial keeps no reference to caller memory
+    p->q.where.consts = nullptr;
+    p->q.where.n_code = p->q.where.n_consts = 0;
+    if ((rc = build_plan(p->hp, t, q, 0))) {
+        delete p;
+        return rc;
+    }
+    ScalarBlock hs{};
+    float ms = 0;
+    rc = run_aggregate_scan(p->hp, p->gt, 0, hs, &ms);
+    if (rc == CQG_OK) rc = check_flags(hs, false);
+    if (rc != CQG_OK) {
+        delete p;
+        return rc;
+    }
+    p->rows_scanned = (int64_t)hs.rows_scanned;
+    p->kernel_ms = ms;
+    *out = p;
+    return CQG_OK;
+}
+
+CQG_API double cqg_partial_kernel_ms(const cqg_partial_t* p) { return p ? p->kernel_ms : 0.0; }
+CQG_API int64_t cqg_partial_rows_scanned(const cqg_partial_t* p) { return p ? p->rows_scanned : 0; }
+CQG_API size_t cqg_partial_record_size(const cqg_partial_t* p) { return p ? (size_t)p->hp.P.entry_bytes : 0; }
+
+CQG_API int64_t cqg_partial_count(const cqg_partial_t* p) {
+    if (!p) return -1;
+    unsigned long long n = 0;
+    if (cudaMemcpy(&n, p->hp.P.gcount, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)n;
+}
+
+CQG_API int cqg_partial_owner_counts(const cqg_partial_t* p, int world, int64_t* counts) {
+    if (!p || !counts || world < 1) return fail(CQG_ERR_ARG, "bad argument");
+    DevBuf d;
+    CU(d.alloc(8 * (size_t)world, 0));
+    CU(cudaMemsetAsync(d.p, 0, 8 * (size_t)world, 0));
+    int grid = (int)std::min<uint64_t>((p->gt.cap + 255) / 256, 148 * 8);
+    owner_count_kernel<<<grid, 256>>>(p->gt.tab.as<uint8_t>(), p->gt.cap, p->hp.P.entry_bytes, world, d.as<unsigned long long>());
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(counts, d.p, 8 * (size_t)world, cudaMemcpyDeviceToHost));
+    return CQG_OK;
+}
+
+CQG_API int cqg_partial_export(const cqg_partial_t* p, int owner, int world, uint64_t dst_device_ptr, int64_t capacity,
+                               int64_t* n_out) {
+    if (!p || !n_out || capacity < 0) return fail(CQG_ERR_ARG, "bad argument");
+    DevBuf cnt;
+    CU(cnt.alloc(8, 0));
+    CU(cudaMemsetAsync(cnt.p, 0, 8, 0));
+    int grid = (int)std::min<uint64_t>((p->gt.cap + 255) / 256, 148 * 8);
+    compact_table_kernel<<<grid, 256>>>(p->gt.tab.as<uint8_t>(), p->gt.cap, p->hp.P.entry_bytes, (uint8_t*)dst_device_ptr,
+                                        (uint64_t)capacity, cnt.as<unsigned long long>(), owner, world);
+    g_launches++;
+    CU(cudaGetLastError());
+    unsigned long long n = 0;
+    CU(cudaMemcpy(&n, cnt.p, 8, cudaMemcpyDeviceToHost));
+    *n_out = (int64_t)n;
+    if ((int64_t)n > capacity) return fail(CQG_ERR_ARG, "export buffer too small: %lld records", (long long)n);
+    return CQG_OK;
+}
+
+CQG_API int cqg_partial_new_like(const cqg_partial_t* like, cqg_partial_t** out) {
+    if (!like || !out) return fail(CQG_ERR_ARG, "null argument");
+    cqg_partial* p = new cqg_partial();
+    p->q = like->q;
+    p->hp.P = like->hp.P;
+    p->hp.entry_init = like->hp.entry_init;
+    p->hp.table_smem_bytes = like->hp.table_smem_bytes;
+    DevPlan& P = p->hp.P;
+    P.pred_kind = 0;  // merging never evaluates the predicate
+    int rc = CQG_OK;
+    do {
+        cudaError_t e = p->hp.d_entry_init.alloc(p->hp.entry_init.size(), 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(p->hp.d_entry_init.p, p->hp.entry_init.data(), p->hp.entry_init.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = p->hp.d_scalars.alloc(sizeof(ScalarBlock), 0);
+        if (e == cudaSuccess) e = cudaMemsetAsync(p->hp.d_scalars.p, 0, sizeof(ScalarBlock), 0);
+        if (e != cudaSuccess) {
+            rc = fail(CQG_ERR_CUDA, "partial_new_like: %s", cudaGetErrorString(e));
+            break;
+        }
+        P.entry_init = p->hp.d_entry_init.as<uint8_t>();
+        ScalarBlock* sb = p->hp.d_scalars.as<ScalarBlock>();
+        P.errflags = &sb->errflags;
+        P.jclass = sb->jclass;
+        P.rows_scanned = &sb->rows_scanned;
+        P.gcount = &sb->gcount;
+        P.sel_count = &sb->sel_count;
+        P.jrow_count = &sb->jrow_count;
+        rc = alloc_group_table(p->hp, p->gt, std::max<uint64_t>(like->gt.cap, 16), 0);
+    } while (0);
+    if (rc != CQG_OK) {
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return CQG_OK;
+}
+
+CQG_API int cqg_partial_merge(cqg_partial_t* p, uint64_t src_device_ptr, int64_t n) {
+    if (!p || n < 0) return fail(CQG_ERR_ARG, "bad argument");
+    if (n == 0) return CQG_OK;
+    DevPlan& P = p->hp.P;
+    for (int attempt = 0; attempt < 12; attempt++) {
+        CU(cudaMemsetAsync(P.errflags, 0, 4, 0));
+        int grid = (int)std::min<int64_t>((n + 127) / 128, 148 * 8);
+        merge_entries_kernel<<<grid, 128>>>(P, (const uint8_t*)src_device_ptr, (uint64_t)n);
+        g_launches++;
+        CU(cudaGetLastError());
+        unsigned f = 0;
+        CU(cudaMemcpy(&f, P.errflags, 4, cudaMemcpyDeviceToHost));
+        if (!(f & KERR_TABLE_FULL)) return CQG_OK;
+        // grow: re-insert what is there into a table four times the size, then try again
+        DevBuf old_entries;
+        uint64_t G = 0;
+        int rc = compact_groups(p->hp, p->gt, 0, 1, old_entries, &G, 0);
+        if (rc) return rc;
+        GroupTable bigger;
+        if ((rc = alloc_group_table(p->hp, bigger, p->gt.cap * 4, 0))) return rc;
+        std::swap(p->gt.tab.p, bigger.tab.p);
+        std::swap(p->gt.tab.n, bigger.tab.n);
+        p->gt.cap = bigger.cap;
+        if (G) {
+            int g2 = (int)std::min<uint64_t>((G + 127) / 128, 148 * 8);
+            merge_entries_kernel<<<g2, 128>>>(P, old_entries.as<uint8_t>(), G);
+            g_launches++;
+            CU(cudaGetLastError());
+            CU(cudaDeviceSynchronize());
+        }
+    }
+    return fail(CQG_ERR_NOMEM, "merge table kept overflowing");
+}
+
+CQG_API int cqg_partial_finish(const cqg_partial_t* pc, const cqg_table_t* t, cqg_result_t** out) {
+    if (!pc || !t || !out) return fail(CQG_ERR_ARG, "null argument");
+    cqg_partial* p = const_cast<cqg_partial*>(pc);
+    DevBuf entries;
+    uint64_t G = 0;
+    int rc = compact_groups(p->hp, p->gt, 0, 1, entries, &G, 0);
+    if (rc) return rc;
+    // first-row decoding and string MIN/MAX read the file `t` views
+    p->hp.P.data = t->d_data;
+    p->hp.P.size = t->size;
+    p->hp.P.global_base = t->global_base;
+    rc = finish_aggregate(p->hp, t, nullptr, &p->q, entries.as<uint8_t>(), G, true, p->rows_scanned, out, 0);
+    if (rc == CQG_OK) {
+        (*out)->kernel_ms = p->kernel_ms;
+        (*out)->kernel_launches = 0;
+    }
+    return rc;
+}
+
+CQG_API void cqg_partial_free(cqg_partial_t* p) { delete p; }
+
+// ------------------------------------------------------------------------------------------
+// synthetic data
+// ------------------------------------------------------------------------------------------
+CQG_API size_t cqg_generate_bigdata_bound(int64_t rows, int64_t key_card) {
+    return 64 + (size_t)rows * (size_t)(31 + (key_card > 0 ? 21 : 0));
+}
+
+CQG_API int cqg_generate_bigdata(uint64_t device_ptr, size_t capacity, int64_t rows, uint64_t seed, int64_t key_card,
+                                 size_t* size_out) {
+    if (!device_ptr || !size_out || rows < 0) return fail(CQG_ERR_ARG, "bad argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (capacity < cqg_generate_bigdata_bound(rows, key_card)) return fail(CQG_ERR_ARG, "capacity below cqg_generate_bigdata_bound");
+    const char* hdr = key_card > 0 ? "name,surname,age,gender,height,uid\n" : "name,surname,age,gender,height\n";
+    size_t hl = strlen(hdr);
+    CU(cudaMemcpy((void*)device_ptr, hdr, hl, cudaMemcpyHostToDevice));
+    int64_t nblocks = (rows + kGenRowsPerBlock - 1) / kGenRowsPerBlock;
+    if (nblocks == 0) {
+        *size_out = hl;
+        return CQG_OK;
+    }
+    if (nblocks > 0x7fffffff) return fail(CQG_ERR_ARG, "too many rows");
+    DevBuf d_sizes;
+    CU(d_sizes.alloc((size_t)nblocks * 8, 0));
+    gen_sizes_kernel<<<(unsigned)nblocks, 256>>>(rows, seed, key_card, d_sizes.as<unsigned long long>());
+    g_launches++;
+    CU(cudaGetLastError());
+    std::vector<unsigned long long> sizes((size_t)nblocks);
+    CU(cudaMemcpy(sizes.data(), d_sizes.p, (size_t)nblocks * 8, cudaMemcpyDeviceToHost));
+    unsigned long long off = hl;
+    for (int64_t b = 0; b < nblocks; b++) {
+        unsigned long long s = sizes[(size_t)b];
+        sizes[(size_t)b] = off;
+        off += s;
+    }
+    if (off > capacity) return fail(CQG_ERR_ARG, "capacity too small");
+    CU(cudaMemcpy(d_sizes.p, sizes.data(), (size_t)nblocks * 8, cudaMemcpyHostToDevice));
+    gen_write_kernel<<<(unsigned)nblocks, 256>>>((uint8_t*)device_ptr, rows, seed, key_card, d_sizes.as<unsigned long long>());
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    *size_out = (size_t)off;
+    return CQG_OK;
+}

@@ -447,6 +447,8 @@ constexpr int kStackMax = 24;
 struct RowView {
     const uint8_t* base;   // left row bytes (smem tile or HBM)
     const uint8_t* rbase;  // right row bytes (HBM) for joined rows
+    const uint8_t* lfile;  // pointer p such that (field address - p) == offset in the left file
+    const uint8_t* rfile;  // same for the right file
     const uint32_t* foff;  // [nslots] field start (relative to base / rbase)
     const uint32_t* flen;  // [nslots] field length; 0 => NULL
     const int16_t* colslot;  // query column -> slot

@@ -1,0 +1,155 @@
+// cqg_plan.cuh — the device-side plan of one query: what the host planner (cqg_api.cu) hands
+// to the scan kernel by value. Layout of group-table entries lives here too because the
+// host sizes and initialises tables with it.
+#pragma once
+#include <cstdint>
+
+#include "cq_gpu.h"
+#include "cqg_device.cuh"
+
+namespace cqg {
+
+constexpr int kMaxSlots = 16;    // distinct CSV columns one side of a query may reference
+constexpr int kMaxQueryCols = 256;  // left + right columns addressable by a plan
+
+// extra kernel error flags (continuing cqg_device.cuh)
+enum : unsigned {
+    KERR_KEY_TAB = 512u,       // composite GROUP BY key part contains '\t' (aliasing in the reference's key string)
+    KERR_JOIN_FANOUT = 1024u,  // one left row matches >= 65536 right rows
+    KERR_STR_LONG = 2048u,     // MIN/MAX string longer than the packed reference allows
+    KERR_OFFSET_RANGE = 4096u, // file offset beyond 2^45
+    KERR_ROW_LONG = 8192u      // internal: row does not fit the tile window (handled, not an error)
+};
+constexpr unsigned kFatalMask = KERR_NUMERIC_RANGE | KERR_SEP_OVERFLOW | KERR_KEY_RANGE | KERR_MINMAX_TIE | KERR_STACK |
+                                KERR_JOIN_MIXED | KERR_BIGINT | KERR_KEY_TAB | KERR_JOIN_FANOUT | KERR_STR_LONG |
+                                KERR_OFFSET_RANGE;
+
+// ---- fused predicate program (host-compiled from cqg_insn_t when no arithmetic is used) ----
+enum : int {
+    F_CMP = 1,    // a,b operand refs; n = CQG_OP_EQ..LE
+    F_IN = 2,     // a operand; b = first index into refs[]; n = item count
+    F_NOT_IN = 3,
+    F_LIKE = 4,   // a,b
+    F_ILIKE = 5,
+    F_AND = 6,
+    F_OR = 7,
+    F_NOT = 8,
+    F_TRUE = 9,
+    F_FALSE = 10
+};
+constexpr int kRefConst = 0x4000;  // ref = kRefConst | const index
+constexpr int kRefNull = 0x7fff;   // unknown column
+
+struct FInsn {
+    int16_t op, a, b, n;
+};
+
+// ---- aggregate state inside a group entry ----
+// SUM/AVG : { int64 sum_i ; double sum_d ; uint64 ncount }                         24 B
+// MIN/MAX : { uint64 first_nonnull ; uint64 num_i ; uint64 num_d ; uint64 date ; uint64 str }  40 B
+//   first_nonnull = (okey << 2 | class) of the earliest non-NULL value (class 1 numeric, 2 string, 3 date)
+//   num_i  = order-preserving image of the extreme INTEGER-typed value
+//   num_d  = order-preserving image of the extreme DOUBLE-typed value
+//   date   = packed y<<16|m<<8|d
+//   str    = table bit 63 | offset << 18 | len   (reference into the resident CSV bytes)
+// MIN keeps the smallest image (empty = ~0), MAX the largest (empty = 0).
+struct AggSpec {
+    int32_t func;
+    int32_t col;
+    int32_t off;  // byte offset of the state inside the entry (-1: COUNT, no state)
+    int32_t pad;
+};
+
+// entry header
+constexpr int kOffHash = 0;    // uint64: 0 empty, bit 63 = being initialised
+constexpr int kOffFirst = 8;   // uint64: min okey of the group's rows
+constexpr int kOffCount = 16;  // uint64 rows
+constexpr int kOffTags = 24;   // uint32 key tags (4 bits per part) ; uint32 pad
+constexpr int kOffKeys = 32;   // ngc x { uint64 w0 ; uint64 w1 }
+constexpr uint64_t kLockBit = 0x8000000000000000ull;
+
+// key part tags
+enum : uint32_t { KT_NULL = 0, KT_INT = 1, KT_DBL_POS = 2, KT_DBL_NEG = 3, KT_STR = 4, KT_STR_HASH = 5, KT_DATE = 6 };
+
+struct JoinSlot {
+    uint64_t h;  // 0 empty, bit 63 lock
+    uint64_t w0, w1;
+    uint32_t tag;
+    uint32_t head;  // index of the most recently added right row + 1 (0: none)
+};
+
+struct DevPlan {
+    // ---- left file ----
+    const uint8_t* data;
+    uint64_t size;        // bytes of the file view
+    uint64_t own_lo;      // rows whose first byte is in [own_lo, own_hi) belong to this scan
+    uint64_t own_hi;
+    uint64_t global_base; // offset of data[0] in the whole (multi-GPU) file: added to row offsets in okeys
+    uint8_t delim, quote;
+    uint8_t exact_only;   // dialect the mask fast path does not cover (whitespace delimiter, exotic quote)
+    uint8_t pad0;
+    int32_t mode;         // ScanMode
+    int32_t first_tile, n_tiles;
+
+    // ---- column slots ----
+    int32_t n_left_cols;              // query column >= n_left_cols addresses the right table
+    int32_t n_cols_total;
+    int32_t nwantL, nwantR;
+    int16_t wantL[kMaxSlots];         // ascending CSV column indices
+    int16_t wantR[kMaxSlots];
+    int16_t colslot[kMaxQueryCols];   // query column -> slot (left slots first), -1 unused
+
+    // ---- predicate ----
+    int32_t pred_kind;  // 0 none, 1 fused, 2 generic
+    int32_t n_fcode;
+    const FInsn* fcode;
+    const int16_t* frefs;
+    DPred pred;
+
+    // ---- aggregation ----
+    int32_t ngc;
+    int16_t gcol[CQG_MAX_GROUP_COLS];
+    int32_t naggs;
+    AggSpec aggs[CQG_MAX_AGGS];
+    int32_t entry_bytes;
+    int32_t scalar_regs;   // no GROUP BY and <= 4 SUM/AVG aggregates: accumulate in registers
+    uint8_t* gtab;         // global table: gcap entries
+    uint64_t gcap;         // power of two
+    unsigned long long* gcount;  // occupied entries
+    const uint8_t* entry_init;   // image of an empty entry
+    int32_t smem_cap;      // entries of the per-CTA table (power of two, 0: none)
+    int32_t smem_table_off;  // byte offset of the table in dynamic shared memory
+
+    // ---- join ----
+    const uint8_t* rdata;  // right file bytes
+    uint64_t rsize;
+    int32_t join;          // 0 none, 1 probe
+    int32_t jl_col, jr_col;   // key columns (query column index; jr_col relative to the right table)
+    JoinSlot* jslots;
+    uint64_t jcap;
+    uint64_t* jrow_off;
+    uint32_t* jrow_next;
+    unsigned long long* jrow_count;
+    uint64_t jrow_cap;
+    unsigned* jclass;   // [2] OR of (1 << class) over left / right key values
+    int32_t need_right_fields;
+
+    // ---- select ----
+    uint64_t* sel_okey;
+    uint64_t* sel_roff;
+    unsigned long long* sel_count;
+    uint64_t sel_cap;
+
+    // ---- bookkeeping ----
+    unsigned* errflags;
+    unsigned long long* rows_scanned;
+};
+
+enum ScanMode : int {
+    SCAN_AGG = 0,
+    SCAN_SELECT = 1,
+    SCAN_COUNT_ROWS = 2,  // only rows_scanned
+    SCAN_JOIN_BUILD = 3   // insert (key, row offset) of every row into the join table
+};
+
+}  // namespace cqg

@@ -1,0 +1,1337 @@
+// cqg_scan.cuh — the fused scan kernel of the cq hot path for sm_100a.
+//
+// One persistent CTA per slot walks tiles of the resident CSV bytes:
+//   TMA bulk copy (cp.async.bulk + mbarrier) of tile + overlap into shared memory
+//   -> phase 1 : SWAR byte classification, 16 bytes per thread: terminator / delimiter bitmasks
+//   -> phase 1b: row starts = terminator->non-terminator transitions, block prefix sum, row list
+//   -> phase 2 : one row per thread: field split on the bitmasks (exact sequential splitter
+//                for rows with quote characters), typed decode, WHERE, then
+//                aggregation (registers / shared-memory table / global table), join probe,
+//                or selection.
+// Reference loops replaced: csv_load line loop src/csv_reader.c:404-427, parse_line :278-338,
+// parse_value :195-240, filter_rows evaluator_utils.c:986-1006, create_groups
+// evaluator_aggregates.c:108-176, evaluate_aggregate :263-326, perform_join
+// evaluator_joins.c:96-140.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "cqg_plan.cuh"
+
+namespace cqg {
+
+// ------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------
+template <int THREADS_, int TILE_, int STAGES_>
+struct Geo {
+    static constexpr int THREADS = THREADS_, TILE = TILE_, STAGES = STAGES_;
+    static constexpr int PRE = 32;                 // bytes kept in front of the tile (>= 1 needed)
+    static constexpr int OVER = 992;               // bytes after the tile a row may run into
+    static constexpr int BUF = PRE + TILE + OVER;  // multiple of 32
+    static constexpr int CHUNKS = BUF / 16;
+    static constexpr int MASKW = BUF / 32 + 4;     // mask words incl. padding for 64-bit windows
+    static constexpr int ROWCAP = 4096;            // rows listed per pass
+    static constexpr int NWARPS = THREADS / 32;
+    static constexpr int WPT = (TILE / 32) / THREADS;  // mask words per thread in phase 1b
+    static_assert((TILE / 32) % THREADS == 0, "tile words must divide by threads");
+    // shared memory layout (bytes)
+    static constexpr int OFF_BUF = 0;
+    static constexpr int OFF_TM = OFF_BUF + STAGES * BUF;
+    static constexpr int OFF_DM = OFF_TM + MASKW * 4;
+    static constexpr int OFF_QM = OFF_DM + MASKW * 4;
+    static constexpr int OFF_ROW = OFF_QM + MASKW * 4;
+    static constexpr int OFF_WSUM = OFF_ROW + ROWCAP * 2;
+    static constexpr int OFF_MBAR = OFF_WSUM + 64 * 4;
+    static constexpr int OFF_TABLE = (OFF_MBAR + STAGES * 8 + 127) / 128 * 128;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// SWAR byte classification
+// ------------------------------------------------------------------------------------------
+// 0x80 in every byte of v that equals the byte replicated in pat
+__device__ __forceinline__ uint32_t eq_flags(uint32_t v, uint32_t pat) {
+    uint32_t t = v ^ pat;
+    uint32_t a = (t & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(a | t | 0x7f7f7f7fu);
+}
+// 0x80 flags -> 4-bit mask in byte order (no carries: the 16 partial-product bits are distinct)
+__device__ __forceinline__ uint32_t flags_to_mask4(uint32_t f) { return (f * 0x00204081u) >> 28; }
+
+__device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t pat) {
+    return flags_to_mask4(eq_flags(v.x, pat)) | (flags_to_mask4(eq_flags(v.y, pat)) << 4) |
+           (flags_to_mask4(eq_flags(v.z, pat)) << 8) | (flags_to_mask4(eq_flags(v.w, pat)) << 12);
+}
+
+// 64-bit window of a bitmask starting at bit `pos`
+__device__ __forceinline__ unsigned long long mask_window(const uint32_t* m, uint32_t pos) {
+    uint32_t w = pos >> 5, b = pos & 31u;
+    uint32_t a0 = m[w], a1 = m[w + 1], a2 = m[w + 2];
+    uint32_t lo = __funnelshift_r(a0, a1, b), hi = __funnelshift_r(a1, a2, b);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// ordered images for MIN/MAX
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t img_of_int(long long i) { return (uint64_t)i ^ 0x8000000000000000ull; }
+__host__ __device__ __forceinline__ long long int_of_img(uint64_t u) { return (long long)(u ^ 0x8000000000000000ull); }
+__host__ __device__ __forceinline__ uint64_t img_of_bits(uint64_t b) {
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ uint64_t bits_of_img(uint64_t u) {
+    return (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+}
+
+// ------------------------------------------------------------------------------------------
+// canonical GROUP BY key parts (the reference's key string, evaluator_aggregates.c:121-141,
+// as (tag, w0, w1) so that equal strings <=> equal triples)
+// ------------------------------------------------------------------------------------------
+// |x| * 10^6 rounded half-even on the exact binary value = the digits "%.6f" prints
+__device__ inline uint64_t dbl_key6(double x, unsigned& err) {
+    uint64_t bits = (uint64_t)__double_as_longlong(x) & 0x7fffffffffffffffull;
+    uint32_t e = (uint32_t)(bits >> 52);
+    if (e == 0) return 0;  // subnormal / zero: far below 5e-7
+    if (e == 0x7ffu) {
+        err |= KERR_KEY_RANGE;
+        return 0;
+    }
+    uint64_t m = (bits & 0xfffffffffffffull) | (1ull << 52);
+    int e2 = (int)e - 1075;  // |x| = m * 2^e2
+    uint64_t lo = m * 1000000ull, hi = __umul64hi(m, 1000000ull);
+    if (e2 >= 0) {
+        if (hi != 0 || e2 >= 63 || (lo >> (63 - e2)) != 0) {
+            err |= KERR_KEY_RANGE;
+            return 0;
+        }
+        return lo << e2;
+    }
+    int s = -e2;
+    if (s >= 74) return 0;  // P < 2^73 <= half of 2^s
+    uint64_t q, rem_hi, rem_lo, half_hi, half_lo;
+    if (s < 64) {
+        q = (lo >> s) | (hi << (64 - s));  // hi < 2^9 so hi >> s == 0 unless s < 9
+        if ((hi >> s) != 0) {
+            err |= KERR_KEY_RANGE;
+            return 0;
+        }
+        rem_hi = 0;
+        rem_lo = lo & ((1ull << s) - 1ull);
+        half_hi = 0;
+        half_lo = 1ull << (s - 1);
+    } else {
+        int t = s - 64;
+        q = t ? (hi >> t) : hi;
+        rem_hi = t ? (hi & ((1ull << t) - 1ull)) : 0;
+        rem_lo = lo;
+        half_hi = t ? (1ull << (t - 1)) : 0;
+        half_lo = t ? 0 : (1ull << 63);
+    }
+    bool gt = rem_hi > half_hi || (rem_hi == half_hi && rem_lo > half_lo);
+    bool eq = rem_hi == half_hi && rem_lo == half_lo;
+    if (gt || (eq && (q & 1ull))) q++;
+    if (q >> 63) {
+        err |= KERR_KEY_RANGE;
+        return 0;
+    }
+    return q;
+}
+
+__device__ __forceinline__ void hash_str2(const uint8_t* p, uint32_t n, uint64_t& h0, uint64_t& h1) {
+    uint64_t a = 0x9E3779B97F4A7C15ull ^ n, b = 0xC2B2AE3D27D4EB4Full + n;
+    for (uint32_t k = 0; k < n; k++) {
+        uint64_t c = p[k];
+        a = (a ^ c) * 0x100000001B3ull;
+        b = (b + c) * 0x9FB21C651E98DF25ull;
+        b ^= b >> 29;
+    }
+    h0 = mix64(a);
+    h1 = mix64(b ^ 0x5555555555555555ull);
+}
+
+__device__ __forceinline__ void pack_str16(const uint8_t* p, uint32_t n, uint64_t& w0, uint64_t& w1) {
+    w0 = 0;
+    w1 = 0;
+    for (uint32_t k = 0; k < n && k < 8; k++) w0 |= (uint64_t)p[k] << (8 * k);
+    for (uint32_t k = 8; k < n; k++) w1 |= (uint64_t)p[k] << (8 * (k - 8));
+}
+
+// group_mode: reference key-string identity (NULL == "NULL", strings cut at 255 bytes, %.6f doubles).
+// join mode : value_compare identity inside one comparison class (numeric as double).
+template <bool GROUP>
+__device__ inline void canon_part(const DVal& v, bool multi, unsigned& err, uint32_t& tag, uint64_t& w0, uint64_t& w1) {
+    w0 = 0;
+    w1 = 0;
+    switch (v.type) {
+        case T_INT:
+            if (GROUP) {
+                tag = KT_INT;
+                w0 = (uint64_t)v.i;
+            } else {
+                if (v.i > (1ll << 53) || v.i < -(1ll << 53)) err |= KERR_BIGINT;
+                double d = (double)v.i;
+                tag = KT_DBL_POS;
+                w0 = (uint64_t)__double_as_longlong(d + 0.0);
+            }
+            break;
+        case T_DBL:
+            if (GROUP) {
+                tag = (__double_as_longlong(v.d) < 0) ? KT_DBL_NEG : KT_DBL_POS;
+                w0 = dbl_key6(v.d, err);
+            } else {
+                tag = KT_DBL_POS;
+                double d = v.d == 0.0 ? 0.0 : v.d;  // -0.0 == 0.0
+                w0 = (uint64_t)__double_as_longlong(d);
+            }
+            break;
+        case T_DATE:
+            tag = KT_DATE;
+            w0 = (uint64_t)v.i;
+            break;
+        case T_STR: {
+            uint32_t n = v.len;
+            if (GROUP && n > 255u) n = 255u;  // strncpy(key, s, 255)
+            if (GROUP && n == 4 && v.s[0] == 'N' && v.s[1] == 'U' && v.s[2] == 'L' && v.s[3] == 'L') {
+                tag = KT_NULL;
+                break;
+            }
+            if (GROUP && multi) {
+                for (uint32_t k = 0; k < n; k++)
+                    if (v.s[k] == '\t') err |= KERR_KEY_TAB;
+            }
+            if (n <= 16u) {
+                tag = KT_STR;
+                pack_str16(v.s, n, w0, w1);
+            } else {
+                tag = KT_STR_HASH;
+                hash_str2(v.s, n, w0, w1);
+            }
+            break;
+        }
+        default:
+            tag = KT_NULL;
+            break;
+    }
+}
+
+__device__ __forceinline__ uint64_t key_hash_step(uint64_t h, uint32_t tag, uint64_t w0, uint64_t w1) {
+    h = (h ^ (w0 + tag)) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 32;
+    h = (h ^ w1) * 0xC4CEB9FE1A85EC53ull;
+    h ^= h >> 29;
+    return h;
+}
+__device__ __forceinline__ uint64_t key_hash_final(uint64_t h) {
+    h = mix64(h);
+    return (h & 0x7fffffffffffffffull) | 1ull;
+}
+
+// ------------------------------------------------------------------------------------------
+// group table: find-or-insert (open addressing, linear probing, 64-bit hash tag per slot)
+// ------------------------------------------------------------------------------------------
+template <bool SM>
+__device__ __forceinline__ uint64_t load_u64(const void* p) {
+    return *(const volatile uint64_t*)p;
+}
+
+__device__ __forceinline__ void copy_entry_init(uint8_t* e, const uint8_t* init, int bytes) {
+    // entry_bytes is a multiple of 8; the hash word (offset 0) is written by the caller
+    for (int o = 8; o < bytes; o += 8) *(uint64_t*)(e + o) = *(const uint64_t*)(init + o);
+}
+
+// returns the entry, or nullptr when the table is full. `fresh_init`: global entries are
+// pre-initialised by the host; shared entries by the CTA prologue — so insertion only writes keys.
+__device__ inline uint8_t* table_find_insert(uint8_t* tab, uint64_t cap, int entry_bytes, int ngc, uint64_t h, uint32_t tags,
+                                             const uint64_t* kw /* [ngc][2] */, unsigned long long* occupancy,
+                                             uint64_t max_occupancy) {
+    uint64_t mask = cap - 1;
+    uint64_t i = (h >> 1) & mask;
+    for (uint64_t probes = 0; probes < cap;) {
+        uint8_t* e = tab + i * (uint64_t)entry_bytes;
+        unsigned long long* hp = (unsigned long long*)(e + kOffHash);
+        unsigned long long cur = *(volatile unsigned long long*)hp;
+        if (cur == 0ull) {
+            if (occupancy && *(volatile unsigned long long*)occupancy >= max_occupancy) return nullptr;
+            cur = atomicCAS(hp, 0ull, (unsigned long long)(h | kLockBit));
+            if (cur == 0ull) {
+                if (occupancy) atomicAdd(occupancy, 1ull);
+                *(uint32_t*)(e + kOffTags) = tags;
+                for (int g = 0; g < ngc; g++) {
+                    *(uint64_t*)(e + kOffKeys + 16 * g) = kw[2 * g];
+                    *(uint64_t*)(e + kOffKeys + 16 * g + 8) = kw[2 * g + 1];
+                }
+                __threadfence();
+                atomicExch(hp, (unsigned long long)h);
+                return e;
+            }
+        }
+        if ((cur & ~kLockBit) == h) {
+            if (cur & kLockBit) continue;  // being initialised by another thread: look again
+            __threadfence();
+            bool same = *(volatile uint32_t*)(e + kOffTags) == tags;
+            for (int g = 0; g < ngc && same; g++)
+                same = *(volatile uint64_t*)(e + kOffKeys + 16 * g) == kw[2 * g] &&
+                       *(volatile uint64_t*)(e + kOffKeys + 16 * g + 8) == kw[2 * g + 1];
+            if (same) return e;
+        }
+        i = (i + 1) & mask;
+        probes++;
+    }
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// aggregate state updates
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void amin64(uint64_t* p, uint64_t v) {
+    if (v < *(volatile uint64_t*)p) atomicMin((unsigned long long*)p, (unsigned long long)v);
+}
+__device__ __forceinline__ void amax64(uint64_t* p, uint64_t v) {
+    if (v > *(volatile uint64_t*)p) atomicMax((unsigned long long*)p, (unsigned long long)v);
+}
+
+__device__ __forceinline__ const uint8_t* str_ref_ptr(const DevPlan& P, uint64_t ref, uint32_t& len) {
+    len = (uint32_t)(ref & 0x3ffffu);
+    uint64_t off = (ref >> 18) & 0x1fffffffffffull;
+    return ((ref >> 63) ? P.rdata : P.data) + off;
+}
+
+// keep the smaller (MIN) / larger (MAX) string; ties keep the incumbent
+__device__ inline void str_extreme(const DevPlan& P, uint64_t* slot, uint64_t cand, bool is_min) {
+    const uint64_t empty = is_min ? ~0ull : 0ull;
+    uint32_t cl;
+    const uint8_t* cp = str_ref_ptr(P, cand, cl);
+    for (;;) {
+        uint64_t cur = *(volatile uint64_t*)slot;
+        if (cur != empty) {
+            uint32_t ul;
+            const uint8_t* up = str_ref_ptr(P, cur, ul);
+            int c = str_cmp(cp, cl, up, ul);
+            if (is_min ? c >= 0 : c <= 0) return;
+        }
+        if (atomicCAS((unsigned long long*)slot, (unsigned long long)cur, (unsigned long long)cand) == cur) return;
+    }
+}
+
+// one value enters a MIN/MAX state (evaluator_aggregates.c:311-326, order-free form)
+__device__ inline void minmax_update(const DevPlan& P, uint8_t* st, bool is_min, const DVal& v, uint64_t okey, bool right_side,
+                                     const uint8_t* field_base_file, unsigned& err) {
+    if (v.type == T_NULL) return;
+    uint64_t* s = (uint64_t*)st;
+    uint32_t cls = (v.type == T_INT || v.type == T_DBL) ? 1u : (v.type == T_STR ? 2u : 3u);
+    amin64(&s[0], (okey << 2) | cls);
+    if (v.type == T_INT) {
+        if (v.i > (1ll << 53) || v.i < -(1ll << 53)) err |= KERR_BIGINT;
+        uint64_t im = img_of_int(v.i);
+        if (is_min) amin64(&s[1], im); else amax64(&s[1], im);
+    } else if (v.type == T_DBL) {
+        uint64_t im = img_of_bits((uint64_t)__double_as_longlong(v.d));
+        if (is_min) amin64(&s[2], im); else amax64(&s[2], im);
+    } else if (v.type == T_DATE) {
+        uint64_t im = (uint64_t)v.i + 1ull;  // keep 0 / ~0 free as "empty"
+        if (is_min) amin64(&s[3], im); else amax64(&s[3], im);
+    } else {
+        // string bytes live in the resident file: reference them
+        uint64_t off = (uint64_t)(v.s - field_base_file);
+        if (v.len > 0x3ffffu) {
+            err |= KERR_STR_LONG;
+            return;
+        }
+        if (off >> 45) {
+            err |= KERR_OFFSET_RANGE;
+            return;
+        }
+        uint64_t ref = (right_side ? (1ull << 63) : 0ull) | (off << 18) | v.len;
+        str_extreme(P, &s[4], ref, is_min);
+    }
+}
+
+// merge MIN/MAX state `src` into `dst` (shared -> global flush, partial merge)
+__device__ inline void minmax_merge(const DevPlan& P, uint8_t* dst, const uint8_t* src, bool is_min) {
+    uint64_t* d = (uint64_t*)dst;
+    const uint64_t* s = (const uint64_t*)src;
+    amin64(&d[0], s[0]);
+    const uint64_t empty = is_min ? ~0ull : 0ull;
+    for (int k = 1; k <= 3; k++) {
+        if (s[k] == empty) continue;
+        if (is_min) amin64(&d[k], s[k]); else amax64(&d[k], s[k]);
+    }
+    if (s[4] != empty) str_extreme(P, &d[4], s[4], is_min);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-thread register accumulators for the no-GROUP-BY case
+// ------------------------------------------------------------------------------------------
+struct ThreadAcc {
+    uint32_t rows;     // data rows seen
+    uint32_t count;    // rows passing WHERE
+    uint64_t first;    // min okey
+    long long si[4];
+    double sd[4];
+    uint32_t sn[4];
+    unsigned err;
+};
+
+// ------------------------------------------------------------------------------------------
+// predicate evaluation
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ DVal const_value(const DPred& P, int idx) {
+    const DConst c = P.consts[idx];
+    DVal v;
+    v.type = c.type;
+    v.len = c.len;
+    v.i = c.bits;
+    if (c.type == T_STR) v.s = P.pool + c.bits;
+    return v;
+}
+
+__device__ __forceinline__ DVal fetch_ref(const DevPlan& P, const RowView& rv, int ref, unsigned& err) {
+    if (ref == kRefNull) {
+        DVal v;
+        v.type = T_NULL;
+        v.len = 0;
+        v.i = 0;
+        return v;
+    }
+    if (ref & kRefConst) return const_value(P.pred, ref & 0x3fff);
+    return row_value(rv, ref, err);
+}
+
+__device__ inline bool eval_fused(const DevPlan& P, const RowView& rv, unsigned& err) {
+    uint32_t bs = 0;  // bit stack, top = bit 0
+    for (int pc = 0; pc < P.n_fcode; pc++) {
+        const FInsn in = P.fcode[pc];
+        bool b;
+        switch (in.op) {
+            case F_CMP: {
+                DVal l = fetch_ref(P, rv, in.a, err), r = fetch_ref(P, rv, in.b, err);
+                int c = val_compare(l, r);
+                b = in.n == CQG_OP_EQ ? c == 0 : in.n == CQG_OP_NE ? c != 0 : in.n == CQG_OP_GT ? c > 0
+                  : in.n == CQG_OP_LT ? c < 0 : in.n == CQG_OP_GE ? c >= 0 : c <= 0;
+                bs = (bs << 1) | (uint32_t)b;
+                break;
+            }
+            case F_IN: case F_NOT_IN: {
+                DVal l = fetch_ref(P, rv, in.a, err);
+                bool found = false;
+                for (int k = 0; k < in.n && !found; k++) {
+                    DVal it = fetch_ref(P, rv, P.frefs[in.b + k], err);
+                    found = val_compare(l, it) == 0;
+                }
+                b = in.op == F_IN ? found : !found;
+                bs = (bs << 1) | (uint32_t)b;
+                break;
+            }
+            case F_LIKE: case F_ILIKE: {
+                DVal l = fetch_ref(P, rv, in.a, err), r = fetch_ref(P, rv, in.b, err);
+                b = (l.type == T_STR && r.type == T_STR) ? like_match(l.s, l.len, r.s, r.len, in.op == F_LIKE) : false;
+                bs = (bs << 1) | (uint32_t)b;
+                break;
+            }
+            case F_AND: bs = ((bs >> 1) & ~1u) | ((bs >> 1) & bs & 1u); break;
+            case F_OR: bs = ((bs >> 1) & ~1u) | (((bs >> 1) | bs) & 1u); break;
+            case F_NOT: bs ^= 1u; break;
+            case F_TRUE: bs = (bs << 1) | 1u; break;
+            default: bs = bs << 1; break;  // F_FALSE
+        }
+    }
+    return (bs & 1u) != 0;
+}
+
+__device__ __forceinline__ bool eval_where(const DevPlan& P, const RowView& rv, unsigned& err) {
+    if (P.pred_kind == 0) return true;
+    if (P.pred_kind == 1) return eval_fused(P, rv, err);
+    return eval_pred(P.pred, rv, err);
+}
+
+// ------------------------------------------------------------------------------------------
+// what happens to one row that passed WHERE
+// ------------------------------------------------------------------------------------------
+struct CtaState {
+    uint8_t* stab;  // shared-memory group table (smem_cap entries) or nullptr
+    unsigned long long* s_occ;  // its occupancy counter (shared)
+};
+
+template <bool SM>
+__device__ __forceinline__ void entry_accumulate(const DevPlan& P, uint8_t* e, const RowView& rv, uint64_t okey, unsigned& err) {
+    amin64((uint64_t*)(e + kOffFirst), okey);
+    if (SM) atomicAdd((unsigned int*)(e + kOffCount), 1u);
+    else atomicAdd((unsigned long long*)(e + kOffCount), 1ull);
+    for (int a = 0; a < P.naggs; a++) {
+        const AggSpec sp = P.aggs[a];
+        if (sp.off < 0) continue;
+        DVal v = row_value(rv, sp.col, err);
+        uint8_t* st = e + sp.off;
+        if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
+            if (v.type == T_INT) {
+                atomicAdd((unsigned long long*)st, (unsigned long long)v.i);
+                if (SM) atomicAdd((unsigned int*)(st + 16), 1u);
+                else atomicAdd((unsigned long long*)(st + 16), 1ull);
+            } else if (v.type == T_DBL) {
+                atomicAdd((double*)(st + 8), v.d);
+                if (SM) atomicAdd((unsigned int*)(st + 16), 1u);
+                else atomicAdd((unsigned long long*)(st + 16), 1ull);
+            }
+        } else {
+            bool right = sp.col >= P.n_left_cols;
+            minmax_update(P, st, sp.func == CQG_AGG_MIN, v, okey, right, right ? rv.rfile : rv.lfile, err);
+        }
+    }
+}
+
+// fold entry `src` (same layout) into `dst`
+__device__ inline void entry_merge(const DevPlan& P, uint8_t* dst, const uint8_t* src) {
+    amin64((uint64_t*)(dst + kOffFirst), *(const uint64_t*)(src + kOffFirst));
+    atomicAdd((unsigned long long*)(dst + kOffCount), (unsigned long long)*(const uint64_t*)(src + kOffCount));
+    for (int a = 0; a < P.naggs; a++) {
+        const AggSpec sp = P.aggs[a];
+        if (sp.off < 0) continue;
+        if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
+            unsigned long long si = *(const unsigned long long*)(src + sp.off);
+            double sd = *(const double*)(src + sp.off + 8);
+            unsigned long long n = *(const unsigned long long*)(src + sp.off + 16);
+            if (si) atomicAdd((unsigned long long*)(dst + sp.off), si);
+            if (sd != 0.0) atomicAdd((double*)(dst + sp.off + 8), sd);
+            if (n) atomicAdd((unsigned long long*)(dst + sp.off + 16), n);
+        } else {
+            minmax_merge(P, dst + sp.off, src + sp.off, sp.func == CQG_AGG_MIN);
+        }
+    }
+}
+
+__device__ inline uint8_t* global_entry_for(const DevPlan& P, uint64_t h, uint32_t tags, const uint64_t* kw, unsigned& err) {
+    uint8_t* e = table_find_insert(P.gtab, P.gcap, P.entry_bytes, P.ngc, h, tags, kw, P.gcount, P.gcap / 2);
+    if (!e) err |= KERR_TABLE_FULL;
+    return e;
+}
+
+__device__ inline void agg_row(const DevPlan& P, const CtaState& cs, const RowView& rv, uint64_t okey, ThreadAcc& acc) {
+    if (P.scalar_regs) {
+        acc.count++;
+        if (okey < acc.first) acc.first = okey;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            if (a < P.naggs) {
+                const AggSpec sp = P.aggs[a];
+                if (sp.off >= 0) {
+                    DVal v = row_value(rv, sp.col, acc.err);
+                    if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
+                        if (v.type == T_INT) {
+                            acc.si[a] += v.i;
+                            acc.sn[a]++;
+                        } else if (v.type == T_DBL) {
+                            acc.sd[a] += v.d;
+                            acc.sn[a]++;
+                        }
+                    } else {
+                        bool right = sp.col >= P.n_left_cols;
+                        minmax_update(P, cs.stab + sp.off, sp.func == CQG_AGG_MIN, v, okey, right, right ? rv.rfile : rv.lfile,
+                                      acc.err);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    uint64_t kw[2 * CQG_MAX_GROUP_COLS];
+    uint32_t tags = 0;
+    uint64_t h = 0x243F6A8885A308D3ull + (uint64_t)P.ngc;
+    for (int g = 0; g < P.ngc; g++) {
+        DVal v = row_value(rv, P.gcol[g], acc.err);
+        uint32_t tag;
+        canon_part<true>(v, P.ngc > 1, acc.err, tag, kw[2 * g], kw[2 * g + 1]);
+        tags |= tag << (4 * g);
+        h = key_hash_step(h, tag, kw[2 * g], kw[2 * g + 1]);
+    }
+    h = key_hash_final(h);
+    if (cs.stab) {
+        uint8_t* e = table_find_insert(cs.stab, (uint64_t)P.smem_cap, P.entry_bytes, P.ngc, h, tags, kw, cs.s_occ,
+                                       (uint64_t)(P.smem_cap - (P.smem_cap >> 2)));
+        if (e) {
+            entry_accumulate<true>(P, e, rv, okey, acc.err);
+            return;
+        }
+    }
+    uint8_t* e = global_entry_for(P, h, tags, kw, acc.err);
+    if (e) entry_accumulate<false>(P, e, rv, okey, acc.err);
+}
+
+__device__ __forceinline__ void select_row(const DevPlan& P, uint64_t okey, uint64_t roff) {
+    unsigned long long idx = atomicAdd(P.sel_count, 1ull);
+    if (idx < P.sel_cap) {
+        P.sel_okey[idx] = okey;
+        if (P.sel_roff) P.sel_roff[idx] = roff;
+    }
+}
+
+__device__ __forceinline__ void row_passes(const DevPlan& P, const CtaState& cs, const RowView& rv, uint64_t okey, uint64_t roff,
+                                           ThreadAcc& acc) {
+    if (!eval_where(P, rv, acc.err)) return;
+    if (P.mode == SCAN_AGG) agg_row(P, cs, rv, okey, acc);
+    else select_row(P, okey, roff);
+}
+
+// ------------------------------------------------------------------------------------------
+// join: build and probe (perform_join, evaluator_joins.c:96-140, as a hash equi-join)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t join_class(const DVal& v) {
+    return v.type == T_NULL ? 0u : ((v.type == T_INT || v.type == T_DBL) ? 1u : (v.type == T_STR ? 2u : 3u));
+}
+
+__device__ inline JoinSlot* join_find(const DevPlan& P, uint64_t h, uint32_t tag, uint64_t w0, uint64_t w1, bool insert) {
+    uint64_t mask = P.jcap - 1;
+    uint64_t i = (h >> 1) & mask;
+    for (uint64_t probes = 0; probes < P.jcap;) {
+        JoinSlot* s = &P.jslots[i];
+        unsigned long long cur = *(volatile unsigned long long*)&s->h;
+        if (cur == 0ull) {
+            if (!insert) return nullptr;
+            cur = atomicCAS((unsigned long long*)&s->h, 0ull, (unsigned long long)(h | kLockBit));
+            if (cur == 0ull) {
+                s->w0 = w0;
+                s->w1 = w1;
+                s->tag = tag;
+                __threadfence();
+                atomicExch((unsigned long long*)&s->h, (unsigned long long)h);
+                return s;
+            }
+        }
+        if ((cur & ~kLockBit) == h) {
+            if (cur & kLockBit) continue;
+            __threadfence();
+            if (*(volatile uint32_t*)&s->tag == tag && *(volatile uint64_t*)&s->w0 == w0 && *(volatile uint64_t*)&s->w1 == w1)
+                return s;
+        }
+        i = (i + 1) & mask;
+        probes++;
+    }
+    return nullptr;
+}
+
+__device__ inline void join_key_of(const DVal& v, unsigned& err, uint32_t& tag, uint64_t& w0, uint64_t& w1, uint64_t& h) {
+    canon_part<false>(v, false, err, tag, w0, w1);
+    h = key_hash_final(key_hash_step(0x13198A2E03707344ull, tag, w0, w1));
+}
+
+__device__ inline void join_build_row(const DevPlan& P, const RowView& rv, uint64_t roff, unsigned& err) {
+    DVal v = row_value(rv, P.jr_col, err);
+    atomicOr(&P.jclass[1], 1u << join_class(v));
+    uint32_t tag;
+    uint64_t w0, w1, h;
+    join_key_of(v, err, tag, w0, w1, h);
+    JoinSlot* s = join_find(P, h, tag, w0, w1, true);
+    if (!s) {
+        err |= KERR_TABLE_FULL;
+        return;
+    }
+    unsigned long long idx = atomicAdd(P.jrow_count, 1ull);
+    if (idx >= P.jrow_cap) {
+        err |= KERR_TABLE_FULL;
+        return;
+    }
+    P.jrow_off[idx] = roff;
+    P.jrow_next[idx] = atomicExch(&s->head, (uint32_t)idx + 1u);
+}
+
+// right row at file offset roff: find its end, split the wanted right columns
+__device__ inline void split_right_row(const DevPlan& P, uint64_t roff, uint32_t* foff, uint32_t* flen) {
+    const uint8_t* b = P.rdata + roff;
+    uint64_t maxlen = P.rsize - roff;
+    uint32_t re = 0;
+    while ((uint64_t)re < maxlen && b[re] != '\n' && b[re] != '\r' && re < 0x7fffffffu) re++;
+    split_row_exact(b, 0, re, P.delim, P.quote, P.wantR, P.nwantR, foff + P.nwantL, flen + P.nwantL);
+}
+
+// ------------------------------------------------------------------------------------------
+// one data row: `base` + foff/flen hold the wanted left fields; goff = file offset of the row
+// ------------------------------------------------------------------------------------------
+__device__ inline void process_row(const DevPlan& P, const CtaState& cs, const uint8_t* base, const uint8_t* lfile, uint32_t* foff,
+                                   uint32_t* flen, uint64_t goff, ThreadAcc& acc) {
+    RowView rv;
+    rv.base = base;
+    rv.rbase = nullptr;
+    rv.lfile = lfile;
+    rv.rfile = P.rdata;
+    rv.foff = foff;
+    rv.flen = flen;
+    rv.colslot = P.colslot;
+    rv.ncols_total = P.n_cols_total;
+    rv.nleft_slots = P.nwantL;
+    uint64_t gabs = P.global_base + goff;
+    if (gabs >> 45) acc.err |= KERR_OFFSET_RANGE;
+    uint64_t okey = gabs << 16;
+    if (P.mode == SCAN_JOIN_BUILD) {
+        join_build_row(P, rv, goff, acc.err);
+        return;
+    }
+    if (!P.join) {
+        row_passes(P, cs, rv, okey, 0, acc);
+        return;
+    }
+    // probe
+    if (P.jl_col < 0 || P.jr_col < 0) return;  // resolve_column -> NULL: condition false (joins.c:54)
+    DVal lk = row_value(rv, P.jl_col, acc.err);
+    atomicOr(&P.jclass[0], 1u << join_class(lk));
+    uint32_t tag;
+    uint64_t w0, w1, h;
+    join_key_of(lk, acc.err, tag, w0, w1, h);
+    JoinSlot* s = join_find(P, h, tag, w0, w1, false);
+    if (!s) return;
+    uint32_t head = s->head;
+    for (uint32_t it = head; it != 0u; it = P.jrow_next[it - 1]) {
+        uint64_t roff = P.jrow_off[it - 1];
+        // rank of this match among the left row's matches = position in right-file order
+        uint32_t rank = 0;
+        if (P.jrow_next[head - 1] != 0u) {
+            for (uint32_t jt = head; jt != 0u; jt = P.jrow_next[jt - 1]) rank += P.jrow_off[jt - 1] < roff;
+        }
+        if (rank > 0xffffu) {
+            acc.err |= KERR_JOIN_FANOUT;
+            rank = 0xffffu;
+        }
+        if (P.need_right_fields) {
+            split_right_row(P, roff, foff, flen);
+            rv.rbase = P.rdata + roff;
+        }
+        row_passes(P, cs, rv, okey | rank, roff, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <class G>
+__global__ void __launch_bounds__(G::THREADS) scan_kernel(const __grid_constant__ DevPlan P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* tm = (uint32_t*)(smem + G::OFF_TM);
+    uint32_t* dm = (uint32_t*)(smem + G::OFF_DM);
+    uint32_t* qm = (uint32_t*)(smem + G::OFF_QM);
+    uint16_t* rowpos = (uint16_t*)(smem + G::OFF_ROW);
+    uint32_t* wsum = (uint32_t*)(smem + G::OFF_WSUM);
+    uint64_t* mbar = (uint64_t*)(smem + G::OFF_MBAR);
+
+    CtaState cs;
+    cs.stab = nullptr;
+    cs.s_occ = (unsigned long long*)(wsum + 48);
+    const bool agg_mode = P.mode == SCAN_AGG;
+    if (agg_mode && (P.smem_cap > 0)) cs.stab = smem + G::OFF_TABLE;
+
+    // ---- prologue: barriers, mask padding, shared table ----
+    if (tid == 0) {
+        for (int s = 0; s < G::STAGES; s++) mbar_init(&mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *cs.s_occ = 0ull;
+    }
+    for (int w = G::BUF / 32 + tid; w < G::MASKW; w += G::THREADS) {
+        tm[w] = 0xffffffffu;
+        dm[w] = 0u;
+        qm[w] = 0u;
+    }
+    if (cs.stab) {
+        const int words = P.smem_cap * P.entry_bytes / 8;
+        const int ew = P.entry_bytes / 8;
+        for (int k = tid; k < words; k += G::THREADS) {
+            int o = k % ew;
+            ((uint64_t*)cs.stab)[k] = o == 0 ? 0ull : ((const uint64_t*)P.entry_init)[o];
+        }
+    }
+    __syncthreads();
+
+    ThreadAcc acc;
+    acc.rows = 0;
+    acc.count = 0;
+    acc.first = ~0ull;
+    acc.err = 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        acc.si[a] = 0;
+        acc.sd[a] = 0.0;
+        acc.sn[a] = 0;
+    }
+
+    const uint64_t size = P.size;
+    const uint64_t copy_end = (size + 15ull) & ~15ull;  // allocation is padded (cqg_device_padding)
+    const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
+    const uint32_t patQ = (uint32_t)P.quote * 0x01010101u;
+
+    auto issue = [&](int it) {
+        long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
+        int stage = it % G::STAGES;
+        long long g0 = tile * (long long)G::TILE - G::PRE;  // file offset of buf[0]
+        uint32_t skip = g0 < 0 ? (uint32_t)(-g0) : 0u;
+        long long src = g0 + skip;
+        long long avail = (long long)copy_end - src;
+        uint32_t bytes = 0;
+        if (avail > 0) bytes = (uint32_t)(avail < (long long)(G::BUF - skip) ? avail : (long long)(G::BUF - skip));
+        uint8_t* dst = smem + G::OFF_BUF + stage * G::BUF + skip;
+        if (bytes) {
+            mbar_expect_tx(&mbar[stage], bytes);
+            tma_load_1d(dst, P.data + src, bytes, &mbar[stage]);
+        } else {
+            mbar_expect_tx(&mbar[stage], 0);
+        }
+    };
+
+    const int my_tiles = (P.n_tiles > (int)blockIdx.x) ? (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (tid == 0)
+        for (int it = 0; it < G::STAGES - 1 && it < my_tiles; it++) issue(it);
+
+    for (int it = 0; it < my_tiles; it++) {
+        const int stage = it % G::STAGES;
+        const uint32_t parity = (uint32_t)(it / G::STAGES) & 1u;
+        if (tid == 0 && it + G::STAGES - 1 < my_tiles) issue(it + G::STAGES - 1);
+        // stop early when a table overflowed: the host will retry with a bigger one
+        const unsigned abort_now = (*(volatile unsigned*)P.errflags) & (KERR_TABLE_FULL | KERR_SEL_OVERFLOW);
+        mbar_wait(&mbar[stage], parity);
+        const uint8_t* buf = smem + G::OFF_BUF + stage * G::BUF;
+        const long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
+        const long long g0 = tile * (long long)G::TILE - G::PRE;
+
+        // ---------------- phase 1: classify ----------------
+        uint32_t spec = 0;
+        for (int c = tid; c < G::CHUNKS; c += G::THREADS) {
+            const uint4 v = *(const uint4*)(buf + 16 * c);
+            uint32_t f0 = eq_flags(v.x, 0x0a0a0a0au), f1 = eq_flags(v.y, 0x0a0a0a0au), f2 = eq_flags(v.z, 0x0a0a0a0au),
+                     f3 = eq_flags(v.w, 0x0a0a0a0au);
+            uint32_t T = flags_to_mask4(f0) | (flags_to_mask4(f1) << 4) | (flags_to_mask4(f2) << 8) | (flags_to_mask4(f3) << 12);
+            uint32_t D = eq_mask16(v, patD);
+            // any byte < 0x23 other than '\n' (CR, quote, blanks, controls): the tile takes the careful path
+            uint32_t x0 = v.x | f0, x1 = v.y | f1, x2 = v.z | f2, x3 = v.w | f3;
+            uint32_t s4 = ((x0 - 0x23232323u) & ~x0) | ((x1 - 0x23232323u) & ~x1) | ((x2 - 0x23232323u) & ~x2) |
+                          ((x3 - 0x23232323u) & ~x3);
+            long long g = g0 + 16 * c;
+            if (g < 0 || g + 16 > (long long)size) {
+                // bytes outside the file are row terminators and nothing else
+                uint32_t valid = 0;
+                for (int j = 0; j < 16; j++)
+                    if (g + j >= 0 && g + j < (long long)size) valid |= 1u << j;
+                T = (T & valid) | (~valid & 0xffffu);
+                D &= valid;
+                s4 = 0x80u;  // partial chunk: be careful
+            }
+            spec |= s4 & 0x80808080u;
+            ((uint16_t*)tm)[c] = (uint16_t)T;
+            ((uint16_t*)dm)[c] = (uint16_t)D;
+        }
+        const int special = __syncthreads_or((int)(spec != 0u)) | (int)P.exact_only;
+        if (special) {
+            for (int c = tid; c < G::CHUNKS; c += G::THREADS) {
+                const uint4 v = *(const uint4*)(buf + 16 * c);
+                uint32_t R = eq_mask16(v, 0x0d0d0d0du), Q = eq_mask16(v, patQ);
+                long long g = g0 + 16 * c;
+                if (g < 0 || g + 16 > (long long)size) {
+                    uint32_t valid = 0;
+                    for (int j = 0; j < 16; j++)
+                        if (g + j >= 0 && g + j < (long long)size) valid |= 1u << j;
+                    R &= valid;
+                    Q &= valid;
+                }
+                ((uint16_t*)tm)[c] |= (uint16_t)R;
+                ((uint16_t*)qm)[c] = (uint16_t)Q;
+            }
+            __syncthreads();
+        }
+
+        // ---------------- phase 1b: row starts ----------------
+        long long olo_l = (long long)P.own_lo - g0, ohi_l = (long long)P.own_hi - g0;
+        const uint32_t olo = (uint32_t)(olo_l < G::PRE ? G::PRE : (olo_l > G::PRE + G::TILE ? G::PRE + G::TILE : olo_l));
+        const uint32_t ohi = (uint32_t)(ohi_l < G::PRE ? G::PRE : (ohi_l > G::PRE + G::TILE ? G::PRE + G::TILE : ohi_l));
+        uint32_t S[G::WPT];
+        uint32_t mycount = 0;
+        {
+            const int w0 = G::PRE / 32 + tid * G::WPT;
+            uint32_t prev = tm[w0 - 1];
+#pragma unroll
+            for (int j = 0; j < G::WPT; j++) {
+                uint32_t t = tm[w0 + j];
+                uint32_t s = ((t << 1) | (prev >> 31)) & ~t;
+                prev = t;
+                uint32_t p0 = (uint32_t)(w0 + j) * 32u;
+                // keep bits in [olo, ohi)
+                uint32_t lo_m = olo <= p0 ? 0xffffffffu : (olo >= p0 + 32u ? 0u : (0xffffffffu << (olo - p0)));
+                uint32_t hi_m = ohi >= p0 + 32u ? 0xffffffffu : (ohi <= p0 ? 0u : (0xffffffffu >> (p0 + 32u - ohi)));
+                s &= lo_m & hi_m;
+                S[j] = s;
+                mycount += __popc(s);
+            }
+        }
+        // block exclusive scan of mycount
+        uint32_t incl = mycount;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        const int abort_all = __syncthreads_or((int)abort_now);
+        uint32_t wbase = 0, nrows = 0;
+#pragma unroll
+        for (int w = 0; w < G::NWARPS; w++) {
+            uint32_t x = wsum[w];
+            if (w < warp) wbase += x;
+            nrows += x;
+        }
+        const uint32_t mybase = wbase + incl - mycount;
+        if (abort_all) nrows = 0;
+
+        for (uint32_t pass_lo = 0; pass_lo < nrows; pass_lo += G::ROWCAP) {
+            {
+                uint32_t idx = mybase;
+                const int w0 = G::PRE / 32 + tid * G::WPT;
+#pragma unroll
+                for (int j = 0; j < G::WPT; j++) {
+                    uint32_t s = S[j];
+                    while (s) {
+                        uint32_t b = __ffs(s) - 1;
+                        s &= s - 1;
+                        uint32_t k = idx - pass_lo;
+                        if (k < (uint32_t)G::ROWCAP) rowpos[k] = (uint16_t)((w0 + j) * 32 + b);
+                        idx++;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---------------- phase 2: rows ----------------
+            const uint32_t npass = nrows - pass_lo < (uint32_t)G::ROWCAP ? nrows - pass_lo : (uint32_t)G::ROWCAP;
+            for (uint32_t r = tid; r < npass; r += G::THREADS) {
+                const uint32_t rs = rowpos[r];
+                acc.rows++;
+                if (P.mode == SCAN_COUNT_ROWS) continue;
+                uint32_t foff[2 * kMaxSlots], flen[2 * kMaxSlots];
+                const uint64_t goff = (uint64_t)(g0 + (long long)rs);
+                // row end: first terminator at or after rs
+                unsigned long long tw = mask_window(tm, rs);
+                uint32_t len;
+                if (tw) {
+                    len = (uint32_t)__ffsll((long long)tw) - 1u;
+                } else {
+                    uint32_t p = rs + 64u;
+                    len = 0xffffffffu;
+                    while (p < (uint32_t)G::BUF) {
+                        unsigned long long w2 = mask_window(tm, p);
+                        if (w2) {
+                            len = p + (uint32_t)__ffsll((long long)w2) - 1u - rs;
+                            break;
+                        }
+                        p += 64u;
+                    }
+                }
+                if (len == 0xffffffffu || rs + len >= (uint32_t)G::BUF) {
+                    // the row runs past the staged window: split it straight from HBM
+                    const uint8_t* b = P.data + goff;
+                    uint64_t maxlen = size - goff;
+                    uint64_t re = 0;
+                    while (re < maxlen && b[re] != '\n' && b[re] != '\r') re++;
+                    if (re > 0x7fffffffull) re = 0x7fffffffull;
+                    split_row_exact(b, 0, (uint32_t)re, P.delim, P.quote, P.wantL, P.nwantL, foff, flen);
+                    process_row(P, cs, b, P.data, foff, flen, goff, acc);
+                    continue;
+                }
+                bool fast = len <= 64u && !P.exact_only;
+                unsigned long long lenmask = len >= 64u ? ~0ull : ((1ull << len) - 1ull);
+                if (fast && special) fast = (mask_window(qm, rs) & lenmask) == 0ull;
+                if (fast) {
+                    unsigned long long dw = mask_window(dm, rs) & lenmask;
+                    int col = 0;
+                    uint32_t startpos = 0;
+                    int k = 0;
+                    for (; k < P.nwantL; k++) {
+                        const int want = P.wantL[k];
+                        while (col < want && dw) {
+                            startpos = (uint32_t)__ffsll((long long)dw);
+                            dw &= dw - 1ull;
+                            col++;
+                        }
+                        if (col < want) break;
+                        uint32_t endpos = dw ? (uint32_t)__ffsll((long long)dw) - 1u : len;
+                        uint32_t fs = startpos;
+                        while (fs < endpos && is_space(buf[rs + fs])) fs++;
+                        foff[k] = rs + fs;
+                        flen[k] = endpos - fs;
+                    }
+                    for (; k < P.nwantL; k++) {
+                        foff[k] = rs;
+                        flen[k] = 0;
+                    }
+                } else {
+                    split_row_exact(buf, rs, rs + len, P.delim, P.quote, P.wantL, P.nwantL, foff, flen);
+                }
+                process_row(P, cs, buf, buf - g0, foff, flen, goff, acc);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+
+    // ---------------- epilogue ----------------
+    // rows seen
+    {
+        uint32_t r = acc.rows;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
+        if (lane == 0 && r) atomicAdd(P.rows_scanned, (unsigned long long)r);
+    }
+    if (agg_mode && P.scalar_regs) {
+        // fold the register accumulators into the single shared entry
+        uint8_t* e = cs.stab;
+        uint32_t c = acc.count;
+        uint64_t f = acc.first;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, d);
+            uint64_t of = __shfl_xor_sync(0xffffffffu, f, d);
+            f = of < f ? of : f;
+        }
+        if (lane == 0 && c) {
+            atomicAdd((unsigned int*)(e + kOffCount), c);
+            amin64((uint64_t*)(e + kOffFirst), f);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            if (a < P.naggs && P.aggs[a].off >= 0 && (P.aggs[a].func == CQG_AGG_SUM || P.aggs[a].func == CQG_AGG_AVG)) {
+                long long si = acc.si[a];
+                double sd = acc.sd[a];
+                uint32_t sn = acc.sn[a];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    si += __shfl_xor_sync(0xffffffffu, si, d);
+                    sd += __shfl_xor_sync(0xffffffffu, sd, d);
+                    sn += __shfl_xor_sync(0xffffffffu, sn, d);
+                }
+                if (lane == 0 && sn) {
+                    uint8_t* st = e + P.aggs[a].off;
+                    atomicAdd((unsigned long long*)st, (unsigned long long)si);
+                    atomicAdd((double*)(st + 8), sd);
+                    atomicAdd((unsigned int*)(st + 16), sn);
+                }
+            }
+        }
+        __syncthreads();
+        // the single group `_all_`
+        if (tid == 0) {
+            uint64_t h = key_hash_final(0x243F6A8885A308D3ull);
+            uint8_t* ge = global_entry_for(P, h, 0u, nullptr, acc.err);
+            if (ge) entry_merge(P, ge, e);
+        }
+    } else if (cs.stab) {
+        __syncthreads();
+        for (int s = tid; s < P.smem_cap; s += G::THREADS) {
+            const uint8_t* e = cs.stab + (size_t)s * P.entry_bytes;
+            uint64_t h = *(const uint64_t*)(e + kOffHash);
+            if (h == 0ull) continue;
+            uint64_t kw[2 * CQG_MAX_GROUP_COLS];
+            for (int g = 0; g < P.ngc; g++) {
+                kw[2 * g] = *(const uint64_t*)(e + kOffKeys + 16 * g);
+                kw[2 * g + 1] = *(const uint64_t*)(e + kOffKeys + 16 * g + 8);
+            }
+            uint8_t* ge = global_entry_for(P, h, *(const uint32_t*)(e + kOffTags), kw, acc.err);
+            if (ge) entry_merge(P, ge, e);
+        }
+    }
+    if (acc.err) atomicOr(P.errflags, acc.err);
+}
+
+// ------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------
+__global__ void init_table_kernel(uint8_t* tab, uint64_t cap, int entry_bytes, const uint8_t* init) {
+    const uint64_t words = cap * (uint64_t)(entry_bytes / 8);
+    const int ew = entry_bytes / 8;
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < words; k += (uint64_t)gridDim.x * blockDim.x)
+        ((uint64_t*)tab)[k] = ((const uint64_t*)init)[k % ew];
+}
+
+// compact the occupied entries of a table into `out` (entry images); *n_out counts them.
+// owner filter: (hash % world) == owner when world > 1.
+__global__ void compact_table_kernel(const uint8_t* tab, uint64_t cap, int entry_bytes, uint8_t* out, uint64_t out_cap,
+                                     unsigned long long* n_out, int owner, int world) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t* e = tab + i * (uint64_t)entry_bytes;
+        uint64_t h = *(const uint64_t*)e;
+        if (h == 0ull) continue;
+        if (world > 1 && (int)((h >> 8) % (uint64_t)world) != owner) continue;
+        unsigned long long idx = atomicAdd(n_out, 1ull);
+        if (idx < out_cap) {
+            uint8_t* o = out + idx * (uint64_t)entry_bytes;
+            for (int k = 0; k < entry_bytes; k += 8) *(uint64_t*)(o + k) = *(const uint64_t*)(e + k);
+        }
+    }
+}
+
+__global__ void owner_count_kernel(const uint8_t* tab, uint64_t cap, int entry_bytes, int world, unsigned long long* counts) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t h = *(const uint64_t*)(tab + i * (uint64_t)entry_bytes);
+        if (h == 0ull) continue;
+        atomicAdd(&counts[world > 1 ? (h >> 8) % (uint64_t)world : 0], 1ull);
+    }
+}
+
+// fold n serialized entries into the table of plan P
+__global__ void merge_entries_kernel(const __grid_constant__ DevPlan P, const uint8_t* recs, uint64_t n) {
+    unsigned err = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t* e = recs + i * (uint64_t)P.entry_bytes;
+        uint64_t h = *(const uint64_t*)(e + kOffHash);
+        uint64_t kw[2 * CQG_MAX_GROUP_COLS];
+        for (int g = 0; g < P.ngc; g++) {
+            kw[2 * g] = *(const uint64_t*)(e + kOffKeys + 16 * g);
+            kw[2 * g + 1] = *(const uint64_t*)(e + kOffKeys + 16 * g + 8);
+        }
+        uint8_t* ge = global_entry_for(P, h, *(const uint32_t*)(e + kOffTags), kw, err);
+        if (ge) entry_merge(P, ge, e);
+    }
+    if (err) atomicOr(P.errflags, err);
+}
+
+// ------------------------------------------------------------------------------------------
+// fetch: decode columns of rows given by file offset (group first rows, selected rows)
+// ------------------------------------------------------------------------------------------
+struct OutCell {
+    int32_t type;
+    uint32_t len;      // STRING: trimmed length
+    uint64_t payload;  // INTEGER / DOUBLE bits / DATE packed / STRING: table bit 63 | file offset
+};
+
+struct FetchParams {
+    const uint8_t* data;
+    uint64_t size;
+    const uint8_t* rdata;
+    uint64_t rsize;
+    uint8_t delim, quote;
+    int32_t n_left_cols;
+    int32_t ncols;                    // output columns
+    int16_t cols[CQG_MAX_OUT_COLS];   // query column index (-1: NULL)
+    const uint64_t* loff;             // [n] left row offsets
+    const uint64_t* roff;             // [n] right row offsets or nullptr
+    uint64_t n;
+    OutCell* out;                     // [n][ncols]
+    unsigned* errflags;
+};
+
+__device__ inline void fetch_one(const uint8_t* file, uint64_t fsize, uint64_t off, uint8_t delim, uint8_t quote, int col,
+                                 bool right, OutCell& oc, unsigned& err) {
+    oc.type = T_NULL;
+    oc.len = 0;
+    oc.payload = 0;
+    if (col < 0 || off >= fsize) return;
+    const uint8_t* b = file + off;
+    uint64_t maxlen = fsize - off;
+    uint64_t re = 0;
+    while (re < maxlen && b[re] != '\n' && b[re] != '\r') re++;
+    if (re > 0x7fffffffull) re = 0x7fffffffull;
+    int16_t want = (int16_t)col;
+    uint32_t fo, fl;
+    split_row_exact(b, 0, (uint32_t)re, delim, quote, &want, 1, &fo, &fl);
+    DVal v = decode_field(b + fo, fl, err);
+    oc.type = v.type;
+    if (v.type == T_STR) {
+        oc.len = v.len;
+        oc.payload = (right ? (1ull << 63) : 0ull) | (uint64_t)(v.s - file);
+    } else if (v.type != T_NULL) {
+        oc.payload = (uint64_t)v.i;
+    }
+}
+
+__global__ void fetch_kernel(const __grid_constant__ FetchParams F) {
+    unsigned err = 0;
+    const uint64_t total = F.n * (uint64_t)F.ncols;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t r = i / (uint64_t)F.ncols;
+        int c = (int)(i % (uint64_t)F.ncols);
+        int col = F.cols[c];
+        OutCell oc;
+        if (col >= F.n_left_cols) {
+            if (F.roff && F.rdata) fetch_one(F.rdata, F.rsize, F.roff[r], F.delim, F.quote, col - F.n_left_cols, true, oc, err);
+            else {
+                oc.type = T_NULL;
+                oc.len = 0;
+                oc.payload = 0;
+            }
+        } else {
+            fetch_one(F.data, F.size, F.loff[r], F.delim, F.quote, col, false, oc, err);
+        }
+        F.out[i] = oc;
+    }
+    if (err) atomicOr(F.errflags, err);
+}
+
+// for aggregated joins: right row of the group's first joined row = the rank-th match of the left row
+__global__ void resolve_first_right_kernel(const __grid_constant__ DevPlan P, const uint64_t* first_okey, uint64_t n,
+                                           uint64_t* roff_out) {
+    unsigned err = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t ok = first_okey[i];
+        roff_out[i] = ~0ull;
+        if (ok == ~0ull) continue;
+        uint64_t loff = (ok >> 16) - P.global_base;
+        uint32_t rank = (uint32_t)(ok & 0xffffu);
+        const uint8_t* b = P.data + loff;
+        uint64_t maxlen = P.size - loff;
+        uint64_t re = 0;
+        while (re < maxlen && b[re] != '\n' && b[re] != '\r') re++;
+        int16_t want = (int16_t)P.jl_col;
+        uint32_t fo, fl;
+        split_row_exact(b, 0, (uint32_t)re, P.delim, P.quote, &want, 1, &fo, &fl);
+        DVal lk = decode_field(b + fo, fl, err);
+        uint32_t tag;
+        uint64_t w0, w1, h;
+        join_key_of(lk, err, tag, w0, w1, h);
+        JoinSlot* s = join_find(P, h, tag, w0, w1, false);
+        if (!s) continue;
+        for (uint32_t it = s->head; it != 0u; it = P.jrow_next[it - 1]) {
+            uint64_t ro = P.jrow_off[it - 1];
+            uint32_t rk = 0;
+            for (uint32_t jt = s->head; jt != 0u; jt = P.jrow_next[jt - 1]) rk += P.jrow_off[jt - 1] < ro;
+            if (rk == rank) {
+                roff_out[i] = ro;
+                break;
+            }
+        }
+    }
+    if (err) atomicOr(P.errflags, err);
+}
+
+// gather string bytes: dst[dst_off[i] .. +len) = file bytes
+__global__ void pack_strings_kernel(const uint8_t* data, const uint8_t* rdata, const uint64_t* refs, const uint32_t* lens,
+                                    const uint64_t* dst_off, uint64_t n, uint8_t* dst) {
+    for (uint64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        uint64_t ref = refs[i];
+        const uint8_t* src = ((ref >> 63) ? rdata : data) + (ref & 0x7fffffffffffffffull);
+        uint8_t* d = dst + dst_off[i];
+        for (uint32_t k = threadIdx.x; k < lens[i]; k += blockDim.x) d[k] = src[k];
+    }
+}
+
+// parse_value on a single field (cqg_parse_value)
+__global__ void parse_value_kernel(const uint8_t* s, uint32_t len, OutCell* out, unsigned* errflags) {
+    unsigned err = 0;
+    DVal v = decode_field(s, len, err);
+    out->type = v.type;
+    out->len = v.type == T_STR ? v.len : 0;
+    out->payload = v.type == T_STR ? (uint64_t)(v.s - s) : (uint64_t)v.i;
+    if (err) atomicOr(errflags, err);
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic data: restatement of utils/generate_big_dataset.py:9-19, row i from (seed, i) only
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t gen_mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__host__ __device__ inline uint32_t gen_row(uint8_t* o, uint64_t seed, uint64_t i, long long key_card) {
+    uint64_t r = gen_mix(seed * 0xD1342543DE82EF95ull + i);
+    uint64_t r2 = gen_mix(r);
+    uint8_t* p = o;
+    uint8_t nm = (uint8_t)('A' + (r & 15));
+    uint8_t sn = (uint8_t)('A' + ((r >> 4) & 15));
+    unsigned age = 10 + (unsigned)(((r >> 8) & 0xffffff) % 71);
+    uint8_t gd = ((r >> 32) & 1) ? 'm' : 'f';
+    unsigned h = 100 + (unsigned)(((r >> 33) & 0xffffff) % 101);
+    for (int k = 0; k < 10; k++) *p++ = nm;
+    *p++ = ',';
+    for (int k = 0; k < 8; k++) *p++ = sn;
+    *p++ = ',';
+    *p++ = (uint8_t)('0' + age / 10);
+    *p++ = (uint8_t)('0' + age % 10);
+    *p++ = ',';
+    *p++ = gd;
+    *p++ = ',';
+    *p++ = (uint8_t)('0' + h / 100);
+    *p++ = '.';
+    unsigned frac = h % 100;
+    *p++ = (uint8_t)('0' + frac / 10);
+    if (frac % 10) *p++ = (uint8_t)('0' + frac % 10);
+    if (key_card > 0) {
+        *p++ = ',';
+        uint64_t uid = r2 % (uint64_t)key_card;
+        uint8_t tmp[24];
+        int n = 0;
+        do {
+            tmp[n++] = (uint8_t)('0' + uid % 10);
+            uid /= 10;
+        } while (uid);
+        while (n) *p++ = tmp[--n];
+    }
+    *p++ = '\n';
+    return (uint32_t)(p - o);
+}
+
+constexpr int kGenRowsPerBlock = 1024;
+// pass 1: bytes of each block of rows
+__global__ void gen_sizes_kernel(long long rows, uint64_t seed, long long key_card, unsigned long long* block_bytes) {
+    __shared__ unsigned int sum;
+    if (threadIdx.x == 0) sum = 0;
+    __syncthreads();
+    uint8_t tmp[64];
+    unsigned my = 0;
+    long long base = (long long)blockIdx.x * kGenRowsPerBlock;
+    for (int k = threadIdx.x; k < kGenRowsPerBlock; k += blockDim.x)
+        if (base + k < rows) my += gen_row(tmp, seed, (uint64_t)(base + k), key_card);
+    atomicAdd(&sum, my);
+    __syncthreads();
+    if (threadIdx.x == 0) block_bytes[blockIdx.x] = sum;
+}
+// pass 2: write the rows of block b at block_off[b]
+__global__ void gen_write_kernel(uint8_t* out, long long rows, uint64_t seed, long long key_card,
+                                 const unsigned long long* block_off) {
+    __shared__ unsigned int lens[kGenRowsPerBlock];
+    __shared__ unsigned int offs[kGenRowsPerBlock];
+    uint8_t tmp[64];
+    long long base = (long long)blockIdx.x * kGenRowsPerBlock;
+    for (int k = threadIdx.x; k < kGenRowsPerBlock; k += blockDim.x)
+        lens[k] = (base + k < rows) ? gen_row(tmp, seed, (uint64_t)(base + k), key_card) : 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int o = 0;
+        for (int k = 0; k < kGenRowsPerBlock; k++) {
+            offs[k] = o;
+            o += lens[k];
+        }
+    }
+    __syncthreads();
+    uint8_t* dst = out + block_off[blockIdx.x];
+    for (int k = threadIdx.x; k < kGenRowsPerBlock; k += blockDim.x) {
+        if (base + k < rows) {
+            uint32_t n = gen_row(tmp, seed, (uint64_t)(base + k), key_card);
+            for (uint32_t j = 0; j < n; j++) dst[offs[k] + j] = tmp[j];
+        }
+    }
+}
+
+}  // namespace cqg

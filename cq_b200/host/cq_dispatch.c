@@ -87,6 +87,7 @@ static int bind_index(const binder_t* b, const char* name) {
 
 /* find_column_index_with_fallback (evaluator_aggregates.c:20-36) */
 static int bind_index_fallback(const binder_t* b, const char* name) {
+    if (!name) return -1;
     int i = bind_index(b, name);
     if (i < 0) {
         const char* dot = strchr(name, '.');
@@ -565,7 +566,7 @@ static ResultSet* run_on_backend(ASTNode* q, bool* fallback) {
             for (int g = 0; g < ng; g++) {
                 const char* gc = gb->group_by.columns[g];
                 ASTNode* gexpr = NULL;
-                if (select->select.column_nodes) {
+                if (gc && select->select.column_nodes) {
                     for (int i = 0; i < ncols_sel; i++) {
                         const char* cs = select->select.columns[i];
                         if (!cs) continue;

@@ -108,6 +108,11 @@ size_t cqg_device_padding(void);
  * taken from the start of the file. */
 int cqg_table_set_shard(cqg_table_t* t, int index, int count);
 
+/* multi-GPU runs in which every rank holds only its own slice of the file: `offset` is the
+ * position of this table's byte 0 in the whole file, added to row offsets so that
+ * first-appearance order (evaluator_aggregates.c:159-163) is global. Default 0. */
+int cqg_table_set_global_offset(cqg_table_t* t, uint64_t offset);
+
 void cqg_table_close(cqg_table_t* t);
 
 /* table->column_count / columns[i].name (src/csv_reader.c:343-357: trimmed, "$i" when
@@ -280,6 +285,9 @@ typedef struct cqg_partial cqg_partial_t;
 
 /* like cqg_execute(AGGREGATE) but keeps the group table on the device. */
 int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_partial_t** out);
+/* device time of the partial's scan kernels (CUDA events) and the data rows it saw */
+double cqg_partial_kernel_ms(const cqg_partial_t* p);
+int64_t cqg_partial_rows_scanned(const cqg_partial_t* p);
 /* record size in bytes and number of records of this partial */
 size_t cqg_partial_record_size(const cqg_partial_t* p);
 int64_t cqg_partial_count(const cqg_partial_t* p);
