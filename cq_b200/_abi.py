@@ -1,8 +1,7 @@
 """ctypes view of include/cq_gpu.h (the C-ABI of libcqgpu.so).
 
-Only declarations live here: struct layouts, enum values and function prototypes. The same
-prototypes fit the CPU restatement in oracle/liboracle.so (prefix ``cqo_``), which only
-tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load.
+Only declarations live here: struct layouts, enum values and function prototypes; `Lib`
+binds them to a shared library under a symbol prefix (``cqg_`` for the product).
 """
 import ctypes as C
 

@@ -669,8 +669,17 @@ static ResultSet* run_on_backend(ASTNode* q, bool* fallback) {
     *fallback = false;
     int rc = BE(execute)(lt, &plan, &res);
     if (rc == CQG_ERR_UNSUPPORTED) {
-        if (trace_enabled()) fprintf(stderr, "[cq-gpu] backend declined: %s\n", BE(last_error)());
-        *fallback = true;
+        /* The operators of this shape belong to the GPU path: there is no silent CPU route for
+         * them. The statement fails with the reason, unless the operator explicitly opted into
+         * the reference evaluator for such inputs (CQ_GPU_FALLBACK=1). */
+        const char* fb = getenv("CQ_GPU_FALLBACK");
+        if (fb && fb[0] == '1') {
+            fprintf(stderr, "[cq-gpu] backend declined (%s): CQ_GPU_FALLBACK=1, using the reference evaluator\n",
+                    BE(last_error)());
+            *fallback = true;
+        } else {
+            fprintf(stderr, "GPU query execution declined: %s\n", BE(last_error)());
+        }
         goto done;
     }
     if (rc != CQG_OK) {

@@ -20,6 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 FIX = os.path.join(ROOT, "tests", "fixtures")
 REF = os.environ.get("CQ_REF", "/root/reference")
 REF_DUMP = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+ORACLE_DUMP = os.path.join(ROOT, "oracle", "_ref", "oracle_dump")
 
 
 def w(name, text, binary=False):
@@ -333,10 +334,12 @@ def make_queries():
     q("SELECT COUNT(*), SUM(price), AVG(tax) FROM 'data/orders.csv' WHERE quantity > 1", kind="refdata")
 
 
-def run(dump, item):
+def run(dump, item, env=None):
     cwd = FIX if item["kind"] == "fix" else REF
-    p = subprocess.run([dump] + item["args"] + [item["sql"]], cwd=cwd, capture_output=True, timeout=120)
-    return p.returncode, p.stdout.decode("latin1")
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([dump] + item["args"] + [item["sql"]], cwd=cwd, capture_output=True, timeout=120, env=e)
+    return p.returncode, p.stdout.decode("latin1"), p.stderr.decode("latin1")
 
 
 def main():
@@ -346,8 +349,12 @@ def main():
         sys.exit("oracle/_ref/ref_dump missing: run `make -C oracle ref`")
     out = []
     for i, item in enumerate(QUERIES):
-        rc, text = run(REF_DUMP, item)
-        out.append({"id": i, "kind": item["kind"], "args": item["args"], "sql": item["sql"], "rc": rc, "expected": text})
+        rc, text, _ = run(REF_DUMP, item)
+        # which statements the planner (cq_dispatch.c) puts on the accelerated path
+        _, _, err = run(ORACLE_DUMP, item, env={"CQ_GPU_TRACE": "1"})
+        route = "gpu" if "route=gpu" in err else "reference"
+        out.append({"id": i, "kind": item["kind"], "args": item["args"], "sql": item["sql"], "rc": rc, "route": route,
+                    "expected": text})
     with open(os.path.join(ROOT, "tests", "golden", "sql_golden.json"), "w") as f:
         json.dump(out, f, indent=0)
     print(f"{len(out)} golden cases written")

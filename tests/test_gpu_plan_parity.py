@@ -1,0 +1,222 @@
+"""GPU parity proper: the CUDA path through the C-ABI vs the pinned CPU oracle on the same
+seeded inputs and the same plans. Integers, keys, row sets: bit-exact; SUM/AVG: 1e-12 relative."""
+import ctypes as C
+import random
+
+import pytest
+
+import parity_cases as pc
+from cq_b200 import _abi as A
+from cq_b200.engine import CqError, Plan, Table, csv_config, gpu
+from oracle_lib import generate_bigdata, oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    data = generate_bigdata(200_000, seed=1)
+    return data, Table.from_bytes(data, lib=gpu()), Table.from_bytes(data, lib=oracle())
+
+
+@pytest.fixture(scope="module")
+def big_uid():
+    data = generate_bigdata(150_000, seed=5, key_card=40_000)
+    return data, Table.from_bytes(data, lib=gpu()), Table.from_bytes(data, lib=oracle())
+
+
+def test_header_and_row_count(big):
+    data, tg, to = big
+    assert tg.columns == to.columns == ["name", "surname", "age", "gender", "height"]
+    assert tg.row_count() == to.row_count() == 200_000
+    assert tg.column_index("HEIGHT") == 4
+
+
+@pytest.mark.parametrize("name", sorted(pc.plans()))
+def test_plan_parity(big, name):
+    data, tg, to = big
+    spec = pc.plans()[name]
+    got = tg.execute(pc.build(spec))
+    want = to.execute(pc.build(spec))
+    assert got["kernel_launches"] > 0
+    pc.compare_results(got, want)
+
+
+@pytest.mark.parametrize("name", sorted(pc.plans_uid()))
+def test_plan_parity_uid(big_uid, name):
+    data, tg, to = big_uid
+    spec = pc.plans_uid()[name]
+    pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
+
+
+@pytest.mark.parametrize("nshards", [2, 3, 8])
+def test_byte_range_shards_partition_the_rows(big, nshards):
+    """§8e: shard i owns the rows whose first byte lies in its byte range; shards are disjoint and complete."""
+    data, tg, to = big
+    spec = pc.plans()["group_name"]
+    total_rows = 0
+    counts = {}
+    for i in range(nshards):
+        tg.set_shard(i, nshards)
+        to.set_shard(i, nshards)
+        try:
+            got = tg.execute(pc.build(spec))
+            want = to.execute(pc.build(spec))
+        finally:
+            tg.set_shard(0, 1)
+            to.set_shard(0, 1)
+        pc.compare_results(got, want)
+        total_rows += got["rows_scanned"]
+        for g in got["groups"]:
+            counts[g["out"][0]] = counts.get(g["out"][0], 0) + g["count"]
+    assert total_rows == 200_000
+    whole = tg.execute(pc.build(spec))
+    assert counts == {g["out"][0]: g["count"] for g in whole["groups"]}
+
+
+def _edge_files():
+    rnd = random.Random(7)
+    files = {
+        "empty_rows_only": b"a,b\n\n\n\n",
+        "header_only": b"a,b",
+        "header_nl": b"a,b\n",
+        "one_row_no_nl": b"a,b\n1,2",
+        "crlf": b"a,b\r\n1,2\r\n3,4\r\n\r\n5,6",
+        "cr_only": b"a,b\r1,2\r3,4\r",
+        "blank_start": b"\n\r\n  \na,b\n1,2\n",
+        "ragged": b"a,b,c\n1\n1,2\n1,2,3\n1,2,3,4\n,,\n,\n",
+        "spaces": b"a,b\n 1 , 2 \n\t3\t,\t4\t\n  ,  \n5,   \n",
+        "quotes": b'a,b\n"1","x,y"\n"2" junk,"say ""hi"""\n"unterminated,3\n4,"also unterminated\n  "5"  ,ok\n',
+        "long_row": b"a,b\n" + b"x" * 5000 + b",7\n1,2\n" + b"y" * 70000 + b",9\n3,4\n",
+        "long_quoted": b'a,b\n"' + b"q," * 3000 + b'",11\n5,6\n',
+        "wide": (",".join(f"c{i}" for i in range(120)) + "\n" + "\n".join(",".join(str(r * 1000 + i) for i in range(120))
+                                                                          for r in range(50)) + "\n").encode(),
+        "tiny_rows": b"a\n" + b"\n".join(str(i % 10).encode() for i in range(40000)) + b"\n",
+        "nul_bytes": b"a,b\n1\x002,x\x00y\n3,4\n",
+        "high_bytes": "a,b\né,ü\n1,2\n".encode("utf-8"),
+    }
+    # rows straddling tile edges at every alignment
+    rows = [b"k,v"]
+    for i in range(30000):
+        rows.append(b"%d,%s" % (rnd.randint(0, 50), b"z" * rnd.randint(0, 40)))
+    files["straddle"] = b"\n".join(rows) + b"\n"
+    return files
+
+
+@pytest.mark.parametrize("name", sorted(_edge_files()))
+def test_edge_files(name):
+    data = _edge_files()[name]
+    specs = [
+        dict(aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 0), (A.AGG_MIN, 1), (A.AGG_MAX, 1)]),
+        dict(group_by=[0], out_cols=[0, 1], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 1), (A.AGG_MAX, 0)]),
+        dict(group_by=[1, 0], out_cols=[1], aggs=[(A.AGG_COUNT, 0)]),
+        dict(mode="select", where=(">", ("col", 0), ("const", 1)), out_cols=[0, 1, 2]),
+        dict(mode="select", out_cols=[1, 0]),
+    ]
+    if name == "wide":
+        specs.append(dict(mode="select", where=("=", ("col", 119), ("const", 3119)), out_cols=[0, 60, 119]))
+    with Table.from_bytes(data, lib=gpu()) as tg, Table.from_bytes(data, lib=oracle()) as to:
+        assert tg.columns == to.columns
+        assert tg.row_count() == to.row_count()
+        for spec in specs:
+            pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
+        for n in (2, 5):
+            for i in range(n):
+                tg.set_shard(i, n)
+                to.set_shard(i, n)
+                pc.compare_results(tg.execute(pc.build(specs[1])), to.execute(pc.build(specs[1])))
+            tg.set_shard(0, 1)
+            to.set_shard(0, 1)
+
+
+def test_no_header_and_delimiters():
+    for data, cfg in [(b"1;a;2.5\n2;b;3\n3;a;\n", csv_config(";", '"', False)),
+                      (b"id|v\n1|x\n2|'p|q'\n", csv_config("|", "'", True)),
+                      (b"id\tv\n1\tx\n2\t\ty\n", csv_config("\t", '"', True))]:
+        with Table.from_bytes(data, cfg, lib=gpu()) as tg, Table.from_bytes(data, cfg, lib=oracle()) as to:
+            assert tg.columns == to.columns
+            for spec in [dict(group_by=[1], out_cols=[1, 0], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 2)]),
+                         dict(mode="select", out_cols=[0, 1, 2])]:
+                pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
+
+
+def _join_tables(n_orders, n_customers, seed):
+    rnd = random.Random(seed)
+    orders = ["id,price,tax,quantity,customer_id"]
+    for i in range(n_orders):
+        cid = rnd.randint(1, int(n_customers * 1.2))
+        orders.append(f"{i + 1},{rnd.randint(100, 99999) / 100:.2f},{rnd.randint(0, 999) / 100:.2f},{rnd.randint(1, 9)},{cid}")
+    customers = ["id,name,email,since"]
+    for i in range(n_customers):
+        customers.append(f"{i + 1},cust{i % 97},c{i}@example.com,{2015 + i % 10}")
+    # duplicates on the right: one left row joins several right rows, in right-file order
+    for i in range(0, n_customers, 50):
+        customers.append(f"{i + 1},dup{i},d{i}@example.com,{2000 + i % 7}")
+    return ("\n".join(orders) + "\n").encode(), ("\n".join(customers) + "\n").encode()
+
+
+def test_join_parity():
+    od, cd = _join_tables(20000, 3000, 11)
+    lib_g, lib_o = gpu(), oracle()
+    with Table.from_bytes(od, lib=lib_g) as og, Table.from_bytes(cd, lib=lib_g) as cg, \
+            Table.from_bytes(od, lib=lib_o) as oo, Table.from_bytes(cd, lib=lib_o) as co:
+        specs = [
+            dict(aggs=[(A.AGG_COUNT_STAR, -1)]),
+            dict(aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 1), (A.AGG_MIN, 6)], where=(">", ("col", 1), ("const", 500))),
+            dict(group_by=[8], out_cols=[8, 6, 0], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 1), (A.AGG_MAX, 7)]),
+            dict(group_by=[6], out_cols=[6], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_AVG, 3)],
+                 where=("like", ("col", 6), ("const", "cust1%"))),
+            dict(mode="select", where=("and", (">", ("col", 1), ("const", 990)), ("<", ("col", 8), ("const", 2016))),
+                 out_cols=[0, 4, 5, 6, 8]),
+            dict(mode="select", out_cols=[0, 6], max_rows=40),
+        ]
+        for spec in specs:
+            got = og.execute(pc.build(spec, join=(cg, 4, 0)))
+            want = oo.execute(pc.build(spec, join=(co, 4, 0)))
+            pc.compare_results(got, want)
+        # unresolved key columns never match (evaluator_joins.c:54)
+        got = og.execute(pc.build(specs[0], join=(cg, -1, 0)))
+        assert got["groups"][0]["count"] == 0
+
+
+def test_parse_value_matches_oracle():
+    lib_g, lib_o = gpu(), oracle()
+    samples = [b"", b"1", b"007", b"-5", b"+8", b"3.25", b".5", b"5.", b"-0.0", b"1e5", b"-", b"abc", b" 12 ", b"12 3",
+               b"20240115", b"2010010100", b"2023-1-5x", b"555-0001", b"2024-01-15", b"01/02/2024", b"31/12/2023",
+               b"2023-02-29", b"9223372036854775807", b"9223372036854775808", b"-9223372036854775809", b"0.1",
+               b"0.30000000000000004", b"123456789.123456789", b"1234567.1234567", b"  padded  ", b"+20240115",
+               b"1234567890123456789", b"12345678.9", b"1.7976931348623157", b"4.35", b"0.000001", b"8.41"]
+    rnd = random.Random(3)
+    for _ in range(300):
+        k = rnd.randint(1, 18)
+        s = "".join(rnd.choice("0123456789") for _ in range(k))
+        if rnd.random() < 0.7:
+            p = rnd.randint(0, len(s))
+            s = s[:p] + "." + s[p:]
+        if rnd.random() < 0.3:
+            s = "-" + s
+        samples.append(s.encode())
+    for s in samples:
+        a, b = A.Value(), A.Value()
+        assert lib_g.parse_value(s, len(s), C.byref(a)) == 0, lib_g.last_error()
+        assert lib_o.parse_value(s, len(s), C.byref(b)) == 0
+        from cq_b200.engine import py_value
+        va, vb = py_value(a), py_value(b)
+        if va[0] == "D":
+            assert vb[0] == "D" and (va[1].hex() == vb[1].hex()), (s, va, vb)
+        else:
+            assert va == vb, (s, va, vb)
+        lib_g.value_release(C.byref(a))
+        lib_o.value_release(C.byref(b))
+
+
+def test_unsupported_inputs_fail_loudly():
+    data = b"k,v\n1,99999999999999999999999999999999999999999999.5\n"
+    with Table.from_bytes(data, lib=gpu()) as tg:
+        try:
+            r = tg.execute(Plan(aggs=[(A.AGG_SUM, 1)]))
+        except CqError as e:
+            assert e.code == A.ERR_UNSUPPORTED
+        else:
+            with Table.from_bytes(data, lib=oracle()) as to:
+                pc.compare_results(r, to.execute(Plan(aggs=[(A.AGG_SUM, 1)])))
