@@ -552,7 +552,6 @@ static int compile_predicate(HostPlan& hp, const cqg_predicate_t& w, cudaStream_
                 int rc = want_column(P, in.a);
                 if (rc) return rc;
                 int ref = (in.a < 0 || in.a >= P.n_cols_total) ? kRefNull : in.a;
-                if (in.a >= 0x4000) fusable = false;
                 stack.push_back({true, ref});
                 break;
             }
@@ -672,9 +671,9 @@ static void layout_entry(HostPlan& hp) {
             continue;
         }
         s.off = off;
-        off += (s.func == CQG_AGG_SUM || s.func == CQG_AGG_AVG) ? 24 : 40;
+        off += (s.func == CQG_AGG_SUM || s.func == CQG_AGG_AVG) ? 32 : 48;
     }
-    P.entry_bytes = (off + 7) / 8 * 8;
+    P.entry_bytes = (off + 15) / 16 * 16;
     hp.entry_init.assign((size_t)P.entry_bytes, 0);
     uint64_t ones = ~0ull;
     memcpy(hp.entry_init.data() + kOffFirst, &ones, 8);
@@ -683,9 +682,13 @@ static void layout_entry(HostPlan& hp) {
         if (s.off < 0) continue;
         if (s.func == CQG_AGG_MIN || s.func == CQG_AGG_MAX) {
             uint64_t* st = (uint64_t*)(hp.entry_init.data() + s.off);
-            st[0] = ~0ull;
             uint64_t empty = s.func == CQG_AGG_MIN ? ~0ull : 0ull;
-            for (int k = 1; k <= 4; k++) st[k] = empty;
+            st[0] = ~0ull;
+            st[1] = empty;
+            st[2] = empty;
+            st[3] = ~0ull;
+            st[4] = empty;
+            st[5] = 0;
         }
     }
 }
@@ -695,9 +698,11 @@ static int build_plan(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, cu
     DevPlan& P = hp.P;
     set_file(P, t, false);
     const cqg_table* rt = q->join.right;
-    P.n_left_cols = (int)t->names.size();
-    P.n_cols_total = P.n_left_cols + (rt ? (int)rt->names.size() : 0);
-    if (P.n_cols_total > kMaxQueryCols) return fail(CQG_ERR_UNSUPPORTED, "more than %d columns", kMaxQueryCols);
+    // a column index is not bounded by the header: a row with more fields than the header still
+    // yields them (row->values[col], evaluator_core.c:165); without a join every index is "left"
+    P.n_left_cols = rt ? (int)t->names.size() : kMaxQueryCols;
+    P.n_cols_total = kMaxQueryCols;
+    if (P.n_left_cols > kMaxQueryCols) return fail(CQG_ERR_UNSUPPORTED, "more than %d columns", kMaxQueryCols);
     for (int c = 0; c < kMaxQueryCols; c++) P.colslot[c] = -1;
     P.mode = q->mode == CQG_MODE_SELECT ? SCAN_SELECT : SCAN_AGG;
     if (q->n_group_cols < 0 || q->n_group_cols > CQG_MAX_GROUP_COLS || q->n_aggs < 0 || q->n_aggs > CQG_MAX_AGGS ||
@@ -972,10 +977,9 @@ static int run_fetch(const cqg_table* t, const cqg_table* rt, const int32_t* col
     F.rsize = rt ? rt->size : 0;
     F.delim = (uint8_t)t->cfg.delimiter;
     F.quote = (uint8_t)t->cfg.quote;
-    F.n_left_cols = (int)t->names.size();
+    F.n_left_cols = rt ? (int)t->names.size() : 0x7fff;
     F.ncols = ncols;
-    int total_cols = F.n_left_cols + (rt ? (int)rt->names.size() : 0);
-    for (int c = 0; c < ncols; c++) F.cols[c] = (int16_t)((cols[c] < 0 || cols[c] >= total_cols) ? -1 : cols[c]);
+    for (int c = 0; c < ncols; c++) F.cols[c] = (int16_t)((cols[c] < 0 || cols[c] >= 0x7fff) ? -1 : cols[c]);
     F.loff = d_loff.as<uint64_t>();
     F.roff = d_roff;
     F.n = n;
@@ -1064,6 +1068,7 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
     r->out = (cqg_value_t*)arena->alloc(sizeof(cqg_value_t) * gn * on);
 
     std::vector<uint64_t> loff(G);
+    std::vector<std::pair<uint64_t, uint64_t>> numfetch[CQG_MAX_AGGS];  // (group, okey) of numeric MIN/MAX results
     std::vector<OutCell> strcells;  // MIN/MAX string results
     std::vector<size_t> strdst;
     unsigned host_flags = 0;
@@ -1104,30 +1109,10 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
                 uint64_t empty = is_min ? ~0ull : 0ull;
                 uint32_t cls = s[0] == ~0ull ? 0u : (uint32_t)(s[0] & 3u);
                 if (cls == 1) {
-                    bool hi = s[1] != empty, hd = s[2] != empty;
-                    long long iv = hi ? int_of_img(s[1]) : 0;
-                    double dv = 0;
-                    if (hd) {
-                        uint64_t b = bits_of_img(s[2]);
-                        memcpy(&dv, &b, 8);
-                    }
-                    bool take_int;
-                    if (hi && hd) {
-                        double x = (double)iv;
-                        if (x == dv) host_flags |= KERR_MINMAX_TIE;
-                        take_int = is_min ? x < dv : x > dv;
-                    } else {
-                        take_int = hi;
-                    }
-                    if (take_int) {
-                        v.type = CQG_TYPE_INTEGER;
-                        v.int_value = iv;
-                    } else {
-                        v.type = CQG_TYPE_DOUBLE;
-                        v.double_value = dv;
-                    }
+                    // type and bits of the extreme come from the row that holds it
+                    numfetch[a].push_back({(uint64_t)gi, s[3]});
                 } else if (cls == 3) {
-                    uint64_t d = s[3] - 1ull;
+                    uint64_t d = s[1] - 1ull;
                     v.type = CQG_TYPE_DATE;
                     v.date_value.year = (int)(d >> 16);
                     v.date_value.month = (int)((d >> 8) & 0xff);
@@ -1150,6 +1135,39 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
         return fail(CQG_ERR_UNSUPPORTED, "%s", flag_text(host_flags));
     }
     int rc = CQG_OK;
+    for (int a = 0; a < q->n_aggs && rc == CQG_OK; a++) {
+        if (numfetch[a].empty()) continue;
+        size_t n = numfetch[a].size();
+        std::vector<uint64_t> lo(n), oks(n);
+        for (size_t k = 0; k < n; k++) {
+            oks[k] = numfetch[a][k].second;
+            lo[k] = (oks[k] >> 16) - P.global_base;
+        }
+        DevBuf d_ok, d_ro;
+        const uint64_t* roff_ptr = nullptr;
+        int32_t col = P.aggs[a].col;
+        if (rt && P.join && col >= P.n_left_cols) {
+            CU(d_ok.alloc(n * 8, st));
+            CU(d_ro.alloc(n * 8, st));
+            CU(cudaMemcpyAsync(d_ok.p, oks.data(), n * 8, cudaMemcpyHostToDevice, st));
+            int grid = (int)std::min<uint64_t>((n + 127) / 128, 148 * 8);
+            resolve_first_right_kernel<<<grid, 128, 0, st>>>(P, d_ok.as<uint64_t>(), n, d_ro.as<uint64_t>());
+            g_launches++;
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(st));
+            roff_ptr = d_ro.as<uint64_t>();
+        }
+        std::vector<OutCell> cells;
+        rc = run_fetch(t, rt, &col, 1, lo, roff_ptr, P.errflags, cells, st);
+        if (rc != CQG_OK) break;
+        std::vector<cqg_value_t> vals(n);
+        rc = cells_to_values(t, rt, cells, vals.data(), arena, st);
+        for (size_t k = 0; k < n && rc == CQG_OK; k++) r->value[(size_t)a * G + numfetch[a][k].first] = vals[k];
+    }
+    if (rc != CQG_OK) {
+        cqg_result_free(r);
+        return rc;
+    }
     if (!strcells.empty()) {
         std::vector<cqg_value_t> sv(strcells.size());
         rc = cells_to_values(t, rt, strcells, sv.data(), arena, st);

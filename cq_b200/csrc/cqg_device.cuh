@@ -192,6 +192,132 @@ __device__ __noinline__ double div_pow10_exact(unsigned long long mant, int fd) 
     return __longlong_as_double((long long)bits);
 }
 
+// ------------------------------------------------------------------------------------------
+// strtod for decimal strings of any length (src/csv_reader.c:210 calls glibc strtod, which is
+// correctly rounded): big-integer long division, used when the 64-bit paths above do not apply.
+// text = [digits][.digits] (sign and blanks already consumed), n bytes.
+// ------------------------------------------------------------------------------------------
+constexpr int kBigLimbs = 52;     // 1664 bits
+constexpr int kBigMaxDigits = 400;
+
+__device__ __forceinline__ int big_bitlen(const uint32_t* a) {
+    for (int i = kBigLimbs - 1; i >= 0; i--)
+        if (a[i]) return 32 * i + (32 - __clz((int)a[i]));
+    return 0;
+}
+__device__ __forceinline__ void big_mul10_add(uint32_t* a, uint32_t d) {
+    unsigned long long carry = d;
+    for (int i = 0; i < kBigLimbs; i++) {
+        unsigned long long t = (unsigned long long)a[i] * 10ull + carry;
+        a[i] = (uint32_t)t;
+        carry = t >> 32;
+    }
+}
+__device__ __forceinline__ void big_shl(uint32_t* a, int s) {  // s >= 0, result must fit
+    int w = s >> 5, b = s & 31;
+    for (int i = kBigLimbs - 1; i >= 0; i--) {
+        uint32_t lo = (i - w >= 0) ? a[i - w] : 0u;
+        uint32_t lo2 = (i - w - 1 >= 0) ? a[i - w - 1] : 0u;
+        a[i] = b ? ((lo << b) | (lo2 >> (32 - b))) : lo;
+    }
+}
+__device__ __forceinline__ void big_shr1(uint32_t* a) {
+    for (int i = 0; i < kBigLimbs; i++) a[i] = (a[i] >> 1) | (i + 1 < kBigLimbs ? (a[i + 1] << 31) : 0u);
+}
+__device__ __forceinline__ bool big_ge(const uint32_t* a, const uint32_t* b) {
+    for (int i = kBigLimbs - 1; i >= 0; i--)
+        if (a[i] != b[i]) return a[i] > b[i];
+    return true;
+}
+__device__ __forceinline__ void big_sub(uint32_t* a, const uint32_t* b) {  // a -= b, a >= b
+    unsigned long long borrow = 0;
+    for (int i = 0; i < kBigLimbs; i++) {
+        unsigned long long t = (unsigned long long)a[i] - b[i] - borrow;
+        a[i] = (uint32_t)t;
+        borrow = (t >> 32) & 1ull;
+    }
+}
+
+__device__ __noinline__ double strtod_big(const uint8_t* p, uint32_t n, unsigned& errflags) {
+    uint32_t A[kBigLimbs], B[kBigLimbs];
+    for (int i = 0; i < kBigLimbs; i++) {
+        A[i] = 0;
+        B[i] = 0;
+    }
+    B[0] = 1;
+    int ndig = 0, fd = 0;
+    bool dot = false;
+    // trailing zeros of the fraction do not change the value: leave them out
+    uint32_t end = n;
+    bool has_dot = false;
+    for (uint32_t k = 0; k < n; k++) has_dot = has_dot || p[k] == '.';
+    if (has_dot)
+        while (end > 0 && p[end - 1] == '0') end--;
+    for (uint32_t k = 0; k < end; k++) {
+        uint32_t c = p[k];
+        if (c == '.') {
+            dot = true;
+            continue;
+        }
+        uint32_t d = c - 48u;
+        if (ndig == 0 && d == 0) {  // leading zero: no digit of M yet
+            if (dot) fd++;
+            continue;
+        }
+        if (ndig >= kBigMaxDigits || fd >= kBigMaxDigits) {
+            errflags |= KERR_NUMERIC_RANGE;
+            return 0.0;
+        }
+        big_mul10_add(A, d);
+        ndig++;
+        if (dot) fd++;
+    }
+    if (ndig == 0) return 0.0;
+    for (int k = 0; k < fd; k++) big_mul10_add(B, 0);
+    int la = big_bitlen(A), lb = big_bitlen(B);
+    int s = 64 + lb - la;  // 2^63 <= floor(A * 2^s / B) < 2^65
+    if (s >= 0) big_shl(A, s);
+    else big_shl(B, -s);
+    big_shl(B, 64);
+    unsigned long long q = 0;
+    bool qtop = false;  // bit 64 of the quotient
+    for (int i = 64; i >= 0; i--) {
+        if (big_ge(A, B)) {
+            big_sub(A, B);
+            if (i == 64) qtop = true;
+            else q |= 1ull << i;
+        }
+        big_shr1(B);
+    }
+    bool sticky = false;
+    for (int i = 0; i < kBigLimbs; i++) sticky = sticky || A[i] != 0;
+    // value = (qtop:q) * 2^-s ; round to 53 bits, nearest even
+    int drop = qtop ? 12 : 11;
+    unsigned long long m, rem, half = 1ull << (drop - 1);
+    if (qtop) {
+        m = (q >> 12) | (1ull << 52);
+        rem = q & 0xfffull;
+    } else {
+        m = q >> 11;
+        rem = q & 0x7ffull;
+    }
+    if (rem > half || (rem == half && (sticky || (m & 1ull)))) {
+        m++;
+        if (m >> 53) {
+            m >>= 1;
+            drop++;
+        }
+    }
+    int e2 = drop - s;  // value = m * 2^e2, m in [2^52, 2^53)
+    int ex = e2 + 52 + 1023;
+    if (ex >= 2047) return __longlong_as_double(0x7ff0000000000000ll);  // HUGE_VAL
+    if (ex <= 0) {  // subnormal result: different rounding position, not handled
+        errflags |= KERR_NUMERIC_RANGE;
+        return 0.0;
+    }
+    return __longlong_as_double((long long)(((unsigned long long)ex << 52) | (m & 0xfffffffffffffull)));
+}
+
 // Decode one field exactly as parse_value does (src/csv_reader.c:195-240).
 // `errflags` collects KERR_* for inputs outside the exact range handled on the device.
 __device__ inline DVal decode_field(const uint8_t* p, uint32_t len, unsigned& errflags) {
@@ -222,6 +348,7 @@ __device__ inline DVal decode_field(const uint8_t* p, uint32_t len, unsigned& er
     int nsig = 0, fd = 0;
     bool int_overflow = false;  // an integer-part digit beyond the 19 kept: magnitude changed
     bool inexact = false;       // a non-zero fraction digit beyond the 19 kept
+    uint32_t k0 = j;            // end of the number text
     if (number) {
         uint32_t k = j;
         while (k < len && !is_space(p[k])) {
@@ -248,6 +375,7 @@ __device__ inline DVal decode_field(const uint8_t* p, uint32_t len, unsigned& er
             }
             k++;
         }
+        k0 = k;
         if (number) {
             while (k < len && is_space(p[k])) k++;
             number = has_digit && k == len;
@@ -269,16 +397,13 @@ __device__ inline DVal decode_field(const uint8_t* p, uint32_t len, unsigned& er
         // strtod (:210), correctly rounded
         v.type = T_DBL;
         double r;
-        if (int_overflow || inexact) {
-            errflags |= KERR_NUMERIC_RANGE;  // >19 significant digits: not decoded on the device
-            r = 0.0;
-        } else if (mant < (1ull << 53) && fd <= 22) {
+        if (!(int_overflow || inexact) && mant < (1ull << 53) && fd <= 22) {
             r = (double)(long long)mant / kPow10[fd];  // one correctly rounded IEEE division
-        } else if (fd <= 19) {
+        } else if (!(int_overflow || inexact) && fd <= 19) {
             r = div_pow10_exact(mant, fd);
         } else {
-            errflags |= KERR_NUMERIC_RANGE;
-            r = 0.0;
+            uint32_t e = k0;  // end of the number text (before trailing blanks)
+            r = strtod_big(p + j, e - j, errflags);
         }
         v.d = neg ? -r : r;
         return v;

@@ -44,15 +44,16 @@ struct FInsn {
     int16_t op, a, b, n;
 };
 
-// ---- aggregate state inside a group entry ----
-// SUM/AVG : { int64 sum_i ; double sum_d ; uint64 ncount }                         24 B
-// MIN/MAX : { uint64 first_nonnull ; uint64 num_i ; uint64 num_d ; uint64 date ; uint64 str }  40 B
-//   first_nonnull = (okey << 2 | class) of the earliest non-NULL value (class 1 numeric, 2 string, 3 date)
-//   num_i  = order-preserving image of the extreme INTEGER-typed value
-//   num_d  = order-preserving image of the extreme DOUBLE-typed value
-//   date   = packed y<<16|m<<8|d
-//   str    = table bit 63 | offset << 18 | len   (reference into the resident CSV bytes)
-// MIN keeps the smallest image (empty = ~0), MAX the largest (empty = 0).
+// ---- aggregate state inside a group entry (every state 16-byte aligned) ----
+// SUM/AVG : { int64 sum_i ; double sum_d ; uint64 ncount ; pad }                         32 B
+//   INTEGER-typed values add into sum_i (exact), DOUBLE-typed into sum_d; SUM = sum_i + sum_d
+// MIN/MAX : { first_nonnull ; date ; num_key ; num_okey ; str ; pad }                    48 B
+//   first_nonnull = (okey << 2 | class) of the earliest non-NULL value (class 1 numeric, 2 string, 3 date):
+//                   the extreme is taken inside that class only (value_compare is 0 across classes)
+//   date          = packed (y<<16|m<<8|d) + 1
+//   num_key/okey  = value as an ordered double image + the earliest row holding it (128-bit CAS)
+//   str           = table bit 63 | offset << 18 | len   (reference into the resident CSV bytes)
+// MIN keeps the smallest image (empty = ~0), MAX the largest (empty = 0); num_okey empty = ~0.
 struct AggSpec {
     int32_t func;
     int32_t col;

@@ -199,8 +199,7 @@ __device__ inline void canon_part(const DVal& v, bool multi, unsigned& err, uint
                 tag = KT_INT;
                 w0 = (uint64_t)v.i;
             } else {
-                if (v.i > (1ll << 53) || v.i < -(1ll << 53)) err |= KERR_BIGINT;
-                double d = (double)v.i;
+                double d = (double)v.i;  // value_compare compares numerics as doubles (csv_reader.c:116-121)
                 tag = KT_DBL_POS;
                 w0 = (uint64_t)__double_as_longlong(d + 0.0);
             }
@@ -344,23 +343,68 @@ __device__ inline void str_extreme(const DevPlan& P, uint64_t* slot, uint64_t ca
     }
 }
 
-// one value enters a MIN/MAX state (evaluator_aggregates.c:311-326, order-free form)
+// 128-bit compare-and-swap (atom.cas.b128, sm_90+): global or shared address, 16-byte aligned
+__device__ __forceinline__ bool cas128(void* addr, uint64_t& exp_lo, uint64_t& exp_hi, uint64_t new_lo, uint64_t new_hi) {
+    uint64_t old_lo, old_hi;
+    if (__isShared(addr)) {
+        asm volatile(
+            "{\n\t.reg .b128 c, s, d;\n\t"
+            "mov.b128 c, {%2, %3};\n\t"
+            "mov.b128 s, {%4, %5};\n\t"
+            "atom.shared.cas.b128 d, [%6], c, s;\n\t"
+            "mov.b128 {%0, %1}, d;\n\t}"
+            : "=l"(old_lo), "=l"(old_hi)
+            : "l"(exp_lo), "l"(exp_hi), "l"(new_lo), "l"(new_hi), "r"(smem_u32(addr))
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .b128 c, s, d;\n\t"
+            "mov.b128 c, {%2, %3};\n\t"
+            "mov.b128 s, {%4, %5};\n\t"
+            "atom.global.cas.b128 d, [%6], c, s;\n\t"
+            "mov.b128 {%0, %1}, d;\n\t}"
+            : "=l"(old_lo), "=l"(old_hi)
+            : "l"(exp_lo), "l"(exp_hi), "l"(new_lo), "l"(new_hi), "l"(addr)
+            : "memory");
+    }
+    bool ok = old_lo == exp_lo && old_hi == exp_hi;
+    exp_lo = old_lo;
+    exp_hi = old_hi;
+    return ok;
+}
+
+// numeric extreme: (key, okey) where key orders the values as value_compare does (as doubles,
+// -0.0 == 0.0) and okey breaks ties towards the earliest row — "keep the first value unless a
+// later one is strictly less/greater" (evaluator_aggregates.c:316-321). The value itself (its
+// type and bits) is re-read from that row when the result is built.
+__device__ __forceinline__ void num_extreme(uint64_t* st /*16B aligned*/, uint64_t key, uint64_t okey, bool is_min) {
+    uint64_t ck = *(volatile uint64_t*)&st[0];
+    uint64_t co = *(volatile uint64_t*)&st[1];
+    for (;;) {
+        bool better = is_min ? (key < ck || (key == ck && okey < co)) : (key > ck || (key == ck && okey < co));
+        if (!better) return;
+        if (cas128(st, ck, co, key, okey)) return;
+    }
+}
+
+__device__ __forceinline__ uint64_t num_key(double d) {
+    d = d + 0.0;  // -0.0 -> +0.0
+    return img_of_bits((uint64_t)__double_as_longlong(d));
+}
+
+// MIN/MAX state: [0] first_nonnull (okey<<2|class)  [1] date  [2,3] numeric (key, okey)  [4] string ref  [5] pad
+// one value enters it (evaluator_aggregates.c:311-326, order-free form)
 __device__ inline void minmax_update(const DevPlan& P, uint8_t* st, bool is_min, const DVal& v, uint64_t okey, bool right_side,
                                      const uint8_t* field_base_file, unsigned& err) {
     if (v.type == T_NULL) return;
     uint64_t* s = (uint64_t*)st;
     uint32_t cls = (v.type == T_INT || v.type == T_DBL) ? 1u : (v.type == T_STR ? 2u : 3u);
     amin64(&s[0], (okey << 2) | cls);
-    if (v.type == T_INT) {
-        if (v.i > (1ll << 53) || v.i < -(1ll << 53)) err |= KERR_BIGINT;
-        uint64_t im = img_of_int(v.i);
-        if (is_min) amin64(&s[1], im); else amax64(&s[1], im);
-    } else if (v.type == T_DBL) {
-        uint64_t im = img_of_bits((uint64_t)__double_as_longlong(v.d));
-        if (is_min) amin64(&s[2], im); else amax64(&s[2], im);
+    if (v.type == T_INT || v.type == T_DBL) {
+        num_extreme(&s[2], num_key(v.type == T_INT ? (double)v.i : v.d), okey, is_min);
     } else if (v.type == T_DATE) {
         uint64_t im = (uint64_t)v.i + 1ull;  // keep 0 / ~0 free as "empty"
-        if (is_min) amin64(&s[3], im); else amax64(&s[3], im);
+        if (is_min) amin64(&s[1], im); else amax64(&s[1], im);
     } else {
         // string bytes live in the resident file: reference them
         uint64_t off = (uint64_t)(v.s - field_base_file);
@@ -383,10 +427,10 @@ __device__ inline void minmax_merge(const DevPlan& P, uint8_t* dst, const uint8_
     const uint64_t* s = (const uint64_t*)src;
     amin64(&d[0], s[0]);
     const uint64_t empty = is_min ? ~0ull : 0ull;
-    for (int k = 1; k <= 3; k++) {
-        if (s[k] == empty) continue;
-        if (is_min) amin64(&d[k], s[k]); else amax64(&d[k], s[k]);
+    if (s[1] != empty) {
+        if (is_min) amin64(&d[1], s[1]); else amax64(&d[1], s[1]);
     }
+    if (s[2] != empty) num_extreme(&d[2], s[2], s[3], is_min);
     if (s[4] != empty) str_extreme(P, &d[4], s[4], is_min);
 }
 
