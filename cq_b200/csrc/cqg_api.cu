@@ -398,13 +398,11 @@ static LaunchCfg g_cfg[64];
 
 static int scan_smem_bytes(int table_bytes) { return ScanGeo::OFF_TABLE + table_bytes; }
 
-static int launch_scan(const DevPlan& P, int table_bytes, cudaStream_t st) {
-    int dev = 0;
-    CU(cudaGetDevice(&dev));
-    int smem = scan_smem_bytes(table_bytes);
+template <int NW>
+static int launch_scan_nw(const DevPlan& P, int smem, int dev, cudaStream_t st) {
     static bool attr_set[64];
     if (!attr_set[dev & 63]) {
-        CU(cudaFuncSetAttribute(scan_kernel<ScanGeo>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(scan_kernel<ScanGeo, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev & 63] = true;
     }
     LaunchCfg& c = g_cfg[dev & 63];
@@ -413,14 +411,23 @@ static int launch_scan(const DevPlan& P, int table_bytes, cudaStream_t st) {
         c.ready = true;
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<ScanGeo>, ScanGeo::THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<ScanGeo, NW>, ScanGeo::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "scan kernel does not fit: %d bytes of shared memory", smem);
-    if (P.n_tiles <= 0) return CQG_OK;
     int grid = std::min(P.n_tiles, c.sms * per_sm);
-    scan_kernel<ScanGeo><<<grid, ScanGeo::THREADS, smem, st>>>(P);
+    scan_kernel<ScanGeo, NW><<<grid, ScanGeo::THREADS, smem, st>>>(P);
     g_launches++;
     CU(cudaGetLastError());
     return CQG_OK;
+}
+
+static int launch_scan(const DevPlan& P, int table_bytes, cudaStream_t st) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (P.n_tiles <= 0) return CQG_OK;
+    int smem = scan_smem_bytes(table_bytes);
+    // wanted fields in registers when there are few of them; the 16-slot build otherwise
+    if (P.nwantL <= 4) return launch_scan_nw<4>(P, smem, dev, st);
+    return launch_scan_nw<kMaxSlots>(P, smem, dev, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -429,7 +436,7 @@ static int launch_scan(const DevPlan& P, int table_bytes, cudaStream_t st) {
 struct HostPlan {
     DevPlan P{};
     std::vector<uint8_t> entry_init;
-    DevBuf d_entry_init, d_fcode, d_frefs, d_code, d_consts, d_pool;
+    DevBuf d_entry_init, d_code, d_consts, d_pool;
     DevBuf d_scalars;  // errflags, rows_scanned, gcount, sel_count, jrow_count, jclass[2]
     int table_smem_bytes = 0;
 };
@@ -632,6 +639,8 @@ static int compile_predicate(HostPlan& hp, const cqg_predicate_t& w, cudaStream_
     if (stack.size() != 1 || stack.back().is_value) return fail(CQG_ERR_ARG, "predicate does not reduce to one condition");
     if (depth_max >= kStackMax - 1) return fail(CQG_ERR_UNSUPPORTED, "predicate nesting deeper than %d", kStackMax - 2);
     if (depth_max > 30) fusable = false;
+    if (fcode.size() > (size_t)kMaxFused || frefs.size() > (size_t)kMaxFusedRefs || consts.size() > (size_t)kMaxFusedConsts)
+        fusable = false;
 
     CU(hp.d_consts.alloc(consts.size() * sizeof(DConst), st));
     CU(cudaMemcpyAsync(hp.d_consts.p, consts.data(), consts.size() * sizeof(DConst), cudaMemcpyHostToDevice, st));
@@ -640,13 +649,9 @@ static int compile_predicate(HostPlan& hp, const cqg_predicate_t& w, cudaStream_
     P.pred.consts = hp.d_consts.as<DConst>();
     P.pred.pool = hp.d_pool.as<uint8_t>();
     if (fusable) {
-        if (frefs.empty()) frefs.push_back(0);
-        CU(hp.d_fcode.alloc(fcode.size() * sizeof(FInsn), st));
-        CU(cudaMemcpyAsync(hp.d_fcode.p, fcode.data(), fcode.size() * sizeof(FInsn), cudaMemcpyHostToDevice, st));
-        CU(hp.d_frefs.alloc(frefs.size() * sizeof(int16_t), st));
-        CU(cudaMemcpyAsync(hp.d_frefs.p, frefs.data(), frefs.size() * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-        P.fcode = hp.d_fcode.as<FInsn>();
-        P.frefs = hp.d_frefs.as<int16_t>();
+        for (size_t k = 0; k < fcode.size(); k++) P.fcode_inl[k] = fcode[k];
+        for (size_t k = 0; k < frefs.size(); k++) P.frefs_inl[k] = frefs[k];
+        for (size_t k = 0; k < consts.size(); k++) P.consts_inl[k] = consts[k];
         P.n_fcode = (int)fcode.size();
         P.pred_kind = 1;
     } else {

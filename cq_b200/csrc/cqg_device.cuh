@@ -320,7 +320,7 @@ __device__ __noinline__ double strtod_big(const uint8_t* p, uint32_t n, unsigned
 
 // Decode one field exactly as parse_value does (src/csv_reader.c:195-240).
 // `errflags` collects KERR_* for inputs outside the exact range handled on the device.
-__device__ inline DVal decode_field(const uint8_t* p, uint32_t len, unsigned& errflags) {
+__device__ __noinline__ DVal decode_field(const uint8_t* p, uint32_t len, unsigned& errflags) {
     DVal v;
     v.type = T_NULL;
     v.len = 0;
@@ -420,6 +420,63 @@ __device__ inline DVal decode_field(const uint8_t* p, uint32_t len, unsigned& er
     while (n > a + 1 && is_space(p[n - 1])) n--;
     v.s = p + a;
     v.len = n - a;
+    return v;
+}
+
+// parse_value for a field of a CLEAN tile: the tile holds no byte below 0x23 other than '\n'
+// (no blanks, no NUL, no quote), so trimming and NUL handling of src/csv_reader.c:143-149,
+// :234-235 are no-ops and the numeric grammar of infer_type (:158-193) is [sign](digit|one dot)+.
+// Anything this routine does not settle in a few instructions goes to decode_field.
+__device__ __forceinline__ DVal decode_field_clean(const uint8_t* p, uint32_t len, unsigned& errflags) {
+    DVal v;
+    v.type = T_NULL;
+    v.len = 0;
+    v.i = 0;
+    if (len == 0) return v;
+    uint32_t c0 = p[0];
+    bool numeric_start = is_digit(c0) || c0 == '+' || c0 == '-' || c0 == '.';
+    if (!numeric_start) {
+        // cannot be a date (every sscanf format starts with %d) nor a number
+        v.type = T_STR;
+        v.s = p;
+        v.len = len;
+        return v;
+    }
+    if (len > 7) return decode_field(p, len, errflags);  // dates (8..10 bytes) and long numbers
+    bool neg = c0 == '-';
+    uint32_t i = (c0 == '+' || c0 == '-') ? 1u : 0u;
+    uint32_t mant = 0, fd = 0;
+    bool dot = false, digit = false, ok = true;
+#pragma unroll
+    for (uint32_t k = 0; k < 7; k++) {
+        if (k >= i && k < len) {
+            uint32_t c = k == 0 ? c0 : (uint32_t)p[k];
+            uint32_t d = c - 48u;
+            bool isdot = c == '.';
+            bool isdig = d <= 9u;
+            ok = ok && (isdig || (isdot && !dot));
+            if (isdig) {
+                mant = mant * 10u + d;
+                digit = true;
+                fd += dot ? 1u : 0u;
+            }
+            dot = dot || isdot;
+        }
+    }
+    if (!(ok && digit)) {  // "-", "+", ".", "1-2", "12ab": STRING (no blanks to trim in a clean tile)
+        v.type = T_STR;
+        v.s = p;
+        v.len = len;
+        return v;
+    }
+    if (!dot) {
+        v.type = T_INT;
+        v.i = neg ? -(long long)mant : (long long)mant;
+        return v;
+    }
+    v.type = T_DBL;
+    double r = (double)mant / kPow10[fd];  // mant < 10^7: one correctly rounded division = strtod
+    v.d = neg ? -r : r;
     return v;
 }
 

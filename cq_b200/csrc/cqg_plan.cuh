@@ -39,6 +39,7 @@ enum : int {
 };
 constexpr int kRefConst = 0x4000;  // ref = kRefConst | const index
 constexpr int kRefNull = 0x7fff;   // unknown column
+constexpr int kMaxFused = 24, kMaxFusedRefs = 32, kMaxFusedConsts = 16;
 
 struct FInsn {
     int16_t op, a, b, n;
@@ -101,11 +102,12 @@ struct DevPlan {
     int16_t colslot[kMaxQueryCols];   // query column -> slot (left slots first), -1 unused
 
     // ---- predicate ----
-    int32_t pred_kind;  // 0 none, 1 fused, 2 generic
+    int32_t pred_kind;  // 0 none, 1 fused (program below, in the parameter block), 2 generic interpreter
     int32_t n_fcode;
-    const FInsn* fcode;
-    const int16_t* frefs;
-    DPred pred;
+    FInsn fcode_inl[kMaxFused];
+    int16_t frefs_inl[kMaxFusedRefs];
+    DConst consts_inl[kMaxFusedConsts];
+    DPred pred;  // generic program + string pool (global memory)
 
     // ---- aggregation ----
     int32_t ngc;

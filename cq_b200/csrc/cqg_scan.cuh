@@ -448,19 +448,69 @@ struct ThreadAcc {
 };
 
 // ------------------------------------------------------------------------------------------
+// rows as the operators see them
+// ------------------------------------------------------------------------------------------
+// FastRow<NW>: a row of a tile staged in shared memory whose wanted fields sit in registers
+// (NW <= 4 keeps off[]/len[] out of local memory). No join. `clean` = the tile has no byte
+// below 0x23 except '\n', which licenses decode_field_clean.
+template <int NW>
+struct FastRow {
+    const uint8_t* base;   // shared-memory tile
+    const uint8_t* lfile;  // base - (file offset of base[0])
+    uint32_t off[NW], len[NW];
+    bool clean;
+    static constexpr bool kJoined = false;
+
+    __device__ __forceinline__ DVal value(const DevPlan& P, int col, unsigned& err) const {
+        DVal v;
+        v.type = T_NULL;
+        v.len = 0;
+        v.i = 0;
+        if (col < 0 || col >= P.n_cols_total) return v;
+        const int s = P.colslot[col];
+        if (s < 0) return v;
+        uint32_t o, l;
+        if (NW <= 4) {
+            o = off[0];
+            l = len[0];
+#pragma unroll
+            for (int k = 1; k < NW; k++)
+                if (s == k) {
+                    o = off[k];
+                    l = len[k];
+                }
+        } else {
+            o = off[s];
+            l = len[s];
+        }
+        return clean ? decode_field_clean(base + o, l, err) : decode_field(base + o, l, err);
+    }
+    __device__ __forceinline__ const uint8_t* file_base(bool) const { return lfile; }
+};
+
+// SlowRow: the general case (joined rows, rows read straight from HBM, generic predicate)
+struct SlowRow {
+    RowView rv;
+    static constexpr bool kJoined = true;
+    __device__ __forceinline__ DVal value(const DevPlan&, int col, unsigned& err) const { return row_value(rv, col, err); }
+    __device__ __forceinline__ const uint8_t* file_base(bool right) const { return right ? rv.rfile : rv.lfile; }
+};
+
+// ------------------------------------------------------------------------------------------
 // predicate evaluation
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ DVal const_value(const DPred& P, int idx) {
-    const DConst c = P.consts[idx];
+__device__ __forceinline__ DVal const_value(const DevPlan& P, int idx) {
+    const DConst c = P.consts_inl[idx];
     DVal v;
     v.type = c.type;
     v.len = c.len;
     v.i = c.bits;
-    if (c.type == T_STR) v.s = P.pool + c.bits;
+    if (c.type == T_STR) v.s = P.pred.pool + c.bits;
     return v;
 }
 
-__device__ __forceinline__ DVal fetch_ref(const DevPlan& P, const RowView& rv, int ref, unsigned& err) {
+template <class Row>
+__device__ __forceinline__ DVal fetch_ref(const DevPlan& P, const Row& row, int ref, unsigned& err) {
     if (ref == kRefNull) {
         DVal v;
         v.type = T_NULL;
@@ -468,29 +518,36 @@ __device__ __forceinline__ DVal fetch_ref(const DevPlan& P, const RowView& rv, i
         v.i = 0;
         return v;
     }
-    if (ref & kRefConst) return const_value(P.pred, ref & 0x3fff);
-    return row_value(rv, ref, err);
+    if (ref & kRefConst) return const_value(P, ref & 0x3fff);
+    return row.value(P, ref, err);
 }
 
-__device__ inline bool eval_fused(const DevPlan& P, const RowView& rv, unsigned& err) {
+// the program lives in the kernel parameter block (constant bank): no dependent global loads
+template <class Row>
+__device__ __forceinline__ bool eval_fused(const DevPlan& P, const Row& row, unsigned& err) {
     uint32_t bs = 0;  // bit stack, top = bit 0
     for (int pc = 0; pc < P.n_fcode; pc++) {
-        const FInsn in = P.fcode[pc];
+        const FInsn in = P.fcode_inl[pc];
         bool b;
         switch (in.op) {
             case F_CMP: {
-                DVal l = fetch_ref(P, rv, in.a, err), r = fetch_ref(P, rv, in.b, err);
-                int c = val_compare(l, r);
+                DVal l = fetch_ref(P, row, in.a, err), r = fetch_ref(P, row, in.b, err);
+                int c;
+                if (l.type == T_INT && r.type == T_INT && ((unsigned long long)(l.i + (1ll << 52)) >> 53) == 0 &&
+                    ((unsigned long long)(r.i + (1ll << 52)) >> 53) == 0)
+                    c = l.i < r.i ? -1 : (l.i > r.i ? 1 : 0);  // same answer as the double compare below 2^52
+                else
+                    c = val_compare(l, r);
                 b = in.n == CQG_OP_EQ ? c == 0 : in.n == CQG_OP_NE ? c != 0 : in.n == CQG_OP_GT ? c > 0
                   : in.n == CQG_OP_LT ? c < 0 : in.n == CQG_OP_GE ? c >= 0 : c <= 0;
                 bs = (bs << 1) | (uint32_t)b;
                 break;
             }
             case F_IN: case F_NOT_IN: {
-                DVal l = fetch_ref(P, rv, in.a, err);
+                DVal l = fetch_ref(P, row, in.a, err);
                 bool found = false;
                 for (int k = 0; k < in.n && !found; k++) {
-                    DVal it = fetch_ref(P, rv, P.frefs[in.b + k], err);
+                    DVal it = fetch_ref(P, row, P.frefs_inl[in.b + k], err);
                     found = val_compare(l, it) == 0;
                 }
                 b = in.op == F_IN ? found : !found;
@@ -498,7 +555,7 @@ __device__ inline bool eval_fused(const DevPlan& P, const RowView& rv, unsigned&
                 break;
             }
             case F_LIKE: case F_ILIKE: {
-                DVal l = fetch_ref(P, rv, in.a, err), r = fetch_ref(P, rv, in.b, err);
+                DVal l = fetch_ref(P, row, in.a, err), r = fetch_ref(P, row, in.b, err);
                 b = (l.type == T_STR && r.type == T_STR) ? like_match(l.s, l.len, r.s, r.len, in.op == F_LIKE) : false;
                 bs = (bs << 1) | (uint32_t)b;
                 break;
@@ -513,12 +570,6 @@ __device__ inline bool eval_fused(const DevPlan& P, const RowView& rv, unsigned&
     return (bs & 1u) != 0;
 }
 
-__device__ __forceinline__ bool eval_where(const DevPlan& P, const RowView& rv, unsigned& err) {
-    if (P.pred_kind == 0) return true;
-    if (P.pred_kind == 1) return eval_fused(P, rv, err);
-    return eval_pred(P.pred, rv, err);
-}
-
 // ------------------------------------------------------------------------------------------
 // what happens to one row that passed WHERE
 // ------------------------------------------------------------------------------------------
@@ -527,15 +578,15 @@ struct CtaState {
     unsigned long long* s_occ;  // its occupancy counter (shared)
 };
 
-template <bool SM>
-__device__ __forceinline__ void entry_accumulate(const DevPlan& P, uint8_t* e, const RowView& rv, uint64_t okey, unsigned& err) {
+template <bool SM, class Row>
+__device__ __forceinline__ void entry_accumulate(const DevPlan& P, uint8_t* e, const Row& row, uint64_t okey, unsigned& err) {
     amin64((uint64_t*)(e + kOffFirst), okey);
     if (SM) atomicAdd((unsigned int*)(e + kOffCount), 1u);
     else atomicAdd((unsigned long long*)(e + kOffCount), 1ull);
     for (int a = 0; a < P.naggs; a++) {
         const AggSpec sp = P.aggs[a];
         if (sp.off < 0) continue;
-        DVal v = row_value(rv, sp.col, err);
+        DVal v = row.value(P, sp.col, err);
         uint8_t* st = e + sp.off;
         if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
             if (v.type == T_INT) {
@@ -549,13 +600,13 @@ __device__ __forceinline__ void entry_accumulate(const DevPlan& P, uint8_t* e, c
             }
         } else {
             bool right = sp.col >= P.n_left_cols;
-            minmax_update(P, st, sp.func == CQG_AGG_MIN, v, okey, right, right ? rv.rfile : rv.lfile, err);
+            minmax_update(P, st, sp.func == CQG_AGG_MIN, v, okey, right, row.file_base(right), err);
         }
     }
 }
 
 // fold entry `src` (same layout) into `dst`
-__device__ inline void entry_merge(const DevPlan& P, uint8_t* dst, const uint8_t* src) {
+__device__ __noinline__ void entry_merge(const DevPlan& P, uint8_t* dst, const uint8_t* src) {
     amin64((uint64_t*)(dst + kOffFirst), *(const uint64_t*)(src + kOffFirst));
     atomicAdd((unsigned long long*)(dst + kOffCount), (unsigned long long)*(const uint64_t*)(src + kOffCount));
     for (int a = 0; a < P.naggs; a++) {
@@ -574,13 +625,14 @@ __device__ inline void entry_merge(const DevPlan& P, uint8_t* dst, const uint8_t
     }
 }
 
-__device__ inline uint8_t* global_entry_for(const DevPlan& P, uint64_t h, uint32_t tags, const uint64_t* kw, unsigned& err) {
+__device__ __noinline__ uint8_t* global_entry_for(const DevPlan& P, uint64_t h, uint32_t tags, const uint64_t* kw, unsigned& err) {
     uint8_t* e = table_find_insert(P.gtab, P.gcap, P.entry_bytes, P.ngc, h, tags, kw, P.gcount, P.gcap / 2);
     if (!e) err |= KERR_TABLE_FULL;
     return e;
 }
 
-__device__ inline void agg_row(const DevPlan& P, const CtaState& cs, const RowView& rv, uint64_t okey, ThreadAcc& acc) {
+template <class Row>
+__device__ __forceinline__ void agg_row(const DevPlan& P, const CtaState& cs, const Row& row, uint64_t okey, ThreadAcc& acc) {
     if (P.scalar_regs) {
         acc.count++;
         if (okey < acc.first) acc.first = okey;
@@ -589,7 +641,7 @@ __device__ inline void agg_row(const DevPlan& P, const CtaState& cs, const RowVi
             if (a < P.naggs) {
                 const AggSpec sp = P.aggs[a];
                 if (sp.off >= 0) {
-                    DVal v = row_value(rv, sp.col, acc.err);
+                    DVal v = row.value(P, sp.col, acc.err);
                     if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
                         if (v.type == T_INT) {
                             acc.si[a] += v.i;
@@ -600,8 +652,7 @@ __device__ inline void agg_row(const DevPlan& P, const CtaState& cs, const RowVi
                         }
                     } else {
                         bool right = sp.col >= P.n_left_cols;
-                        minmax_update(P, cs.stab + sp.off, sp.func == CQG_AGG_MIN, v, okey, right, right ? rv.rfile : rv.lfile,
-                                      acc.err);
+                        minmax_update(P, cs.stab + sp.off, sp.func == CQG_AGG_MIN, v, okey, right, row.file_base(right), acc.err);
                     }
                 }
             }
@@ -612,7 +663,7 @@ __device__ inline void agg_row(const DevPlan& P, const CtaState& cs, const RowVi
     uint32_t tags = 0;
     uint64_t h = 0x243F6A8885A308D3ull + (uint64_t)P.ngc;
     for (int g = 0; g < P.ngc; g++) {
-        DVal v = row_value(rv, P.gcol[g], acc.err);
+        DVal v = row.value(P, P.gcol[g], acc.err);
         uint32_t tag;
         canon_part<true>(v, P.ngc > 1, acc.err, tag, kw[2 * g], kw[2 * g + 1]);
         tags |= tag << (4 * g);
@@ -623,12 +674,12 @@ __device__ inline void agg_row(const DevPlan& P, const CtaState& cs, const RowVi
         uint8_t* e = table_find_insert(cs.stab, (uint64_t)P.smem_cap, P.entry_bytes, P.ngc, h, tags, kw, cs.s_occ,
                                        (uint64_t)(P.smem_cap - (P.smem_cap >> 2)));
         if (e) {
-            entry_accumulate<true>(P, e, rv, okey, acc.err);
+            entry_accumulate<true>(P, e, row, okey, acc.err);
             return;
         }
     }
     uint8_t* e = global_entry_for(P, h, tags, kw, acc.err);
-    if (e) entry_accumulate<false>(P, e, rv, okey, acc.err);
+    if (e) entry_accumulate<false>(P, e, row, okey, acc.err);
 }
 
 __device__ __forceinline__ void select_row(const DevPlan& P, uint64_t okey, uint64_t roff) {
@@ -637,13 +688,6 @@ __device__ __forceinline__ void select_row(const DevPlan& P, uint64_t okey, uint
         P.sel_okey[idx] = okey;
         if (P.sel_roff) P.sel_roff[idx] = roff;
     }
-}
-
-__device__ __forceinline__ void row_passes(const DevPlan& P, const CtaState& cs, const RowView& rv, uint64_t okey, uint64_t roff,
-                                           ThreadAcc& acc) {
-    if (!eval_where(P, rv, acc.err)) return;
-    if (P.mode == SCAN_AGG) agg_row(P, cs, rv, okey, acc);
-    else select_row(P, okey, roff);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -718,11 +762,13 @@ __device__ inline void split_right_row(const DevPlan& P, uint64_t roff, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
-// one data row: `base` + foff/flen hold the wanted left fields; goff = file offset of the row
+// one data row, general route: `base` + foff/flen hold the wanted left fields; goff = file
+// offset of the row. Kept out of line: the hot loop only pays for it when it is taken.
 // ------------------------------------------------------------------------------------------
-__device__ inline void process_row(const DevPlan& P, const CtaState& cs, const uint8_t* base, const uint8_t* lfile, uint32_t* foff,
-                                   uint32_t* flen, uint64_t goff, ThreadAcc& acc) {
-    RowView rv;
+__device__ __noinline__ void process_row_slow(const DevPlan& P, const CtaState& cs, const uint8_t* base, const uint8_t* lfile,
+                                              uint32_t* foff, uint32_t* flen, uint64_t goff, ThreadAcc& acc) {
+    SlowRow row;
+    RowView& rv = row.rv;
     rv.base = base;
     rv.rbase = nullptr;
     rv.lfile = lfile;
@@ -740,7 +786,10 @@ __device__ inline void process_row(const DevPlan& P, const CtaState& cs, const u
         return;
     }
     if (!P.join) {
-        row_passes(P, cs, rv, okey, 0, acc);
+        bool pass = P.pred_kind == 0 ? true : (P.pred_kind == 1 ? eval_fused(P, row, acc.err) : eval_pred(P.pred, rv, acc.err));
+        if (!pass) return;
+        if (P.mode == SCAN_AGG) agg_row(P, cs, row, okey, acc);
+        else select_row(P, okey, 0);
         return;
     }
     // probe
@@ -768,15 +817,50 @@ __device__ inline void process_row(const DevPlan& P, const CtaState& cs, const u
             split_right_row(P, roff, foff, flen);
             rv.rbase = P.rdata + roff;
         }
-        row_passes(P, cs, rv, okey | rank, roff, acc);
+        bool pass = P.pred_kind == 0 ? true : (P.pred_kind == 1 ? eval_fused(P, row, acc.err) : eval_pred(P.pred, rv, acc.err));
+        if (!pass) continue;
+        if (P.mode == SCAN_AGG) agg_row(P, cs, row, okey | rank, acc);
+        else select_row(P, okey | rank, roff);
     }
+}
+
+// a row that does not fit the staged window: found and split straight from HBM
+__device__ __noinline__ void process_long_row(const DevPlan& P, const CtaState& cs, uint64_t goff, ThreadAcc& acc) {
+    uint32_t foff[2 * kMaxSlots], flen[2 * kMaxSlots];
+    const uint8_t* b = P.data + goff;
+    uint64_t maxlen = P.size - goff;
+    uint64_t re = 0;
+    while (re < maxlen && b[re] != '\n' && b[re] != '\r') re++;
+    if (re > 0x7fffffffull) re = 0x7fffffffull;
+    split_row_exact(b, 0, (uint32_t)re, P.delim, P.quote, P.wantL, P.nwantL, foff, flen);
+    process_row_slow(P, cs, b, P.data, foff, flen, goff, acc);
+}
+
+// a row inside the staged window that needs the exact splitter or the general operators
+__device__ __noinline__ void process_window_row_slow(const DevPlan& P, const CtaState& cs, const uint8_t* buf, long long g0,
+                                                     uint32_t rs, uint32_t len, ThreadAcc& acc) {
+    uint32_t foff[2 * kMaxSlots], flen[2 * kMaxSlots];
+    split_row_exact(buf, rs, rs + len, P.delim, P.quote, P.wantL, P.nwantL, foff, flen);
+    process_row_slow(P, cs, buf, buf - g0, foff, flen, (uint64_t)(g0 + (long long)rs), acc);
 }
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <class G>
-__global__ void __launch_bounds__(G::THREADS) scan_kernel(const __grid_constant__ DevPlan P) {
+// 0x80 in every byte of v equal to the (ASCII) byte replicated in pat: 3 instructions
+__device__ __forceinline__ uint32_t eq_flags7(uint32_t v, uint32_t pat) {
+    uint32_t a = ((v ^ pat) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(a | v) & 0x80808080u;
+}
+// four flag words -> 16-bit mask in byte order, through the high half of four multiplies
+__device__ __forceinline__ uint32_t flags_to_mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    uint32_t lo = (__umulhi(f0, 0x02040810u) & 0x0fu) | (__umulhi(f1, 0x20408100u) & 0xf0u);
+    uint32_t hi = (__umulhi(f2, 0x02040810u) & 0x0fu) | (__umulhi(f3, 0x20408100u) & 0xf0u);
+    return hi * 256u + lo;
+}
+
+template <class G, int NW>
+__global__ void __launch_bounds__(G::THREADS, 2) scan_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* tm = (uint32_t*)(smem + G::OFF_TM);
@@ -791,6 +875,9 @@ __global__ void __launch_bounds__(G::THREADS) scan_kernel(const __grid_constant_
     cs.s_occ = (unsigned long long*)(wsum + 48);
     const bool agg_mode = P.mode == SCAN_AGG;
     if (agg_mode && (P.smem_cap > 0)) cs.stab = smem + G::OFF_TABLE;
+    // rows of this plan can take the register route: single table, no generic-interpreter predicate
+    const bool fast_plan = !P.join && P.pred_kind != 2 && (P.mode == SCAN_AGG || P.mode == SCAN_SELECT) && P.nwantL <= NW &&
+                           !P.exact_only;
 
     // ---- prologue: barriers, mask padding, shared table ----
     if (tid == 0) {
@@ -862,34 +949,45 @@ __global__ void __launch_bounds__(G::THREADS) scan_kernel(const __grid_constant_
         const uint8_t* buf = smem + G::OFF_BUF + stage * G::BUF;
         const long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
         const long long g0 = tile * (long long)G::TILE - G::PRE;
+        const bool edge_tile = g0 < 0 || g0 + G::BUF > (long long)size;  // some staged bytes lie outside the file
 
         // ---------------- phase 1: classify ----------------
         uint32_t spec = 0;
-        for (int c = tid; c < G::CHUNKS; c += G::THREADS) {
-            const uint4 v = *(const uint4*)(buf + 16 * c);
-            uint32_t f0 = eq_flags(v.x, 0x0a0a0a0au), f1 = eq_flags(v.y, 0x0a0a0a0au), f2 = eq_flags(v.z, 0x0a0a0a0au),
-                     f3 = eq_flags(v.w, 0x0a0a0a0au);
-            uint32_t T = flags_to_mask4(f0) | (flags_to_mask4(f1) << 4) | (flags_to_mask4(f2) << 8) | (flags_to_mask4(f3) << 12);
-            uint32_t D = eq_mask16(v, patD);
-            // any byte < 0x23 other than '\n' (CR, quote, blanks, controls): the tile takes the careful path
-            uint32_t x0 = v.x | f0, x1 = v.y | f1, x2 = v.z | f2, x3 = v.w | f3;
-            uint32_t s4 = ((x0 - 0x23232323u) & ~x0) | ((x1 - 0x23232323u) & ~x1) | ((x2 - 0x23232323u) & ~x2) |
-                          ((x3 - 0x23232323u) & ~x3);
-            long long g = g0 + 16 * c;
-            if (g < 0 || g + 16 > (long long)size) {
-                // bytes outside the file are row terminators and nothing else
-                uint32_t valid = 0;
-                for (int j = 0; j < 16; j++)
-                    if (g + j >= 0 && g + j < (long long)size) valid |= 1u << j;
-                T = (T & valid) | (~valid & 0xffffu);
-                D &= valid;
-                s4 = 0x80u;  // partial chunk: be careful
+        if (!edge_tile && !P.exact_only) {
+#pragma unroll 2
+            for (int c = tid; c < G::CHUNKS; c += G::THREADS) {
+                const uint4 v = *(const uint4*)(buf + 16 * c);
+                uint32_t f0 = eq_flags7(v.x, 0x0a0a0a0au), f1 = eq_flags7(v.y, 0x0a0a0a0au), f2 = eq_flags7(v.z, 0x0a0a0a0au),
+                         f3 = eq_flags7(v.w, 0x0a0a0a0au);
+                uint32_t T = flags_to_mask16(f0, f1, f2, f3);
+                uint32_t D = flags_to_mask16(eq_flags7(v.x, patD), eq_flags7(v.y, patD), eq_flags7(v.z, patD), eq_flags7(v.w, patD));
+                // any byte < 0x23 other than '\n' (CR, quote, blanks, NUL, controls): the tile takes the careful path
+                uint32_t x0 = v.x | f0, x1 = v.y | f1, x2 = v.z | f2, x3 = v.w | f3;
+                spec |= ((x0 - 0x23232323u) & ~x0) | ((x1 - 0x23232323u) & ~x1) | ((x2 - 0x23232323u) & ~x2) |
+                        ((x3 - 0x23232323u) & ~x3);
+                ((uint16_t*)tm)[c] = (uint16_t)T;
+                ((uint16_t*)dm)[c] = (uint16_t)D;
             }
-            spec |= s4 & 0x80808080u;
-            ((uint16_t*)tm)[c] = (uint16_t)T;
-            ((uint16_t*)dm)[c] = (uint16_t)D;
+            spec &= 0x80808080u;
+        } else {
+            spec = 1;  // edge tiles and exotic dialects: always the careful path
+            for (int c = tid; c < G::CHUNKS; c += G::THREADS) {
+                const uint4 v = *(const uint4*)(buf + 16 * c);
+                uint32_t T = eq_mask16(v, 0x0a0a0a0au), D = eq_mask16(v, patD);
+                long long g = g0 + 16 * c;
+                if (g < 0 || g + 16 > (long long)size) {
+                    // bytes outside the file are row terminators and nothing else
+                    uint32_t valid = 0;
+                    for (int j = 0; j < 16; j++)
+                        if (g + j >= 0 && g + j < (long long)size) valid |= 1u << j;
+                    T = (T & valid) | (~valid & 0xffffu);
+                    D &= valid;
+                }
+                ((uint16_t*)tm)[c] = (uint16_t)T;
+                ((uint16_t*)dm)[c] = (uint16_t)D;
+            }
         }
-        const int special = __syncthreads_or((int)(spec != 0u)) | (int)P.exact_only;
+        const int special = __syncthreads_or((int)(spec != 0u));
         if (special) {
             for (int c = tid; c < G::CHUNKS; c += G::THREADS) {
                 const uint4 v = *(const uint4*)(buf + 16 * c);
@@ -969,70 +1067,79 @@ __global__ void __launch_bounds__(G::THREADS) scan_kernel(const __grid_constant_
             __syncthreads();
             // ---------------- phase 2: rows ----------------
             const uint32_t npass = nrows - pass_lo < (uint32_t)G::ROWCAP ? nrows - pass_lo : (uint32_t)G::ROWCAP;
-            for (uint32_t r = tid; r < npass; r += G::THREADS) {
-                const uint32_t rs = rowpos[r];
-                acc.rows++;
-                if (P.mode == SCAN_COUNT_ROWS) continue;
-                uint32_t foff[2 * kMaxSlots], flen[2 * kMaxSlots];
-                const uint64_t goff = (uint64_t)(g0 + (long long)rs);
-                // row end: first terminator at or after rs
-                unsigned long long tw = mask_window(tm, rs);
-                uint32_t len;
-                if (tw) {
-                    len = (uint32_t)__ffsll((long long)tw) - 1u;
-                } else {
-                    uint32_t p = rs + 64u;
-                    len = 0xffffffffu;
-                    while (p < (uint32_t)G::BUF) {
-                        unsigned long long w2 = mask_window(tm, p);
-                        if (w2) {
-                            len = p + (uint32_t)__ffsll((long long)w2) - 1u - rs;
-                            break;
+            if (P.mode == SCAN_COUNT_ROWS) {
+                for (uint32_t r = tid; r < npass; r += G::THREADS) acc.rows++;
+            } else {
+                for (uint32_t r = tid; r < npass; r += G::THREADS) {
+                    const uint32_t rs = rowpos[r];
+                    acc.rows++;
+                    // row end: first terminator at or after rs
+                    const unsigned long long tw = mask_window(tm, rs);
+                    if (tw == 0ull) {
+                        // longer than 64 bytes: look further, then take the general route
+                        uint32_t p = rs + 64u, len = 0xffffffffu;
+                        while (p < (uint32_t)G::BUF) {
+                            unsigned long long w2 = mask_window(tm, p);
+                            if (w2) {
+                                len = p + (uint32_t)__ffsll((long long)w2) - 1u - rs;
+                                break;
+                            }
+                            p += 64u;
                         }
-                        p += 64u;
+                        if (len == 0xffffffffu || rs + len >= (uint32_t)G::BUF) process_long_row(P, cs, (uint64_t)(g0 + (long long)rs), acc);
+                        else process_window_row_slow(P, cs, buf, g0, rs, len, acc);
+                        continue;
                     }
-                }
-                if (len == 0xffffffffu || rs + len >= (uint32_t)G::BUF) {
-                    // the row runs past the staged window: split it straight from HBM
-                    const uint8_t* b = P.data + goff;
-                    uint64_t maxlen = size - goff;
-                    uint64_t re = 0;
-                    while (re < maxlen && b[re] != '\n' && b[re] != '\r') re++;
-                    if (re > 0x7fffffffull) re = 0x7fffffffull;
-                    split_row_exact(b, 0, (uint32_t)re, P.delim, P.quote, P.wantL, P.nwantL, foff, flen);
-                    process_row(P, cs, b, P.data, foff, flen, goff, acc);
-                    continue;
-                }
-                bool fast = len <= 64u && !P.exact_only;
-                unsigned long long lenmask = len >= 64u ? ~0ull : ((1ull << len) - 1ull);
-                if (fast && special) fast = (mask_window(qm, rs) & lenmask) == 0ull;
-                if (fast) {
-                    unsigned long long dw = mask_window(dm, rs) & lenmask;
-                    int col = 0;
-                    uint32_t startpos = 0;
-                    int k = 0;
-                    for (; k < P.nwantL; k++) {
-                        const int want = P.wantL[k];
-                        while (col < want && dw) {
-                            startpos = (uint32_t)__ffsll((long long)dw);
-                            dw &= dw - 1ull;
-                            col++;
+                    const uint32_t len = (uint32_t)__ffsll((long long)tw) - 1u;
+                    if (rs + len >= (uint32_t)G::BUF) {
+                        process_long_row(P, cs, (uint64_t)(g0 + (long long)rs), acc);
+                        continue;
+                    }
+                    const unsigned long long lenmask = (1ull << len) - 1ull;  // len <= 63 here
+                    bool fast = fast_plan;
+                    if (fast && special) fast = (mask_window(qm, rs) & lenmask) == 0ull;
+                    if (!fast) {
+                        process_window_row_slow(P, cs, buf, g0, rs, len, acc);
+                        continue;
+                    }
+                    // ---- register route ----
+                    FastRow<NW> row;
+                    row.base = buf;
+                    row.lfile = buf - g0;
+                    row.clean = !special;
+                    {
+                        unsigned long long dw = mask_window(dm, rs) & lenmask;
+                        int col = 0;
+                        uint32_t startpos = 0;
+                        bool missing = false;
+#pragma unroll
+                        for (int k = 0; k < NW; k++) {
+                            row.off[k] = rs;
+                            row.len[k] = 0;
+                            if (k < P.nwantL) {
+                                const int want = P.wantL[k];
+                                while (col < want && dw) {
+                                    startpos = (uint32_t)__ffsll((long long)dw);
+                                    dw &= dw - 1ull;
+                                    col++;
+                                }
+                                missing = missing || col < want;
+                                uint32_t endpos = dw ? (uint32_t)__ffsll((long long)dw) - 1u : len;
+                                uint32_t fs = startpos;
+                                if (special)
+                                    while (fs < endpos && is_space(buf[rs + fs])) fs++;
+                                row.off[k] = rs + fs;
+                                row.len[k] = missing ? 0u : endpos - fs;
+                            }
                         }
-                        if (col < want) break;
-                        uint32_t endpos = dw ? (uint32_t)__ffsll((long long)dw) - 1u : len;
-                        uint32_t fs = startpos;
-                        while (fs < endpos && is_space(buf[rs + fs])) fs++;
-                        foff[k] = rs + fs;
-                        flen[k] = endpos - fs;
                     }
-                    for (; k < P.nwantL; k++) {
-                        foff[k] = rs;
-                        flen[k] = 0;
-                    }
-                } else {
-                    split_row_exact(buf, rs, rs + len, P.delim, P.quote, P.wantL, P.nwantL, foff, flen);
+                    const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
+                    if (gabs >> 45) acc.err |= KERR_OFFSET_RANGE;
+                    const uint64_t okey = gabs << 16;
+                    if (P.pred_kind == 1 && !eval_fused(P, row, acc.err)) continue;
+                    if (P.mode == SCAN_AGG) agg_row(P, cs, row, okey, acc);
+                    else select_row(P, okey, 0);
                 }
-                process_row(P, cs, buf, buf - g0, foff, flen, goff, acc);
             }
             __syncthreads();
         }
