@@ -387,7 +387,7 @@ CQG_API uint64_t cqg_table_device_ptr(const cqg_table_t* t) { return t ? (uint64
 // ------------------------------------------------------------------------------------------
 // kernel configuration
 // ------------------------------------------------------------------------------------------
-using ScanGeo = Geo<256, 32768, 2>;
+using ScanGeo = Geo<128, 16384, 2>;
 
 struct LaunchCfg {
     int sms = 0;
@@ -494,6 +494,75 @@ static int want_column(DevPlan& P, int col) {
     return CQG_OK;
 }
 
+// shortest decimal form of a double with <= 15 significant digits: value = mant / 10^fd
+static bool exact_decimal(double x, long long& mant, int& fd) {
+    if (!(x >= 0.0) || x > 1e9) return false;
+    for (int k = 0; k <= 6; k++) {
+        double scaled = x * std::pow(10.0, k);
+        double r = std::nearbyint(scaled);
+        if (r > 9e14) return false;
+        char a[64], b[64];
+        snprintf(a, sizeof a, "%.17g", (double)r / std::pow(10.0, k));
+        snprintf(b, sizeof b, "%.17g", x);
+        if (strcmp(a, b) == 0) {  // r / 10^k rounds to exactly x: x is the double of that decimal
+            mant = (long long)r;
+            fd = k;
+            return true;
+        }
+    }
+    return false;
+}
+
+// DevPlan::simple — see cqg_plan.cuh. Called before fused refs are rewritten to slots.
+static void plan_simple_route(DevPlan& P) {
+    P.simple = 0;
+    if (P.join || P.mode != SCAN_AGG || !P.scalar_regs || P.exact_only || P.nwantL > 4) return;
+    for (int a = 0; a < P.naggs; a++)
+        if (P.aggs[a].func == CQG_AGG_MIN || P.aggs[a].func == CQG_AGG_MAX) return;
+    P.s_has_pred = 0;
+    if (P.pred_kind == 2) return;
+    if (P.pred_kind == 1) {
+        if (P.n_fcode != 1 || P.fcode_inl[0].op != F_CMP) return;
+        FInsn in = P.fcode_inl[0];
+        int op = in.n;
+        int col_ref = in.a, const_ref = in.b;
+        if ((col_ref & kRefConst) && col_ref != kRefNull) {  // literal on the left: mirror the operator
+            std::swap(col_ref, const_ref);
+            op = op == CQG_OP_GT ? CQG_OP_LT : op == CQG_OP_LT ? CQG_OP_GT : op == CQG_OP_GE ? CQG_OP_LE
+               : op == CQG_OP_LE ? CQG_OP_GE : op;
+        }
+        if (col_ref == kRefNull || (col_ref & kRefConst) || !(const_ref & kRefConst) || const_ref == kRefNull) return;
+        int slot = (col_ref >= 0 && col_ref < kMaxQueryCols) ? P.colslot[col_ref] : -1;
+        if (slot < 0 || slot >= P.nwantL) return;
+        const DConst& c = P.consts_inl[const_ref & 0x1fff];
+        long long cm;
+        int cfd;
+        if (c.type == CQG_TYPE_INTEGER) {
+            if (c.bits < 0 || c.bits > 1000000000ll) return;
+            cm = c.bits;
+            cfd = 0;
+        } else if (c.type == CQG_TYPE_DOUBLE) {
+            double d;
+            memcpy(&d, &c.bits, 8);
+            if (!exact_decimal(d, cm, cfd) || cm > 1000000000ll) return;
+        } else {
+            return;
+        }
+        for (int fd = 0; fd < 4; fd++) {
+            int K = std::max(fd, cfd);
+            long long A = 1, B = cm;
+            for (int i = 0; i < K - fd; i++) A *= 10;
+            for (int i = 0; i < K - cfd; i++) B *= 10;
+            P.s_A[fd] = A;
+            P.s_B[fd] = B;
+        }
+        P.s_has_pred = 1;
+        P.s_slot = slot;
+        P.s_op = op;
+    }
+    P.simple = 1;
+}
+
 static int number_slots(DevPlan& P) {
     P.nwantL = P.nwantR = 0;
     for (int c = 0; c < P.n_left_cols && c < kMaxQueryCols; c++)
@@ -508,6 +577,29 @@ static int number_slots(DevPlan& P) {
         }
     for (int k = 0; k < P.nwantL; k++) P.colslot[P.wantL[k]] = (int16_t)k;
     for (int k = 0; k < P.nwantR; k++) P.colslot[P.n_left_cols + P.wantR[k]] = (int16_t)(P.nwantL + k);
+    for (int k = 0; k < P.nwantL; k++) P.gap[k] = (int16_t)(k == 0 ? P.wantL[0] : P.wantL[k] - P.wantL[k - 1]);
+    // operators address fields by slot from here on
+    auto slot_of = [&](int col) { return (col < 0 || col >= kMaxQueryCols) ? -1 : (int)P.colslot[col]; };
+    for (int a = 0; a < P.naggs; a++) P.aggs[a].slot = slot_of(P.aggs[a].col);
+    for (int g = 0; g < P.ngc; g++) P.gslot[g] = (int16_t)slot_of(P.gcol[g]);
+    auto ref_slot = [&](int16_t ref) -> int16_t {
+        if (ref == kRefNull || (ref & kRefConst)) return ref;
+        int sl = slot_of(ref);
+        return (int16_t)(sl < 0 ? kRefNull : (kRefSlot | sl));
+    };
+    plan_simple_route(P);
+    if (P.pred_kind == 1) {
+        for (int k = 0; k < P.n_fcode; k++) {
+            FInsn& in = P.fcode_inl[k];
+            if (in.op == F_CMP || in.op == F_LIKE || in.op == F_ILIKE) {
+                in.a = ref_slot(in.a);
+                in.b = ref_slot(in.b);
+            } else if (in.op == F_IN || in.op == F_NOT_IN) {
+                in.a = ref_slot(in.a);
+                for (int j = 0; j < in.n; j++) P.frefs_inl[in.b + j] = ref_slot(P.frefs_inl[in.b + j]);
+            }
+        }
+    }
     return CQG_OK;
 }
 
@@ -1102,7 +1194,8 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
                 long long si = *(const long long*)(e + sp.off);
                 double sd = *(const double*)(e + sp.off + 8);
                 int64_t n = (int64_t) * (const uint64_t*)(e + sp.off + 16);
-                double sum = (double)si + sd;
+                long long s3 = *(const long long*)(e + sp.off + 24);
+                double sum = (double)si + sd + (double)s3 / 1000.0;
                 r->sum[ix] = sum;
                 r->ncount[ix] = n;
                 v.type = CQG_TYPE_DOUBLE;

@@ -444,23 +444,18 @@ __device__ __forceinline__ DVal decode_field_clean(const uint8_t* p, uint32_t le
     }
     if (len > 7) return decode_field(p, len, errflags);  // dates (8..10 bytes) and long numbers
     bool neg = c0 == '-';
-    uint32_t i = (c0 == '+' || c0 == '-') ? 1u : 0u;
     uint32_t mant = 0, fd = 0;
     bool dot = false, digit = false, ok = true;
-#pragma unroll
-    for (uint32_t k = 0; k < 7; k++) {
-        if (k >= i && k < len) {
-            uint32_t c = k == 0 ? c0 : (uint32_t)p[k];
-            uint32_t d = c - 48u;
-            bool isdot = c == '.';
-            bool isdig = d <= 9u;
-            ok = ok && (isdig || (isdot && !dot));
-            if (isdig) {
-                mant = mant * 10u + d;
-                digit = true;
-                fd += dot ? 1u : 0u;
-            }
-            dot = dot || isdot;
+    for (uint32_t k = (c0 == '+' || c0 == '-') ? 1u : 0u; k < len; k++) {  // len <= 7: mant < 10^7
+        uint32_t c = p[k];
+        uint32_t d = c - 48u;
+        if (d <= 9u) {
+            mant = mant * 10u + d;
+            digit = true;
+            fd += dot ? 1u : 0u;
+        } else {
+            ok = ok && c == '.' && !dot;
+            dot = true;
         }
     }
     if (!(ok && digit)) {  // "-", "+", ".", "1-2", "12ab": STRING (no blanks to trim in a clean tile)

@@ -39,6 +39,7 @@ enum : int {
 };
 constexpr int kRefConst = 0x4000;  // ref = kRefConst | const index
 constexpr int kRefNull = 0x7fff;   // unknown column
+constexpr int kRefSlot = 0x2000;   // fused programs address fields by slot: ref = kRefSlot | slot
 constexpr int kMaxFused = 24, kMaxFusedRefs = 32, kMaxFusedConsts = 16;
 
 struct FInsn {
@@ -46,8 +47,9 @@ struct FInsn {
 };
 
 // ---- aggregate state inside a group entry (every state 16-byte aligned) ----
-// SUM/AVG : { int64 sum_i ; double sum_d ; uint64 ncount ; pad }                         32 B
-//   INTEGER-typed values add into sum_i (exact), DOUBLE-typed into sum_d; SUM = sum_i + sum_d
+// SUM/AVG : { int64 sum_i ; double sum_d ; uint64 ncount ; int64 sum_3 }                 32 B
+//   INTEGER-typed values add into sum_i (exact), DOUBLE-typed into sum_d, short decimals of the simple
+//   route into sum_3 as value*1000 (exact); SUM = sum_i + sum_d + sum_3/1000
 // MIN/MAX : { first_nonnull ; date ; num_key ; num_okey ; str ; pad }                    48 B
 //   first_nonnull = (okey << 2 | class) of the earliest non-NULL value (class 1 numeric, 2 string, 3 date):
 //                   the extreme is taken inside that class only (value_compare is 0 across classes)
@@ -58,8 +60,8 @@ struct FInsn {
 struct AggSpec {
     int32_t func;
     int32_t col;
-    int32_t off;  // byte offset of the state inside the entry (-1: COUNT, no state)
-    int32_t pad;
+    int32_t off;   // byte offset of the state inside the entry (-1: COUNT, no state)
+    int32_t slot;  // field slot of `col` (-1: reads as NULL)
 };
 
 // entry header
@@ -100,6 +102,7 @@ struct DevPlan {
     int16_t wantL[kMaxSlots];         // ascending CSV column indices
     int16_t wantR[kMaxSlots];
     int16_t colslot[kMaxQueryCols];   // query column -> slot (left slots first), -1 unused
+    int16_t gap[kMaxSlots];           // delimiters between wanted left field k-1 and k (gap[0] = wantL[0])
 
     // ---- predicate ----
     int32_t pred_kind;  // 0 none, 1 fused (program below, in the parameter block), 2 generic interpreter
@@ -109,9 +112,20 @@ struct DevPlan {
     DConst consts_inl[kMaxFusedConsts];
     DPred pred;  // generic program + string pool (global memory)
 
+    // ---- "simple" route: no GROUP BY, COUNT/SUM/AVG only, WHERE empty or `column <op> decimal literal`.
+    // Short unsigned decimals (<= 4 bytes) are decoded and compared as scaled integers:
+    //   field = mant / 10^fd  <op>  literal   <=>   mant * s_A[fd]  <op>  s_B[fd]
+    // which orders exactly like the reference's double compare for decimals of <= 15 digits.
+    int32_t simple;
+    int32_t s_has_pred;
+    int32_t s_slot;   // slot of the predicate column
+    int32_t s_op;     // CQG_OP_EQ..LE with the column on the left
+    long long s_A[4], s_B[4];
+
     // ---- aggregation ----
     int32_t ngc;
     int16_t gcol[CQG_MAX_GROUP_COLS];
+    int16_t gslot[CQG_MAX_GROUP_COLS];  // field slots of the key columns (-1: NULL)
     int32_t naggs;
     AggSpec aggs[CQG_MAX_AGGS];
     int32_t entry_bytes;

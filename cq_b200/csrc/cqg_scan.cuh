@@ -31,7 +31,7 @@ struct Geo {
     static constexpr int BUF = PRE + TILE + OVER;  // multiple of 32
     static constexpr int CHUNKS = BUF / 16;
     static constexpr int MASKW = BUF / 32 + 4;     // mask words incl. padding for 64-bit windows
-    static constexpr int ROWCAP = 4096;            // rows listed per pass
+    static constexpr int ROWCAP = 2048;            // rows listed per pass
     static constexpr int NWARPS = THREADS / 32;
     static constexpr int WPT = (TILE / 32) / THREADS;  // mask words per thread in phase 1b
     static_assert((TILE / 32) % THREADS == 0, "tile words must divide by threads");
@@ -92,6 +92,18 @@ __device__ __forceinline__ uint32_t flags_to_mask4(uint32_t f) { return (f * 0x0
 __device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t pat) {
     return flags_to_mask4(eq_flags(v.x, pat)) | (flags_to_mask4(eq_flags(v.y, pat)) << 4) |
            (flags_to_mask4(eq_flags(v.z, pat)) << 8) | (flags_to_mask4(eq_flags(v.w, pat)) << 12);
+}
+
+// 0x80 in every byte of v equal to the (ASCII) byte replicated in pat: 3 instructions
+__device__ __forceinline__ uint32_t eq_flags7(uint32_t v, uint32_t pat) {
+    uint32_t a = ((v ^ pat) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(a | v) & 0x80808080u;
+}
+// four flag words -> 16-bit mask in byte order, through the high half of four multiplies
+__device__ __forceinline__ uint32_t flags_to_mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    uint32_t lo = (__umulhi(f0, 0x02040810u) & 0x0fu) | (__umulhi(f1, 0x20408100u) & 0xf0u);
+    uint32_t hi = (__umulhi(f2, 0x02040810u) & 0x0fu) | (__umulhi(f3, 0x20408100u) & 0xf0u);
+    return hi * 256u + lo;
 }
 
 // 64-bit window of a bitmask starting at bit `pos`
@@ -441,11 +453,43 @@ struct ThreadAcc {
     uint32_t rows;     // data rows seen
     uint32_t count;    // rows passing WHERE
     uint64_t first;    // min okey
-    long long si[4];
-    double sd[4];
+    long long si[4];   // INTEGER-typed values
+    double sd[4];      // DOUBLE-typed values
+    long long s3[4];   // short decimals, summed exactly as value * 1000 (simple route)
     uint32_t sn[4];
     unsigned err;
 };
+
+// A field of at most 4 bytes that is an unsigned decimal ("45", "1.84", "2.0", ".5"): value =
+// mant / 10^fd with fd <= 3. Returns false for anything else (signs, letters, two dots, no digit).
+// `buf` is the shared-memory tile; the 4 bytes are fetched with two aligned loads.
+__device__ __forceinline__ bool decode_tiny(const uint8_t* buf, uint32_t off, uint32_t len, uint32_t& mant, uint32_t& fd) {
+    const uint32_t a = off & ~3u, sh = (off & 3u) * 8u;
+    const uint32_t w0 = *(const uint32_t*)(buf + a), w1 = *(const uint32_t*)(buf + a + 4);
+    uint32_t w = __funnelshift_r(w0, w1, sh);
+    // right-align: last character in byte 3, '0' padding in front
+    const uint32_t pad = 8u * (4u - len);  // len in 1..4
+    w = len == 4u ? w : ((w << pad) | (0x30303030u >> (8u * len)));
+    uint32_t dotf = eq_flags7(w, 0x2e2e2e2eu);
+    uint32_t t = w ^ 0x30303030u;
+    fd = 0;
+    uint32_t ndig = len;
+    if (dotf) {
+        if (dotf & (dotf - 1u)) return false;          // two dots
+        const uint32_t j = (31u - __clz(dotf)) >> 3;   // byte index of the dot
+        fd = 3u - j;
+        const uint32_t lowmask = (1u << (8u * j)) - 1u;  // bytes in front of the dot
+        const uint32_t high = j == 3u ? 0u : (t & ~((1u << (8u * (j + 1u))) - 1u));
+        t = ((t & lowmask) << 8) | high;
+        ndig = len - 1u;
+    }
+    if (ndig == 0u) return false;
+    if (((t + 0x76767676u) | t) & 0x80808080u) return false;  // a byte that is not a digit
+    t = t * 10u + (t >> 8);                        // byte 0 = b0*10+b1, byte 2 = b2*10+b3
+    t &= 0x00ff00ffu;
+    mant = (t * 100u + (t >> 16)) & 0xffffu;
+    return true;
+}
 
 // ------------------------------------------------------------------------------------------
 // rows as the operators see them
@@ -485,6 +529,31 @@ struct FastRow {
         }
         return clean ? decode_field_clean(base + o, l, err) : decode_field(base + o, l, err);
     }
+    // field by slot (the host resolves columns to slots once per plan)
+    __device__ __forceinline__ DVal value_slot(const DevPlan&, int s, unsigned& err) const {
+        if (s < 0) {
+            DVal v;
+            v.type = T_NULL;
+            v.len = 0;
+            v.i = 0;
+            return v;
+        }
+        uint32_t o, l;
+        if (NW <= 4) {
+            o = off[0];
+            l = len[0];
+#pragma unroll
+            for (int k = 1; k < NW; k++)
+                if (s == k) {
+                    o = off[k];
+                    l = len[k];
+                }
+        } else {
+            o = off[s];
+            l = len[s];
+        }
+        return clean ? decode_field_clean(base + o, l, err) : decode_field(base + o, l, err);
+    }
     __device__ __forceinline__ const uint8_t* file_base(bool) const { return lfile; }
 };
 
@@ -493,6 +562,17 @@ struct SlowRow {
     RowView rv;
     static constexpr bool kJoined = true;
     __device__ __forceinline__ DVal value(const DevPlan&, int col, unsigned& err) const { return row_value(rv, col, err); }
+    __device__ __forceinline__ DVal value_slot(const DevPlan&, int s, unsigned& err) const {
+        if (s < 0) {
+            DVal v;
+            v.type = T_NULL;
+            v.len = 0;
+            v.i = 0;
+            return v;
+        }
+        const uint8_t* b = s < rv.nleft_slots ? rv.base : rv.rbase;
+        return decode_field(b + rv.foff[s], rv.flen[s], err);
+    }
     __device__ __forceinline__ const uint8_t* file_base(bool right) const { return right ? rv.rfile : rv.lfile; }
 };
 
@@ -518,28 +598,34 @@ __device__ __forceinline__ DVal fetch_ref(const DevPlan& P, const Row& row, int 
         v.i = 0;
         return v;
     }
-    if (ref & kRefConst) return const_value(P, ref & 0x3fff);
-    return row.value(P, ref, err);
+    if (ref & kRefConst) return const_value(P, ref & 0x1fff);
+    return row.value_slot(P, ref & 0x1fff, err);
 }
 
 // the program lives in the kernel parameter block (constant bank): no dependent global loads
 template <class Row>
+__device__ __forceinline__ bool leaf_cmp(const DevPlan& P, const Row& row, const FInsn in, unsigned& err) {
+    DVal l = fetch_ref(P, row, in.a, err), r = fetch_ref(P, row, in.b, err);
+    int c;
+    if (l.type == T_INT && r.type == T_INT && ((unsigned long long)(l.i + (1ll << 52)) >> 53) == 0 &&
+        ((unsigned long long)(r.i + (1ll << 52)) >> 53) == 0)
+        c = l.i < r.i ? -1 : (l.i > r.i ? 1 : 0);  // same answer as the double compare below 2^52
+    else
+        c = val_compare(l, r);
+    return in.n == CQG_OP_EQ ? c == 0 : in.n == CQG_OP_NE ? c != 0 : in.n == CQG_OP_GT ? c > 0
+         : in.n == CQG_OP_LT ? c < 0 : in.n == CQG_OP_GE ? c >= 0 : c <= 0;
+}
+
+template <class Row>
 __device__ __forceinline__ bool eval_fused(const DevPlan& P, const Row& row, unsigned& err) {
+    if (P.n_fcode == 1 && P.fcode_inl[0].op == F_CMP) return leaf_cmp(P, row, P.fcode_inl[0], err);  // `col op literal`
     uint32_t bs = 0;  // bit stack, top = bit 0
     for (int pc = 0; pc < P.n_fcode; pc++) {
         const FInsn in = P.fcode_inl[pc];
         bool b;
         switch (in.op) {
             case F_CMP: {
-                DVal l = fetch_ref(P, row, in.a, err), r = fetch_ref(P, row, in.b, err);
-                int c;
-                if (l.type == T_INT && r.type == T_INT && ((unsigned long long)(l.i + (1ll << 52)) >> 53) == 0 &&
-                    ((unsigned long long)(r.i + (1ll << 52)) >> 53) == 0)
-                    c = l.i < r.i ? -1 : (l.i > r.i ? 1 : 0);  // same answer as the double compare below 2^52
-                else
-                    c = val_compare(l, r);
-                b = in.n == CQG_OP_EQ ? c == 0 : in.n == CQG_OP_NE ? c != 0 : in.n == CQG_OP_GT ? c > 0
-                  : in.n == CQG_OP_LT ? c < 0 : in.n == CQG_OP_GE ? c >= 0 : c <= 0;
+                b = leaf_cmp(P, row, in, err);
                 bs = (bs << 1) | (uint32_t)b;
                 break;
             }
@@ -586,7 +672,7 @@ __device__ __forceinline__ void entry_accumulate(const DevPlan& P, uint8_t* e, c
     for (int a = 0; a < P.naggs; a++) {
         const AggSpec sp = P.aggs[a];
         if (sp.off < 0) continue;
-        DVal v = row.value(P, sp.col, err);
+        DVal v = row.value_slot(P, sp.slot, err);
         uint8_t* st = e + sp.off;
         if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
             if (v.type == T_INT) {
@@ -616,9 +702,11 @@ __device__ __noinline__ void entry_merge(const DevPlan& P, uint8_t* dst, const u
             unsigned long long si = *(const unsigned long long*)(src + sp.off);
             double sd = *(const double*)(src + sp.off + 8);
             unsigned long long n = *(const unsigned long long*)(src + sp.off + 16);
+            unsigned long long s3 = *(const unsigned long long*)(src + sp.off + 24);
             if (si) atomicAdd((unsigned long long*)(dst + sp.off), si);
             if (sd != 0.0) atomicAdd((double*)(dst + sp.off + 8), sd);
             if (n) atomicAdd((unsigned long long*)(dst + sp.off + 16), n);
+            if (s3) atomicAdd((unsigned long long*)(dst + sp.off + 24), s3);
         } else {
             minmax_merge(P, dst + sp.off, src + sp.off, sp.func == CQG_AGG_MIN);
         }
@@ -641,7 +729,7 @@ __device__ __forceinline__ void agg_row(const DevPlan& P, const CtaState& cs, co
             if (a < P.naggs) {
                 const AggSpec sp = P.aggs[a];
                 if (sp.off >= 0) {
-                    DVal v = row.value(P, sp.col, acc.err);
+                    DVal v = row.value_slot(P, sp.slot, acc.err);
                     if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
                         if (v.type == T_INT) {
                             acc.si[a] += v.i;
@@ -663,7 +751,7 @@ __device__ __forceinline__ void agg_row(const DevPlan& P, const CtaState& cs, co
     uint32_t tags = 0;
     uint64_t h = 0x243F6A8885A308D3ull + (uint64_t)P.ngc;
     for (int g = 0; g < P.ngc; g++) {
-        DVal v = row.value(P, P.gcol[g], acc.err);
+        DVal v = row.value_slot(P, P.gslot[g], acc.err);
         uint32_t tag;
         canon_part<true>(v, P.ngc > 1, acc.err, tag, kw[2 * g], kw[2 * g + 1]);
         tags |= tag << (4 * g);
@@ -845,22 +933,114 @@ __device__ __noinline__ void process_window_row_slow(const DevPlan& P, const Cta
 }
 
 // ------------------------------------------------------------------------------------------
-// the kernel
+// the "simple" route for one row of a clean tile (DevPlan::simple). W is the width of the mask
+// window: uint32_t covers rows shorter than 32 bytes, unsigned long long rows shorter than 64.
+// Returns false when the row needs a wider window.
 // ------------------------------------------------------------------------------------------
-// 0x80 in every byte of v equal to the (ASCII) byte replicated in pat: 3 instructions
-__device__ __forceinline__ uint32_t eq_flags7(uint32_t v, uint32_t pat) {
-    uint32_t a = ((v ^ pat) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-    return ~(a | v) & 0x80808080u;
+__device__ __forceinline__ uint32_t ffs_w(uint32_t x) { return (uint32_t)__ffs((int)x); }
+__device__ __forceinline__ uint32_t ffs_w(unsigned long long x) { return (uint32_t)__ffsll((long long)x); }
+__device__ __forceinline__ void win_w(const uint32_t* m, uint32_t pos, uint32_t& out) {
+    const uint32_t w = pos >> 5, b = pos & 31u;
+    out = __funnelshift_r(m[w], m[w + 1], b);
 }
-// four flag words -> 16-bit mask in byte order, through the high half of four multiplies
-__device__ __forceinline__ uint32_t flags_to_mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
-    uint32_t lo = (__umulhi(f0, 0x02040810u) & 0x0fu) | (__umulhi(f1, 0x20408100u) & 0xf0u);
-    uint32_t hi = (__umulhi(f2, 0x02040810u) & 0x0fu) | (__umulhi(f3, 0x20408100u) & 0xf0u);
-    return hi * 256u + lo;
+__device__ __forceinline__ void win_w(const uint32_t* m, uint32_t pos, unsigned long long& out) { out = mask_window(m, pos); }
+
+template <class W, int NW>
+__device__ __forceinline__ bool simple_row(const DevPlan& P, const CtaState& cs, const uint8_t* buf, const uint32_t* tm,
+                                           const uint32_t* dm, long long g0, uint32_t rs, uint32_t bufsize, ThreadAcc& acc) {
+    W tw;
+    win_w(tm, rs, tw);
+    if (tw == (W)0) return false;
+    const uint32_t len = ffs_w(tw) - 1u;  // < bits of W
+    if (rs + len >= bufsize) return false;
+    W dw;
+    win_w(dm, rs, dw);
+    dw &= (((W)1) << len) - (W)1;
+    FastRow<NW> row;
+    row.base = buf;
+    row.lfile = buf - g0;
+    row.clean = true;
+    uint32_t startpos = 0;
+    bool missing = false;
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        row.off[k] = rs;
+        row.len[k] = 0;
+        if (k < P.nwantL) {
+            const int gap = P.gap[k];
+            if (gap > 0) {
+                for (int i = 1; i < gap; i++) dw &= dw - (W)1;
+                missing = missing || dw == (W)0;
+                startpos = ffs_w(dw);
+                dw &= dw - (W)1;
+            }
+            const uint32_t endpos = dw ? ffs_w(dw) - 1u : len;
+            row.off[k] = rs + startpos;
+            row.len[k] = missing ? 0u : endpos - startpos;
+        }
+    }
+    // ---- WHERE ----
+    if (P.s_has_pred) {
+        uint32_t o = row.off[0], l = row.len[0];
+#pragma unroll
+        for (int k = 1; k < NW; k++)
+            if (P.s_slot == k) {
+                o = row.off[k];
+                l = row.len[k];
+            }
+        uint32_t mant, fd;
+        bool pass;
+        if (l - 1u < 4u && decode_tiny(buf, o, l, mant, fd)) {
+            const long long lhs = (long long)mant * P.s_A[fd], rhs = P.s_B[fd];
+            const int op = P.s_op;
+            pass = op == CQG_OP_GT ? lhs > rhs : op == CQG_OP_LT ? lhs < rhs : op == CQG_OP_GE ? lhs >= rhs
+                 : op == CQG_OP_LE ? lhs <= rhs : op == CQG_OP_EQ ? lhs == rhs : lhs != rhs;
+        } else {
+            pass = leaf_cmp(P, row, P.fcode_inl[0], acc.err);
+        }
+        if (!pass) return true;
+    }
+    // ---- COUNT / SUM / AVG in registers ----
+    const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
+    const uint64_t okey = gabs << 16;
+    acc.count++;
+    if (okey < acc.first) acc.first = okey;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        if (a < P.naggs && P.aggs[a].off >= 0) {
+            const int sl = P.aggs[a].slot;
+            if (sl < 0) continue;
+            uint32_t o = row.off[0], l = row.len[0];
+#pragma unroll
+            for (int k = 1; k < NW; k++)
+                if (sl == k) {
+                    o = row.off[k];
+                    l = row.len[k];
+                }
+            uint32_t mant, fd;
+            if (l - 1u < 4u && decode_tiny(buf, o, l, mant, fd)) {
+                acc.s3[a] += (long long)(mant * (fd == 0u ? 1000u : fd == 1u ? 100u : fd == 2u ? 10u : 1u));
+                acc.sn[a]++;
+            } else {
+                DVal v = decode_field_clean(buf + o, l, acc.err);
+                if (v.type == T_INT) {
+                    acc.si[a] += v.i;
+                    acc.sn[a]++;
+                } else if (v.type == T_DBL) {
+                    acc.sd[a] += v.d;
+                    acc.sn[a]++;
+                }
+            }
+        }
+    }
+    return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
 template <class G, int NW>
-__global__ void __launch_bounds__(G::THREADS, 2) scan_kernel(const __grid_constant__ DevPlan P) {
+__global__ void __launch_bounds__(G::THREADS, 4) scan_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* tm = (uint32_t*)(smem + G::OFF_TM);
@@ -909,6 +1089,7 @@ __global__ void __launch_bounds__(G::THREADS, 2) scan_kernel(const __grid_consta
     for (int a = 0; a < 4; a++) {
         acc.si[a] = 0;
         acc.sd[a] = 0.0;
+        acc.s3[a] = 0;
         acc.sn[a] = 0;
     }
 
@@ -1069,6 +1250,25 @@ __global__ void __launch_bounds__(G::THREADS, 2) scan_kernel(const __grid_consta
             const uint32_t npass = nrows - pass_lo < (uint32_t)G::ROWCAP ? nrows - pass_lo : (uint32_t)G::ROWCAP;
             if (P.mode == SCAN_COUNT_ROWS) {
                 for (uint32_t r = tid; r < npass; r += G::THREADS) acc.rows++;
+            } else if (P.simple && !special) {
+                for (uint32_t r = tid; r < npass; r += G::THREADS) {
+                    const uint32_t rs = rowpos[r];
+                    acc.rows++;
+                    if (simple_row<uint32_t, NW>(P, cs, buf, tm, dm, g0, rs, (uint32_t)G::BUF, acc)) continue;
+                    if (simple_row<unsigned long long, NW>(P, cs, buf, tm, dm, g0, rs, (uint32_t)G::BUF, acc)) continue;
+                    // 64 bytes or more: the general route
+                    uint32_t p = rs + 64u, len = 0xffffffffu;
+                    while (p < (uint32_t)G::BUF) {
+                        unsigned long long w2 = mask_window(tm, p);
+                        if (w2) {
+                            len = p + (uint32_t)__ffsll((long long)w2) - 1u - rs;
+                            break;
+                        }
+                        p += 64u;
+                    }
+                    if (len == 0xffffffffu || rs + len >= (uint32_t)G::BUF) process_long_row(P, cs, (uint64_t)(g0 + (long long)rs), acc);
+                    else process_window_row_slow(P, cs, buf, g0, rs, len, acc);
+                }
             } else {
                 for (uint32_t r = tid; r < npass; r += G::THREADS) {
                     const uint32_t rs = rowpos[r];
@@ -1108,8 +1308,9 @@ __global__ void __launch_bounds__(G::THREADS, 2) scan_kernel(const __grid_consta
                     row.lfile = buf - g0;
                     row.clean = !special;
                     {
+                        // wanted field k starts after gap[k] further delimiters: clear gap-1 of the
+                        // remaining delimiter bits, the next one marks the start, the one after the end
                         unsigned long long dw = mask_window(dm, rs) & lenmask;
-                        int col = 0;
                         uint32_t startpos = 0;
                         bool missing = false;
 #pragma unroll
@@ -1117,13 +1318,13 @@ __global__ void __launch_bounds__(G::THREADS, 2) scan_kernel(const __grid_consta
                             row.off[k] = rs;
                             row.len[k] = 0;
                             if (k < P.nwantL) {
-                                const int want = P.wantL[k];
-                                while (col < want && dw) {
+                                const int gap = P.gap[k];
+                                if (gap > 0) {
+                                    for (int i = 1; i < gap; i++) dw &= dw - 1ull;
+                                    missing = missing || dw == 0ull;
                                     startpos = (uint32_t)__ffsll((long long)dw);
                                     dw &= dw - 1ull;
-                                    col++;
                                 }
-                                missing = missing || col < want;
                                 uint32_t endpos = dw ? (uint32_t)__ffsll((long long)dw) - 1u : len;
                                 uint32_t fs = startpos;
                                 if (special)
@@ -1172,12 +1373,13 @@ __global__ void __launch_bounds__(G::THREADS, 2) scan_kernel(const __grid_consta
 #pragma unroll
         for (int a = 0; a < 4; a++) {
             if (a < P.naggs && P.aggs[a].off >= 0 && (P.aggs[a].func == CQG_AGG_SUM || P.aggs[a].func == CQG_AGG_AVG)) {
-                long long si = acc.si[a];
+                long long si = acc.si[a], s3 = acc.s3[a];
                 double sd = acc.sd[a];
                 uint32_t sn = acc.sn[a];
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
                     si += __shfl_xor_sync(0xffffffffu, si, d);
+                    s3 += __shfl_xor_sync(0xffffffffu, s3, d);
                     sd += __shfl_xor_sync(0xffffffffu, sd, d);
                     sn += __shfl_xor_sync(0xffffffffu, sn, d);
                 }
@@ -1186,6 +1388,7 @@ __global__ void __launch_bounds__(G::THREADS, 2) scan_kernel(const __grid_consta
                     atomicAdd((unsigned long long*)st, (unsigned long long)si);
                     atomicAdd((double*)(st + 8), sd);
                     atomicAdd((unsigned int*)(st + 16), sn);
+                    atomicAdd((unsigned long long*)(st + 24), (unsigned long long)s3);  // short decimals, x1000
                 }
             }
         }
