@@ -23,7 +23,7 @@
 #include <cuda_runtime.h>
 
 #include "cq_gpu.h"
-#include "cqg_scan.cuh"
+#include "cqg_lean.cuh"
 
 using namespace cqg;
 
@@ -420,6 +420,31 @@ static int launch_scan_nw(const DevPlan& P, int smem, int dev, cudaStream_t st) 
     return CQG_OK;
 }
 
+static int launch_lean(const DevPlan& P, cudaStream_t st) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (P.n_tiles <= 0) return CQG_OK;
+    const int smem = ScanGeo::OFF_TABLE;
+    static bool attr_set[64];
+    if (!attr_set[dev & 63]) {
+        CU(cudaFuncSetAttribute(lean_kernel<ScanGeo>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev & 63] = true;
+    }
+    LaunchCfg& c = g_cfg[dev & 63];
+    if (!c.ready) {
+        CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+        c.ready = true;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean_kernel<ScanGeo>, ScanGeo::THREADS, smem));
+    if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean kernel does not fit");
+    int grid = std::min(P.n_tiles, c.sms * per_sm);
+    lean_kernel<ScanGeo><<<grid, ScanGeo::THREADS, smem, st>>>(P);
+    g_launches++;
+    CU(cudaGetLastError());
+    return CQG_OK;
+}
+
 static int launch_scan(const DevPlan& P, int table_bytes, cudaStream_t st) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
@@ -445,7 +470,7 @@ struct ScalarBlock {
     unsigned errflags;
     unsigned jclass[2];
     unsigned pad;
-    unsigned long long rows_scanned, gcount, sel_count, jrow_count;
+    unsigned long long rows_scanned, gcount, sel_count, jrow_count, def_tile_count, def_row_count;
 };
 
 static void shard_range(const cqg_table* t, uint64_t& lo, uint64_t& hi) {
@@ -1310,6 +1335,72 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
 // ------------------------------------------------------------------------------------------
 // execute
 // ------------------------------------------------------------------------------------------
+static int read_scalars(HostPlan& hp, ScalarBlock& hs, cudaStream_t st) {
+    cudaError_t ce = cudaMemcpyAsync(&hs, hp.d_scalars.p, sizeof hs, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) return fail(CQG_ERR_CUDA, "scan kernel: %s", cudaGetErrorString(ce));
+    return CQG_OK;
+}
+
+// DevPlan::simple plans: the lean kernel, then the general kernel on whatever it handed over.
+// Returns 1 when the scan is complete, 0 when the caller must run the general scan instead.
+static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBlock& hs, float* ms_out, cudaEvent_t e0,
+                         cudaEvent_t e1, int* done) {
+    DevPlan& P = hp.P;
+    *done = 0;
+    int rc;
+    if ((rc = alloc_group_table(hp, gt, 16, st))) return rc;
+    DevBuf d_tiles, d_rows;
+    const uint64_t row_cap = (uint64_t)P.n_tiles * 8u + 1024u;
+    CU(d_tiles.alloc((size_t)(P.n_tiles + 1) * 4, st));
+    CU(d_rows.alloc(row_cap * 8, st));
+    ScalarBlock* sb = hp.d_scalars.as<ScalarBlock>();
+    CU(cudaMemsetAsync(sb, 0, sizeof(ScalarBlock), st));
+    P.def_tiles = d_tiles.as<int32_t>();
+    P.def_rows = d_rows.as<uint64_t>();
+    P.def_tile_count = &sb->def_tile_count;
+    P.def_row_count = &sb->def_row_count;
+    P.def_row_cap = row_cap;
+    P.tile_list = nullptr;
+    cudaEventRecord(e0, st);
+    if ((rc = launch_lean(P, st))) return rc;
+    cudaEventRecord(e1, st);
+    if ((rc = read_scalars(hp, hs, st))) return rc;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out += ms;
+    if ((hs.errflags & KERR_LEAN_ABORT) || hs.def_row_count > row_cap) {
+        P.simple = 0;  // the data is not what the lean kernel is for
+        return CQG_OK;
+    }
+    if (hs.def_tile_count || hs.def_row_count) {
+        cudaEventRecord(e0, st);
+        if (hs.def_tile_count) {
+            DevPlan T = P;
+            T.tile_list = P.def_tiles;
+            T.first_tile = 0;
+            T.n_tiles = (int32_t)hs.def_tile_count;
+            if ((rc = launch_scan(T, hp.table_smem_bytes, st))) return rc;
+        }
+        if (hs.def_row_count) {
+            DevPlan R = P;
+            R.simple = 0;
+            R.scalar_regs = 0;
+            R.smem_cap = 0;
+            int grid = (int)std::min<uint64_t>((hs.def_row_count + 127) / 128, 148 * 8);
+            deferred_rows_kernel<<<grid, 128, 0, st>>>(R, P.def_rows, hs.def_row_count);
+            g_launches++;
+            CU(cudaGetLastError());
+        }
+        cudaEventRecord(e1, st);
+        if ((rc = read_scalars(hp, hs, st))) return rc;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out += ms;
+    }
+    *done = 1;
+    return CQG_OK;
+}
+
 static int run_aggregate_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBlock& hs, float* ms_out) {
     DevPlan& P = hp.P;
     uint64_t cap = initial_group_cap(P);
@@ -1317,19 +1408,22 @@ static int run_aggregate_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, Sca
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     int rc = CQG_OK;
+    if (P.simple) {
+        int done = 0;
+        rc = run_lean_scan(hp, gt, st, hs, ms_out, e0, e1, &done);
+        if (rc != CQG_OK || done) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return rc;
+        }
+    }
     for (int attempt = 0; attempt < 12; attempt++) {
         if ((rc = alloc_group_table(hp, gt, cap, st))) break;
-        cudaMemsetAsync(P.errflags, 0, 4, st);
-        cudaMemsetAsync(P.rows_scanned, 0, 8, st);
+        cudaMemsetAsync(hp.d_scalars.p, 0, sizeof(ScalarBlock), st);
         cudaEventRecord(e0, st);
         if ((rc = launch_scan(P, hp.table_smem_bytes, st))) break;
         cudaEventRecord(e1, st);
-        cudaError_t ce = cudaMemcpyAsync(&hs, hp.d_scalars.p, sizeof hs, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-        if (ce != cudaSuccess) {
-            rc = fail(CQG_ERR_CUDA, "scan kernel: %s", cudaGetErrorString(ce));
-            break;
-        }
+        if ((rc = read_scalars(hp, hs, st))) break;
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         *ms_out += ms;

@@ -1,0 +1,430 @@
+// cqg_lean.cuh — the lean scan kernel: the same fused pipeline as cqg_scan.cuh (TMA tile ->
+// SWAR masks -> row list -> one row per thread) stripped to what DevPlan::simple plans need:
+// no GROUP BY, COUNT/SUM/AVG, WHERE empty or `column <op> decimal literal`, fields that are
+// short decimals. Everything else is HANDED OVER, never approximated:
+//   * a tile holding any byte below 0x23 other than '\n' (CR, quote, blank, NUL) or touching a
+//     file edge goes on def_tiles;
+//   * a row of 64 bytes or more, or with a wanted field that is not a decimal of <= 7 bytes,
+//     goes on def_rows;
+// and the general kernel processes those afterwards into the same group entry. When more than
+// 1/8 of a tile's rows are handed over the kernel raises KERR_LEAN_ABORT and the host reruns the
+// whole scan on the general kernel.
+// All shared-memory traffic uses 32-bit shared addresses (ld.shared / st.shared).
+#pragma once
+#include "cqg_scan.cuh"
+
+namespace cqg {
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// unsigned decimal of 1..7 bytes at shared address `fa`: value = mant / 10^fd. false: not one.
+__device__ __forceinline__ bool lean_decimal(uint32_t fa, uint32_t len, uint32_t& mant, uint32_t& fd) {
+    const uint32_t a = fa & ~3u, sh = (fa & 3u) * 8u;
+    const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
+    if (len <= 4u) {
+        uint32_t w = __funnelshift_r(w0, w1, sh);
+        w = len == 4u ? w : ((w << (8u * (4u - len))) | (0x30303030u >> (8u * len)));
+        uint32_t dotf = ~((((w ^ 0x2e2e2e2eu) & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+        uint32_t t = w ^ 0x30303030u;
+        fd = 0;
+        uint32_t ndig = len;
+        if (dotf) {
+            if (dotf & (dotf - 1u)) return false;
+            const uint32_t j = (31u - __clz(dotf)) >> 3;
+            fd = 3u - j;
+            const uint32_t high = j == 3u ? 0u : (t & ~((1u << (8u * (j + 1u))) - 1u));
+            t = ((t & ((1u << (8u * j)) - 1u)) << 8) | high;
+            ndig = len - 1u;
+        }
+        if (ndig == 0u) return false;
+        if (((t + 0x76767676u) | t) & 0x80808080u) return false;
+        t = t * 10u + (t >> 8);
+        t &= 0x00ff00ffu;
+        mant = (t * 100u + (t >> 16)) & 0xffffu;
+        return true;
+    }
+    // 5..7 bytes: digit by digit out of three registers
+    const uint32_t w2 = lds32(a + 8);
+    uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    uint32_t m = 0, f = 0;
+    bool dot = false, ok = true, digit = false;
+#pragma unroll
+    for (uint32_t k = 0; k < 7u; k++) {
+        if (k < len) {
+            const uint32_t c = (k < 4u ? (lo >> (8u * k)) : (hi >> (8u * (k - 4u)))) & 0xffu;
+            const uint32_t d = c - 48u;
+            if (d <= 9u) {
+                m = m * 10u + d;
+                digit = true;
+                f += dot ? 1u : 0u;
+            } else {
+                ok = ok && c == '.' && !dot;
+                dot = true;
+            }
+        }
+    }
+    mant = m;
+    fd = f;
+    return ok && digit && f <= 3u;  // more than 3 fraction digits: leave to the general kernel
+}
+
+template <class G>
+__global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_constant__ DevPlan P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t s_tm = sbase + G::OFF_TM, s_dm = sbase + G::OFF_DM, s_row = sbase + G::OFF_ROW, s_wsum = sbase + G::OFF_WSUM;
+    uint64_t* mbar = (uint64_t*)(smem + G::OFF_MBAR);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < G::STAGES; s++) mbar_init(&mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int w = G::BUF / 32 + tid; w < G::MASKW; w += G::THREADS) {
+        sts32(s_tm + 4 * w, 0xffffffffu);
+        sts32(s_dm + 4 * w, 0u);
+    }
+    __syncthreads();
+
+    uint32_t rows = 0, count = 0;
+    uint64_t first = ~0ull;
+    long long s3[4];
+    uint32_t sn[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        s3[a] = 0;
+        sn[a] = 0;
+    }
+    const uint64_t size = P.size;
+    const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
+
+    auto issue = [&](int it) {
+        const long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
+        const int stage = it % G::STAGES;
+        const long long g0 = tile * (long long)G::TILE - G::PRE;
+        uint32_t bytes = 0;
+        if (g0 >= 0 && g0 + G::BUF <= (long long)size) bytes = G::BUF;  // edge tiles are handed over, not loaded
+        if (bytes) {
+            mbar_expect_tx(&mbar[stage], bytes);
+            tma_load_1d(smem + G::OFF_BUF + stage * G::BUF, P.data + g0, bytes, &mbar[stage]);
+        } else {
+            mbar_expect_tx(&mbar[stage], 0);
+        }
+    };
+    const int my_tiles = (P.n_tiles > (int)blockIdx.x) ? (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (tid == 0)
+        for (int it = 0; it < G::STAGES - 1 && it < my_tiles; it++) issue(it);
+
+    for (int it = 0; it < my_tiles; it++) {
+        const int stage = it % G::STAGES;
+        const uint32_t parity = (uint32_t)(it / G::STAGES) & 1u;
+        if (tid == 0 && it + G::STAGES - 1 < my_tiles) issue(it + G::STAGES - 1);
+        const unsigned abort_now = (*(volatile unsigned*)P.errflags) & KERR_LEAN_ABORT;
+        mbar_wait(&mbar[stage], parity);
+        const uint32_t s_buf = sbase + G::OFF_BUF + stage * G::BUF;
+        const long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
+        const long long g0 = tile * (long long)G::TILE - G::PRE;
+        const bool edge = g0 < 0 || g0 + G::BUF > (long long)size;
+
+        // ---- phase 1: terminator / delimiter masks, and "is the tile clean" ----
+        uint32_t spec = edge ? 0x80u : 0u;
+        if (!edge) {
+#pragma unroll 2
+            for (int c = tid; c < G::CHUNKS; c += G::THREADS) {
+                const uint4 v = lds128(s_buf + 16 * c);
+                const uint32_t v0 = v.x & 0x7f7f7f7fu, v1 = v.y & 0x7f7f7f7fu, v2 = v.z & 0x7f7f7f7fu, v3 = v.w & 0x7f7f7f7fu;
+                const uint32_t f0 = ~(((v0 ^ 0x0a0a0a0au) + 0x7f7f7f7fu) | v.x) & 0x80808080u;
+                const uint32_t f1 = ~(((v1 ^ 0x0a0a0a0au) + 0x7f7f7f7fu) | v.y) & 0x80808080u;
+                const uint32_t f2 = ~(((v2 ^ 0x0a0a0a0au) + 0x7f7f7f7fu) | v.z) & 0x80808080u;
+                const uint32_t f3 = ~(((v3 ^ 0x0a0a0a0au) + 0x7f7f7f7fu) | v.w) & 0x80808080u;
+                const uint32_t d0 = ~(((v0 ^ patD) + 0x7f7f7f7fu) | v.x) & 0x80808080u;
+                const uint32_t d1 = ~(((v1 ^ patD) + 0x7f7f7f7fu) | v.y) & 0x80808080u;
+                const uint32_t d2 = ~(((v2 ^ patD) + 0x7f7f7f7fu) | v.z) & 0x80808080u;
+                const uint32_t d3 = ~(((v3 ^ patD) + 0x7f7f7f7fu) | v.w) & 0x80808080u;
+                const uint32_t x0 = v.x | f0, x1 = v.y | f1, x2 = v.z | f2, x3 = v.w | f3;
+                spec |= ((x0 - 0x23232323u) & ~x0) | ((x1 - 0x23232323u) & ~x1) | ((x2 - 0x23232323u) & ~x2) |
+                        ((x3 - 0x23232323u) & ~x3);
+                sts16(s_tm + 2 * c, flags_to_mask16(f0, f1, f2, f3));
+                sts16(s_dm + 2 * c, flags_to_mask16(d0, d1, d2, d3));
+            }
+            spec &= 0x80808080u;
+        }
+        const int special = __syncthreads_or((int)(spec != 0u) | (int)abort_now);
+        if (special) {
+            if (tid == 0 && !abort_now) {
+                // does this tile own any byte at all? (the general kernel applies the exact ownership)
+                unsigned long long k = atomicAdd(P.def_tile_count, 1ull);
+                P.def_tiles[k] = (int32_t)tile;
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- phase 1b: row starts ----
+        long long olo_l = (long long)P.own_lo - g0, ohi_l = (long long)P.own_hi - g0;
+        const uint32_t olo = (uint32_t)(olo_l < G::PRE ? G::PRE : (olo_l > G::PRE + G::TILE ? G::PRE + G::TILE : olo_l));
+        const uint32_t ohi = (uint32_t)(ohi_l < G::PRE ? G::PRE : (ohi_l > G::PRE + G::TILE ? G::PRE + G::TILE : ohi_l));
+        uint32_t S[G::WPT];
+        uint32_t mycount = 0;
+        const uint32_t w0 = G::PRE / 32 + tid * G::WPT;
+        {
+            uint32_t prev = lds32(s_tm + 4 * (w0 - 1));
+#pragma unroll
+            for (int j = 0; j < G::WPT; j++) {
+                const uint32_t t = lds32(s_tm + 4 * (w0 + j));
+                uint32_t s = ((t << 1) | (prev >> 31)) & ~t;
+                prev = t;
+                const uint32_t p0 = (w0 + j) * 32u;
+                if (olo > p0) s &= olo >= p0 + 32u ? 0u : (0xffffffffu << (olo - p0));
+                if (ohi < p0 + 32u) s &= ohi <= p0 ? 0u : (0xffffffffu >> (p0 + 32u - ohi));
+                S[j] = s;
+                mycount += __popc(s);
+            }
+        }
+        uint32_t incl = mycount;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) sts32(s_wsum + 4 * warp, incl);
+        __syncthreads();
+        uint32_t wbase = 0, nrows = 0;
+#pragma unroll
+        for (int w = 0; w < G::NWARPS; w++) {
+            const uint32_t x = lds32(s_wsum + 4 * w);
+            if (w < warp) wbase += x;
+            nrows += x;
+        }
+        const uint32_t mybase = wbase + incl - mycount;
+        uint32_t handed = 0;
+
+        for (uint32_t pass_lo = 0; pass_lo < nrows; pass_lo += G::ROWCAP) {
+            {
+                uint32_t idx = mybase - pass_lo;
+#pragma unroll
+                for (int j = 0; j < G::WPT; j++) {
+                    uint32_t s = S[j];
+                    while (s) {
+                        const uint32_t b = __ffs(s) - 1;
+                        s &= s - 1;
+                        if (idx < (uint32_t)G::ROWCAP) sts16(s_row + 2 * idx, (w0 + j) * 32 + b);
+                        idx++;
+                    }
+                }
+            }
+            __syncthreads();
+            const uint32_t npass = nrows - pass_lo < (uint32_t)G::ROWCAP ? nrows - pass_lo : (uint32_t)G::ROWCAP;
+            for (uint32_t r = tid; r < npass; r += G::THREADS) {
+                const uint32_t rs = lds16(s_row + 2 * r);
+                rows++;
+                const uint32_t wi = rs >> 5, bi = rs & 31u;
+                uint32_t off[4], flen[4];
+                bool ok = true;
+                const uint32_t t0 = lds32(s_tm + 4 * wi), t1 = lds32(s_tm + 4 * wi + 4);
+                const uint32_t tw = __funnelshift_r(t0, t1, bi);
+                if (tw) {
+                    // the row ends inside a 32-bit window
+                    const uint32_t len = __ffs(tw) - 1u;
+                    uint32_t dw = __funnelshift_r(lds32(s_dm + 4 * wi), lds32(s_dm + 4 * wi + 4), bi) & ((1u << len) - 1u);
+                    uint32_t startpos = 0;
+                    bool missing = false;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        off[k] = 0;
+                        flen[k] = 0;
+                        if (k < P.nwantL) {
+                            const int gap = P.gap[k];
+                            if (gap > 0) {
+                                for (int i = 1; i < gap; i++) dw &= dw - 1u;
+                                missing = missing || dw == 0u;
+                                startpos = __ffs(dw);
+                                dw &= dw - 1u;
+                            }
+                            const uint32_t endpos = dw ? __ffs(dw) - 1u : len;
+                            off[k] = rs + startpos;
+                            flen[k] = missing ? 0u : endpos - startpos;
+                        }
+                    }
+                } else {
+                    const uint32_t t2 = lds32(s_tm + 4 * wi + 8);
+                    const uint32_t tw2 = __funnelshift_r(t1, t2, bi);
+                    if (tw2 == 0u || rs + 64u > (uint32_t)G::BUF) {
+                        ok = false;  // 64 bytes or more
+                    } else {
+                        const uint32_t len = 32u + __ffs(tw2) - 1u;
+                        const uint32_t d0 = lds32(s_dm + 4 * wi), d1 = lds32(s_dm + 4 * wi + 4), d2 = lds32(s_dm + 4 * wi + 8);
+                        unsigned long long dw = (((unsigned long long)__funnelshift_r(d1, d2, bi) << 32) | __funnelshift_r(d0, d1, bi)) &
+                                                ((1ull << len) - 1ull);
+                        uint32_t startpos = 0;
+                        bool missing = false;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            off[k] = 0;
+                            flen[k] = 0;
+                            if (k < P.nwantL) {
+                                const int gap = P.gap[k];
+                                if (gap > 0) {
+                                    for (int i = 1; i < gap; i++) dw &= dw - 1ull;
+                                    missing = missing || dw == 0ull;
+                                    startpos = (uint32_t)__ffsll((long long)dw);
+                                    dw &= dw - 1ull;
+                                }
+                                const uint32_t endpos = dw ? (uint32_t)__ffsll((long long)dw) - 1u : len;
+                                off[k] = rs + startpos;
+                                flen[k] = missing ? 0u : endpos - startpos;
+                            }
+                        }
+                    }
+                }
+                // ---- WHERE on a short decimal ----
+                bool pass = true;
+                if (ok && P.s_has_pred) {
+                    uint32_t o = off[0], l = flen[0];
+#pragma unroll
+                    for (int k = 1; k < 4; k++)
+                        if (P.s_slot == k) {
+                            o = off[k];
+                            l = flen[k];
+                        }
+                    uint32_t mant, fd;
+                    if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd)) {
+                        const long long lhs = (long long)mant * P.s_A[fd], rhs = P.s_B[fd];
+                        const int op = P.s_op;
+                        pass = op == CQG_OP_GT ? lhs > rhs : op == CQG_OP_LT ? lhs < rhs : op == CQG_OP_GE ? lhs >= rhs
+                             : op == CQG_OP_LE ? lhs <= rhs : op == CQG_OP_EQ ? lhs == rhs : lhs != rhs;
+                    } else {
+                        ok = false;  // NULL, text, date, signed or long number: general kernel
+                    }
+                }
+                // ---- SUM / AVG operands ----
+                unsigned long long add[4];
+                if (ok && pass) {
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        add[a] = ~0ull;
+                        if (a < P.naggs && P.aggs[a].off >= 0 && P.aggs[a].slot >= 0) {
+                            const int sl = P.aggs[a].slot;
+                            uint32_t o = off[0], l = flen[0];
+#pragma unroll
+                            for (int k = 1; k < 4; k++)
+                                if (sl == k) {
+                                    o = off[k];
+                                    l = flen[k];
+                                }
+                            uint32_t mant, fd;
+                            if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd)) {
+                                add[a] = (unsigned long long)mant * (fd == 0u ? 1000u : fd == 1u ? 100u : fd == 2u ? 10u : 1u);
+                            } else if (l != 0u) {
+                                ok = false;  // a value this kernel does not decode (NULL is simply not summed)
+                            }
+                        }
+                    }
+                }
+                if (!ok) {
+                    unsigned long long k = atomicAdd(P.def_row_count, 1ull);
+                    if (k < P.def_row_cap) P.def_rows[k] = (uint64_t)(g0 + (long long)rs);
+                    handed++;
+                    rows--;  // counted by the general kernel
+                    continue;
+                }
+                if (!pass) continue;
+                count++;
+                const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
+                if (gabs < first) first = gabs;
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    if (a < P.naggs && P.aggs[a].off >= 0 && P.aggs[a].slot >= 0 && add[a] != ~0ull) {
+                        s3[a] += (long long)add[a];
+                        sn[a]++;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // too many rows outside this kernel's repertoire: let the general kernel do the whole scan
+        const int many = __syncthreads_or((int)(handed * 8u > (nrows / G::THREADS) + 8u));
+        if (many && tid == 0) atomicOr(P.errflags, KERR_LEAN_ABORT);
+    }
+
+    // ---- epilogue: fold the registers into the single group `_all_` ----
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        rows += __shfl_xor_sync(0xffffffffu, rows, d);
+        count += __shfl_xor_sync(0xffffffffu, count, d);
+        const uint64_t of = __shfl_xor_sync(0xffffffffu, first, d);
+        first = of < first ? of : first;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            s3[a] += __shfl_xor_sync(0xffffffffu, s3[a], d);
+            sn[a] += __shfl_xor_sync(0xffffffffu, sn[a], d);
+        }
+    }
+    if (lane == 0) {
+        if (rows) atomicAdd(P.rows_scanned, (unsigned long long)rows);
+        if (count) {
+            unsigned err = 0;
+            const uint64_t h = key_hash_final(0x243F6A8885A308D3ull);
+            uint8_t* ge = global_entry_for(P, h, 0u, nullptr, err);
+            if (ge) {
+                atomicAdd((unsigned long long*)(ge + kOffCount), (unsigned long long)count);
+                amin64((uint64_t*)(ge + kOffFirst), first << 16);
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    if (a < P.naggs && P.aggs[a].off >= 0 && sn[a]) {
+                        atomicAdd((unsigned long long*)(ge + P.aggs[a].off + 16), (unsigned long long)sn[a]);
+                        atomicAdd((unsigned long long*)(ge + P.aggs[a].off + 24), (unsigned long long)s3[a]);
+                    }
+                }
+            }
+            if (err) atomicOr(P.errflags, err);
+        }
+    }
+}
+
+// rows handed over one by one: each is found and split straight from HBM by the general operators
+__global__ void deferred_rows_kernel(const __grid_constant__ DevPlan P, const uint64_t* rows, uint64_t n) {
+    CtaState cs;
+    cs.stab = nullptr;
+    cs.s_occ = nullptr;
+    ThreadAcc acc;
+    acc.rows = 0;
+    acc.count = 0;
+    acc.first = ~0ull;
+    acc.err = 0;
+    for (int a = 0; a < 4; a++) {
+        acc.si[a] = 0;
+        acc.sd[a] = 0.0;
+        acc.s3[a] = 0;
+        acc.sn[a] = 0;
+    }
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        acc.rows++;
+        process_long_row(P, cs, rows[i], acc);
+    }
+    if (acc.rows) atomicAdd(P.rows_scanned, (unsigned long long)acc.rows);
+    if (acc.err) atomicOr(P.errflags, acc.err);
+}
+
+}  // namespace cqg

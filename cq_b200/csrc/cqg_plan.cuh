@@ -18,7 +18,8 @@ enum : unsigned {
     KERR_JOIN_FANOUT = 1024u,  // one left row matches >= 65536 right rows
     KERR_STR_LONG = 2048u,     // MIN/MAX string longer than the packed reference allows
     KERR_OFFSET_RANGE = 4096u, // file offset beyond 2^45
-    KERR_ROW_LONG = 8192u      // internal: row does not fit the tile window (handled, not an error)
+    KERR_ROW_LONG = 8192u,     // internal: row does not fit the tile window (handled, not an error)
+    KERR_LEAN_ABORT = 16384u   // internal: the lean kernel met too many rows it does not cover; rerun on the general kernel
 };
 constexpr unsigned kFatalMask = KERR_NUMERIC_RANGE | KERR_SEP_OVERFLOW | KERR_KEY_RANGE | KERR_MINMAX_TIE | KERR_STACK |
                                 KERR_JOIN_MIXED | KERR_BIGINT | KERR_KEY_TAB | KERR_JOIN_FANOUT | KERR_STR_LONG |
@@ -121,6 +122,13 @@ struct DevPlan {
     int32_t s_slot;   // slot of the predicate column
     int32_t s_op;     // CQG_OP_EQ..LE with the column on the left
     long long s_A[4], s_B[4];
+    // work the lean kernel hands to the general one
+    int32_t* def_tiles;                 // tiles with bytes the lean kernel does not classify (CR, quotes, blanks, file edges)
+    unsigned long long* def_tile_count;
+    uint64_t* def_rows;                 // single rows (64 bytes or longer, fields that are not short decimals)
+    unsigned long long* def_row_count;
+    uint64_t def_row_cap;
+    const int32_t* tile_list;           // general kernel: when set, tile i of this launch is tile_list[i]
 
     // ---- aggregation ----
     int32_t ngc;

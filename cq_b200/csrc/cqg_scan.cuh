@@ -1099,7 +1099,8 @@ __global__ void __launch_bounds__(G::THREADS, 4) scan_kernel(const __grid_consta
     const uint32_t patQ = (uint32_t)P.quote * 0x01010101u;
 
     auto issue = [&](int it) {
-        long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
+        const long long ti = (long long)blockIdx.x + (long long)it * gridDim.x;
+        long long tile = P.tile_list ? (long long)P.tile_list[ti] : (long long)P.first_tile + ti;
         int stage = it % G::STAGES;
         long long g0 = tile * (long long)G::TILE - G::PRE;  // file offset of buf[0]
         uint32_t skip = g0 < 0 ? (uint32_t)(-g0) : 0u;
@@ -1128,7 +1129,8 @@ __global__ void __launch_bounds__(G::THREADS, 4) scan_kernel(const __grid_consta
         const unsigned abort_now = (*(volatile unsigned*)P.errflags) & (KERR_TABLE_FULL | KERR_SEL_OVERFLOW);
         mbar_wait(&mbar[stage], parity);
         const uint8_t* buf = smem + G::OFF_BUF + stage * G::BUF;
-        const long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
+        const long long ti = (long long)blockIdx.x + (long long)it * gridDim.x;
+        const long long tile = P.tile_list ? (long long)P.tile_list[ti] : (long long)P.first_tile + ti;
         const long long g0 = tile * (long long)G::TILE - G::PRE;
         const bool edge_tile = g0 < 0 || g0 + G::BUF > (long long)size;  // some staged bytes lie outside the file
 
