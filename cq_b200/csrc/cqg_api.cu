@@ -584,6 +584,9 @@ static void plan_simple_route(DevPlan& P) {
         P.s_has_pred = 1;
         P.s_slot = slot;
         P.s_op = op;
+        // integers on both sides: a >= b  <=>  a > b - 1
+        P.s_lop = (op == CQG_OP_GT || op == CQG_OP_GE) ? 0 : (op == CQG_OP_LT || op == CQG_OP_LE) ? 1 : op == CQG_OP_EQ ? 2 : 3;
+        for (int fd = 0; fd < 4; fd++) P.s_LB[fd] = P.s_B[fd] + (op == CQG_OP_GE ? -1 : op == CQG_OP_LE ? 1 : 0);
     }
     P.simple = 1;
 }

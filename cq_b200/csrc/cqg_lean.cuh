@@ -93,9 +93,9 @@ template <class G>
 __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t s_tm = sbase + G::OFF_TM, s_dm = sbase + G::OFF_DM, s_row = sbase + G::OFF_ROW, s_wsum = sbase + G::OFF_WSUM;
+    const uint32_t s_tm = sbase + G::OFF_TM, s_dm = sbase + G::OFF_DM;
     uint64_t* mbar = (uint64_t*)(smem + G::OFF_MBAR);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     if (tid == 0) {
         for (int s = 0; s < G::STAGES; s++) mbar_init(&mbar[s], 1);
@@ -116,18 +116,30 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
         s3[a] = 0;
         sn[a] = 0;
     }
+    // plan constants the row loop uses, once
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
+    const int nwant = P.nwantL;
+    const int gap0 = P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
+    const int has_pred = P.s_has_pred, pslot = P.s_slot, pop = P.s_lop;
+    uint32_t summask = 0;  // aggregates that sum a column
+    int aslot[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        aslot[a] = 0;
+        if (a < P.naggs && P.aggs[a].off >= 0 && P.aggs[a].slot >= 0) {
+            summask |= 1u << a;
+            aslot[a] = P.aggs[a].slot;
+        }
+    }
 
     auto issue = [&](int it) {
         const long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
         const int stage = it % G::STAGES;
         const long long g0 = tile * (long long)G::TILE - G::PRE;
-        uint32_t bytes = 0;
-        if (g0 >= 0 && g0 + G::BUF <= (long long)size) bytes = G::BUF;  // edge tiles are handed over, not loaded
-        if (bytes) {
-            mbar_expect_tx(&mbar[stage], bytes);
-            tma_load_1d(smem + G::OFF_BUF + stage * G::BUF, P.data + g0, bytes, &mbar[stage]);
+        if (g0 >= 0 && g0 + G::BUF <= (long long)size) {  // edge tiles are handed over, not loaded
+            mbar_expect_tx(&mbar[stage], G::BUF);
+            tma_load_1d(smem + G::OFF_BUF + stage * G::BUF, P.data + g0, G::BUF, &mbar[stage]);
         } else {
             mbar_expect_tx(&mbar[stage], 0);
         }
@@ -173,7 +185,6 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
         const int special = __syncthreads_or((int)(spec != 0u) | (int)abort_now);
         if (special) {
             if (tid == 0 && !abort_now) {
-                // does this tile own any byte at all? (the general kernel applies the exact ownership)
                 unsigned long long k = atomicAdd(P.def_tile_count, 1ull);
                 P.def_tiles[k] = (int32_t)tile;
             }
@@ -181,190 +192,179 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
             continue;
         }
 
-        // ---- phase 1b: row starts ----
+        // ---- phase 2: every thread walks the rows that START in its own 32*WPT bytes ----
         long long olo_l = (long long)P.own_lo - g0, ohi_l = (long long)P.own_hi - g0;
         const uint32_t olo = (uint32_t)(olo_l < G::PRE ? G::PRE : (olo_l > G::PRE + G::TILE ? G::PRE + G::TILE : olo_l));
         const uint32_t ohi = (uint32_t)(ohi_l < G::PRE ? G::PRE : (ohi_l > G::PRE + G::TILE ? G::PRE + G::TILE : ohi_l));
-        uint32_t S[G::WPT];
-        uint32_t mycount = 0;
         const uint32_t w0 = G::PRE / 32 + tid * G::WPT;
+        uint32_t handed = 0, myrows = 0;
+        static_assert(G::WPT == 4, "the row walk below keeps four start words in registers");
+        uint32_t S0, S1, S2, S3;
         {
             uint32_t prev = lds32(s_tm + 4 * (w0 - 1));
+            uint32_t S[4];
 #pragma unroll
-            for (int j = 0; j < G::WPT; j++) {
+            for (int j = 0; j < 4; j++) {
                 const uint32_t t = lds32(s_tm + 4 * (w0 + j));
-                uint32_t s = ((t << 1) | (prev >> 31)) & ~t;
+                uint32_t s = ((t << 1) | (prev >> 31)) & ~t;  // row starts: a terminator, then a byte that is none
                 prev = t;
                 const uint32_t p0 = (w0 + j) * 32u;
                 if (olo > p0) s &= olo >= p0 + 32u ? 0u : (0xffffffffu << (olo - p0));
                 if (ohi < p0 + 32u) s &= ohi <= p0 ? 0u : (0xffffffffu >> (p0 + 32u - ohi));
                 S[j] = s;
-                mycount += __popc(s);
             }
+            S0 = S[0];
+            S1 = S[1];
+            S2 = S[2];
+            S3 = S[3];
         }
-        uint32_t incl = mycount;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += n;
-        }
-        if (lane == 31) sts32(s_wsum + 4 * warp, incl);
-        __syncthreads();
-        uint32_t wbase = 0, nrows = 0;
-#pragma unroll
-        for (int w = 0; w < G::NWARPS; w++) {
-            const uint32_t x = lds32(s_wsum + 4 * w);
-            if (w < warp) wbase += x;
-            nrows += x;
-        }
-        const uint32_t mybase = wbase + incl - mycount;
-        uint32_t handed = 0;
-
-        for (uint32_t pass_lo = 0; pass_lo < nrows; pass_lo += G::ROWCAP) {
-            {
-                uint32_t idx = mybase - pass_lo;
-#pragma unroll
-                for (int j = 0; j < G::WPT; j++) {
-                    uint32_t s = S[j];
-                    while (s) {
-                        const uint32_t b = __ffs(s) - 1;
-                        s &= s - 1;
-                        if (idx < (uint32_t)G::ROWCAP) sts16(s_row + 2 * idx, (w0 + j) * 32 + b);
-                        idx++;
-                    }
+        // all rows of the span back to back, so that lanes with 4 and lanes with 5 rows stay together
+        {
+            int j = 0;
+            uint32_t s = S0;
+            for (;;) {
+                while (s == 0u && j < 3) {
+                    j++;
+                    s = j == 1 ? S1 : (j == 2 ? S2 : S3);
                 }
-            }
-            __syncthreads();
-            const uint32_t npass = nrows - pass_lo < (uint32_t)G::ROWCAP ? nrows - pass_lo : (uint32_t)G::ROWCAP;
-            for (uint32_t r = tid; r < npass; r += G::THREADS) {
-                const uint32_t rs = lds16(s_row + 2 * r);
-                rows++;
-                const uint32_t wi = rs >> 5, bi = rs & 31u;
-                uint32_t off[4], flen[4];
+                if (s == 0u) break;
+                const uint32_t bi = __ffs(s) - 1u;
+                s &= s - 1u;
+                const uint32_t t = lds32(s_tm + 4 * (w0 + j));
+                const uint32_t p0 = (w0 + j) * 32u;
+                const uint32_t rs = p0 + bi;
+                const uint32_t wa = 4u * (w0 + j);
+                myrows++;
+                uint32_t off0 = 0, off1 = 0, off2 = 0, off3 = 0, len0 = 0, len1 = 0, len2 = 0, len3 = 0;
                 bool ok = true;
-                const uint32_t t0 = lds32(s_tm + 4 * wi), t1 = lds32(s_tm + 4 * wi + 4);
-                const uint32_t tw = __funnelshift_r(t0, t1, bi);
+                const uint32_t t1 = lds32(s_tm + wa + 4);
+                const uint32_t tw = __funnelshift_r(t, t1, bi);
                 if (tw) {
                     // the row ends inside a 32-bit window
                     const uint32_t len = __ffs(tw) - 1u;
-                    uint32_t dw = __funnelshift_r(lds32(s_dm + 4 * wi), lds32(s_dm + 4 * wi + 4), bi) & ((1u << len) - 1u);
-                    uint32_t startpos = 0;
+                    uint32_t dw = __funnelshift_r(lds32(s_dm + wa), lds32(s_dm + wa + 4), bi) & ((1u << len) - 1u);
+                    uint32_t sp = 0;
                     bool missing = false;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        off[k] = 0;
-                        flen[k] = 0;
-                        if (k < P.nwantL) {
-                            const int gap = P.gap[k];
-                            if (gap > 0) {
-                                for (int i = 1; i < gap; i++) dw &= dw - 1u;
-                                missing = missing || dw == 0u;
-                                startpos = __ffs(dw);
-                                dw &= dw - 1u;
-                            }
-                            const uint32_t endpos = dw ? __ffs(dw) - 1u : len;
-                            off[k] = rs + startpos;
-                            flen[k] = missing ? 0u : endpos - startpos;
-                        }
-                    }
+#define CQG_LEAN_FIELD(K, GAP, OFF, LEN)                                 \
+    if (nwant > K) {                                                     \
+        if (GAP > 0) {                                                   \
+            for (int i = 1; i < GAP; i++) dw &= dw - 1u;                 \
+            missing = missing || dw == 0u;                               \
+            sp = __ffs(dw);                                              \
+            dw &= dw - 1u;                                               \
+        }                                                                \
+        const uint32_t ep = dw ? __ffs(dw) - 1u : len;                   \
+        OFF = rs + sp;                                                   \
+        LEN = missing ? 0u : ep - sp;                                    \
+    }
+                    CQG_LEAN_FIELD(0, gap0, off0, len0)
+                    CQG_LEAN_FIELD(1, gap1, off1, len1)
+                    CQG_LEAN_FIELD(2, gap2, off2, len2)
+                    CQG_LEAN_FIELD(3, gap3, off3, len3)
+#undef CQG_LEAN_FIELD
                 } else {
-                    const uint32_t t2 = lds32(s_tm + 4 * wi + 8);
+                    const uint32_t t2 = lds32(s_tm + wa + 8);
                     const uint32_t tw2 = __funnelshift_r(t1, t2, bi);
-                    if (tw2 == 0u || rs + 64u > (uint32_t)G::BUF) {
+                    if (tw2 == 0u) {
                         ok = false;  // 64 bytes or more
                     } else {
                         const uint32_t len = 32u + __ffs(tw2) - 1u;
-                        const uint32_t d0 = lds32(s_dm + 4 * wi), d1 = lds32(s_dm + 4 * wi + 4), d2 = lds32(s_dm + 4 * wi + 8);
+                        const uint32_t d0 = lds32(s_dm + wa), d1 = lds32(s_dm + wa + 4), d2 = lds32(s_dm + wa + 8);
                         unsigned long long dw = (((unsigned long long)__funnelshift_r(d1, d2, bi) << 32) | __funnelshift_r(d0, d1, bi)) &
                                                 ((1ull << len) - 1ull);
-                        uint32_t startpos = 0;
+                        uint32_t sp = 0;
                         bool missing = false;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            off[k] = 0;
-                            flen[k] = 0;
-                            if (k < P.nwantL) {
-                                const int gap = P.gap[k];
-                                if (gap > 0) {
-                                    for (int i = 1; i < gap; i++) dw &= dw - 1ull;
-                                    missing = missing || dw == 0ull;
-                                    startpos = (uint32_t)__ffsll((long long)dw);
-                                    dw &= dw - 1ull;
-                                }
-                                const uint32_t endpos = dw ? (uint32_t)__ffsll((long long)dw) - 1u : len;
-                                off[k] = rs + startpos;
-                                flen[k] = missing ? 0u : endpos - startpos;
-                            }
-                        }
+#define CQG_LEAN_FIELD(K, GAP, OFF, LEN)                                 \
+    if (nwant > K) {                                                     \
+        if (GAP > 0) {                                                   \
+            for (int i = 1; i < GAP; i++) dw &= dw - 1ull;               \
+            missing = missing || dw == 0ull;                             \
+            sp = (uint32_t)__ffsll((long long)dw);                       \
+            dw &= dw - 1ull;                                             \
+        }                                                                \
+        const uint32_t ep = dw ? (uint32_t)__ffsll((long long)dw) - 1u : len; \
+        OFF = rs + sp;                                                   \
+        LEN = missing ? 0u : ep - sp;                                    \
+    }
+                        CQG_LEAN_FIELD(0, gap0, off0, len0)
+                        CQG_LEAN_FIELD(1, gap1, off1, len1)
+                        CQG_LEAN_FIELD(2, gap2, off2, len2)
+                        CQG_LEAN_FIELD(3, gap3, off3, len3)
+#undef CQG_LEAN_FIELD
                     }
                 }
                 // ---- WHERE on a short decimal ----
                 bool pass = true;
-                if (ok && P.s_has_pred) {
-                    uint32_t o = off[0], l = flen[0];
-#pragma unroll
-                    for (int k = 1; k < 4; k++)
-                        if (P.s_slot == k) {
-                            o = off[k];
-                            l = flen[k];
-                        }
+                if (ok && has_pred) {
+                    const uint32_t o = pslot == 0 ? off0 : pslot == 1 ? off1 : pslot == 2 ? off2 : off3;
+                    const uint32_t l = pslot == 0 ? len0 : pslot == 1 ? len1 : pslot == 2 ? len2 : len3;
                     uint32_t mant, fd;
                     if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd)) {
-                        const long long lhs = (long long)mant * P.s_A[fd], rhs = P.s_B[fd];
-                        const int op = P.s_op;
-                        pass = op == CQG_OP_GT ? lhs > rhs : op == CQG_OP_LT ? lhs < rhs : op == CQG_OP_GE ? lhs >= rhs
-                             : op == CQG_OP_LE ? lhs <= rhs : op == CQG_OP_EQ ? lhs == rhs : lhs != rhs;
+                        const long long lhs = (long long)((unsigned long long)mant * (unsigned long long)(uint32_t)P.s_A[fd]);
+                        const long long rhs = P.s_LB[fd];
+                        // s_op was normalised by the host: 0 lhs > rhs, 1 lhs < rhs, 2 ==, 3 !=
+                        pass = pop == 0 ? lhs > rhs : pop == 1 ? lhs < rhs : pop == 2 ? lhs == rhs : lhs != rhs;
                     } else {
                         ok = false;  // NULL, text, date, signed or long number: general kernel
                     }
                 }
                 // ---- SUM / AVG operands ----
-                unsigned long long add[4];
-                if (ok && pass) {
-#pragma unroll
-                    for (int a = 0; a < 4; a++) {
-                        add[a] = ~0ull;
-                        if (a < P.naggs && P.aggs[a].off >= 0 && P.aggs[a].slot >= 0) {
-                            const int sl = P.aggs[a].slot;
-                            uint32_t o = off[0], l = flen[0];
-#pragma unroll
-                            for (int k = 1; k < 4; k++)
-                                if (sl == k) {
-                                    o = off[k];
-                                    l = flen[k];
-                                }
-                            uint32_t mant, fd;
-                            if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd)) {
-                                add[a] = (unsigned long long)mant * (fd == 0u ? 1000u : fd == 1u ? 100u : fd == 2u ? 10u : 1u);
-                            } else if (l != 0u) {
-                                ok = false;  // a value this kernel does not decode (NULL is simply not summed)
-                            }
-                        }
-                    }
+                unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
+                uint32_t addmask = 0;
+                if (ok && pass && summask) {
+#define CQG_LEAN_AGG(A, ADD)                                                                             \
+    if (summask & (1u << A)) {                                                                           \
+        const int sl = aslot[A];                                                                         \
+        const uint32_t o = sl == 0 ? off0 : sl == 1 ? off1 : sl == 2 ? off2 : off3;                      \
+        const uint32_t l = sl == 0 ? len0 : sl == 1 ? len1 : sl == 2 ? len2 : len3;                      \
+        uint32_t mant, fd;                                                                               \
+        if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd)) {                                       \
+            ADD = (unsigned long long)mant * (fd == 0u ? 1000u : fd == 1u ? 100u : fd == 2u ? 10u : 1u); \
+            addmask |= 1u << A;                                                                          \
+        } else if (l != 0u) {                                                                            \
+            ok = false; /* a value this kernel does not decode (NULL is simply not summed) */           \
+        }                                                                                                \
+    }
+                    CQG_LEAN_AGG(0, add0)
+                    CQG_LEAN_AGG(1, add1)
+                    CQG_LEAN_AGG(2, add2)
+                    CQG_LEAN_AGG(3, add3)
+#undef CQG_LEAN_AGG
                 }
                 if (!ok) {
                     unsigned long long k = atomicAdd(P.def_row_count, 1ull);
                     if (k < P.def_row_cap) P.def_rows[k] = (uint64_t)(g0 + (long long)rs);
                     handed++;
-                    rows--;  // counted by the general kernel
                     continue;
                 }
+                rows++;
                 if (!pass) continue;
                 count++;
                 const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
                 if (gabs < first) first = gabs;
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    if (a < P.naggs && P.aggs[a].off >= 0 && P.aggs[a].slot >= 0 && add[a] != ~0ull) {
-                        s3[a] += (long long)add[a];
-                        sn[a]++;
+                if (addmask) {
+                    if (addmask & 1u) {
+                        s3[0] += (long long)add0;
+                        sn[0]++;
+                    }
+                    if (addmask & 2u) {
+                        s3[1] += (long long)add1;
+                        sn[1]++;
+                    }
+                    if (addmask & 4u) {
+                        s3[2] += (long long)add2;
+                        sn[2]++;
+                    }
+                    if (addmask & 8u) {
+                        s3[3] += (long long)add3;
+                        sn[3]++;
                     }
                 }
             }
-            __syncthreads();
         }
-        // too many rows outside this kernel's repertoire: let the general kernel do the whole scan
-        const int many = __syncthreads_or((int)(handed * 8u > (nrows / G::THREADS) + 8u));
+        // too many rows outside this kernel's repertoire: let the general kernel do the whole scan.
+        // The barrier also keeps the tile and its masks alive until every thread is done with them.
+        const int many = __syncthreads_or((int)(handed * 8u > myrows + 8u));
         if (many && tid == 0) atomicOr(P.errflags, KERR_LEAN_ABORT);
     }
 

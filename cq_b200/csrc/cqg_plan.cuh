@@ -120,8 +120,11 @@ struct DevPlan {
     int32_t simple;
     int32_t s_has_pred;
     int32_t s_slot;   // slot of the predicate column
-    int32_t s_op;     // CQG_OP_EQ..LE with the column on the left
+    int32_t s_op;     // CQG_OP_EQ..LE with the column on the left (general kernel)
     long long s_A[4], s_B[4];
+    int32_t s_lop;    // lean kernel: 0 lhs > s_LB, 1 lhs < s_LB, 2 ==, 3 !=  (>= and <= folded into the bound)
+    int32_t s_pad;
+    long long s_LB[4];
     // work the lean kernel hands to the general one
     int32_t* def_tiles;                 // tiles with bytes the lean kernel does not classify (CR, quotes, blanks, file edges)
     unsigned long long* def_tile_count;
