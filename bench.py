@@ -77,7 +77,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv:
@@ -347,7 +347,7 @@ def main():
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "cqg::scan_kernel", "kernel_ms": kernel_avg,
+                    "traffic": traffic, "kernel": "cqg::lean_kernel (simple plans; cqg::scan_kernel for what it hands over)", "kernel_ms": kernel_avg,
                     "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                     "frac_of_nominal_8TBs": achieved / 8000.0}
         if world == 1:

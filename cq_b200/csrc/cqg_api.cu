@@ -420,14 +420,21 @@ static int launch_scan_nw(const DevPlan& P, int smem, int dev, cudaStream_t st) 
     return CQG_OK;
 }
 
-static int launch_lean(const DevPlan& P, cudaStream_t st) {
+template <class LG, int MINB, bool GROUPED>
+static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
+    DevPlan P = P0;
+    // tiles of this geometry covering the same ownership range
+    if (P.own_hi > P.own_lo) {
+        P.first_tile = (int32_t)(P.own_lo / LG::TILE);
+        P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
+    }
     if (P.n_tiles <= 0) return CQG_OK;
-    const int smem = ScanGeo::OFF_TABLE;
+    const int smem = LG::OFF_TABLE + (GROUPED ? kLeanDictCap * kLeanDictEntry + 16 + LG::NWARPS * kLeanWarpAcc : 0);
     static bool attr_set[64];
     if (!attr_set[dev & 63]) {
-        CU(cudaFuncSetAttribute(lean_kernel<ScanGeo>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(lean_kernel<LG, MINB, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev & 63] = true;
     }
     LaunchCfg& c = g_cfg[dev & 63];
@@ -436,13 +443,19 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
         c.ready = true;
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean_kernel<ScanGeo>, ScanGeo::THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean_kernel<LG, MINB, GROUPED>, LG::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean kernel does not fit");
     int grid = std::min(P.n_tiles, c.sms * per_sm);
-    lean_kernel<ScanGeo><<<grid, ScanGeo::THREADS, smem, st>>>(P);
+    lean_kernel<LG, MINB, GROUPED><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
     CU(cudaGetLastError());
     return CQG_OK;
+}
+
+// the lean kernel hands tiles over by index: its tile size must be the general kernel's
+static int launch_lean(const DevPlan& P, cudaStream_t st) {
+    if (P.simple == 2) return launch_lean_geo<Geo<128, 16384, 1>, 4, true>(P, st);
+    return launch_lean_geo<Geo<128, 16384, 1>, 8, false>(P, st);
 }
 
 static int launch_scan(const DevPlan& P, int table_bytes, cudaStream_t st) {
@@ -541,7 +554,8 @@ static bool exact_decimal(double x, long long& mant, int& fd) {
 // DevPlan::simple — see cqg_plan.cuh. Called before fused refs are rewritten to slots.
 static void plan_simple_route(DevPlan& P) {
     P.simple = 0;
-    if (P.join || P.mode != SCAN_AGG || !P.scalar_regs || P.exact_only || P.nwantL > 4) return;
+    if (P.join || P.mode != SCAN_AGG || P.exact_only || P.nwantL > 4 || P.naggs > 4 || P.ngc > 4) return;
+    if (P.ngc == 0 && !P.scalar_regs) return;
     for (int a = 0; a < P.naggs; a++)
         if (P.aggs[a].func == CQG_AGG_MIN || P.aggs[a].func == CQG_AGG_MAX) return;
     P.s_has_pred = 0;
@@ -588,7 +602,7 @@ static void plan_simple_route(DevPlan& P) {
         P.s_lop = (op == CQG_OP_GT || op == CQG_OP_GE) ? 0 : (op == CQG_OP_LT || op == CQG_OP_LE) ? 1 : op == CQG_OP_EQ ? 2 : 3;
         for (int fd = 0; fd < 4; fd++) P.s_LB[fd] = P.s_B[fd] + (op == CQG_OP_GE ? -1 : op == CQG_OP_LE ? 1 : 0);
     }
-    P.simple = 1;
+    P.simple = P.ngc == 0 ? 1 : 2;  // 2: lean GROUP BY (per-CTA dictionary, up to 64 groups per CTA)
 }
 
 static int number_slots(DevPlan& P) {
@@ -1352,7 +1366,7 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     DevPlan& P = hp.P;
     *done = 0;
     int rc;
-    if ((rc = alloc_group_table(hp, gt, 16, st))) return rc;
+    if ((rc = alloc_group_table(hp, gt, P.ngc == 0 ? 16 : 1u << 14, st))) return rc;
     DevBuf d_tiles, d_rows;
     const uint64_t row_cap = (uint64_t)P.n_tiles * 8u + 1024u;
     CU(d_tiles.alloc((size_t)(P.n_tiles + 1) * 4, st));
@@ -1372,7 +1386,7 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     *ms_out += ms;
-    if ((hs.errflags & KERR_LEAN_ABORT) || hs.def_row_count > row_cap) {
+    if ((hs.errflags & (KERR_LEAN_ABORT | KERR_TABLE_FULL)) || hs.def_row_count > row_cap) {
         P.simple = 0;  // the data is not what the lean kernel is for
         return CQG_OK;
     }

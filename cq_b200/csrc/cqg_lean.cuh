@@ -39,7 +39,8 @@ __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // unsigned decimal of 1..7 bytes at shared address `fa`: value = mant / 10^fd. false: not one.
-__device__ __forceinline__ bool lean_decimal(uint32_t fa, uint32_t len, uint32_t& mant, uint32_t& fd) {
+// `hasdot`: the text had a '.', i.e. the reference types it DOUBLE, not INTEGER.
+__device__ __forceinline__ bool lean_decimal(uint32_t fa, uint32_t len, uint32_t& mant, uint32_t& fd, bool& hasdot) {
     const uint32_t a = fa & ~3u, sh = (fa & 3u) * 8u;
     const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
     if (len <= 4u) {
@@ -48,6 +49,7 @@ __device__ __forceinline__ bool lean_decimal(uint32_t fa, uint32_t len, uint32_t
         uint32_t dotf = ~((((w ^ 0x2e2e2e2eu) & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
         uint32_t t = w ^ 0x30303030u;
         fd = 0;
+        hasdot = dotf != 0u;
         uint32_t ndig = len;
         if (dotf) {
             if (dotf & (dotf - 1u)) return false;
@@ -86,16 +88,75 @@ __device__ __forceinline__ bool lean_decimal(uint32_t fa, uint32_t len, uint32_t
     }
     mant = m;
     fd = f;
+    hasdot = dot;
     return ok && digit && f <= 3u;  // more than 3 fraction digits: leave to the general kernel
 }
 
-template <class G>
-__global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_constant__ DevPlan P) {
+// ---- lean GROUP BY: key parts of a clean tile ----
+// One GROUP BY key part exactly as canon_part<true> builds it, for the two shapes this kernel
+// covers: text of <= 16 bytes that cannot start a number, and unsigned decimals of <= 7 bytes.
+// false: hand the row over (dates, signed or long numbers, long strings, "1-2" and the like).
+__device__ __forceinline__ bool lean_key_part(uint32_t fa, uint32_t len, uint32_t& tag, uint64_t& w0, uint64_t& w1) {
+    w0 = 0;
+    w1 = 0;
+    if (len == 0u) {
+        tag = KT_NULL;
+        return true;
+    }
+    const uint32_t c0 = lds8(fa);
+    const bool numeric_start = (c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.';
+    if (!numeric_start) {
+        if (len > 16u) return false;
+        const uint32_t a = fa & ~3u, sh = (fa & 3u) * 8u;
+        const uint32_t x0 = lds32(a), x1 = lds32(a + 4), x2 = lds32(a + 8), x3 = lds32(a + 12), x4 = lds32(a + 16);
+        uint64_t lo = ((uint64_t)__funnelshift_r(x1, x2, sh) << 32) | __funnelshift_r(x0, x1, sh);
+        uint64_t hi = ((uint64_t)__funnelshift_r(x3, x4, sh) << 32) | __funnelshift_r(x2, x3, sh);
+        if (len < 8u) {
+            lo &= (1ull << (8u * len)) - 1ull;
+            hi = 0;
+        } else if (len < 16u) {
+            hi &= (1ull << (8u * (len - 8u))) - 1ull;  // len == 8: mask 0
+        }
+        if (len == 4u && (uint32_t)lo == 0x4c4c554eu) {  // the text NULL is the NULL group
+            tag = KT_NULL;
+            return true;
+        }
+        tag = KT_STR;
+        w0 = lo;
+        w1 = hi;
+        return true;
+    }
+    if (len > 7u || c0 == '+' || c0 == '-') return false;
+    uint32_t mant, fd;
+    bool hasdot;
+    if (!lean_decimal(fa, len, mant, fd, hasdot)) return false;
+    if (!hasdot) {
+        tag = KT_INT;
+        w0 = mant;
+    } else {
+        tag = KT_DBL_POS;  // |x|*10^6 rounded = mant * 10^(6-fd) exactly (mant < 10^7)
+        w0 = (uint64_t)mant * (fd == 0u ? 1000000u : fd == 1u ? 100000u : fd == 2u ? 10000u : 1000u);
+    }
+    return true;
+}
+
+// per-CTA dictionary of the lean GROUP BY: key -> small group number
+constexpr int kLeanGroups = 64;     // groups a CTA can number; one more aborts to the general kernel
+constexpr int kLeanDictCap = 128;   // slots
+constexpr int kLeanDictEntry = 96;  // hash 8 | gid 4 | tags 4 | first okey 8 | pad 8 | 4 x key part 16
+// per-warp accumulators (only that warp writes them): count u32 [G] | 4 x ( s3 lo u32 [G] | s3 hi u32 [G] | sn u32 [G] )
+constexpr int kLeanWarpAcc = kLeanGroups * 4 + 4 * (kLeanGroups * 8 + kLeanGroups * 4);
+
+template <class G, int MINB, bool GROUPED>
+__global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t s_tm = sbase + G::OFF_TM, s_dm = sbase + G::OFF_DM;
     uint64_t* mbar = (uint64_t*)(smem + G::OFF_MBAR);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* dict = smem + G::OFF_TABLE;                              // GROUPED only
+    uint8_t* wacc = dict + kLeanDictCap * kLeanDictEntry + 16 + warp * kLeanWarpAcc;
+    unsigned int* ngroups = (unsigned int*)(dict + kLeanDictCap * kLeanDictEntry);
 
     if (tid == 0) {
         for (int s = 0; s < G::STAGES; s++) mbar_init(&mbar[s], 1);
@@ -104,6 +165,12 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
     for (int w = G::BUF / 32 + tid; w < G::MASKW; w += G::THREADS) {
         sts32(s_tm + 4 * w, 0xffffffffu);
         sts32(s_dm + 4 * w, 0u);
+    }
+    if (GROUPED) {
+        const int words = (kLeanDictCap * kLeanDictEntry + 16 + G::NWARPS * kLeanWarpAcc) / 4;
+        for (int k = tid; k < words; k += G::THREADS) ((uint32_t*)dict)[k] = 0u;
+        __syncthreads();
+        for (int k = tid; k < kLeanDictCap; k += G::THREADS) *(uint64_t*)(dict + k * kLeanDictEntry + 16) = ~0ull;  // first okey
     }
     __syncthreads();
 
@@ -122,6 +189,7 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
     const int nwant = P.nwantL;
     const int gap0 = P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
     const int has_pred = P.s_has_pred, pslot = P.s_slot, pop = P.s_lop;
+    const int ngc = GROUPED ? P.ngc : 0;
     uint32_t summask = 0;  // aggregates that sum a column
     int aslot[4];
 #pragma unroll
@@ -227,24 +295,27 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
                     j++;
                     s = j == 1 ? S1 : (j == 2 ? S2 : S3);
                 }
-                if (s == 0u) break;
-                const uint32_t bi = __ffs(s) - 1u;
-                s &= s - 1u;
-                const uint32_t t = lds32(s_tm + 4 * (w0 + j));
-                const uint32_t p0 = (w0 + j) * 32u;
-                const uint32_t rs = p0 + bi;
-                const uint32_t wa = 4u * (w0 + j);
-                myrows++;
-                uint32_t off0 = 0, off1 = 0, off2 = 0, off3 = 0, len0 = 0, len1 = 0, len2 = 0, len3 = 0;
-                bool ok = true;
-                const uint32_t t1 = lds32(s_tm + wa + 4);
-                const uint32_t tw = __funnelshift_r(t, t1, bi);
-                if (tw) {
-                    // the row ends inside a 32-bit window
-                    const uint32_t len = __ffs(tw) - 1u;
-                    uint32_t dw = __funnelshift_r(lds32(s_dm + wa), lds32(s_dm + wa + 4), bi) & ((1u << len) - 1u);
-                    uint32_t sp = 0;
-                    bool missing = false;
+                const bool has = s != 0u;
+                if (!has) break;
+                bool ok = true, pass = true;
+                uint32_t gid = 0xffffffffu, addmask = 0, rs = 0;
+                unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
+                if (has) {
+                    const uint32_t bi = __ffs(s) - 1u;
+                    s &= s - 1u;
+                    const uint32_t t = lds32(s_tm + 4 * (w0 + j));
+                    rs = (w0 + j) * 32u + bi;
+                    const uint32_t wa = 4u * (w0 + j);
+                    myrows++;
+                    uint32_t off0 = 0, off1 = 0, off2 = 0, off3 = 0, len0 = 0, len1 = 0, len2 = 0, len3 = 0;
+                    const uint32_t t1 = lds32(s_tm + wa + 4);
+                    const uint32_t tw = __funnelshift_r(t, t1, bi);
+                    if (tw) {
+                        // the row ends inside a 32-bit window
+                        const uint32_t len = __ffs(tw) - 1u;
+                        uint32_t dw = __funnelshift_r(lds32(s_dm + wa), lds32(s_dm + wa + 4), bi) & ((1u << len) - 1u);
+                        uint32_t sp = 0;
+                        bool missing = false;
 #define CQG_LEAN_FIELD(K, GAP, OFF, LEN)                                 \
     if (nwant > K) {                                                     \
         if (GAP > 0) {                                                   \
@@ -257,23 +328,24 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
         OFF = rs + sp;                                                   \
         LEN = missing ? 0u : ep - sp;                                    \
     }
-                    CQG_LEAN_FIELD(0, gap0, off0, len0)
-                    CQG_LEAN_FIELD(1, gap1, off1, len1)
-                    CQG_LEAN_FIELD(2, gap2, off2, len2)
-                    CQG_LEAN_FIELD(3, gap3, off3, len3)
+                        CQG_LEAN_FIELD(0, gap0, off0, len0)
+                        CQG_LEAN_FIELD(1, gap1, off1, len1)
+                        CQG_LEAN_FIELD(2, gap2, off2, len2)
+                        CQG_LEAN_FIELD(3, gap3, off3, len3)
 #undef CQG_LEAN_FIELD
-                } else {
-                    const uint32_t t2 = lds32(s_tm + wa + 8);
-                    const uint32_t tw2 = __funnelshift_r(t1, t2, bi);
-                    if (tw2 == 0u) {
-                        ok = false;  // 64 bytes or more
                     } else {
-                        const uint32_t len = 32u + __ffs(tw2) - 1u;
-                        const uint32_t d0 = lds32(s_dm + wa), d1 = lds32(s_dm + wa + 4), d2 = lds32(s_dm + wa + 8);
-                        unsigned long long dw = (((unsigned long long)__funnelshift_r(d1, d2, bi) << 32) | __funnelshift_r(d0, d1, bi)) &
-                                                ((1ull << len) - 1ull);
-                        uint32_t sp = 0;
-                        bool missing = false;
+                        const uint32_t t2 = lds32(s_tm + wa + 8);
+                        const uint32_t tw2 = __funnelshift_r(t1, t2, bi);
+                        if (tw2 == 0u) {
+                            ok = false;  // 64 bytes or more
+                        } else {
+                            const uint32_t len = 32u + __ffs(tw2) - 1u;
+                            const uint32_t d0 = lds32(s_dm + wa), d1 = lds32(s_dm + wa + 4), d2 = lds32(s_dm + wa + 8);
+                            unsigned long long dw =
+                                (((unsigned long long)__funnelshift_r(d1, d2, bi) << 32) | __funnelshift_r(d0, d1, bi)) &
+                                ((1ull << len) - 1ull);
+                            uint32_t sp = 0;
+                            bool missing = false;
 #define CQG_LEAN_FIELD(K, GAP, OFF, LEN)                                 \
     if (nwant > K) {                                                     \
         if (GAP > 0) {                                                   \
@@ -286,78 +358,173 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
         OFF = rs + sp;                                                   \
         LEN = missing ? 0u : ep - sp;                                    \
     }
-                        CQG_LEAN_FIELD(0, gap0, off0, len0)
-                        CQG_LEAN_FIELD(1, gap1, off1, len1)
-                        CQG_LEAN_FIELD(2, gap2, off2, len2)
-                        CQG_LEAN_FIELD(3, gap3, off3, len3)
+                            CQG_LEAN_FIELD(0, gap0, off0, len0)
+                            CQG_LEAN_FIELD(1, gap1, off1, len1)
+                            CQG_LEAN_FIELD(2, gap2, off2, len2)
+                            CQG_LEAN_FIELD(3, gap3, off3, len3)
 #undef CQG_LEAN_FIELD
+                        }
                     }
-                }
-                // ---- WHERE on a short decimal ----
-                bool pass = true;
-                if (ok && has_pred) {
-                    const uint32_t o = pslot == 0 ? off0 : pslot == 1 ? off1 : pslot == 2 ? off2 : off3;
-                    const uint32_t l = pslot == 0 ? len0 : pslot == 1 ? len1 : pslot == 2 ? len2 : len3;
-                    uint32_t mant, fd;
-                    if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd)) {
-                        const long long lhs = (long long)((unsigned long long)mant * (unsigned long long)(uint32_t)P.s_A[fd]);
-                        const long long rhs = P.s_LB[fd];
-                        // s_op was normalised by the host: 0 lhs > rhs, 1 lhs < rhs, 2 ==, 3 !=
-                        pass = pop == 0 ? lhs > rhs : pop == 1 ? lhs < rhs : pop == 2 ? lhs == rhs : lhs != rhs;
-                    } else {
-                        ok = false;  // NULL, text, date, signed or long number: general kernel
+#define CQG_LEAN_SLOT(SL, O, L)                                                  \
+    const uint32_t O = SL == 0 ? off0 : SL == 1 ? off1 : SL == 2 ? off2 : off3; \
+    const uint32_t L = SL == 0 ? len0 : SL == 1 ? len1 : SL == 2 ? len2 : len3;
+                    // ---- WHERE on a short decimal ----
+                    if (ok && has_pred) {
+                        CQG_LEAN_SLOT(pslot, o, l)
+                        uint32_t mant, fd;
+                        bool hd;
+                        if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd, hd)) {
+                            const long long lhs = (long long)((unsigned long long)mant * (unsigned long long)(uint32_t)P.s_A[fd]);
+                            const long long rhs = P.s_LB[fd];
+                            // s_lop was normalised by the host: 0 lhs > rhs, 1 lhs < rhs, 2 ==, 3 !=
+                            pass = pop == 0 ? lhs > rhs : pop == 1 ? lhs < rhs : pop == 2 ? lhs == rhs : lhs != rhs;
+                        } else {
+                            ok = false;  // NULL, text, date, signed or long number: general kernel
+                        }
                     }
-                }
-                // ---- SUM / AVG operands ----
-                unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
-                uint32_t addmask = 0;
-                if (ok && pass && summask) {
+                    // ---- SUM / AVG operands ----
+                    if (ok && pass && summask) {
 #define CQG_LEAN_AGG(A, ADD)                                                                             \
     if (summask & (1u << A)) {                                                                           \
         const int sl = aslot[A];                                                                         \
-        const uint32_t o = sl == 0 ? off0 : sl == 1 ? off1 : sl == 2 ? off2 : off3;                      \
-        const uint32_t l = sl == 0 ? len0 : sl == 1 ? len1 : sl == 2 ? len2 : len3;                      \
+        CQG_LEAN_SLOT(sl, o, l)                                                                          \
         uint32_t mant, fd;                                                                               \
-        if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd)) {                                       \
+        bool hd;                                                                                         \
+        if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd, hd)) {                                   \
             ADD = (unsigned long long)mant * (fd == 0u ? 1000u : fd == 1u ? 100u : fd == 2u ? 10u : 1u); \
             addmask |= 1u << A;                                                                          \
         } else if (l != 0u) {                                                                            \
             ok = false; /* a value this kernel does not decode (NULL is simply not summed) */           \
         }                                                                                                \
     }
-                    CQG_LEAN_AGG(0, add0)
-                    CQG_LEAN_AGG(1, add1)
-                    CQG_LEAN_AGG(2, add2)
-                    CQG_LEAN_AGG(3, add3)
+                        CQG_LEAN_AGG(0, add0)
+                        CQG_LEAN_AGG(1, add1)
+                        CQG_LEAN_AGG(2, add2)
+                        CQG_LEAN_AGG(3, add3)
 #undef CQG_LEAN_AGG
+                    }
+                    // ---- GROUP BY: key -> group number of this CTA ----
+                    if (GROUPED && ok && pass) {
+                        uint64_t kw[8];
+                        uint32_t tags = 0;
+                        uint64_t h = 0x243F6A8885A308D3ull + (uint64_t)ngc;
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            kw[2 * g] = 0;
+                            kw[2 * g + 1] = 0;
+                            if (g < ngc && ok) {
+                                const int sl = P.gslot[g];
+                                uint32_t tag = KT_NULL;
+                                if (sl >= 0) {
+                                    CQG_LEAN_SLOT(sl, o, l)
+                                    ok = lean_key_part(s_buf + o, l, tag, kw[2 * g], kw[2 * g + 1]);
+                                }
+                                tags |= tag << (4 * g);
+                                h = key_hash_step(h, tag, kw[2 * g], kw[2 * g + 1]);
+                            }
+                        }
+                        if (ok) {
+                            h = key_hash_final(h);
+                            // find-or-insert in the CTA dictionary
+                            uint32_t i = (uint32_t)(h >> 1) & (kLeanDictCap - 1);
+                            for (int probes = 0; probes < kLeanDictCap;) {
+                                uint8_t* e = dict + i * kLeanDictEntry;
+                                unsigned long long cur = *(volatile unsigned long long*)e;
+                                if (cur == 0ull) {
+                                    cur = atomicCAS((unsigned long long*)e, 0ull, (unsigned long long)(h | kLockBit));
+                                    if (cur == 0ull) {
+                                        const unsigned int id = atomicAdd(ngroups, 1u);
+                                        *(uint32_t*)(e + 8) = id;
+                                        *(uint32_t*)(e + 12) = tags;
+#pragma unroll
+                                        for (int g = 0; g < 4; g++) {
+                                            *(uint64_t*)(e + 32 + 16 * g) = kw[2 * g];
+                                            *(uint64_t*)(e + 40 + 16 * g) = kw[2 * g + 1];
+                                        }
+                                        __threadfence_block();
+                                        atomicExch((unsigned long long*)e, (unsigned long long)h);
+                                        gid = id;
+                                        break;
+                                    }
+                                }
+                                if ((cur & ~kLockBit) == h) {
+                                    if (cur & kLockBit) continue;  // being written: look again
+                                    bool same = *(volatile uint32_t*)(e + 12) == tags;
+#pragma unroll
+                                    for (int g = 0; g < 4; g++)
+                                        same = same && *(volatile uint64_t*)(e + 32 + 16 * g) == kw[2 * g] &&
+                                               *(volatile uint64_t*)(e + 40 + 16 * g) == kw[2 * g + 1];
+                                    if (same) {
+                                        gid = *(volatile uint32_t*)(e + 8);
+                                        break;
+                                    }
+                                }
+                                i = (i + 1) & (kLeanDictCap - 1);
+                                probes++;
+                            }
+                            if (gid >= (uint32_t)kLeanGroups) {
+                                // more groups than this kernel numbers: the general kernel takes the scan
+                                atomicOr(P.errflags, KERR_LEAN_ABORT);
+                                gid = 0xffffffffu;
+                            } else {
+                                const uint64_t okey = (P.global_base + (uint64_t)(g0 + (long long)rs)) << 16;
+                                uint64_t* fp = (uint64_t*)(dict + i * kLeanDictEntry + 16);
+                                if (okey < *(volatile uint64_t*)fp) atomicMin((unsigned long long*)fp, (unsigned long long)okey);
+                            }
+                        }
+                    }
+#undef CQG_LEAN_SLOT
+                    if (!ok) {
+                        unsigned long long k = atomicAdd(P.def_row_count, 1ull);
+                        if (k < P.def_row_cap) P.def_rows[k] = (uint64_t)(g0 + (long long)rs);
+                        handed++;
+                        gid = 0xffffffffu;
+                    } else {
+                        rows++;
+                    }
                 }
-                if (!ok) {
-                    unsigned long long k = atomicAdd(P.def_row_count, 1ull);
-                    if (k < P.def_row_cap) P.def_rows[k] = (uint64_t)(g0 + (long long)rs);
-                    handed++;
-                    continue;
-                }
-                rows++;
-                if (!pass) continue;
-                count++;
-                const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
-                if (gabs < first) first = gabs;
-                if (addmask) {
-                    if (addmask & 1u) {
-                        s3[0] += (long long)add0;
-                        sn[0]++;
+                const bool take = has && ok && pass;
+                if (!GROUPED) {
+                    if (take) {
+                        count++;
+                        const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
+                        if (gabs < first) first = gabs;
+                        if (addmask & 1u) {
+                            s3[0] += (long long)add0;
+                            sn[0]++;
+                        }
+                        if (addmask & 2u) {
+                            s3[1] += (long long)add1;
+                            sn[1]++;
+                        }
+                        if (addmask & 4u) {
+                            s3[2] += (long long)add2;
+                            sn[2]++;
+                        }
+                        if (addmask & 8u) {
+                            s3[3] += (long long)add3;
+                            sn[3]++;
+                        }
                     }
-                    if (addmask & 2u) {
-                        s3[1] += (long long)add1;
-                        sn[1]++;
-                    }
-                    if (addmask & 4u) {
-                        s3[2] += (long long)add2;
-                        sn[2]++;
-                    }
-                    if (addmask & 8u) {
-                        s3[3] += (long long)add3;
-                        sn[3]++;
+                } else {
+                    // ---- group step: this warp's own accumulators in shared memory, native 32-bit
+                    // atomics only; a 64-bit sum is (lo, hi) with the carry added by the lane that wrapped lo ----
+                    if (take && gid != 0xffffffffu) {
+                        atomicAdd((unsigned int*)(wacc + 4 * gid), 1u);
+#define CQG_LEAN_GSUM(A, ADD)                                                                  \
+    if ((addmask >> A) & 1u) {                                                                 \
+        uint8_t* b = wacc + kLeanGroups * 4 + A * (kLeanGroups * 12);                          \
+        const uint32_t vlo = (uint32_t)ADD, vhi = (uint32_t)(ADD >> 32);                       \
+        const uint32_t old = atomicAdd((unsigned int*)(b + 4 * gid), vlo);                     \
+        const uint32_t up = vhi + ((old + vlo) < old ? 1u : 0u);                               \
+        if (up) atomicAdd((unsigned int*)(b + kLeanGroups * 4 + 4 * gid), up);                 \
+        atomicAdd((unsigned int*)(b + kLeanGroups * 8 + 4 * gid), 1u);                         \
+    }
+                        CQG_LEAN_GSUM(0, add0)
+                        CQG_LEAN_GSUM(1, add1)
+                        CQG_LEAN_GSUM(2, add2)
+                        CQG_LEAN_GSUM(3, add3)
+#undef CQG_LEAN_GSUM
                     }
                 }
             }
@@ -368,22 +535,24 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
         if (many && tid == 0) atomicOr(P.errflags, KERR_LEAN_ABORT);
     }
 
-    // ---- epilogue: fold the registers into the single group `_all_` ----
+    // ---- epilogue ----
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        rows += __shfl_xor_sync(0xffffffffu, rows, d);
-        count += __shfl_xor_sync(0xffffffffu, count, d);
-        const uint64_t of = __shfl_xor_sync(0xffffffffu, first, d);
-        first = of < first ? of : first;
+    for (int d = 16; d > 0; d >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, d);
+    if (lane == 0 && rows) atomicAdd(P.rows_scanned, (unsigned long long)rows);
+    if (!GROUPED) {
+        // fold the registers into the single group `_all_`
 #pragma unroll
-        for (int a = 0; a < 4; a++) {
-            s3[a] += __shfl_xor_sync(0xffffffffu, s3[a], d);
-            sn[a] += __shfl_xor_sync(0xffffffffu, sn[a], d);
+        for (int d = 16; d > 0; d >>= 1) {
+            count += __shfl_xor_sync(0xffffffffu, count, d);
+            const uint64_t of = __shfl_xor_sync(0xffffffffu, first, d);
+            first = of < first ? of : first;
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                s3[a] += __shfl_xor_sync(0xffffffffu, s3[a], d);
+                sn[a] += __shfl_xor_sync(0xffffffffu, sn[a], d);
+            }
         }
-    }
-    if (lane == 0) {
-        if (rows) atomicAdd(P.rows_scanned, (unsigned long long)rows);
-        if (count) {
+        if (lane == 0 && count) {
             unsigned err = 0;
             const uint64_t h = key_hash_final(0x243F6A8885A308D3ull);
             uint8_t* ge = global_entry_for(P, h, 0u, nullptr, err);
@@ -400,6 +569,44 @@ __global__ void __launch_bounds__(G::THREADS, 6) lean_kernel(const __grid_consta
             }
             if (err) atomicOr(P.errflags, err);
         }
+    } else {
+        // every dictionary entry: add up the warps' accumulators and fold them into the global table
+        __syncthreads();
+        unsigned err = 0;
+        for (int sidx = tid; sidx < kLeanDictCap; sidx += G::THREADS) {
+            const uint8_t* e = dict + sidx * kLeanDictEntry;
+            const uint64_t h = *(const uint64_t*)e;
+            if (h == 0ull) continue;
+            const uint32_t gid = *(const uint32_t*)(e + 8);
+            if (gid >= (uint32_t)kLeanGroups) continue;
+            unsigned long long c = 0;
+            for (int w = 0; w < G::NWARPS; w++) c += *(const uint32_t*)(dict + kLeanDictCap * kLeanDictEntry + 16 + w * kLeanWarpAcc + 4 * gid);
+            if (c == 0ull) continue;
+            uint64_t kw[2 * CQG_MAX_GROUP_COLS];
+            for (int g = 0; g < 4; g++) {
+                kw[2 * g] = *(const uint64_t*)(e + 32 + 16 * g);
+                kw[2 * g + 1] = *(const uint64_t*)(e + 40 + 16 * g);
+            }
+            uint8_t* ge = global_entry_for(P, h, *(const uint32_t*)(e + 12), kw, err);
+            if (!ge) continue;
+            atomicAdd((unsigned long long*)(ge + kOffCount), c);
+            amin64((uint64_t*)(ge + kOffFirst), *(const uint64_t*)(e + 16));
+            for (int a = 0; a < 4; a++) {
+                if (a < P.naggs && P.aggs[a].off >= 0 && P.aggs[a].slot >= 0) {
+                    unsigned long long t3 = 0, tn = 0;
+                    for (int w = 0; w < G::NWARPS; w++) {
+                        const uint8_t* b = dict + kLeanDictCap * kLeanDictEntry + 16 + w * kLeanWarpAcc + kLeanGroups * 4 + a * (kLeanGroups * 12);
+                        t3 += ((unsigned long long)*(const uint32_t*)(b + kLeanGroups * 4 + 4 * gid) << 32) + *(const uint32_t*)(b + 4 * gid);
+                        tn += *(const uint32_t*)(b + kLeanGroups * 8 + 4 * gid);
+                    }
+                    if (tn) {
+                        atomicAdd((unsigned long long*)(ge + P.aggs[a].off + 16), tn);
+                        atomicAdd((unsigned long long*)(ge + P.aggs[a].off + 24), t3);
+                    }
+                }
+            }
+        }
+        if (err) atomicOr(P.errflags, err);
     }
 }
 

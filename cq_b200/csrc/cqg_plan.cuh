@@ -74,7 +74,7 @@ constexpr int kOffKeys = 32;   // ngc x { uint64 w0 ; uint64 w1 }
 constexpr uint64_t kLockBit = 0x8000000000000000ull;
 
 // key part tags
-enum : uint32_t { KT_NULL = 0, KT_INT = 1, KT_DBL_POS = 2, KT_DBL_NEG = 3, KT_STR = 4, KT_STR_HASH = 5, KT_DATE = 6 };
+enum : uint32_t { KT_NULL = 0, KT_INT = 1, KT_DBL_POS = 2, KT_DBL_NEG = 3, KT_STR = 4, KT_STR_HASH = 5, KT_DATE = 6, KT_DBL_BIG = 7 };
 
 struct JoinSlot {
     uint64_t h;  // 0 empty, bit 63 lock

@@ -130,41 +130,32 @@ __host__ __device__ __forceinline__ uint64_t bits_of_img(uint64_t u) {
 // canonical GROUP BY key parts (the reference's key string, evaluator_aggregates.c:121-141,
 // as (tag, w0, w1) so that equal strings <=> equal triples)
 // ------------------------------------------------------------------------------------------
-// |x| * 10^6 rounded half-even on the exact binary value = the digits "%.6f" prints
-__device__ inline uint64_t dbl_key6(double x, unsigned& err) {
+// |x| * 10^6 rounded half-even on the exact binary value = the digits "%.6f" prints, as a
+// 128-bit integer (w1:w0). Returns false for |x| >= 2^53 (an integer: the caller keys on the bits).
+__device__ inline bool dbl_key6(double x, uint64_t& w0, uint64_t& w1) {
     uint64_t bits = (uint64_t)__double_as_longlong(x) & 0x7fffffffffffffffull;
     uint32_t e = (uint32_t)(bits >> 52);
-    if (e == 0) return 0;  // subnormal / zero: far below 5e-7
-    if (e == 0x7ffu) {
-        err |= KERR_KEY_RANGE;
-        return 0;
-    }
+    w0 = 0;
+    w1 = 0;
+    if (e == 0) return true;  // subnormal / zero: far below 5e-7
     uint64_t m = (bits & 0xfffffffffffffull) | (1ull << 52);
     int e2 = (int)e - 1075;  // |x| = m * 2^e2
-    uint64_t lo = m * 1000000ull, hi = __umul64hi(m, 1000000ull);
-    if (e2 >= 0) {
-        if (hi != 0 || e2 >= 63 || (lo >> (63 - e2)) != 0) {
-            err |= KERR_KEY_RANGE;
-            return 0;
-        }
-        return lo << e2;
-    }
+    if (e2 >= 0) return false;
+    uint64_t lo = m * 1000000ull, hi = __umul64hi(m, 1000000ull);  // P = m * 10^6 < 2^73
     int s = -e2;
-    if (s >= 74) return 0;  // P < 2^73 <= half of 2^s
-    uint64_t q, rem_hi, rem_lo, half_hi, half_lo;
+    if (s >= 74) return true;  // P < half of 2^s
+    uint64_t q_lo, q_hi, rem_hi, rem_lo, half_hi, half_lo;
     if (s < 64) {
-        q = (lo >> s) | (hi << (64 - s));  // hi < 2^9 so hi >> s == 0 unless s < 9
-        if ((hi >> s) != 0) {
-            err |= KERR_KEY_RANGE;
-            return 0;
-        }
+        q_lo = (lo >> s) | (hi << (64 - s));
+        q_hi = hi >> s;
         rem_hi = 0;
         rem_lo = lo & ((1ull << s) - 1ull);
         half_hi = 0;
         half_lo = 1ull << (s - 1);
     } else {
         int t = s - 64;
-        q = t ? (hi >> t) : hi;
+        q_lo = t ? (hi >> t) : hi;
+        q_hi = 0;
         rem_hi = t ? (hi & ((1ull << t) - 1ull)) : 0;
         rem_lo = lo;
         half_hi = t ? (1ull << (t - 1)) : 0;
@@ -172,12 +163,13 @@ __device__ inline uint64_t dbl_key6(double x, unsigned& err) {
     }
     bool gt = rem_hi > half_hi || (rem_hi == half_hi && rem_lo > half_lo);
     bool eq = rem_hi == half_hi && rem_lo == half_lo;
-    if (gt || (eq && (q & 1ull))) q++;
-    if (q >> 63) {
-        err |= KERR_KEY_RANGE;
-        return 0;
+    if (gt || (eq && (q_lo & 1ull))) {
+        q_lo++;
+        if (q_lo == 0ull) q_hi++;
     }
-    return q;
+    w0 = q_lo;
+    w1 = q_hi;
+    return true;
 }
 
 __device__ __forceinline__ void hash_str2(const uint8_t* p, uint32_t n, uint64_t& h0, uint64_t& h1) {
@@ -219,7 +211,10 @@ __device__ inline void canon_part(const DVal& v, bool multi, unsigned& err, uint
         case T_DBL:
             if (GROUP) {
                 tag = (__double_as_longlong(v.d) < 0) ? KT_DBL_NEG : KT_DBL_POS;
-                w0 = dbl_key6(v.d, err);
+                if (!dbl_key6(v.d, w0, w1)) {  // |x| >= 2^53: "%.6f" prints the integer itself
+                    tag = KT_DBL_BIG;
+                    w0 = (uint64_t)__double_as_longlong(v.d);
+                }
             } else {
                 tag = KT_DBL_POS;
                 double d = v.d == 0.0 ? 0.0 : v.d;  // -0.0 == 0.0
@@ -675,8 +670,12 @@ __device__ __forceinline__ void entry_accumulate(const DevPlan& P, uint8_t* e, c
         DVal v = row.value_slot(P, sp.slot, err);
         uint8_t* st = e + sp.off;
         if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
-            if (v.type == T_INT) {
-                atomicAdd((unsigned long long*)st, (unsigned long long)v.i);
+            if (v.type == T_INT && (unsigned long long)(v.i + (1ll << 31)) >> 32 == 0) {
+                atomicAdd((unsigned long long*)st, (unsigned long long)v.i);  // exact, cannot overflow below 2^31 rows
+                if (SM) atomicAdd((unsigned int*)(st + 16), 1u);
+                else atomicAdd((unsigned long long*)(st + 16), 1ull);
+            } else if (v.type == T_INT) {
+                atomicAdd((double*)(st + 8), (double)v.i);
                 if (SM) atomicAdd((unsigned int*)(st + 16), 1u);
                 else atomicAdd((unsigned long long*)(st + 16), 1ull);
             } else if (v.type == T_DBL) {
@@ -731,8 +730,11 @@ __device__ __forceinline__ void agg_row(const DevPlan& P, const CtaState& cs, co
                 if (sp.off >= 0) {
                     DVal v = row.value_slot(P, sp.slot, acc.err);
                     if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
-                        if (v.type == T_INT) {
+                        if (v.type == T_INT && (unsigned long long)(v.i + (1ll << 31)) >> 32 == 0) {
                             acc.si[a] += v.i;
+                            acc.sn[a]++;
+                        } else if (v.type == T_INT) {
+                            acc.sd[a] += (double)v.i;
                             acc.sn[a]++;
                         } else if (v.type == T_DBL) {
                             acc.sd[a] += v.d;
@@ -1023,8 +1025,11 @@ __device__ __forceinline__ bool simple_row(const DevPlan& P, const CtaState& cs,
                 acc.sn[a]++;
             } else {
                 DVal v = decode_field_clean(buf + o, l, acc.err);
-                if (v.type == T_INT) {
+                if (v.type == T_INT && (unsigned long long)(v.i + (1ll << 31)) >> 32 == 0) {
                     acc.si[a] += v.i;
+                    acc.sn[a]++;
+                } else if (v.type == T_INT) {
+                    acc.sd[a] += (double)v.i;
                     acc.sn[a]++;
                 } else if (v.type == T_DBL) {
                     acc.sd[a] += v.d;
@@ -1252,7 +1257,7 @@ __global__ void __launch_bounds__(G::THREADS, 4) scan_kernel(const __grid_consta
             const uint32_t npass = nrows - pass_lo < (uint32_t)G::ROWCAP ? nrows - pass_lo : (uint32_t)G::ROWCAP;
             if (P.mode == SCAN_COUNT_ROWS) {
                 for (uint32_t r = tid; r < npass; r += G::THREADS) acc.rows++;
-            } else if (P.simple && !special) {
+            } else if (P.simple == 1 && !special) {
                 for (uint32_t r = tid; r < npass; r += G::THREADS) {
                     const uint32_t rs = rowpos[r];
                     acc.rows++;

@@ -37,6 +37,13 @@ def plans():
     P["group_high_card"] = dict(group_by=[NAME, SURNAME, AGE, HEIGHT], out_cols=[NAME, SURNAME, AGE, HEIGHT],
                                 aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE), (A.AGG_MIN, HEIGHT), (A.AGG_MAX, HEIGHT),
                                       (A.AGG_AVG, HEIGHT)])
+    # lean GROUP BY kernel shapes: few groups (stays lean), and more groups than a CTA numbers (aborts to general)
+    P["lean_group_two_keys"] = dict(where=("<=", col(HEIGHT), const(1.9)), group_by=[NAME, GENDER], out_cols=[NAME, GENDER],
+                                    aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE), (A.AGG_AVG, HEIGHT), (A.AGG_COUNT, SURNAME)])
+    P["lean_group_gender_height"] = dict(group_by=[GENDER, HEIGHT], out_cols=[GENDER, HEIGHT],
+                                         aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, HEIGHT)])
+    P["lean_group_abort_many"] = dict(where=(">", col(AGE), const(15)), group_by=[NAME, SURNAME, AGE],
+                                      out_cols=[NAME, SURNAME, AGE], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, HEIGHT)])
     P["filter_between_in"] = dict(where=("and", ("and", (">=", col(AGE), const(20)), ("<=", col(AGE), const(60))),
                                          ("in", col(NAME), [const("AAAAAAAAAA"), const("CCCCCCCCCC"), const(5)])),
                                   aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE)])
