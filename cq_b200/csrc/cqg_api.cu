@@ -474,6 +474,7 @@ static int launch_scan(const DevPlan& P, int table_bytes, cudaStream_t st) {
 struct HostPlan {
     DevPlan P{};
     std::vector<uint8_t> entry_init;
+    std::vector<uint8_t> pool;  // host copy of the predicate's string pool
     DevBuf d_entry_init, d_code, d_consts, d_pool;
     DevBuf d_scalars;  // errflags, rows_scanned, gcount, sel_count, jrow_count, jclass[2]
     int table_smem_bytes = 0;
@@ -551,9 +552,67 @@ static bool exact_decimal(double x, long long& mant, int& fd) {
     return false;
 }
 
+// one F_CMP leaf of a fused program -> a lean leaf; false when the lean kernel cannot evaluate it
+static bool make_lean_leaf(DevPlan& P, const FInsn& in, LeanLeaf& L) {
+    int op = in.n;
+    int col_ref = in.a, const_ref = in.b;
+    if ((col_ref & kRefConst) && col_ref != kRefNull) {  // literal on the left: mirror the operator
+        std::swap(col_ref, const_ref);
+        op = op == CQG_OP_GT ? CQG_OP_LT : op == CQG_OP_LT ? CQG_OP_GT : op == CQG_OP_GE ? CQG_OP_LE
+           : op == CQG_OP_LE ? CQG_OP_GE : op;
+    }
+    if (col_ref == kRefNull || (col_ref & kRefConst) || !(const_ref & kRefConst) || const_ref == kRefNull) return false;
+    int slot = (col_ref >= 0 && col_ref < kMaxQueryCols) ? P.colslot[col_ref] : -1;
+    if (slot < 0 || slot >= P.nwantL || slot >= 4) return false;
+    const DConst& c = P.consts_inl[const_ref & 0x1fff];
+    memset(&L, 0, sizeof L);
+    L.slot = slot;
+    if (c.type == CQG_TYPE_STRING) {
+        if (op != CQG_OP_EQ && op != CQG_OP_NE) return false;
+        if (c.len < 1 || c.len > 16) return false;
+        const uint8_t* sp = nullptr;
+        (void)sp;
+        return false;  // filled by the caller, which owns the host copy of the string pool
+    }
+    long long cm;
+    int cfd;
+    if (c.type == CQG_TYPE_INTEGER) {
+        if (c.bits < 0 || c.bits > 1000000000ll) return false;
+        cm = c.bits;
+        cfd = 0;
+    } else if (c.type == CQG_TYPE_DOUBLE) {
+        double d;
+        memcpy(&d, &c.bits, 8);
+        if (!exact_decimal(d, cm, cfd) || cm > 1000000000ll) return false;
+    } else {
+        return false;
+    }
+    L.kind = 0;
+    for (int fd = 0; fd < 4; fd++) {
+        int K = std::max(fd, cfd);
+        long long A = 1, B = cm;
+        for (int i = 0; i < K - fd; i++) A *= 10;
+        for (int i = 0; i < K - cfd; i++) B *= 10;
+        L.A[fd] = (uint32_t)A;
+        // integers on both sides: a >= b  <=>  a > b - 1
+        L.LB[fd] = B + (op == CQG_OP_GE ? -1 : op == CQG_OP_LE ? 1 : 0);
+        if (&L == &L) {
+            P.s_A[fd] = A;  // the general kernel's single-leaf route reads these
+            P.s_B[fd] = B;
+        }
+    }
+    L.lop = (op == CQG_OP_GT || op == CQG_OP_GE) ? 0 : (op == CQG_OP_LT || op == CQG_OP_LE) ? 1 : op == CQG_OP_EQ ? 2 : 3;
+    P.s_slot = slot;
+    P.s_op = op;
+    return true;
+}
+
 // DevPlan::simple — see cqg_plan.cuh. Called before fused refs are rewritten to slots.
-static void plan_simple_route(DevPlan& P) {
+// `pool`: host copy of the predicate's string pool (DConst::bits are offsets into it).
+static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
     P.simple = 0;
+    P.s_single = 0;
+    P.l_nleaf = P.l_nprog = 0;
     if (P.join || P.mode != SCAN_AGG || P.exact_only || P.nwantL > 4 || P.naggs > 4 || P.ngc > 4) return;
     if (P.ngc == 0 && !P.scalar_regs) return;
     for (int a = 0; a < P.naggs; a++)
@@ -561,51 +620,54 @@ static void plan_simple_route(DevPlan& P) {
     P.s_has_pred = 0;
     if (P.pred_kind == 2) return;
     if (P.pred_kind == 1) {
-        if (P.n_fcode != 1 || P.fcode_inl[0].op != F_CMP) return;
-        FInsn in = P.fcode_inl[0];
-        int op = in.n;
-        int col_ref = in.a, const_ref = in.b;
-        if ((col_ref & kRefConst) && col_ref != kRefNull) {  // literal on the left: mirror the operator
-            std::swap(col_ref, const_ref);
-            op = op == CQG_OP_GT ? CQG_OP_LT : op == CQG_OP_LT ? CQG_OP_GT : op == CQG_OP_GE ? CQG_OP_LE
-               : op == CQG_OP_LE ? CQG_OP_GE : op;
-        }
-        if (col_ref == kRefNull || (col_ref & kRefConst) || !(const_ref & kRefConst) || const_ref == kRefNull) return;
-        int slot = (col_ref >= 0 && col_ref < kMaxQueryCols) ? P.colslot[col_ref] : -1;
-        if (slot < 0 || slot >= P.nwantL) return;
-        const DConst& c = P.consts_inl[const_ref & 0x1fff];
-        long long cm;
-        int cfd;
-        if (c.type == CQG_TYPE_INTEGER) {
-            if (c.bits < 0 || c.bits > 1000000000ll) return;
-            cm = c.bits;
-            cfd = 0;
-        } else if (c.type == CQG_TYPE_DOUBLE) {
-            double d;
-            memcpy(&d, &c.bits, 8);
-            if (!exact_decimal(d, cm, cfd) || cm > 1000000000ll) return;
-        } else {
-            return;
-        }
-        for (int fd = 0; fd < 4; fd++) {
-            int K = std::max(fd, cfd);
-            long long A = 1, B = cm;
-            for (int i = 0; i < K - fd; i++) A *= 10;
-            for (int i = 0; i < K - cfd; i++) B *= 10;
-            P.s_A[fd] = A;
-            P.s_B[fd] = B;
+        for (int k = 0; k < P.n_fcode; k++) {
+            const FInsn& in = P.fcode_inl[k];
+            if (P.l_nprog >= 16) return;
+            if (in.op == F_AND) P.l_prog[P.l_nprog++] = -1;
+            else if (in.op == F_OR) P.l_prog[P.l_nprog++] = -2;
+            else if (in.op == F_NOT) P.l_prog[P.l_nprog++] = -3;
+            else if (in.op == F_CMP) {
+                if (P.l_nleaf >= kMaxLeanLeaf) return;
+                LeanLeaf& L = P.l_leaf[P.l_nleaf];
+                if (!make_lean_leaf(P, in, L)) {
+                    // text equality: pack the literal like a key part
+                    int op = in.n, col_ref = in.a, const_ref = in.b;
+                    if ((col_ref & kRefConst) && col_ref != kRefNull) std::swap(col_ref, const_ref);
+                    if (col_ref == kRefNull || (col_ref & kRefConst) || !(const_ref & kRefConst) || const_ref == kRefNull) return;
+                    int slot = (col_ref >= 0 && col_ref < kMaxQueryCols) ? P.colslot[col_ref] : -1;
+                    const DConst& c = P.consts_inl[const_ref & 0x1fff];
+                    if (slot < 0 || slot >= P.nwantL || slot >= 4 || c.type != CQG_TYPE_STRING) return;
+                    if ((op != CQG_OP_EQ && op != CQG_OP_NE) || c.len < 1 || c.len > 16) return;
+                    if ((size_t)c.bits + c.len > pool.size()) return;
+                    const uint8_t* sp = pool.data() + c.bits;
+                    unsigned c0 = sp[0];
+                    // a literal that could be typed as a number/date is not a STRING const; blanks cannot
+                    // occur in a clean tile's field, so such a literal simply never matches there
+                    memset(&L, 0, sizeof L);
+                    L.slot = slot;
+                    L.kind = op == CQG_OP_EQ ? 1 : 2;
+                    L.slen = (int32_t)c.len;
+                    for (uint32_t i = 0; i < c.len; i++) {
+                        if (i < 8) L.w0 |= (uint64_t)sp[i] << (8 * i);
+                        else L.w1 |= (uint64_t)sp[i] << (8 * (i - 8));
+                    }
+                    (void)c0;
+                }
+                P.l_prog[P.l_nprog++] = (int8_t)P.l_nleaf;
+                P.l_nleaf++;
+            } else {
+                return;  // IN, LIKE, TRUE/FALSE: general kernel
+            }
         }
         P.s_has_pred = 1;
-        P.s_slot = slot;
-        P.s_op = op;
-        // integers on both sides: a >= b  <=>  a > b - 1
-        P.s_lop = (op == CQG_OP_GT || op == CQG_OP_GE) ? 0 : (op == CQG_OP_LT || op == CQG_OP_LE) ? 1 : op == CQG_OP_EQ ? 2 : 3;
-        for (int fd = 0; fd < 4; fd++) P.s_LB[fd] = P.s_B[fd] + (op == CQG_OP_GE ? -1 : op == CQG_OP_LE ? 1 : 0);
+        P.s_single = P.l_nleaf == 1 && P.l_nprog == 1 && P.l_leaf[0].kind == 0;
+    } else {
+        P.s_single = 1;
     }
     P.simple = P.ngc == 0 ? 1 : 2;  // 2: lean GROUP BY (per-CTA dictionary, up to 64 groups per CTA)
 }
 
-static int number_slots(DevPlan& P) {
+static int number_slots(DevPlan& P, const std::vector<uint8_t>& pool) {
     P.nwantL = P.nwantR = 0;
     for (int c = 0; c < P.n_left_cols && c < kMaxQueryCols; c++)
         if (P.colslot[c] == -2) {
@@ -629,7 +691,7 @@ static int number_slots(DevPlan& P) {
         int sl = slot_of(ref);
         return (int16_t)(sl < 0 ? kRefNull : (kRefSlot | sl));
     };
-    plan_simple_route(P);
+    plan_simple_route(P, pool);
     if (P.pred_kind == 1) {
         for (int k = 0; k < P.n_fcode; k++) {
             FInsn& in = P.fcode_inl[k];
@@ -652,7 +714,8 @@ static int compile_predicate(HostPlan& hp, const cqg_predicate_t& w, cudaStream_
     if (!w.code || w.n_code <= 0) return CQG_OK;
     // constants + string pool
     std::vector<DConst> consts((size_t)std::max(w.n_consts, 1));
-    std::vector<uint8_t> pool(8, 0);
+    std::vector<uint8_t>& pool = hp.pool;
+    pool.assign(8, 0);
     for (int i = 0; i < w.n_consts; i++) {
         const cqg_value_t& c = w.consts[i];
         DConst d{};
@@ -890,7 +953,7 @@ static int build_plan(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, cu
         CU(cudaMemcpyAsync(hp.d_entry_init.p, hp.entry_init.data(), hp.entry_init.size(), cudaMemcpyHostToDevice, st));
         P.entry_init = hp.d_entry_init.as<uint8_t>();
     }
-    if ((rc = number_slots(P))) return rc;
+    if ((rc = number_slots(P, hp.pool))) return rc;
     P.need_right_fields = P.nwantR > 0;
     CU(hp.d_scalars.alloc(sizeof(ScalarBlock), st));
     CU(cudaMemsetAsync(hp.d_scalars.p, 0, sizeof(ScalarBlock), st));

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
     const int nwant = P.nwantL;
     const int gap0 = P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
-    const int has_pred = P.s_has_pred, pslot = P.s_slot, pop = P.s_lop;
+    const int nprog = P.l_nprog;
     const int ngc = GROUPED ? P.ngc : 0;
     uint32_t summask = 0;  // aggregates that sum a column
     int aslot[4];
@@ -368,19 +368,60 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
 #define CQG_LEAN_SLOT(SL, O, L)                                                  \
     const uint32_t O = SL == 0 ? off0 : SL == 1 ? off1 : SL == 2 ? off2 : off3; \
     const uint32_t L = SL == 0 ? len0 : SL == 1 ? len1 : SL == 2 ? len2 : len3;
-                    // ---- WHERE on a short decimal ----
-                    if (ok && has_pred) {
-                        CQG_LEAN_SLOT(pslot, o, l)
-                        uint32_t mant, fd;
-                        bool hd;
-                        if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd, hd)) {
-                            const long long lhs = (long long)((unsigned long long)mant * (unsigned long long)(uint32_t)P.s_A[fd]);
-                            const long long rhs = P.s_LB[fd];
-                            // s_lop was normalised by the host: 0 lhs > rhs, 1 lhs < rhs, 2 ==, 3 !=
-                            pass = pop == 0 ? lhs > rhs : pop == 1 ? lhs < rhs : pop == 2 ? lhs == rhs : lhs != rhs;
-                        } else {
-                            ok = false;  // NULL, text, date, signed or long number: general kernel
+                    // ---- WHERE: leaves on short decimals and short texts, combined on a bit stack ----
+                    if (ok && nprog) {
+                        uint32_t bs = 0;
+                        for (int pc = 0; pc < nprog; pc++) {
+                            const int c = P.l_prog[pc];
+                            if (c >= 0) {
+                                const int sl = P.l_leaf[c].slot, kind = P.l_leaf[c].kind;
+                                CQG_LEAN_SLOT(sl, o, l)
+                                bool bv = false;
+                                if (kind == 0) {
+                                    uint32_t mant, fd;
+                                    bool hd;
+                                    if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd, hd)) {
+                                        const long long lhs = (long long)((unsigned long long)mant * (unsigned long long)P.l_leaf[c].A[fd]);
+                                        const long long rhs = P.l_leaf[c].LB[fd];
+                                        const int lop = P.l_leaf[c].lop;
+                                        bv = lop == 0 ? lhs > rhs : lop == 1 ? lhs < rhs : lop == 2 ? lhs == rhs : lhs != rhs;
+                                    } else {
+                                        ok = false;  // NULL, text, date, signed or long number: general kernel
+                                    }
+                                } else {
+                                    // text equality: value_compare is strcmp for two strings, "less" for a NULL field,
+                                    // and 0 ("equal") for a number or date against text - those rows are handed over
+                                    uint32_t tag;
+                                    uint64_t w0, w1;
+                                    if (l == 0u) {
+                                        bv = kind == 2;
+                                    } else if (l > 16u) {
+                                        const uint32_t c0 = lds8(s_buf + o);
+                                        const bool ns = (c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.';
+                                        if (ns) ok = false;
+                                        bv = kind == 2;  // longer than the literal: different
+                                    } else if (lean_key_part(s_buf + o, l, tag, w0, w1) && (tag == KT_STR || tag == KT_NULL)) {
+                                        // (the text NULL packs as KT_NULL with zero words: compare its bytes directly)
+                                        if (tag == KT_NULL) {
+                                            w0 = 0x4c4c554eull;
+                                            w1 = 0;
+                                        }
+                                        const bool eq = (uint32_t)P.l_leaf[c].slen == l && w0 == P.l_leaf[c].w0 && w1 == P.l_leaf[c].w1;
+                                        bv = kind == 1 ? eq : !eq;
+                                    } else {
+                                        ok = false;
+                                    }
+                                }
+                                bs = (bs << 1) | (bv ? 1u : 0u);
+                            } else if (c == -1) {
+                                bs = ((bs >> 1) & ~1u) | ((bs >> 1) & bs & 1u);
+                            } else if (c == -2) {
+                                bs = ((bs >> 1) & ~1u) | (((bs >> 1) | bs) & 1u);
+                            } else {
+                                bs ^= 1u;
+                            }
                         }
+                        pass = (bs & 1u) != 0u;
                     }
                     // ---- SUM / AVG operands ----
                     if (ok && pass && summask) {

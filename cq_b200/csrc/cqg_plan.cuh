@@ -58,6 +58,14 @@ struct FInsn {
 //   num_key/okey  = value as an ordered double image + the earliest row holding it (128-bit CAS)
 //   str           = table bit 63 | offset << 18 | len   (reference into the resident CSV bytes)
 // MIN keeps the smallest image (empty = ~0), MAX the largest (empty = 0); num_okey empty = ~0.
+constexpr int kMaxLeanLeaf = 6;
+struct LeanLeaf {
+    int32_t slot, kind, lop, slen;
+    uint32_t A[4];
+    long long LB[4];
+    uint64_t w0, w1;
+};
+
 struct AggSpec {
     int32_t func;
     int32_t col;
@@ -125,6 +133,15 @@ struct DevPlan {
     int32_t s_lop;    // lean kernel: 0 lhs > s_LB, 1 lhs < s_LB, 2 ==, 3 !=  (>= and <= folded into the bound)
     int32_t s_pad;
     long long s_LB[4];
+    // lean kernel WHERE: postfix program over up to kMaxLeanLeaf leaves. Leaf kinds:
+    //   0  column <op> decimal literal   (mant * A[fd] vs LB[fd]; lop 0 >, 1 <, 2 ==, 3 !=)
+    //   1  column =  'text'  /  2  column != 'text'   (text of 1..16 bytes, packed like a key part)
+    // prog[i] >= 0: push leaf i; -1 AND, -2 OR, -3 NOT.
+    int32_t l_nleaf, l_nprog;
+    LeanLeaf l_leaf[kMaxLeanLeaf];
+    int8_t l_prog[16];
+    int32_t s_single;  // the general kernel's own simple route handles no WHERE / one decimal leaf only
+    int32_t s_pad2;
     // work the lean kernel hands to the general one
     int32_t* def_tiles;                 // tiles with bytes the lean kernel does not classify (CR, quotes, blanks, file edges)
     unsigned long long* def_tile_count;

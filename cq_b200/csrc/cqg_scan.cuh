@@ -1257,7 +1257,7 @@ __global__ void __launch_bounds__(G::THREADS, 4) scan_kernel(const __grid_consta
             const uint32_t npass = nrows - pass_lo < (uint32_t)G::ROWCAP ? nrows - pass_lo : (uint32_t)G::ROWCAP;
             if (P.mode == SCAN_COUNT_ROWS) {
                 for (uint32_t r = tid; r < npass; r += G::THREADS) acc.rows++;
-            } else if (P.simple == 1 && !special) {
+            } else if (P.simple == 1 && P.s_single && !special) {
                 for (uint32_t r = tid; r < npass; r += G::THREADS) {
                     const uint32_t rs = rowpos[r];
                     acc.rows++;
