@@ -237,7 +237,8 @@ static int check_dialect(cqg_csv_config_t cfg) {
 }
 
 static int stage_to_device(cqg_table* t, const uint8_t* src, size_t size, bool pinned) {
-    CU(cudaMalloc((void**)&t->d_data, size + kDevPad));
+    // stream-ordered allocation from the device pool (kept warm: release threshold is unlimited)
+    CU(cudaMallocAsync((void**)&t->d_data, size + kDevPad, 0));
     t->owns_device = true;
     CU(cudaMemsetAsync(t->d_data + size, '\n', kDevPad, 0));
     if (pinned) {
@@ -366,7 +367,7 @@ CQG_API int cqg_table_set_global_offset(cqg_table_t* t, uint64_t offset) {
 
 CQG_API void cqg_table_close(cqg_table_t* t) {
     if (!t) return;
-    if (t->owns_device && t->d_data) cudaFree(t->d_data);
+    if (t->owns_device && t->d_data) cudaFreeAsync(t->d_data, 0);
     if (t->map) munmap(t->map, t->map_len);
     delete t;
 }

@@ -220,3 +220,53 @@ def test_unsupported_inputs_fail_loudly():
         else:
             with Table.from_bytes(data, lib=oracle()) as to:
                 pc.compare_results(r, to.execute(Plan(aggs=[(A.AGG_SUM, 1)])))
+
+
+@pytest.mark.parametrize("name", ["group_name", "group_gender_minmax", "group_name_surname", "scalar_aggs", "group_height",
+                                  "lean_group_two_keys", "count_age_gt_40"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_partial_aggregates_merge(big, name, world):
+    """The multi-GPU exchange on one device: every "rank" scans its byte-range shard into a partial
+    (cqg_execute_partial), the records are exported (all of them, or split by owner = hash % world as
+    an all-to-all would), merged into a fresh table (cqg_partial_merge) and finished. Must equal the
+    single scan of the whole file."""
+    import torch
+    data, tg, to = big
+    lib = gpu()
+    spec = pc.plans()[name]
+    plan = pc.build(spec)
+    want = to.execute(pc.build(spec))
+    parts = []
+    try:
+        for r in range(world):
+            tg.set_shard(r, world)
+            p = C.c_void_p()
+            assert lib.execute_partial(tg.handle, C.byref(plan.q), C.byref(p)) == 0, lib.last_error()
+            parts.append(p)
+        tg.set_shard(0, 1)
+        rec = lib.partial_record_size(parts[0])
+        merged = C.c_void_p()
+        assert lib.partial_new_like(parts[0], C.byref(merged)) == 0, lib.last_error()
+        for p in parts:
+            n = lib.partial_count(p)
+            counts = (C.c_int64 * world)()
+            assert lib.partial_owner_counts(p, world, counts) == 0
+            assert sum(counts) == n
+            for owner in range(world):  # owner-filtered export, as the all-to-all of many groups does
+                buf = torch.zeros(max(counts[owner], 1) * rec, dtype=torch.uint8, device="cuda")
+                got = C.c_int64()
+                assert lib.partial_export(p, owner, world, buf.data_ptr(), counts[owner], C.byref(got)) == 0, lib.last_error()
+                assert got.value == counts[owner]
+                assert lib.partial_merge(merged, buf.data_ptr(), got.value) == 0, lib.last_error()
+        res = C.POINTER(A.Result)()
+        assert lib.partial_finish(merged, tg.handle, C.byref(res)) == 0, lib.last_error()
+        from cq_b200.engine import decode_result
+        got = decode_result(res.contents, plan)
+        lib.result_free(res)
+        lib.partial_free(merged)
+        got["rows_scanned"] = sum(lib.partial_rows_scanned(p) for p in parts)
+        pc.compare_results(got, want)
+    finally:
+        tg.set_shard(0, 1)
+        for p in parts:
+            lib.partial_free(p)
