@@ -459,6 +459,22 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
     return launch_lean_geo<Geo<128, 16384, 1>, 8, false>(P, st);
 }
 
+// [4][10000] doubles: mant / 10^fd, correctly rounded (one IEEE division each), per device
+static const double* decimal_table(int dev) {
+    static double* tab[64];
+    if (!tab[dev & 63]) {
+        std::vector<double> h(4 * 10000);
+        const double p10[4] = {1.0, 10.0, 100.0, 1000.0};
+        for (int fd = 0; fd < 4; fd++)
+            for (int m = 0; m < 10000; m++) h[(size_t)fd * 10000 + m] = (double)m / p10[fd];
+        double* d = nullptr;
+        if (cudaMalloc((void**)&d, h.size() * 8) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        tab[dev & 63] = d;
+    }
+    return tab[dev & 63];
+}
+
 static int launch_scan(const DevPlan& P, int table_bytes, cudaStream_t st) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
@@ -614,10 +630,15 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
     P.simple = 0;
     P.s_single = 0;
     P.l_nleaf = P.l_nprog = 0;
-    if (P.join || P.mode != SCAN_AGG || P.exact_only || P.nwantL > 4 || P.naggs > 4 || P.ngc > 4) return;
-    if (P.ngc == 0 && !P.scalar_regs) return;
+    if (P.join || P.mode != SCAN_AGG || P.exact_only || P.nwantL > 4 || P.ngc > 4) return;
+    P.l_nagg = 0;
+    for (int a = 0; a < P.naggs; a++) {
+        if (P.aggs[a].off < 0) continue;  // COUNT(*), COUNT(col), unknown column: no state
+        if (P.aggs[a].slot < 0 || P.aggs[a].slot >= 4 || P.l_nagg >= 4) return;
+        P.l_agg[P.l_nagg++] = a;
+    }
     for (int a = 0; a < P.naggs; a++)
-        if (P.aggs[a].func == CQG_AGG_MIN || P.aggs[a].func == CQG_AGG_MAX) return;
+        if ((P.aggs[a].func == CQG_AGG_MIN || P.aggs[a].func == CQG_AGG_MAX) && P.ngc == 0) return;  // scalar MIN/MAX: general kernel
     P.s_has_pred = 0;
     if (P.pred_kind == 2) return;
     if (P.pred_kind == 1) {
@@ -661,9 +682,9 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
             }
         }
         P.s_has_pred = 1;
-        P.s_single = P.l_nleaf == 1 && P.l_nprog == 1 && P.l_leaf[0].kind == 0;
+        P.s_single = P.l_nleaf == 1 && P.l_nprog == 1 && P.l_leaf[0].kind == 0 && P.scalar_regs;
     } else {
-        P.s_single = 1;
+        P.s_single = P.scalar_regs;
     }
     P.simple = P.ngc == 0 ? 1 : 2;  // 2: lean GROUP BY (per-CTA dictionary, up to 64 groups per CTA)
 }
@@ -1424,59 +1445,98 @@ static int read_scalars(HostPlan& hp, ScalarBlock& hs, cudaStream_t st) {
 }
 
 // DevPlan::simple plans: the lean kernel, then the general kernel on whatever it handed over.
-// Returns 1 when the scan is complete, 0 when the caller must run the general scan instead.
+// GROUP BY first numbers groups per CTA (shared-memory dictionary, <= 64 groups per CTA); when a CTA
+// meets more, the lean kernel is rerun updating the global table directly. *done = 0: the caller must
+// run the general scan instead.
 static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBlock& hs, float* ms_out, cudaEvent_t e0,
                          cudaEvent_t e1, int* done) {
     DevPlan& P = hp.P;
     *done = 0;
     int rc;
-    if ((rc = alloc_group_table(hp, gt, P.ngc == 0 ? 16 : 1u << 14, st))) return rc;
     DevBuf d_tiles, d_rows;
     const uint64_t row_cap = (uint64_t)P.n_tiles * 8u + 1024u;
     CU(d_tiles.alloc((size_t)(P.n_tiles + 1) * 4, st));
     CU(d_rows.alloc(row_cap * 8, st));
     ScalarBlock* sb = hp.d_scalars.as<ScalarBlock>();
-    CU(cudaMemsetAsync(sb, 0, sizeof(ScalarBlock), st));
     P.def_tiles = d_tiles.as<int32_t>();
     P.def_rows = d_rows.as<uint64_t>();
     P.def_tile_count = &sb->def_tile_count;
     P.def_row_count = &sb->def_row_count;
     P.def_row_cap = row_cap;
     P.tile_list = nullptr;
-    cudaEventRecord(e0, st);
-    if ((rc = launch_lean(P, st))) return rc;
-    cudaEventRecord(e1, st);
-    if ((rc = read_scalars(hp, hs, st))) return rc;
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    *ms_out += ms;
+    P.lean_global = 0;
+    {
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        P.dec_table = decimal_table(dev);
+        if (!P.dec_table) return fail(CQG_ERR_CUDA, "decimal table allocation failed");
+    }
+    uint64_t cap = P.ngc == 0 ? 16 : (1u << 14);
+    for (int attempt = 0; attempt < 14; attempt++) {
+        if ((rc = alloc_group_table(hp, gt, cap, st))) return rc;
+        CU(cudaMemsetAsync(sb, 0, sizeof(ScalarBlock), st));
+        cudaEventRecord(e0, st);
+        if ((rc = launch_lean(P, st))) return rc;
+        cudaEventRecord(e1, st);
+        if ((rc = read_scalars(hp, hs, st))) return rc;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out += ms;
+        if ((hs.errflags & KERR_LEAN_GROUPS) && !P.lean_global) {
+            P.lean_global = 1;  // too many groups for per-CTA numbering
+            cap = initial_group_cap(P);
+            continue;
+        }
+        if (hs.errflags & KERR_TABLE_FULL) {
+            cap *= 4;
+            if (cap > (1ull << 32)) return fail(CQG_ERR_NOMEM, "group table beyond 2^32 entries");
+            continue;
+        }
+        break;
+    }
     if ((hs.errflags & (KERR_LEAN_ABORT | KERR_TABLE_FULL)) || hs.def_row_count > row_cap) {
         P.simple = 0;  // the data is not what the lean kernel is for
+        P.lean_global = 0;
         return CQG_OK;
     }
     if (hs.def_tile_count || hs.def_row_count) {
-        cudaEventRecord(e0, st);
-        if (hs.def_tile_count) {
-            DevPlan T = P;
-            T.tile_list = P.def_tiles;
-            T.first_tile = 0;
-            T.n_tiles = (int32_t)hs.def_tile_count;
-            if ((rc = launch_scan(T, hp.table_smem_bytes, st))) return rc;
+        for (int attempt = 0; attempt < 12; attempt++) {
+            cudaEventRecord(e0, st);
+            CU(cudaMemsetAsync(&sb->errflags, 0, 4, st));
+            if (hs.def_tile_count) {
+                DevPlan T = P;
+                T.tile_list = P.def_tiles;
+                T.first_tile = 0;
+                T.n_tiles = (int32_t)hs.def_tile_count;
+                if ((rc = launch_scan(T, hp.table_smem_bytes, st))) return rc;
+            }
+            if (hs.def_row_count) {
+                DevPlan R = P;
+                R.simple = 0;
+                R.scalar_regs = 0;
+                R.smem_cap = 0;
+                int grid = (int)std::min<uint64_t>((hs.def_row_count + 127) / 128, 148 * 8);
+                deferred_rows_kernel<<<grid, 128, 0, st>>>(R, P.def_rows, hs.def_row_count);
+                g_launches++;
+                CU(cudaGetLastError());
+            }
+            cudaEventRecord(e1, st);
+            ScalarBlock h2{};
+            if ((rc = read_scalars(hp, h2, st))) return rc;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            *ms_out += ms;
+            hs.errflags |= h2.errflags & ~KERR_TABLE_FULL;
+            hs.rows_scanned = h2.rows_scanned;
+            hs.gcount = h2.gcount;
+            if (h2.errflags & KERR_TABLE_FULL) {
+                // the handed-over part overflowed the table the lean pass sized: start over on the general kernel
+                P.simple = 0;
+                P.lean_global = 0;
+                return CQG_OK;
+            }
+            break;
         }
-        if (hs.def_row_count) {
-            DevPlan R = P;
-            R.simple = 0;
-            R.scalar_regs = 0;
-            R.smem_cap = 0;
-            int grid = (int)std::min<uint64_t>((hs.def_row_count + 127) / 128, 148 * 8);
-            deferred_rows_kernel<<<grid, 128, 0, st>>>(R, P.def_rows, hs.def_row_count);
-            g_launches++;
-            CU(cudaGetLastError());
-        }
-        cudaEventRecord(e1, st);
-        if ((rc = read_scalars(hp, hs, st))) return rc;
-        cudaEventElapsedTime(&ms, e0, e1);
-        *ms_out += ms;
     }
     *done = 1;
     return CQG_OK;

@@ -144,8 +144,9 @@ __device__ __forceinline__ bool lean_key_part(uint32_t fa, uint32_t len, uint32_
 constexpr int kLeanGroups = 64;     // groups a CTA can number; one more aborts to the general kernel
 constexpr int kLeanDictCap = 128;   // slots
 constexpr int kLeanDictEntry = 96;  // hash 8 | gid 4 | tags 4 | first okey 8 | pad 8 | 4 x key part 16
-// per-warp accumulators (only that warp writes them): count u32 [G] | 4 x ( s3 lo u32 [G] | s3 hi u32 [G] | sn u32 [G] )
-constexpr int kLeanWarpAcc = kLeanGroups * 4 + 4 * (kLeanGroups * 8 + kLeanGroups * 4);
+// per-warp accumulators (only that warp writes them): count u32 [G] | 4 aggregate blocks
+constexpr int kLeanAggBlock = kLeanGroups * 32;  // SUM/AVG: lo[G] hi[G] n[G] (u32) ; MIN/MAX: G x { fn u64, pad, key u64, okey u64 }
+constexpr int kLeanWarpAcc = kLeanGroups * 4 + 4 * kLeanAggBlock;
 
 template <class G, int MINB, bool GROUPED>
 __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_constant__ DevPlan P) {
@@ -171,6 +172,18 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
         for (int k = tid; k < words; k += G::THREADS) ((uint32_t*)dict)[k] = 0u;
         __syncthreads();
         for (int k = tid; k < kLeanDictCap; k += G::THREADS) *(uint64_t*)(dict + k * kLeanDictEntry + 16) = ~0ull;  // first okey
+        for (int a = 0; a < 4; a++) {
+            if (a < P.l_nagg && (P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX)) {
+                const uint64_t empty = P.aggs[P.l_agg[a]].func == CQG_AGG_MIN ? ~0ull : 0ull;
+                for (int k = tid; k < G::NWARPS * kLeanGroups; k += G::THREADS) {
+                    uint64_t* st = (uint64_t*)(dict + kLeanDictCap * kLeanDictEntry + 16 + (k / kLeanGroups) * kLeanWarpAcc +
+                                               kLeanGroups * 4 + a * kLeanAggBlock + 32 * (k % kLeanGroups));
+                    st[0] = ~0ull;
+                    st[2] = empty;
+                    st[3] = ~0ull;
+                }
+            }
+        }
     }
     __syncthreads();
 
@@ -190,14 +203,18 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     const int gap0 = P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
     const int nprog = P.l_nprog;
     const int ngc = GROUPED ? P.ngc : 0;
-    uint32_t summask = 0;  // aggregates that sum a column
+    const bool lean_global = GROUPED && P.lean_global != 0;
+    uint32_t summask = 0;  // aggregates that read a column: SUM/AVG, and (bits 4..7) those that are MIN/MAX, (8..11) MIN
     int aslot[4];
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         aslot[a] = 0;
-        if (a < P.naggs && P.aggs[a].off >= 0 && P.aggs[a].slot >= 0) {
+        if (a < P.l_nagg) {
+            const AggSpec sp = P.aggs[P.l_agg[a]];
             summask |= 1u << a;
-            aslot[a] = P.aggs[a].slot;
+            if (sp.func == CQG_AGG_MIN || sp.func == CQG_AGG_MAX) summask |= 16u << a;
+            if (sp.func == CQG_AGG_MIN) summask |= 256u << a;
+            aslot[a] = sp.slot;
         }
     }
 
@@ -299,6 +316,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                 if (!has) break;
                 bool ok = true, pass = true;
                 uint32_t gid = 0xffffffffu, addmask = 0, rs = 0;
+                uint8_t* gentry = nullptr;
                 unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
                 if (has) {
                     const uint32_t bi = __ffs(s) - 1u;
@@ -424,7 +442,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                         pass = (bs & 1u) != 0u;
                     }
                     // ---- SUM / AVG operands ----
-                    if (ok && pass && summask) {
+                    if (ok && pass && (summask & 15u)) {
 #define CQG_LEAN_AGG(A, ADD)                                                                             \
     if (summask & (1u << A)) {                                                                           \
         const int sl = aslot[A];                                                                         \
@@ -432,7 +450,13 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
         uint32_t mant, fd;                                                                               \
         bool hd;                                                                                         \
         if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd, hd)) {                                   \
-            ADD = (unsigned long long)mant * (fd == 0u ? 1000u : fd == 1u ? 100u : fd == 2u ? 10u : 1u); \
+            if (summask & (16u << A)) {                                                                  \
+                /* MIN/MAX: the key value_compare orders by = the double the reference parses */        \
+                const double dv = mant < 10000u ? P.dec_table[fd * 10000u + mant] : (double)mant / kPow10[fd]; \
+                ADD = num_key(dv);                                                                       \
+            } else {                                                                                     \
+                ADD = (unsigned long long)mant * (fd == 0u ? 1000u : fd == 1u ? 100u : fd == 2u ? 10u : 1u); \
+            }                                                                                            \
             addmask |= 1u << A;                                                                          \
         } else if (l != 0u) {                                                                            \
             ok = false; /* a value this kernel does not decode (NULL is simply not summed) */           \
@@ -464,7 +488,17 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                                 h = key_hash_step(h, tag, kw[2 * g], kw[2 * g + 1]);
                             }
                         }
-                        if (ok) {
+                        if (ok && lean_global) {
+                            // many groups: straight into the global table
+                            h = key_hash_final(h);
+                            gentry = table_find_insert(P.gtab, P.gcap, P.entry_bytes, ngc, h, tags, kw, P.gcount, P.gcap / 2);
+                            if (!gentry) {
+                                atomicOr(P.errflags, KERR_TABLE_FULL);
+                            } else {
+                                gid = 0;
+                                amin64((uint64_t*)(gentry + kOffFirst), (P.global_base + (uint64_t)(g0 + (long long)rs)) << 16);
+                            }
+                        } else if (ok) {
                             h = key_hash_final(h);
                             // find-or-insert in the CTA dictionary
                             uint32_t i = (uint32_t)(h >> 1) & (kLeanDictCap - 1);
@@ -504,8 +538,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                                 probes++;
                             }
                             if (gid >= (uint32_t)kLeanGroups) {
-                                // more groups than this kernel numbers: the general kernel takes the scan
-                                atomicOr(P.errflags, KERR_LEAN_ABORT);
+                                // more groups than a CTA numbers: rerun on the global table
+                                atomicOr(P.errflags, KERR_LEAN_ABORT | KERR_LEAN_GROUPS);
                                 gid = 0xffffffffu;
                             } else {
                                 const uint64_t okey = (P.global_base + (uint64_t)(g0 + (long long)rs)) << 16;
@@ -550,16 +584,41 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                 } else {
                     // ---- group step: this warp's own accumulators in shared memory, native 32-bit
                     // atomics only; a 64-bit sum is (lo, hi) with the carry added by the lane that wrapped lo ----
-                    if (take && gid != 0xffffffffu) {
+                    const uint64_t okey_row = (P.global_base + (uint64_t)(g0 + (long long)rs)) << 16;
+                    if (take && gentry) {
+                        atomicAdd((unsigned long long*)(gentry + kOffCount), 1ull);
+#define CQG_LEAN_GSUMG(A, ADD)                                                                         \
+    if ((addmask >> A) & 1u) {                                                                         \
+        if (summask & (16u << A)) {                                                                    \
+            uint64_t* st = (uint64_t*)(gentry + P.aggs[P.l_agg[A]].off);                                        \
+            amin64(&st[0], (okey_row << 2) | 1u);                                                      \
+            num_extreme(&st[2], ADD, okey_row, (summask & (256u << A)) != 0u);                         \
+        } else {                                                                                       \
+            atomicAdd((unsigned long long*)(gentry + P.aggs[P.l_agg[A]].off + 24), (unsigned long long)ADD);    \
+            atomicAdd((unsigned long long*)(gentry + P.aggs[P.l_agg[A]].off + 16), 1ull);                       \
+        }                                                                                              \
+    }
+                        CQG_LEAN_GSUMG(0, add0)
+                        CQG_LEAN_GSUMG(1, add1)
+                        CQG_LEAN_GSUMG(2, add2)
+                        CQG_LEAN_GSUMG(3, add3)
+#undef CQG_LEAN_GSUMG
+                    } else if (take && gid != 0xffffffffu) {
                         atomicAdd((unsigned int*)(wacc + 4 * gid), 1u);
 #define CQG_LEAN_GSUM(A, ADD)                                                                  \
     if ((addmask >> A) & 1u) {                                                                 \
-        uint8_t* b = wacc + kLeanGroups * 4 + A * (kLeanGroups * 12);                          \
-        const uint32_t vlo = (uint32_t)ADD, vhi = (uint32_t)(ADD >> 32);                       \
-        const uint32_t old = atomicAdd((unsigned int*)(b + 4 * gid), vlo);                     \
-        const uint32_t up = vhi + ((old + vlo) < old ? 1u : 0u);                               \
-        if (up) atomicAdd((unsigned int*)(b + kLeanGroups * 4 + 4 * gid), up);                 \
-        atomicAdd((unsigned int*)(b + kLeanGroups * 8 + 4 * gid), 1u);                         \
+        uint8_t* b = wacc + kLeanGroups * 4 + A * kLeanAggBlock;                               \
+        if (summask & (16u << A)) {                                                            \
+            uint64_t* st = (uint64_t*)(b + 32 * gid);                                          \
+            amin64(&st[0], (okey_row << 2) | 1u);                                              \
+            num_extreme(&st[2], ADD, okey_row, (summask & (256u << A)) != 0u);                 \
+        } else {                                                                               \
+            const uint32_t vlo = (uint32_t)ADD, vhi = (uint32_t)(ADD >> 32);                   \
+            const uint32_t old = atomicAdd((unsigned int*)(b + 4 * gid), vlo);                 \
+            const uint32_t up = vhi + ((old + vlo) < old ? 1u : 0u);                           \
+            if (up) atomicAdd((unsigned int*)(b + kLeanGroups * 4 + 4 * gid), up);             \
+            atomicAdd((unsigned int*)(b + kLeanGroups * 8 + 4 * gid), 1u);                     \
+        }                                                                                      \
     }
                         CQG_LEAN_GSUM(0, add0)
                         CQG_LEAN_GSUM(1, add1)
@@ -602,9 +661,9 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                 amin64((uint64_t*)(ge + kOffFirst), first << 16);
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
-                    if (a < P.naggs && P.aggs[a].off >= 0 && sn[a]) {
-                        atomicAdd((unsigned long long*)(ge + P.aggs[a].off + 16), (unsigned long long)sn[a]);
-                        atomicAdd((unsigned long long*)(ge + P.aggs[a].off + 24), (unsigned long long)s3[a]);
+                    if (a < P.l_nagg && sn[a]) {
+                        atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 16), (unsigned long long)sn[a]);
+                        atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 24), (unsigned long long)s3[a]);
                     }
                 }
             }
@@ -633,16 +692,26 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
             atomicAdd((unsigned long long*)(ge + kOffCount), c);
             amin64((uint64_t*)(ge + kOffFirst), *(const uint64_t*)(e + 16));
             for (int a = 0; a < 4; a++) {
-                if (a < P.naggs && P.aggs[a].off >= 0 && P.aggs[a].slot >= 0) {
+                if (a < P.l_nagg && (P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX)) {
+                    const bool is_min = P.aggs[P.l_agg[a]].func == CQG_AGG_MIN;
+                    uint64_t* gs = (uint64_t*)(ge + P.aggs[P.l_agg[a]].off);
+                    for (int w = 0; w < G::NWARPS; w++) {
+                        const uint64_t* st = (const uint64_t*)(dict + kLeanDictCap * kLeanDictEntry + 16 + w * kLeanWarpAcc +
+                                                               kLeanGroups * 4 + a * kLeanAggBlock + 32 * gid);
+                        if (st[0] == ~0ull) continue;
+                        amin64(&gs[0], st[0]);
+                        num_extreme(&gs[2], st[2], st[3], is_min);
+                    }
+                } else if (a < P.l_nagg) {
                     unsigned long long t3 = 0, tn = 0;
                     for (int w = 0; w < G::NWARPS; w++) {
-                        const uint8_t* b = dict + kLeanDictCap * kLeanDictEntry + 16 + w * kLeanWarpAcc + kLeanGroups * 4 + a * (kLeanGroups * 12);
+                        const uint8_t* b = dict + kLeanDictCap * kLeanDictEntry + 16 + w * kLeanWarpAcc + kLeanGroups * 4 + a * kLeanAggBlock;
                         t3 += ((unsigned long long)*(const uint32_t*)(b + kLeanGroups * 4 + 4 * gid) << 32) + *(const uint32_t*)(b + 4 * gid);
                         tn += *(const uint32_t*)(b + kLeanGroups * 8 + 4 * gid);
                     }
                     if (tn) {
-                        atomicAdd((unsigned long long*)(ge + P.aggs[a].off + 16), tn);
-                        atomicAdd((unsigned long long*)(ge + P.aggs[a].off + 24), t3);
+                        atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 16), tn);
+                        atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 24), t3);
                     }
                 }
             }

@@ -19,7 +19,8 @@ enum : unsigned {
     KERR_STR_LONG = 2048u,     // MIN/MAX string longer than the packed reference allows
     KERR_OFFSET_RANGE = 4096u, // file offset beyond 2^45
     KERR_ROW_LONG = 8192u,     // internal: row does not fit the tile window (handled, not an error)
-    KERR_LEAN_ABORT = 16384u   // internal: the lean kernel met too many rows it does not cover; rerun on the general kernel
+    KERR_LEAN_ABORT = 16384u,  // internal: the lean kernel met too many rows it does not cover; rerun on the general kernel
+    KERR_LEAN_GROUPS = 32768u  // internal: more groups than a CTA dictionary numbers; rerun the lean kernel on the global table
 };
 constexpr unsigned kFatalMask = KERR_NUMERIC_RANGE | KERR_SEP_OVERFLOW | KERR_KEY_RANGE | KERR_MINMAX_TIE | KERR_STACK |
                                 KERR_JOIN_MIXED | KERR_BIGINT | KERR_KEY_TAB | KERR_JOIN_FANOUT | KERR_STR_LONG |
@@ -141,7 +142,11 @@ struct DevPlan {
     LeanLeaf l_leaf[kMaxLeanLeaf];
     int8_t l_prog[16];
     int32_t s_single;  // the general kernel's own simple route handles no WHERE / one decimal leaf only
-    int32_t s_pad2;
+    int32_t lean_global;  // lean GROUP BY updates the global table directly (any number of groups)
+    int32_t l_nagg;       // aggregates with a state (SUM/AVG/MIN/MAX over a known column): at most 4 on the lean kernel
+    int32_t l_agg[4];     // their indices in aggs[]
+    int32_t l_pad;
+    const double* dec_table;  // [4][10000]: correctly rounded mant / 10^fd for mant < 10000 (lean MIN/MAX keys)
     // work the lean kernel hands to the general one
     int32_t* def_tiles;                 // tiles with bytes the lean kernel does not classify (CR, quotes, blanks, file edges)
     unsigned long long* def_tile_count;

@@ -67,6 +67,8 @@ def plans_uid():
     P = {}
     P["group_uid"] = dict(group_by=[UID], out_cols=[UID],
                           aggs=[(A.AGG_SUM, AGE), (A.AGG_MIN, HEIGHT), (A.AGG_MAX, HEIGHT), (A.AGG_AVG, HEIGHT)])
+    P["lean_group_uid_sum"] = dict(where=(">=", col(AGE), const(18)), group_by=[UID], out_cols=[UID],
+                                   aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE), (A.AGG_AVG, HEIGHT)])
     return P
 
 
