@@ -28,6 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "csv_scan_filter_groupby_throughput"
 UNIT = "GB/s"
 QUERY = "SELECT COUNT(*) FROM f WHERE age > 40"
+WORKLOAD = f"BASELINE configs[1]: 10 GB synthetic CSV (seeded restatement of utils/generate_big_dataset.py): {QUERY}"
 
 
 def parse_args():
@@ -165,7 +166,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"10 GB synthetic CSV (generate_big_dataset restatement, seed 1): {QUERY}",
+            "config": {"workload": WORKLOAD,
                        "sample_bytes": n, "note": "the reference's CPU path on host cores; bounded sample per step"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -359,7 +360,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"10 GB synthetic CSV (generate_big_dataset restatement, seed 1+rank): {QUERY}",
+            "config": {"workload": WORKLOAD,
                        "bytes_per_gpu": nbytes, "rows_per_gpu": int(last["rows_scanned"]), "total_bytes": total_bytes,
                        "l2": "no flush: the 10 GB input is far larger than the 126 MB L2",
                        "parallelism": f"byte-range shards x{world}" + (", NCCL all_gather of partial aggregates" if world > 1 else ""),

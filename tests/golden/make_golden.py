@@ -319,7 +319,8 @@ def make_queries():
     q(f"SELECT o.id, c.name {J} WHERE o.price > 60 AND c.year = 2023")
     q(f"SELECT COUNT(*), SUM(o.price), AVG(o.tax) {J} WHERE c.name LIKE 'C%'")
     q(f"SELECT o.id, c.email {J} LIMIT 3")
-    q("SELECT COUNT(*) FROM 'orders.csv' AS o JOIN 'customers.csv' AS c ON c.id = o.customer_id")
+    # (ON with the right table's column first indexes the other table's column position into the row:
+    #  out-of-bounds read in the reference, evaluator_joins.c:49-52 - kept out of the corpus)
     q("SELECT COUNT(*) FROM 'orders.csv' AS o JOIN 'customers.csv' AS c ON o.nosuch = c.id")
     q("SELECT COUNT(*) FROM 'orders.csv' JOIN 'customers.csv' ON customer_id = id")
     q("SELECT p.name, t.label FROM 'people.csv' AS p JOIN 'tags.csv' AS t ON p.role = t.code")
