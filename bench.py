@@ -183,6 +183,12 @@ def main():
         reference_arm(args)
         return
 
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner,
+    # torchrun notices) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -369,7 +375,8 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "extra": extra,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
