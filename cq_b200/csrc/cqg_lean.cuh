@@ -145,17 +145,31 @@ constexpr int kLeanGroups = 64;     // groups a CTA can number; one more aborts 
 constexpr int kLeanDictCap = 128;   // slots
 constexpr int kLeanDictEntry = 96;  // hash 8 | gid 4 | tags 4 | first okey 8 | pad 8 | 4 x key part 16
 // per-warp accumulators (only that warp writes them): count u32 [G] | 4 aggregate blocks
-constexpr int kLeanAggBlock = kLeanGroups * 32;  // SUM/AVG: lo[G] hi[G] n[G] (u32) ; MIN/MAX: G x { fn u64, pad, key u64, okey u64 }
-constexpr int kLeanWarpAcc = kLeanGroups * 4 + 4 * kLeanAggBlock;
+// aggregate block: SUM/AVG lo[G] hi[G] n[G] (u32); with MIN/MAX in the plan G x { fn u64, pad, key u64, okey u64 }
+__host__ __device__ constexpr int lean_agg_block(bool minmax) { return kLeanGroups * (minmax ? 32 : 12); }
+__host__ __device__ constexpr int lean_warp_acc(bool minmax) { return kLeanGroups * 4 + 4 * lean_agg_block(minmax); }
 
-template <class G, int MINB, bool GROUPED>
+// shared-memory layout of the lean kernel: tile ring, two masks, barriers, then the GROUP BY area
+template <class G>
+struct LeanLayout {
+    static constexpr int OFF_TM = G::STAGES * G::BUF;
+    static constexpr int OFF_DM = OFF_TM + G::MASKW * 4;
+    static constexpr int OFF_MBAR = OFF_DM + G::MASKW * 4;
+    static constexpr int OFF_TABLE = (OFF_MBAR + G::STAGES * 8 + 127) / 128 * 128;
+};
+
+// ONELEAF: the commonest shape, `COUNT(*) ... WHERE column <op> decimal literal` (one wanted field, no
+// aggregate state): the WHERE program loop, slot selects and operand bookkeeping compile away.
+template <class G, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX>
 __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t s_tm = sbase + G::OFF_TM, s_dm = sbase + G::OFF_DM;
-    uint64_t* mbar = (uint64_t*)(smem + G::OFF_MBAR);
+    using LL = LeanLayout<G>;
+    constexpr int kLeanAggBlock = lean_agg_block(MINMAX), kLeanWarpAcc = lean_warp_acc(MINMAX);
+    const uint32_t s_tm = sbase + LL::OFF_TM, s_dm = sbase + LL::OFF_DM;
+    uint64_t* mbar = (uint64_t*)(smem + LL::OFF_MBAR);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint8_t* dict = smem + G::OFF_TABLE;                              // GROUPED only
+    uint8_t* dict = smem + LL::OFF_TABLE;                              // GROUPED only
     uint8_t* wacc = dict + kLeanDictCap * kLeanDictEntry + 16 + warp * kLeanWarpAcc;
     unsigned int* ngroups = (unsigned int*)(dict + kLeanDictCap * kLeanDictEntry);
 
@@ -173,7 +187,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
         __syncthreads();
         for (int k = tid; k < kLeanDictCap; k += G::THREADS) *(uint64_t*)(dict + k * kLeanDictEntry + 16) = ~0ull;  // first okey
         for (int a = 0; a < 4; a++) {
-            if (a < P.l_nagg && (P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX)) {
+            if (MINMAX && a < P.l_nagg && (P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX)) {
                 const uint64_t empty = P.aggs[P.l_agg[a]].func == CQG_AGG_MIN ? ~0ull : 0ull;
                 for (int k = tid; k < G::NWARPS * kLeanGroups; k += G::THREADS) {
                     uint64_t* st = (uint64_t*)(dict + kLeanDictCap * kLeanDictEntry + 16 + (k / kLeanGroups) * kLeanWarpAcc +
@@ -202,6 +216,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     const int nwant = P.nwantL;
     const int gap0 = P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
     const int nprog = P.l_nprog;
+    const int leaf0_lop = P.l_leaf[0].lop;
     const int ngc = GROUPED ? P.ngc : 0;
     const bool lean_global = GROUPED && P.lean_global != 0;
     uint32_t summask = 0;  // aggregates that read a column: SUM/AVG, and (bits 4..7) those that are MIN/MAX, (8..11) MIN
@@ -387,7 +402,17 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     const uint32_t O = SL == 0 ? off0 : SL == 1 ? off1 : SL == 2 ? off2 : off3; \
     const uint32_t L = SL == 0 ? len0 : SL == 1 ? len1 : SL == 2 ? len2 : len3;
                     // ---- WHERE: leaves on short decimals and short texts, combined on a bit stack ----
-                    if (ok && nprog) {
+                    if (ONELEAF) {
+                        uint32_t mant, fd;
+                        bool hd;
+                        if (ok && len0 - 1u < 7u && lean_decimal(s_buf + off0, len0, mant, fd, hd)) {
+                            const long long lhs = (long long)((unsigned long long)mant * (unsigned long long)P.l_leaf[0].A[fd]);
+                            const long long rhs = P.l_leaf[0].LB[fd];
+                            pass = leaf0_lop == 0 ? lhs > rhs : leaf0_lop == 1 ? lhs < rhs : leaf0_lop == 2 ? lhs == rhs : lhs != rhs;
+                        } else {
+                            ok = false;
+                        }
+                    } else if (ok && nprog) {
                         uint32_t bs = 0;
                         for (int pc = 0; pc < nprog; pc++) {
                             const int c = P.l_prog[pc];
@@ -442,7 +467,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                         pass = (bs & 1u) != 0u;
                     }
                     // ---- SUM / AVG operands ----
-                    if (ok && pass && (summask & 15u)) {
+                    if (!ONELEAF && ok && pass && (summask & 15u)) {
 #define CQG_LEAN_AGG(A, ADD)                                                                             \
     if (summask & (1u << A)) {                                                                           \
         const int sl = aslot[A];                                                                         \
@@ -450,7 +475,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
         uint32_t mant, fd;                                                                               \
         bool hd;                                                                                         \
         if (l - 1u < 7u && lean_decimal(s_buf + o, l, mant, fd, hd)) {                                   \
-            if (summask & (16u << A)) {                                                                  \
+            if (MINMAX && (summask & (16u << A))) {                                                      \
                 /* MIN/MAX: the key value_compare orders by = the double the reference parses */        \
                 const double dv = mant < 10000u ? P.dec_table[fd * 10000u + mant] : (double)mant / kPow10[fd]; \
                 ADD = num_key(dv);                                                                       \
@@ -564,19 +589,19 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                         count++;
                         const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
                         if (gabs < first) first = gabs;
-                        if (addmask & 1u) {
+                        if (!ONELEAF && (addmask & 1u)) {
                             s3[0] += (long long)add0;
                             sn[0]++;
                         }
-                        if (addmask & 2u) {
+                        if (!ONELEAF && (addmask & 2u)) {
                             s3[1] += (long long)add1;
                             sn[1]++;
                         }
-                        if (addmask & 4u) {
+                        if (!ONELEAF && (addmask & 4u)) {
                             s3[2] += (long long)add2;
                             sn[2]++;
                         }
-                        if (addmask & 8u) {
+                        if (!ONELEAF && (addmask & 8u)) {
                             s3[3] += (long long)add3;
                             sn[3]++;
                         }
@@ -589,7 +614,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                         atomicAdd((unsigned long long*)(gentry + kOffCount), 1ull);
 #define CQG_LEAN_GSUMG(A, ADD)                                                                         \
     if ((addmask >> A) & 1u) {                                                                         \
-        if (summask & (16u << A)) {                                                                    \
+        if (MINMAX && (summask & (16u << A))) {                                                        \
             uint64_t* st = (uint64_t*)(gentry + P.aggs[P.l_agg[A]].off);                                        \
             amin64(&st[0], (okey_row << 2) | 1u);                                                      \
             num_extreme(&st[2], ADD, okey_row, (summask & (256u << A)) != 0u);                         \
@@ -608,7 +633,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
 #define CQG_LEAN_GSUM(A, ADD)                                                                  \
     if ((addmask >> A) & 1u) {                                                                 \
         uint8_t* b = wacc + kLeanGroups * 4 + A * kLeanAggBlock;                               \
-        if (summask & (16u << A)) {                                                            \
+        if (MINMAX && (summask & (16u << A))) {                                                \
             uint64_t* st = (uint64_t*)(b + 32 * gid);                                          \
             amin64(&st[0], (okey_row << 2) | 1u);                                              \
             num_extreme(&st[2], ADD, okey_row, (summask & (256u << A)) != 0u);                 \
@@ -692,7 +717,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
             atomicAdd((unsigned long long*)(ge + kOffCount), c);
             amin64((uint64_t*)(ge + kOffFirst), *(const uint64_t*)(e + 16));
             for (int a = 0; a < 4; a++) {
-                if (a < P.l_nagg && (P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX)) {
+                if (MINMAX && a < P.l_nagg && (P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX)) {
                     const bool is_min = P.aggs[P.l_agg[a]].func == CQG_AGG_MIN;
                     uint64_t* gs = (uint64_t*)(ge + P.aggs[P.l_agg[a]].off);
                     for (int w = 0; w < G::NWARPS; w++) {
