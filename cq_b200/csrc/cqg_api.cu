@@ -421,7 +421,7 @@ static int launch_scan_nw(const DevPlan& P, int smem, int dev, cudaStream_t st) 
     return CQG_OK;
 }
 
-template <class LG, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX>
+template <class LG, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX, bool GLOBAL>
 static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
@@ -432,10 +432,10 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
         P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
     }
     if (P.n_tiles <= 0) return CQG_OK;
-    const int smem = LeanLayout<LG>::OFF_TABLE + (GROUPED ? kLeanDictCap * kLeanDictEntry + 16 + LG::NWARPS * lean_warp_acc(MINMAX) : 0);
+    const int smem = LeanLayout<LG>::OFF_TABLE + ((GROUPED && !GLOBAL) ? kLeanDictCap * kLeanDictEntry + 16 + LG::NWARPS * lean_warp_acc(MINMAX) : 0);
     static bool attr_set[64];
     if (!attr_set[dev & 63]) {
-        CU(cudaFuncSetAttribute(lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev & 63] = true;
     }
     LaunchCfg& c = g_cfg[dev & 63];
@@ -444,10 +444,10 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
         c.ready = true;
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX>, LG::THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL>, LG::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean kernel does not fit");
     int grid = std::min(P.n_tiles, c.sms * per_sm);
-    lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX><<<grid, LG::THREADS, smem, st>>>(P);
+    lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
     CU(cudaGetLastError());
     return CQG_OK;
@@ -458,13 +458,17 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
     if (P.simple == 2) {
         bool mm = false;
         for (int a = 0; a < P.l_nagg; a++) mm = mm || P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX;
-        if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 4, true, false, true>(P, st);
-        return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false>(P, st);
+        if (P.lean_global) {
+            if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, true, true>(P, st);
+            return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false, true>(P, st);
+        }
+        if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 4, true, false, true, false>(P, st);
+        return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false, false>(P, st);
     }
     const bool oneleaf = P.l_nprog == 1 && P.l_nleaf == 1 && P.l_leaf[0].kind == 0 && P.l_leaf[0].slot == 0 && P.l_nagg == 0 &&
                          P.nwantL == 1;
-    if (oneleaf) return launch_lean_geo<Geo<128, 16384, 1>, 9, false, true, false>(P, st);
-    return launch_lean_geo<Geo<128, 16384, 1>, 8, false, false, false>(P, st);
+    if (oneleaf) return launch_lean_geo<Geo<128, 16384, 1>, 9, false, true, false, false>(P, st);
+    return launch_lean_geo<Geo<128, 16384, 1>, 8, false, false, false, false>(P, st);
 }
 
 // [4][10000] doubles: mant / 10^fd, correctly rounded (one IEEE division each), per device

@@ -140,6 +140,57 @@ __device__ __forceinline__ bool lean_key_part(uint32_t fa, uint32_t len, uint32_
     return true;
 }
 
+// find-or-insert in the global table for the lean GROUP BY (<= 4 key parts). The steady state is a
+// lookup: one acquire load of the slot's hash word, then tags and key parts as independent 16-byte
+// loads (no dependent chain), compared without short-circuit.
+__device__ __forceinline__ uint64_t ld_acquire_u64(const void* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint8_t* lean_global_find(const DevPlan& P, int ngc, uint64_t h, uint32_t tags, const uint64_t* kw) {
+    const uint64_t mask = P.gcap - 1;
+    uint64_t i = (h >> 1) & mask;
+    for (uint64_t probes = 0; probes < P.gcap;) {
+        uint8_t* e = P.gtab + i * (uint64_t)P.entry_bytes;
+        unsigned long long cur = ld_acquire_u64(e);
+        if (cur == 0ull) {
+            if (*(volatile unsigned long long*)P.gcount >= P.gcap / 2) return nullptr;
+            cur = atomicCAS((unsigned long long*)e, 0ull, (unsigned long long)(h | kLockBit));
+            if (cur == 0ull) {
+                atomicAdd(P.gcount, 1ull);
+                *(uint32_t*)(e + kOffTags) = tags;
+                for (int g = 0; g < ngc; g++) {
+                    *(uint64_t*)(e + kOffKeys + 16 * g) = kw[2 * g];
+                    *(uint64_t*)(e + kOffKeys + 16 * g + 8) = kw[2 * g + 1];
+                }
+                __threadfence();
+                atomicExch((unsigned long long*)e, (unsigned long long)h);
+                return e;
+            }
+        }
+        if ((cur & ~kLockBit) == h) {
+            if (cur & kLockBit) continue;  // being initialised by another thread: look again
+            const uint32_t t = __ldcg((const uint32_t*)(e + kOffTags));
+            const uint4 k0 = __ldcg((const uint4*)(e + kOffKeys));
+            const uint4 k1 = ngc > 1 ? __ldcg((const uint4*)(e + kOffKeys + 16)) : make_uint4(0, 0, 0, 0);
+            const uint4 k2 = ngc > 2 ? __ldcg((const uint4*)(e + kOffKeys + 32)) : make_uint4(0, 0, 0, 0);
+            const uint4 k3 = ngc > 3 ? __ldcg((const uint4*)(e + kOffKeys + 48)) : make_uint4(0, 0, 0, 0);
+            auto lo = [](const uint4& k) { return ((uint64_t)k.y << 32) | k.x; };
+            auto hi = [](const uint4& k) { return ((uint64_t)k.w << 32) | k.z; };
+            bool same = t == tags;
+            same &= lo(k0) == kw[0] & hi(k0) == kw[1];
+            if (ngc > 1) same &= lo(k1) == kw[2] & hi(k1) == kw[3];
+            if (ngc > 2) same &= lo(k2) == kw[4] & hi(k2) == kw[5];
+            if (ngc > 3) same &= lo(k3) == kw[6] & hi(k3) == kw[7];
+            if (same) return e;
+        }
+        i = (i + 1) & mask;
+        probes++;
+    }
+    return nullptr;
+}
+
 // per-CTA dictionary of the lean GROUP BY: key -> small group number
 constexpr int kLeanGroups = 64;     // groups a CTA can number; one more aborts to the general kernel
 constexpr int kLeanDictCap = 128;   // slots
@@ -160,7 +211,7 @@ struct LeanLayout {
 
 // ONELEAF: the commonest shape, `COUNT(*) ... WHERE column <op> decimal literal` (one wanted field, no
 // aggregate state): the WHERE program loop, slot selects and operand bookkeeping compile away.
-template <class G, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX>
+template <class G, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX, bool GLOBAL>
 __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -181,7 +232,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
         sts32(s_tm + 4 * w, 0xffffffffu);
         sts32(s_dm + 4 * w, 0u);
     }
-    if (GROUPED) {
+    if (GROUPED && !GLOBAL) {
         const int words = (kLeanDictCap * kLeanDictEntry + 16 + G::NWARPS * kLeanWarpAcc) / 4;
         for (int k = tid; k < words; k += G::THREADS) ((uint32_t*)dict)[k] = 0u;
         __syncthreads();
@@ -218,7 +269,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     const int nprog = P.l_nprog;
     const int leaf0_lop = P.l_leaf[0].lop;
     const int ngc = GROUPED ? P.ngc : 0;
-    const bool lean_global = GROUPED && P.lean_global != 0;
+    constexpr bool lean_global = GROUPED && GLOBAL;
     uint32_t summask = 0;  // aggregates that read a column: SUM/AVG, and (bits 4..7) those that are MIN/MAX, (8..11) MIN
     int aslot[4];
 #pragma unroll
@@ -516,7 +567,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                         if (ok && lean_global) {
                             // many groups: straight into the global table
                             h = key_hash_final(h);
-                            gentry = table_find_insert(P.gtab, P.gcap, P.entry_bytes, ngc, h, tags, kw, P.gcount, P.gcap / 2);
+                            gentry = lean_global_find(P, ngc, h, tags, kw);
                             if (!gentry) {
                                 atomicOr(P.errflags, KERR_TABLE_FULL);
                             } else {
@@ -694,7 +745,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
             }
             if (err) atomicOr(P.errflags, err);
         }
-    } else {
+    } else if (!GLOBAL) {
         // every dictionary entry: add up the warps' accumulators and fold them into the global table
         __syncthreads();
         unsigned err = 0;
