@@ -200,6 +200,16 @@ constexpr int kLeanDictEntry = 96;  // hash 8 | gid 4 | tags 4 | first okey 8 | 
 __host__ __device__ constexpr int lean_agg_block(bool minmax) { return kLeanGroups * (minmax ? 32 : 12); }
 __host__ __device__ constexpr int lean_warp_acc(bool minmax) { return kLeanGroups * 4 + 4 * lean_agg_block(minmax); }
 
+// four flag words -> 16-bit mask in byte order: the multiplies leave the nibbles at bits 0..3 / 4..7 of the
+// high word with garbage only above bit 7, so one select merges two of them and one byte-permute the halves
+__device__ __forceinline__ uint32_t flags_to_mask16b(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    const uint32_t h0 = __umulhi(f0, 0x02040810u), h1 = __umulhi(f1, 0x20408100u);
+    const uint32_t h2 = __umulhi(f2, 0x02040810u), h3 = __umulhi(f3, 0x20408100u);
+    const uint32_t lo = (h0 & 0x0fu) | (h1 & ~0x0fu);  // byte 0 valid
+    const uint32_t hi = (h2 & 0x0fu) | (h3 & ~0x0fu);
+    return __byte_perm(lo, hi, 0x7740);  // byte0(lo), byte0(hi), zero... selector 7 = byte 3 of hi: cleared below
+}
+
 // shared-memory layout of the lean kernel: tile ring, two masks, barriers, then the GROUP BY area
 template <class G>
 struct LeanLayout {
@@ -264,6 +274,9 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     // plan constants the row loop uses, once
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
+    uint32_t patN, patDv;  // opaque to the compiler: stay in vector registers
+    asm volatile("mov.u32 %0, 0x0a0a0a0a;" : "=r"(patN));
+    asm volatile("mov.u32 %0, %1;" : "=r"(patDv) : "r"(patD));
     const int nwant = P.nwantL;
     const int gap0 = P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
     const int nprog = P.l_nprog;
@@ -316,20 +329,22 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
 #pragma unroll 2
             for (int c = tid; c < G::CHUNKS; c += G::THREADS) {
                 const uint4 v = lds128(s_buf + 16 * c);
-                const uint32_t v0 = v.x & 0x7f7f7f7fu, v1 = v.y & 0x7f7f7f7fu, v2 = v.z & 0x7f7f7f7fu, v3 = v.w & 0x7f7f7f7fu;
-                const uint32_t f0 = ~(((v0 ^ 0x0a0a0a0au) + 0x7f7f7f7fu) | v.x) & 0x80808080u;
-                const uint32_t f1 = ~(((v1 ^ 0x0a0a0a0au) + 0x7f7f7f7fu) | v.y) & 0x80808080u;
-                const uint32_t f2 = ~(((v2 ^ 0x0a0a0a0au) + 0x7f7f7f7fu) | v.z) & 0x80808080u;
-                const uint32_t f3 = ~(((v3 ^ 0x0a0a0a0au) + 0x7f7f7f7fu) | v.w) & 0x80808080u;
-                const uint32_t d0 = ~(((v0 ^ patD) + 0x7f7f7f7fu) | v.x) & 0x80808080u;
-                const uint32_t d1 = ~(((v1 ^ patD) + 0x7f7f7f7fu) | v.y) & 0x80808080u;
-                const uint32_t d2 = ~(((v2 ^ patD) + 0x7f7f7f7fu) | v.z) & 0x80808080u;
-                const uint32_t d3 = ~(((v3 ^ patD) + 0x7f7f7f7fu) | v.w) & 0x80808080u;
+                // 0x80 where the byte equals the pattern: ((v ^ pat) & 0x7f..) + 0x7f.. has bit 7 set iff the low 7
+                // bits differ; OR v brings in bit 7 of the byte itself. Patterns sit in registers so that the first
+                // step is ONE lop3 with the 0x7f.. immediate.
+                const uint32_t f0 = ~(((v.x ^ patN) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.x) & 0x80808080u;
+                const uint32_t f1 = ~(((v.y ^ patN) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.y) & 0x80808080u;
+                const uint32_t f2 = ~(((v.z ^ patN) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.z) & 0x80808080u;
+                const uint32_t f3 = ~(((v.w ^ patN) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.w) & 0x80808080u;
+                const uint32_t d0 = ~(((v.x ^ patDv) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.x) & 0x80808080u;
+                const uint32_t d1 = ~(((v.y ^ patDv) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.y) & 0x80808080u;
+                const uint32_t d2 = ~(((v.z ^ patDv) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.z) & 0x80808080u;
+                const uint32_t d3 = ~(((v.w ^ patDv) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.w) & 0x80808080u;
                 const uint32_t x0 = v.x | f0, x1 = v.y | f1, x2 = v.z | f2, x3 = v.w | f3;
                 spec |= ((x0 - 0x23232323u) & ~x0) | ((x1 - 0x23232323u) & ~x1) | ((x2 - 0x23232323u) & ~x2) |
                         ((x3 - 0x23232323u) & ~x3);
-                sts16(s_tm + 2 * c, flags_to_mask16(f0, f1, f2, f3));
-                sts16(s_dm + 2 * c, flags_to_mask16(d0, d1, d2, d3));
+                sts16(s_tm + 2 * c, flags_to_mask16b(f0, f1, f2, f3));
+                sts16(s_dm + 2 * c, flags_to_mask16b(d0, d1, d2, d3));
             }
             spec &= 0x80808080u;
         }
