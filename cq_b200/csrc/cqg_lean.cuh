@@ -200,6 +200,14 @@ constexpr int kLeanDictEntry = 96;  // hash 8 | gid 4 | tags 4 | first okey 8 | 
 __host__ __device__ constexpr int lean_agg_block(bool minmax) { return kLeanGroups * (minmax ? 32 : 12); }
 __host__ __device__ constexpr int lean_warp_acc(bool minmax) { return kLeanGroups * 4 + 4 * lean_agg_block(minmax); }
 
+// a + c issued as IMAD (a * 1 + c) so that it runs on the FMA pipe: LOP3/IADD3/SHF all share the ALU pipe,
+// which takes one warp instruction every two cycles; phase 1 is otherwise all-ALU (B300_MICROARCH: pipe rates)
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t one, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
+    return d;
+}
+
 // four flag words -> 16-bit mask in byte order: the multiplies leave the nibbles at bits 0..3 / 4..7 of the
 // high word with garbage only above bit 7, so one select merges two of them and one byte-permute the halves
 __device__ __forceinline__ uint32_t flags_to_mask16b(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
@@ -275,6 +283,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
     uint32_t patN, patDv;  // opaque to the compiler: stay in vector registers
+    uint32_t one;
+    asm volatile("mov.u32 %0, 1;" : "=r"(one));
     asm volatile("mov.u32 %0, 0x0a0a0a0a;" : "=r"(patN));
     asm volatile("mov.u32 %0, %1;" : "=r"(patDv) : "r"(patD));
     const int nwant = P.nwantL;
@@ -332,17 +342,17 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                 // 0x80 where the byte equals the pattern: ((v ^ pat) & 0x7f..) + 0x7f.. has bit 7 set iff the low 7
                 // bits differ; OR v brings in bit 7 of the byte itself. Patterns sit in registers so that the first
                 // step is ONE lop3 with the 0x7f.. immediate.
-                const uint32_t f0 = ~(((v.x ^ patN) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.x) & 0x80808080u;
-                const uint32_t f1 = ~(((v.y ^ patN) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.y) & 0x80808080u;
-                const uint32_t f2 = ~(((v.z ^ patN) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.z) & 0x80808080u;
-                const uint32_t f3 = ~(((v.w ^ patN) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.w) & 0x80808080u;
-                const uint32_t d0 = ~(((v.x ^ patDv) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.x) & 0x80808080u;
-                const uint32_t d1 = ~(((v.y ^ patDv) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.y) & 0x80808080u;
-                const uint32_t d2 = ~(((v.z ^ patDv) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.z) & 0x80808080u;
-                const uint32_t d3 = ~(((v.w ^ patDv) & 0x7f7f7f7fu) + 0x7f7f7f7fu | v.w) & 0x80808080u;
+                const uint32_t f0 = ~(add_fma((v.x ^ patN) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.x) & 0x80808080u;
+                const uint32_t f1 = ~(add_fma((v.y ^ patN) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.y) & 0x80808080u;
+                const uint32_t f2 = ~(add_fma((v.z ^ patN) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.z) & 0x80808080u;
+                const uint32_t f3 = ~(add_fma((v.w ^ patN) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.w) & 0x80808080u;
+                const uint32_t d0 = ~(add_fma((v.x ^ patDv) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.x) & 0x80808080u;
+                const uint32_t d1 = ~(add_fma((v.y ^ patDv) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.y) & 0x80808080u;
+                const uint32_t d2 = ~(add_fma((v.z ^ patDv) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.z) & 0x80808080u;
+                const uint32_t d3 = ~(add_fma((v.w ^ patDv) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.w) & 0x80808080u;
                 const uint32_t x0 = v.x | f0, x1 = v.y | f1, x2 = v.z | f2, x3 = v.w | f3;
-                spec |= ((x0 - 0x23232323u) & ~x0) | ((x1 - 0x23232323u) & ~x1) | ((x2 - 0x23232323u) & ~x2) |
-                        ((x3 - 0x23232323u) & ~x3);
+                spec |= (add_fma(x0, one, 0xdcdcdcddu) & ~x0) | (add_fma(x1, one, 0xdcdcdcddu) & ~x1) |
+                        (add_fma(x2, one, 0xdcdcdcddu) & ~x2) | (add_fma(x3, one, 0xdcdcdcddu) & ~x3);  // x - 0x23232323
                 sts16(s_tm + 2 * c, flags_to_mask16b(f0, f1, f2, f3));
                 sts16(s_dm + 2 * c, flags_to_mask16b(d0, d1, d2, d3));
             }
