@@ -16,11 +16,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <numeric>
 #include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "cq_gpu.h"
 #include "cqg_lean.cuh"
@@ -1105,15 +1107,55 @@ static int build_join(HostPlan& probe, JoinState& js, const cqg_table* rt, int r
 // ------------------------------------------------------------------------------------------
 // results
 // ------------------------------------------------------------------------------------------
+// bump allocator: results hold millions of small strings, one calloc each would dominate
 struct Arena {
     std::vector<void*> blocks;
+    char* cur = nullptr;
+    size_t left = 0;
     void* alloc(size_t n) {
-        void* p = calloc(1, n ? n : 1);
-        blocks.push_back(p);
+        n = (n + 15) & ~(size_t)15;
+        if (n == 0) n = 16;
+        if (n > (1u << 20)) {
+            void* p = calloc(1, n);
+            blocks.push_back(p);
+            return p;
+        }
+        if (n > left) {
+            size_t sz = 4u << 20;
+            cur = (char*)calloc(1, sz);
+            blocks.push_back(cur);
+            left = sz;
+        }
+        void* p = cur;
+        cur += n;
+        left -= n;
         return p;
     }
     ~Arena() {
         for (void* p : blocks) free(p);
+    }
+};
+
+// CQG_TIMING=1: phase timings of the host side on stderr
+struct PhaseTimer {
+    bool on;
+    double t0;
+    static double now() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    PhaseTimer() {
+        const char* e = getenv("CQG_TIMING");
+        on = e && e[0] == '1';
+        t0 = now();
+    }
+    void lap(const char* what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        double t = now();
+        fprintf(stderr, "[cqg timing] %-28s %9.3f ms\n", what, t - t0);
+        t0 = t;
     }
 };
 
@@ -1184,8 +1226,8 @@ static int cells_to_values(const cqg_table* t, const cqg_table* rt, const std::v
         CU(cudaMemcpyAsync(d_refs.p, refs.data(), refs.size() * 8, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_lens.p, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_offs.p, offs.data(), offs.size() * 8, cudaMemcpyHostToDevice, st));
-        int grid = (int)std::min<size_t>(refs.size(), 65535);
-        pack_strings_kernel<<<grid, 64, 0, st>>>(t->d_data, rt ? rt->d_data : nullptr, d_refs.as<uint64_t>(), d_lens.as<uint32_t>(),
+        int grid = (int)std::min<size_t>((refs.size() + 127) / 128, 148 * 16);
+        pack_strings_kernel<<<grid, 128, 0, st>>>(t->d_data, rt ? rt->d_data : nullptr, d_refs.as<uint64_t>(), d_lens.as<uint32_t>(),
                                                  d_offs.as<uint64_t>(), refs.size(), d_dst.as<uint8_t>());
         g_launches++;
         CU(cudaGetLastError());
@@ -1264,15 +1306,65 @@ static uint64_t initial_group_cap(const DevPlan& P) {
 static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* rt, const cqg_query_t* q, const uint8_t* d_entries,
                             uint64_t G, bool entries_on_device, int64_t rows_scanned, cqg_result_t** out, cudaStream_t st) {
     DevPlan& P = hp.P;
+    PhaseTimer pt;
     const int eb = P.entry_bytes;
-    std::vector<uint8_t> ent((size_t)G * eb + 8);
-    if (G) {
-        if (entries_on_device) {
-            CU(cudaMemcpyAsync(ent.data(), d_entries, (size_t)G * eb, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-        } else {
-            memcpy(ent.data(), d_entries, (size_t)G * eb);
+    std::vector<uint8_t> ent;
+    const uint8_t* entp = nullptr;
+    bool presorted = false;
+    if (G && entries_on_device && G > 4096) {
+        // many groups: order them by first appearance on the device (radix sort of the first-offset keys,
+        // then a gather), and bring them over through a page-locked staging buffer
+        DevBuf d_keys, d_keys2, d_idx, d_idx2, d_tmp, d_sorted;
+        CU(d_keys.alloc(G * 8, st));
+        CU(d_keys2.alloc(G * 8, st));
+        CU(d_idx.alloc(G * 4, st));
+        CU(d_idx2.alloc(G * 4, st));
+        int grid = (int)std::min<uint64_t>((G + 255) / 256, 148 * 8);
+        extract_first_kernel<<<grid, 256, 0, st>>>(d_entries, G, eb, d_keys.as<uint64_t>(), d_idx.as<uint32_t>());
+        g_launches++;
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.as<uint64_t>(), d_keys2.as<uint64_t>(), d_idx.as<uint32_t>(),
+                                        d_idx2.as<uint32_t>(), (int)G, 0, 64, st);
+        CU(d_tmp.alloc(tmp_bytes, st));
+        cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys.as<uint64_t>(), d_keys2.as<uint64_t>(), d_idx.as<uint32_t>(),
+                                        d_idx2.as<uint32_t>(), (int)G, 0, 64, st);
+        g_launches += 4;
+        CU(d_sorted.alloc(G * (uint64_t)eb, st));
+        int g2 = (int)std::min<uint64_t>((G * (uint64_t)(eb / 16) + 255) / 256, 148 * 16);
+        gather_entries_kernel<<<g2, 256, 0, st>>>(d_entries, d_idx2.as<uint32_t>(), G, eb, d_sorted.as<uint8_t>());
+        g_launches++;
+        CU(cudaGetLastError());
+        static void* pinned = nullptr;
+        static size_t pinned_bytes = 0;
+        size_t need = (size_t)G * eb;
+        if (need > pinned_bytes) {
+            if (pinned) cudaFreeHost(pinned);
+            pinned = nullptr;
+            pinned_bytes = 0;
+            if (cudaMallocHost(&pinned, need) == cudaSuccess) pinned_bytes = need;
         }
+        if (pinned_bytes >= need) {
+            CU(cudaMemcpyAsync(pinned, d_sorted.p, need, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            entp = (const uint8_t*)pinned;  // read in place (valid until the next finish on this process)
+        } else {
+            ent.resize(need + 8);
+            CU(cudaMemcpyAsync(ent.data(), d_sorted.p, need, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            entp = ent.data();
+        }
+        presorted = true;
+    } else {
+        ent.resize((size_t)G * eb + 8);
+        if (G) {
+            if (entries_on_device) {
+                CU(cudaMemcpyAsync(ent.data(), d_entries, (size_t)G * eb, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+            } else {
+                memcpy(ent.data(), d_entries, (size_t)G * eb);
+            }
+        }
+        entp = ent.data();
     }
     // create_groups with an unknown single key column makes no group at all (aggregates.c:114-116)
     bool zero_groups = q->n_group_cols == 1 && q->group_cols[0] < 0;
@@ -1281,13 +1373,16 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
     bool synth = false;
     if (q->n_group_cols == 0 && G == 0) {
         ent.assign(hp.entry_init.begin(), hp.entry_init.end());
+        entp = ent.data();
         G = 1;
         synth = true;
     }
+    pt.lap("entries to host");
     std::vector<uint32_t> order((size_t)G);
     std::iota(order.begin(), order.end(), 0u);
-    auto first_of = [&](uint32_t i) { return *(const uint64_t*)(ent.data() + (size_t)i * eb + kOffFirst); };
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return first_of(a) < first_of(b); });
+    auto first_of = [&](uint32_t i) { return *(const uint64_t*)(entp + (size_t)i * eb + kOffFirst); };
+    if (!presorted) std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return first_of(a) < first_of(b); });
+    pt.lap("sort by first appearance");
 
     Arena* arena;
     cqg_result_t* r = new_result(&arena);
@@ -1309,7 +1404,7 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
     std::vector<size_t> strdst;
     unsigned host_flags = 0;
     for (uint64_t gi = 0; gi < G; gi++) {
-        const uint8_t* e = ent.data() + (size_t)order[gi] * eb;
+        const uint8_t* e = entp + (size_t)order[gi] * eb;
         uint64_t first = *(const uint64_t*)(e + kOffFirst);
         int64_t count = (int64_t) * (const uint64_t*)(e + kOffCount);
         loff[gi] = first == ~0ull ? ~0ull : (first >> 16) - P.global_base;
@@ -1371,6 +1466,7 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
         cqg_result_free(r);
         return fail(CQG_ERR_UNSUPPORTED, "%s", flag_text(host_flags));
     }
+    pt.lap("aggregate values");
     int rc = CQG_OK;
     for (int a = 0; a < q->n_aggs && rc == CQG_OK; a++) {
         if (numfetch[a].empty()) continue;
@@ -1411,13 +1507,14 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
         if (rc == CQG_OK)
             for (size_t k = 0; k < sv.size(); k++) r->value[strdst[k]] = sv[k];
     }
+    pt.lap("min/max rows re-read");
     // bare columns: the group's first row (evaluator_aggregates.c:679-689)
     if (rc == CQG_OK && q->n_out_cols > 0 && G > 0 && !synth) {
         DevBuf d_first, d_roff;
         const uint64_t* roff_ptr = nullptr;
         if (rt && P.join) {
             std::vector<uint64_t> firsts(G);
-            for (uint64_t gi = 0; gi < G; gi++) firsts[gi] = *(const uint64_t*)(ent.data() + (size_t)order[gi] * eb + kOffFirst);
+            for (uint64_t gi = 0; gi < G; gi++) firsts[gi] = *(const uint64_t*)(entp + (size_t)order[gi] * eb + kOffFirst);
             CU(d_first.alloc(G * 8, st));
             CU(d_roff.alloc(G * 8, st));
             CU(cudaMemcpyAsync(d_first.p, firsts.data(), G * 8, cudaMemcpyHostToDevice, st));
@@ -1438,6 +1535,7 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
             rc = cells_to_values(t, rt, tr, r->out, arena, st);
         }
     }
+    pt.lap("first-row columns");
     if (rc != CQG_OK) {
         cqg_result_free(r);
         return rc;

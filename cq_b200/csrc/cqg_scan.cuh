@@ -1459,6 +1459,22 @@ __global__ void owner_count_kernel(const uint8_t* tab, uint64_t cap, int entry_b
     }
 }
 
+// first-appearance keys of dense entries, and the gather that puts entries in sorted order
+__global__ void extract_first_kernel(const uint8_t* ent, uint64_t n, int entry_bytes, uint64_t* keys, uint32_t* idx) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        keys[i] = *(const uint64_t*)(ent + i * (uint64_t)entry_bytes + kOffFirst);
+        idx[i] = (uint32_t)i;
+    }
+}
+__global__ void gather_entries_kernel(const uint8_t* ent, const uint32_t* idx, uint64_t n, int entry_bytes, uint8_t* out) {
+    const uint64_t per = (uint64_t)entry_bytes / 16;
+    const uint64_t total = n * per;
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < total; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = k / per, w = k % per;
+        ((uint4*)out)[k] = ((const uint4*)(ent + (uint64_t)idx[e] * entry_bytes))[w];
+    }
+}
+
 // fold n serialized entries into the table of plan P
 __global__ void merge_entries_kernel(const __grid_constant__ DevPlan P, const uint8_t* recs, uint64_t n) {
     unsigned err = 0;
@@ -1584,14 +1600,15 @@ __global__ void resolve_first_right_kernel(const __grid_constant__ DevPlan P, co
     if (err) atomicOr(P.errflags, err);
 }
 
-// gather string bytes: dst[dst_off[i] .. +len) = file bytes
+// gather string bytes: dst[dst_off[i] .. +len) = file bytes. One thread per string (result strings are short).
 __global__ void pack_strings_kernel(const uint8_t* data, const uint8_t* rdata, const uint64_t* refs, const uint32_t* lens,
                                     const uint64_t* dst_off, uint64_t n, uint8_t* dst) {
-    for (uint64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t ref = refs[i];
         const uint8_t* src = ((ref >> 63) ? rdata : data) + (ref & 0x7fffffffffffffffull);
         uint8_t* d = dst + dst_off[i];
-        for (uint32_t k = threadIdx.x; k < lens[i]; k += blockDim.x) d[k] = src[k];
+        const uint32_t len = lens[i];
+        for (uint32_t k = 0; k < len; k++) d[k] = src[k];
     }
 }
 
