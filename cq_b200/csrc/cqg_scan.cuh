@@ -232,6 +232,22 @@ __device__ inline void canon_part(const DVal& v, bool multi, unsigned& err, uint
                 tag = KT_NULL;
                 break;
             }
+            if (GROUP && n == 10 && v.s[4] == '-' && v.s[7] == '-') {
+                // a text that reads exactly like a rendered date ("%04d-%02d-%02d") shares the DATE's key string;
+                // it is text only because blanks made the raw field longer than the 10 bytes parse_date is tried on
+                bool dig = true;
+                for (int k = 0; k < 10; k++)
+                    if (k != 4 && k != 7) dig = dig && is_digit(v.s[k]);
+                if (dig) {
+                    long long y = (v.s[0] - 48) * 1000 + (v.s[1] - 48) * 100 + (v.s[2] - 48) * 10 + (v.s[3] - 48);
+                    long long mo = (v.s[5] - 48) * 10 + (v.s[6] - 48), d = (v.s[8] - 48) * 10 + (v.s[9] - 48);
+                    if (valid_date(y, mo, d)) {
+                        tag = KT_DATE;
+                        w0 = (uint64_t)((y << 16) | (mo << 8) | d);
+                        break;
+                    }
+                }
+            }
             if (GROUP && multi) {
                 for (uint32_t k = 0; k < n; k++)
                     if (v.s[k] == '\t') err |= KERR_KEY_TAB;

@@ -270,3 +270,69 @@ def test_partial_aggregates_merge(big, name, world):
         tg.set_shard(0, 1)
         for p in parts:
             lib.partial_free(p)
+
+
+def _lean_stress_table(n, seed, clean):
+    """Rows of mixed width (under 32, 32..63, 64 and more bytes) and mixed value shapes in the columns the lean
+    kernel decodes: short and 5..7 digit decimals, up to 3 and more fraction digits, signed numbers, dates,
+    empty fields, long and short texts. `clean=False` sprinkles blanks / CR / quotes so that tiles get handed
+    over to the general kernel."""
+    rnd = random.Random(seed)
+    words = ["a", "bb", "ccc", "delta", "echo-echo", "f" * 16, "g" * 17, "h" * 40, "NULL", "x1", "k_9"]
+    rows = ["k1,k2,n1,n2,pad,d1"]
+    for i in range(n):
+        k1 = rnd.choice(words[:6] if i % 7 else words)
+        k2 = rnd.choice(["u", "v", "w", "12", "1.5", "", "007"])
+        r = rnd.random()
+        if r < 0.55:
+            n1 = str(rnd.randint(0, 9999))
+        elif r < 0.75:
+            n1 = str(rnd.randint(10000, 9999999))
+        elif r < 0.85:
+            n1 = f"{rnd.randint(0, 999)}.{rnd.randint(0, 999):03d}"
+        elif r < 0.9:
+            n1 = str(-rnd.randint(1, 500))
+        elif r < 0.93:
+            n1 = ""
+        elif r < 0.96:
+            n1 = "2024-01-15"
+        else:
+            n1 = f"{rnd.randint(0, 99)}.{rnd.randint(0, 99999):05d}"
+        n2 = rnd.choice(["1", "2.5", "10", "0.125", "3.", ".5", "99999", "1234567", "12345678", "abc", ""])
+        pad = "p" * rnd.choice([0, 0, 0, 3, 9, 20, 45, 70])
+        d1 = rnd.choice(["2.0", "1.25", "7", "", "1e3"])
+        if not clean and i % 53 == 0:
+            k1 = '"q,uoted"'
+        if not clean and i % 31 == 0:
+            n1 = " " + n1 + " "
+        rows.append(f"{k1},{k2},{n1},{n2},{pad},{d1}")
+    text = ("\r\n" if not clean else "\n").join(rows) + "\n"
+    return text.encode()
+
+
+@pytest.mark.parametrize("clean", [True, False])
+def test_lean_kernel_hand_over_paths(clean):
+    data = _lean_stress_table(60_000, 21, clean)
+    K1, K2, N1, N2, PAD, D1 = range(6)
+    specs = [
+        dict(where=(">", ("col", N1), ("const", 5000)), aggs=[(A.AGG_COUNT_STAR, -1)]),
+        dict(where=("<=", ("col", N1), ("const", 123.5)), aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, N2), (A.AGG_AVG, N1)]),
+        dict(where=("and", ("!=", ("col", K2), ("const", "u")), (">=", ("col", N2), ("const", 1))),
+             aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, D1), (A.AGG_COUNT, K1)]),
+        dict(where=("or", ("=", ("col", K1), ("const", "delta")), ("<", ("col", N1), ("const", 10))),
+             aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_AVG, N2)]),
+        dict(group_by=[K2], out_cols=[K2], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, N1), (A.AGG_AVG, N2)]),
+        dict(where=("not", ("=", ("col", N2), ("const", 2.5))), group_by=[K1, K2], out_cols=[K1, K2],
+             aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, N2), (A.AGG_MIN, N1), (A.AGG_MAX, N1)]),
+        dict(group_by=[N2], out_cols=[N2], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_MAX, D1), (A.AGG_MIN, N2)]),
+        dict(group_by=[K1, N1], out_cols=[K1, N1], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, N2)]),  # many groups: global mode
+        dict(group_by=[D1, K2, K1], out_cols=[D1], aggs=[(A.AGG_COUNT, N1), (A.AGG_AVG, N1), (A.AGG_MAX, N2)]),
+    ]
+    with Table.from_bytes(data, lib=gpu()) as tg, Table.from_bytes(data, lib=oracle()) as to:
+        for spec in specs:
+            pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)), rel=1e-11)
+        for i in range(3):
+            tg.set_shard(i, 3)
+            to.set_shard(i, 3)
+            for spec in (specs[1], specs[5]):
+                pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)), rel=1e-11)
