@@ -627,14 +627,8 @@ static bool make_lean_leaf(DevPlan& P, const FInsn& in, LeanLeaf& L) {
         L.A[fd] = (uint32_t)A;
         // integers on both sides: a >= b  <=>  a > b - 1
         L.LB[fd] = B + (op == CQG_OP_GE ? -1 : op == CQG_OP_LE ? 1 : 0);
-        if (&L == &L) {
-            P.s_A[fd] = A;  // the general kernel's single-leaf route reads these
-            P.s_B[fd] = B;
-        }
     }
     L.lop = (op == CQG_OP_GT || op == CQG_OP_GE) ? 0 : (op == CQG_OP_LT || op == CQG_OP_LE) ? 1 : op == CQG_OP_EQ ? 2 : 3;
-    P.s_slot = slot;
-    P.s_op = op;
     return true;
 }
 
@@ -642,7 +636,6 @@ static bool make_lean_leaf(DevPlan& P, const FInsn& in, LeanLeaf& L) {
 // `pool`: host copy of the predicate's string pool (DConst::bits are offsets into it).
 static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
     P.simple = 0;
-    P.s_single = 0;
     P.l_nleaf = P.l_nprog = 0;
     if (P.join || P.mode != SCAN_AGG || P.exact_only || P.nwantL > 4 || P.ngc > 4) return;
     P.l_nagg = 0;
@@ -653,7 +646,6 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
     }
     for (int a = 0; a < P.naggs; a++)
         if ((P.aggs[a].func == CQG_AGG_MIN || P.aggs[a].func == CQG_AGG_MAX) && P.ngc == 0) return;  // scalar MIN/MAX: general kernel
-    P.s_has_pred = 0;
     if (P.pred_kind == 2) return;
     if (P.pred_kind == 1) {
         for (int k = 0; k < P.n_fcode; k++) {
@@ -695,10 +687,6 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
                 return;  // IN, LIKE, TRUE/FALSE: general kernel
             }
         }
-        P.s_has_pred = 1;
-        P.s_single = P.l_nleaf == 1 && P.l_nprog == 1 && P.l_leaf[0].kind == 0 && P.scalar_regs;
-    } else {
-        P.s_single = P.scalar_regs;
     }
     P.simple = P.ngc == 0 ? 1 : 2;  // 2: lean GROUP BY (per-CTA dictionary, up to 64 groups per CTA)
 }
@@ -1924,18 +1912,17 @@ CQG_API void cqg_value_release(cqg_value_t* v) {
 struct cqg_partial {
     HostPlan hp;
     GroupTable gt;
+    JoinState js;  // build side of an equi-join (whole right table, replicated on every rank)
     cqg_query_t q{};
     int64_t rows_scanned = 0;
     double kernel_ms = 0;
 };
 
-static bool partial_query_ok(const cqg_query_t* q) {
-    return q->mode == CQG_MODE_AGGREGATE && q->join.right == nullptr;
-}
+static bool partial_query_ok(const cqg_query_t* q) { return q->mode == CQG_MODE_AGGREGATE; }
 
 CQG_API int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_partial_t** out) {
     if (!t || !q || !out) return fail(CQG_ERR_ARG, "null argument");
-    if (!partial_query_ok(q)) return fail(CQG_ERR_UNSUPPORTED, "partials cover single-table aggregates");
+    if (!partial_query_ok(q)) return fail(CQG_ERR_UNSUPPORTED, "partials cover aggregates (with or without a join)");
     int rc = ensure_device();
     if (rc) return rc;
     cqg_partial* p = new cqg_partial();
@@ -1949,8 +1936,13 @@ CQG_API int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_
     }
     ScalarBlock hs{};
     float ms = 0;
+    // joins: every rank builds the WHOLE right table and probes it with its own shard of the left one
+    if (q->join.right && (rc = build_join(p->hp, p->js, q->join.right, q->join.right_col, 0))) {
+        delete p;
+        return rc;
+    }
     rc = run_aggregate_scan(p->hp, p->gt, 0, hs, &ms);
-    if (rc == CQG_OK) rc = check_flags(hs, false);
+    if (rc == CQG_OK) rc = check_flags(hs, q->join.right != nullptr);
     if (rc != CQG_OK) {
         delete p;
         return rc;
@@ -2086,7 +2078,7 @@ CQG_API int cqg_partial_finish(const cqg_partial_t* pc, const cqg_table_t* t, cq
     p->hp.P.data = t->d_data;
     p->hp.P.size = t->size;
     p->hp.P.global_base = t->global_base;
-    rc = finish_aggregate(p->hp, t, nullptr, &p->q, entries.as<uint8_t>(), G, true, p->rows_scanned, out, 0);
+    rc = finish_aggregate(p->hp, t, p->q.join.right, &p->q, entries.as<uint8_t>(), G, true, p->rows_scanned, out, 0);
     if (rc == CQG_OK) {
         (*out)->kernel_ms = p->kernel_ms;
         (*out)->kernel_launches = 0;

@@ -122,18 +122,9 @@ struct DevPlan {
     DConst consts_inl[kMaxFusedConsts];
     DPred pred;  // generic program + string pool (global memory)
 
-    // ---- "simple" route: no GROUP BY, COUNT/SUM/AVG only, WHERE empty or `column <op> decimal literal`.
-    // Short unsigned decimals (<= 4 bytes) are decoded and compared as scaled integers:
-    //   field = mant / 10^fd  <op>  literal   <=>   mant * s_A[fd]  <op>  s_B[fd]
-    // which orders exactly like the reference's double compare for decimals of <= 15 digits.
+    // ---- lean kernel plans (cqg_lean.cuh): 1 = no GROUP BY, 2 = GROUP BY; 0 = general kernel only ----
     int32_t simple;
-    int32_t s_has_pred;
-    int32_t s_slot;   // slot of the predicate column
-    int32_t s_op;     // CQG_OP_EQ..LE with the column on the left (general kernel)
-    long long s_A[4], s_B[4];
-    int32_t s_lop;    // lean kernel: 0 lhs > s_LB, 1 lhs < s_LB, 2 ==, 3 !=  (>= and <= folded into the bound)
-    int32_t s_pad;
-    long long s_LB[4];
+    int32_t lean_pad;
     // lean kernel WHERE: postfix program over up to kMaxLeanLeaf leaves. Leaf kinds:
     //   0  column <op> decimal literal   (mant * A[fd] vs LB[fd]; lop 0 >, 1 <, 2 ==, 3 !=)
     //   1  column =  'text'  /  2  column != 'text'   (text of 1..16 bytes, packed like a key part)
@@ -141,7 +132,6 @@ struct DevPlan {
     int32_t l_nleaf, l_nprog;
     LeanLeaf l_leaf[kMaxLeanLeaf];
     int8_t l_prog[16];
-    int32_t s_single;  // the general kernel's own simple route handles no WHERE / one decimal leaf only
     int32_t lean_global;  // lean GROUP BY updates the global table directly (any number of groups)
     int32_t l_nagg;       // aggregates with a state (SUM/AVG/MIN/MAX over a known column): at most 4 on the lean kernel
     int32_t l_agg[4];     // their indices in aggs[]

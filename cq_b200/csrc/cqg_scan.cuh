@@ -471,37 +471,6 @@ struct ThreadAcc {
     unsigned err;
 };
 
-// A field of at most 4 bytes that is an unsigned decimal ("45", "1.84", "2.0", ".5"): value =
-// mant / 10^fd with fd <= 3. Returns false for anything else (signs, letters, two dots, no digit).
-// `buf` is the shared-memory tile; the 4 bytes are fetched with two aligned loads.
-__device__ __forceinline__ bool decode_tiny(const uint8_t* buf, uint32_t off, uint32_t len, uint32_t& mant, uint32_t& fd) {
-    const uint32_t a = off & ~3u, sh = (off & 3u) * 8u;
-    const uint32_t w0 = *(const uint32_t*)(buf + a), w1 = *(const uint32_t*)(buf + a + 4);
-    uint32_t w = __funnelshift_r(w0, w1, sh);
-    // right-align: last character in byte 3, '0' padding in front
-    const uint32_t pad = 8u * (4u - len);  // len in 1..4
-    w = len == 4u ? w : ((w << pad) | (0x30303030u >> (8u * len)));
-    uint32_t dotf = eq_flags7(w, 0x2e2e2e2eu);
-    uint32_t t = w ^ 0x30303030u;
-    fd = 0;
-    uint32_t ndig = len;
-    if (dotf) {
-        if (dotf & (dotf - 1u)) return false;          // two dots
-        const uint32_t j = (31u - __clz(dotf)) >> 3;   // byte index of the dot
-        fd = 3u - j;
-        const uint32_t lowmask = (1u << (8u * j)) - 1u;  // bytes in front of the dot
-        const uint32_t high = j == 3u ? 0u : (t & ~((1u << (8u * (j + 1u))) - 1u));
-        t = ((t & lowmask) << 8) | high;
-        ndig = len - 1u;
-    }
-    if (ndig == 0u) return false;
-    if (((t + 0x76767676u) | t) & 0x80808080u) return false;  // a byte that is not a digit
-    t = t * 10u + (t >> 8);                        // byte 0 = b0*10+b1, byte 2 = b2*10+b3
-    t &= 0x00ff00ffu;
-    mant = (t * 100u + (t >> 16)) & 0xffffu;
-    return true;
-}
-
 // ------------------------------------------------------------------------------------------
 // rows as the operators see them
 // ------------------------------------------------------------------------------------------
@@ -951,113 +920,6 @@ __device__ __noinline__ void process_window_row_slow(const DevPlan& P, const Cta
 }
 
 // ------------------------------------------------------------------------------------------
-// the "simple" route for one row of a clean tile (DevPlan::simple). W is the width of the mask
-// window: uint32_t covers rows shorter than 32 bytes, unsigned long long rows shorter than 64.
-// Returns false when the row needs a wider window.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ffs_w(uint32_t x) { return (uint32_t)__ffs((int)x); }
-__device__ __forceinline__ uint32_t ffs_w(unsigned long long x) { return (uint32_t)__ffsll((long long)x); }
-__device__ __forceinline__ void win_w(const uint32_t* m, uint32_t pos, uint32_t& out) {
-    const uint32_t w = pos >> 5, b = pos & 31u;
-    out = __funnelshift_r(m[w], m[w + 1], b);
-}
-__device__ __forceinline__ void win_w(const uint32_t* m, uint32_t pos, unsigned long long& out) { out = mask_window(m, pos); }
-
-template <class W, int NW>
-__device__ __forceinline__ bool simple_row(const DevPlan& P, const CtaState& cs, const uint8_t* buf, const uint32_t* tm,
-                                           const uint32_t* dm, long long g0, uint32_t rs, uint32_t bufsize, ThreadAcc& acc) {
-    W tw;
-    win_w(tm, rs, tw);
-    if (tw == (W)0) return false;
-    const uint32_t len = ffs_w(tw) - 1u;  // < bits of W
-    if (rs + len >= bufsize) return false;
-    W dw;
-    win_w(dm, rs, dw);
-    dw &= (((W)1) << len) - (W)1;
-    FastRow<NW> row;
-    row.base = buf;
-    row.lfile = buf - g0;
-    row.clean = true;
-    uint32_t startpos = 0;
-    bool missing = false;
-#pragma unroll
-    for (int k = 0; k < NW; k++) {
-        row.off[k] = rs;
-        row.len[k] = 0;
-        if (k < P.nwantL) {
-            const int gap = P.gap[k];
-            if (gap > 0) {
-                for (int i = 1; i < gap; i++) dw &= dw - (W)1;
-                missing = missing || dw == (W)0;
-                startpos = ffs_w(dw);
-                dw &= dw - (W)1;
-            }
-            const uint32_t endpos = dw ? ffs_w(dw) - 1u : len;
-            row.off[k] = rs + startpos;
-            row.len[k] = missing ? 0u : endpos - startpos;
-        }
-    }
-    // ---- WHERE ----
-    if (P.s_has_pred) {
-        uint32_t o = row.off[0], l = row.len[0];
-#pragma unroll
-        for (int k = 1; k < NW; k++)
-            if (P.s_slot == k) {
-                o = row.off[k];
-                l = row.len[k];
-            }
-        uint32_t mant, fd;
-        bool pass;
-        if (l - 1u < 4u && decode_tiny(buf, o, l, mant, fd)) {
-            const long long lhs = (long long)mant * P.s_A[fd], rhs = P.s_B[fd];
-            const int op = P.s_op;
-            pass = op == CQG_OP_GT ? lhs > rhs : op == CQG_OP_LT ? lhs < rhs : op == CQG_OP_GE ? lhs >= rhs
-                 : op == CQG_OP_LE ? lhs <= rhs : op == CQG_OP_EQ ? lhs == rhs : lhs != rhs;
-        } else {
-            pass = leaf_cmp(P, row, P.fcode_inl[0], acc.err);
-        }
-        if (!pass) return true;
-    }
-    // ---- COUNT / SUM / AVG in registers ----
-    const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
-    const uint64_t okey = gabs << 16;
-    acc.count++;
-    if (okey < acc.first) acc.first = okey;
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        if (a < P.naggs && P.aggs[a].off >= 0) {
-            const int sl = P.aggs[a].slot;
-            if (sl < 0) continue;
-            uint32_t o = row.off[0], l = row.len[0];
-#pragma unroll
-            for (int k = 1; k < NW; k++)
-                if (sl == k) {
-                    o = row.off[k];
-                    l = row.len[k];
-                }
-            uint32_t mant, fd;
-            if (l - 1u < 4u && decode_tiny(buf, o, l, mant, fd)) {
-                acc.s3[a] += (long long)(mant * (fd == 0u ? 1000u : fd == 1u ? 100u : fd == 2u ? 10u : 1u));
-                acc.sn[a]++;
-            } else {
-                DVal v = decode_field_clean(buf + o, l, acc.err);
-                if (v.type == T_INT && (unsigned long long)(v.i + (1ll << 31)) >> 32 == 0) {
-                    acc.si[a] += v.i;
-                    acc.sn[a]++;
-                } else if (v.type == T_INT) {
-                    acc.sd[a] += (double)v.i;
-                    acc.sn[a]++;
-                } else if (v.type == T_DBL) {
-                    acc.sd[a] += v.d;
-                    acc.sn[a]++;
-                }
-            }
-        }
-    }
-    return true;
-}
-
-// ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <class G, int NW>
@@ -1273,25 +1135,6 @@ __global__ void __launch_bounds__(G::THREADS, 4) scan_kernel(const __grid_consta
             const uint32_t npass = nrows - pass_lo < (uint32_t)G::ROWCAP ? nrows - pass_lo : (uint32_t)G::ROWCAP;
             if (P.mode == SCAN_COUNT_ROWS) {
                 for (uint32_t r = tid; r < npass; r += G::THREADS) acc.rows++;
-            } else if (P.simple == 1 && P.s_single && !special) {
-                for (uint32_t r = tid; r < npass; r += G::THREADS) {
-                    const uint32_t rs = rowpos[r];
-                    acc.rows++;
-                    if (simple_row<uint32_t, NW>(P, cs, buf, tm, dm, g0, rs, (uint32_t)G::BUF, acc)) continue;
-                    if (simple_row<unsigned long long, NW>(P, cs, buf, tm, dm, g0, rs, (uint32_t)G::BUF, acc)) continue;
-                    // 64 bytes or more: the general route
-                    uint32_t p = rs + 64u, len = 0xffffffffu;
-                    while (p < (uint32_t)G::BUF) {
-                        unsigned long long w2 = mask_window(tm, p);
-                        if (w2) {
-                            len = p + (uint32_t)__ffsll((long long)w2) - 1u - rs;
-                            break;
-                        }
-                        p += 64u;
-                    }
-                    if (len == 0xffffffffu || rs + len >= (uint32_t)G::BUF) process_long_row(P, cs, (uint64_t)(g0 + (long long)rs), acc);
-                    else process_window_row_slow(P, cs, buf, g0, rs, len, acc);
-                }
             } else {
                 for (uint32_t r = tid; r < npass; r += G::THREADS) {
                     const uint32_t rs = rowpos[r];

@@ -283,7 +283,9 @@ void cqg_value_release(cqg_value_t* v);
 
 typedef struct cqg_partial cqg_partial_t;
 
-/* like cqg_execute(AGGREGATE) but keeps the group table on the device. */
+/* like cqg_execute(AGGREGATE) but keeps the group table on the device. With a join, the build side is
+ * the whole right table on every rank (replicated) and the left table is this rank's shard; the right
+ * table, and the partial given to cqg_partial_new_like, must stay open until the merged partial is freed. */
 int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_partial_t** out);
 /* device time of the partial's scan kernels (CUDA events) and the data rows it saw */
 double cqg_partial_kernel_ms(const cqg_partial_t* p);

@@ -336,3 +336,43 @@ def test_lean_kernel_hand_over_paths(clean):
             to.set_shard(i, 3)
             for spec in (specs[1], specs[5]):
                 pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)), rel=1e-11)
+
+
+def test_partial_aggregates_merge_with_join():
+    """Sharded left table, replicated build side: two partials merged must equal the single join."""
+    import torch
+    od, cd = _join_tables(20000, 3000, 13)
+    lib, lo = gpu(), oracle()
+    spec = dict(group_by=[8], out_cols=[8, 6], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 1), (A.AGG_MAX, 3)],
+                where=(">", ("col", 1), ("const", 100)))
+    with Table.from_bytes(od, lib=lib) as og, Table.from_bytes(cd, lib=lib) as cg, \
+            Table.from_bytes(od, lib=lo) as oo, Table.from_bytes(cd, lib=lo) as co:
+        want = oo.execute(pc.build(spec, join=(co, 4, 0)))
+        plan = pc.build(spec, join=(cg, 4, 0))
+        parts = []
+        world = 2
+        for r in range(world):
+            og.set_shard(r, world)
+            p = C.c_void_p()
+            assert lib.execute_partial(og.handle, C.byref(plan.q), C.byref(p)) == 0, lib.last_error()
+            parts.append(p)
+        og.set_shard(0, 1)
+        rec = lib.partial_record_size(parts[0])
+        merged = C.c_void_p()
+        assert lib.partial_new_like(parts[0], C.byref(merged)) == 0
+        for p in parts:
+            n = lib.partial_count(p)
+            buf = torch.zeros(max(n, 1) * rec, dtype=torch.uint8, device="cuda")
+            got = C.c_int64()
+            assert lib.partial_export(p, 0, 1, buf.data_ptr(), n, C.byref(got)) == 0
+            assert lib.partial_merge(merged, buf.data_ptr(), got.value) == 0
+        res = C.POINTER(A.Result)()
+        assert lib.partial_finish(merged, og.handle, C.byref(res)) == 0, lib.last_error()
+        from cq_b200.engine import decode_result
+        got = decode_result(res.contents, plan)
+        lib.result_free(res)
+        got["rows_scanned"] = sum(lib.partial_rows_scanned(p) for p in parts)
+        pc.compare_results(got, want)
+        lib.partial_free(merged)
+        for p in parts:
+            lib.partial_free(p)
