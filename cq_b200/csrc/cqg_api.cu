@@ -469,7 +469,16 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
     }
     const bool oneleaf = P.l_nprog == 1 && P.l_nleaf == 1 && P.l_leaf[0].kind == 0 && P.l_leaf[0].slot == 0 && P.l_nagg == 0 &&
                          P.nwantL == 1;
-    if (oneleaf) return launch_lean_geo<Geo<128, 16384, 1>, 9, false, true, false, false>(P, st);
+    if (oneleaf) {
+        static int variant = -1;
+        if (variant < 0) {
+            const char* e = getenv("CQG_LEAN_GEO");
+            variant = e ? atoi(e) : 0;
+        }
+        if (variant == 1) return launch_lean_geo<Geo<128, 16384, 2>, 6, false, true, false, false>(P, st);
+        if (variant == 2) return launch_lean_geo<Geo<128, 16384, 1>, 12, false, true, false, false>(P, st);
+        return launch_lean_geo<Geo<128, 16384, 1>, 9, false, true, false, false>(P, st);
+    }
     return launch_lean_geo<Geo<128, 16384, 1>, 8, false, false, false, false>(P, st);
 }
 
