@@ -644,6 +644,14 @@ struct CtaState {
     unsigned long long* s_occ;  // its occupancy counter (shared)
 };
 
+// 64-bit integer add in shared memory with native 32-bit atomics: the lane that wraps the low word adds the carry
+__device__ __forceinline__ void smem_add64(void* p, unsigned long long v) {
+    const uint32_t vlo = (uint32_t)v, vhi = (uint32_t)(v >> 32);
+    const uint32_t old = atomicAdd((unsigned int*)p, vlo);
+    const uint32_t up = vhi + ((old + vlo) < old ? 1u : 0u);
+    if (up) atomicAdd((unsigned int*)p + 1, up);
+}
+
 template <bool SM, class Row>
 __device__ __forceinline__ void entry_accumulate(const DevPlan& P, uint8_t* e, const Row& row, uint64_t okey, unsigned& err) {
     amin64((uint64_t*)(e + kOffFirst), okey);
@@ -656,7 +664,8 @@ __device__ __forceinline__ void entry_accumulate(const DevPlan& P, uint8_t* e, c
         uint8_t* st = e + sp.off;
         if (sp.func == CQG_AGG_SUM || sp.func == CQG_AGG_AVG) {
             if (v.type == T_INT && (unsigned long long)(v.i + (1ll << 31)) >> 32 == 0) {
-                atomicAdd((unsigned long long*)st, (unsigned long long)v.i);  // exact, cannot overflow below 2^31 rows
+                if (SM) smem_add64(st, (unsigned long long)v.i);
+                else atomicAdd((unsigned long long*)st, (unsigned long long)v.i);  // exact, cannot overflow below 2^31 rows
                 if (SM) atomicAdd((unsigned int*)(st + 16), 1u);
                 else atomicAdd((unsigned long long*)(st + 16), 1ull);
             } else if (v.type == T_INT) {
@@ -919,6 +928,69 @@ __device__ __noinline__ void process_window_row_slow(const DevPlan& P, const Cta
     process_row_slow(P, cs, buf, buf - g0, foff, flen, (uint64_t)(g0 + (long long)rs), acc);
 }
 
+// parse_line (src/csv_reader.c:285-338) on the row's delimiter and quote bitmasks instead of byte by
+// byte: a field is quoted iff its first non-blank byte is the quote character; inside quotes `""` is
+// skipped (and counts 2 towards the length of an unterminated field), the first lone quote closes, the
+// rest up to the delimiter is dropped. dw/qw: delimiter/quote bits of the row (bit i = byte rs+i), len <= 63.
+template <int NW>
+__device__ __forceinline__ void split_quoted_masks(const DevPlan& P, const uint8_t* buf, uint32_t rs, uint32_t len,
+                                                   unsigned long long dw, unsigned long long qw, uint32_t* off, uint32_t* flen) {
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        off[k] = rs;
+        flen[k] = 0;
+    }
+    uint32_t pos = 0;
+    int field = 0, wi = 0;
+    while (pos < len && wi < P.nwantL) {
+        while (pos < len && is_space(buf[rs + pos])) pos++;
+        if (pos >= len) break;
+        uint32_t fs = pos, fl = 0;
+        if ((qw >> pos) & 1ull) {
+            pos++;
+            fs = pos;
+            for (;;) {
+                const unsigned long long q = pos < 64u ? (qw & (~0ull << pos)) : 0ull;
+                if (!q) {  // unterminated: swallow the rest of the line
+                    pos = len;
+                    break;
+                }
+                const uint32_t p = (uint32_t)__ffsll((long long)q) - 1u;
+                if (p + 1u < len && ((qw >> (p + 1u)) & 1ull)) {
+                    fl += 2;
+                    pos = p + 2u;
+                    continue;
+                }
+                fl = p - fs;
+                pos = p + 1u;
+                break;
+            }
+            const unsigned long long d = pos < 64u ? (dw & (~0ull << pos)) : 0ull;
+            pos = d ? (uint32_t)__ffsll((long long)d) - 1u : len;
+        } else {
+            const unsigned long long d = dw & (~0ull << pos);
+            pos = d ? (uint32_t)__ffsll((long long)d) - 1u : len;
+            fl = pos - fs;
+        }
+        if (P.wantL[wi] == field) {
+            if (NW <= 4) {
+#pragma unroll
+                for (int k = 0; k < NW; k++)
+                    if (k == wi) {
+                        off[k] = rs + fs;
+                        flen[k] = fl;
+                    }
+            } else {
+                off[wi] = rs + fs;
+                flen[wi] = fl;
+            }
+            wi++;
+        }
+        field++;
+        if (pos < len) pos++;  // the delimiter
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
@@ -1162,9 +1234,7 @@ __global__ void __launch_bounds__(G::THREADS, 4) scan_kernel(const __grid_consta
                         continue;
                     }
                     const unsigned long long lenmask = (1ull << len) - 1ull;  // len <= 63 here
-                    bool fast = fast_plan;
-                    if (fast && special) fast = (mask_window(qm, rs) & lenmask) == 0ull;
-                    if (!fast) {
+                    if (!fast_plan) {
                         process_window_row_slow(P, cs, buf, g0, rs, len, acc);
                         continue;
                     }
@@ -1173,7 +1243,11 @@ __global__ void __launch_bounds__(G::THREADS, 4) scan_kernel(const __grid_consta
                     row.base = buf;
                     row.lfile = buf - g0;
                     row.clean = !special;
-                    {
+                    const unsigned long long qw = special ? (mask_window(qm, rs) & lenmask) : 0ull;
+                    if (qw) {
+                        // quote characters in the row: the quote-aware split, still on bitmasks
+                        split_quoted_masks<NW>(P, buf, rs, len, mask_window(dm, rs) & lenmask, qw, row.off, row.len);
+                    } else {
                         // wanted field k starts after gap[k] further delimiters: clear gap-1 of the
                         // remaining delimiter bits, the next one marks the start, the one after the end
                         unsigned long long dw = mask_window(dm, rs) & lenmask;
