@@ -479,6 +479,9 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
         if (variant == 2) return launch_lean_geo<Geo<128, 16384, 1>, 12, false, true, false, false>(P, st);
         return launch_lean_geo<Geo<128, 16384, 1>, 9, false, true, false, false>(P, st);
     }
+    bool mm = false;
+    for (int a = 0; a < P.l_nagg; a++) mm = mm || P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX;
+    if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 6, false, false, true, false>(P, st);
     return launch_lean_geo<Geo<128, 16384, 1>, 8, false, false, false, false>(P, st);
 }
 
@@ -653,8 +656,9 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
         if (P.aggs[a].slot < 0 || P.aggs[a].slot >= 4 || P.l_nagg >= 4) return;
         P.l_agg[P.l_nagg++] = a;
     }
+    bool scalar_minmax = false;  // no GROUP BY but MIN/MAX: the grouped kernel with a one-group dictionary
     for (int a = 0; a < P.naggs; a++)
-        if ((P.aggs[a].func == CQG_AGG_MIN || P.aggs[a].func == CQG_AGG_MAX) && P.ngc == 0) return;  // scalar MIN/MAX: general kernel
+        if ((P.aggs[a].func == CQG_AGG_MIN || P.aggs[a].func == CQG_AGG_MAX) && P.aggs[a].off >= 0 && P.ngc == 0) scalar_minmax = true;
     if (P.pred_kind == 2) return;
     if (P.pred_kind == 1) {
         for (int k = 0; k < P.n_fcode; k++) {
@@ -697,6 +701,7 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
             }
         }
     }
+    (void)scalar_minmax;
     P.simple = P.ngc == 0 ? 1 : 2;  // 2: lean GROUP BY (per-CTA dictionary, up to 64 groups per CTA)
 }
 

@@ -274,10 +274,14 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     uint64_t first = ~0ull;
     long long s3[4];
     uint32_t sn[4];
+    uint64_t mmk[4], mmo[4], mmf[4];  // scalar MIN/MAX (MINMAX && !GROUPED): extreme key, its row, first non-NULL row
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         s3[a] = 0;
         sn[a] = 0;
+        mmk[a] = 0;
+        mmo[a] = ~0ull;
+        mmf[a] = ~0ull;
     }
     // plan constants the row loop uses, once
     const uint64_t size = P.size;
@@ -304,6 +308,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
             if (sp.func == CQG_AGG_MIN || sp.func == CQG_AGG_MAX) summask |= 16u << a;
             if (sp.func == CQG_AGG_MIN) summask |= 256u << a;
             aslot[a] = sp.slot;
+            if (sp.func == CQG_AGG_MIN) mmk[a] = ~0ull;
         }
     }
 
@@ -666,20 +671,60 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                         const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
                         if (gabs < first) first = gabs;
                         if (!ONELEAF && (addmask & 1u)) {
-                            s3[0] += (long long)add0;
-                            sn[0]++;
+                            if (MINMAX && (summask & (16u << 0))) {
+                                const uint64_t ok_ = gabs << 16;
+                                const bool mn = (summask & (256u << 0)) != 0u;
+                                if (mn ? (add0 < mmk[0] || (add0 == mmk[0] && ok_ < mmo[0])) : (add0 > mmk[0] || (add0 == mmk[0] && ok_ < mmo[0]))) {
+                                    mmk[0] = add0;
+                                    mmo[0] = ok_;
+                                }
+                                if (ok_ < mmf[0]) mmf[0] = ok_;
+                            } else {
+                                s3[0] += (long long)add0;
+                                sn[0]++;
+                            }
                         }
                         if (!ONELEAF && (addmask & 2u)) {
-                            s3[1] += (long long)add1;
-                            sn[1]++;
+                            if (MINMAX && (summask & (16u << 1))) {
+                                const uint64_t ok_ = gabs << 16;
+                                const bool mn = (summask & (256u << 1)) != 0u;
+                                if (mn ? (add1 < mmk[1] || (add1 == mmk[1] && ok_ < mmo[1])) : (add1 > mmk[1] || (add1 == mmk[1] && ok_ < mmo[1]))) {
+                                    mmk[1] = add1;
+                                    mmo[1] = ok_;
+                                }
+                                if (ok_ < mmf[1]) mmf[1] = ok_;
+                            } else {
+                                s3[1] += (long long)add1;
+                                sn[1]++;
+                            }
                         }
                         if (!ONELEAF && (addmask & 4u)) {
-                            s3[2] += (long long)add2;
-                            sn[2]++;
+                            if (MINMAX && (summask & (16u << 2))) {
+                                const uint64_t ok_ = gabs << 16;
+                                const bool mn = (summask & (256u << 2)) != 0u;
+                                if (mn ? (add2 < mmk[2] || (add2 == mmk[2] && ok_ < mmo[2])) : (add2 > mmk[2] || (add2 == mmk[2] && ok_ < mmo[2]))) {
+                                    mmk[2] = add2;
+                                    mmo[2] = ok_;
+                                }
+                                if (ok_ < mmf[2]) mmf[2] = ok_;
+                            } else {
+                                s3[2] += (long long)add2;
+                                sn[2]++;
+                            }
                         }
                         if (!ONELEAF && (addmask & 8u)) {
-                            s3[3] += (long long)add3;
-                            sn[3]++;
+                            if (MINMAX && (summask & (16u << 3))) {
+                                const uint64_t ok_ = gabs << 16;
+                                const bool mn = (summask & (256u << 3)) != 0u;
+                                if (mn ? (add3 < mmk[3] || (add3 == mmk[3] && ok_ < mmo[3])) : (add3 > mmk[3] || (add3 == mmk[3] && ok_ < mmo[3]))) {
+                                    mmk[3] = add3;
+                                    mmo[3] = ok_;
+                                }
+                                if (ok_ < mmf[3]) mmf[3] = ok_;
+                            } else {
+                                s3[3] += (long long)add3;
+                                sn[3]++;
+                            }
                         }
                     }
                 } else {
@@ -753,6 +798,23 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                 sn[a] += __shfl_xor_sync(0xffffffffu, sn[a], d);
             }
         }
+        if (MINMAX) {
+            // warp-reduce the extremes (lexicographic on (key, okey)), then lane 0 merges them below
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const bool mn = (summask & (256u << a)) != 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const uint64_t k2 = __shfl_xor_sync(0xffffffffu, mmk[a], d), o2 = __shfl_xor_sync(0xffffffffu, mmo[a], d);
+                    const uint64_t f2 = __shfl_xor_sync(0xffffffffu, mmf[a], d);
+                    if (mn ? (k2 < mmk[a] || (k2 == mmk[a] && o2 < mmo[a])) : (k2 > mmk[a] || (k2 == mmk[a] && o2 < mmo[a]))) {
+                        mmk[a] = k2;
+                        mmo[a] = o2;
+                    }
+                    if (f2 < mmf[a]) mmf[a] = f2;
+                }
+            }
+        }
         if (lane == 0 && count) {
             unsigned err = 0;
             const uint64_t h = key_hash_final(0x243F6A8885A308D3ull);
@@ -762,7 +824,13 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                 amin64((uint64_t*)(ge + kOffFirst), first << 16);
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
-                    if (a < P.l_nagg && sn[a]) {
+                    if (MINMAX && a < P.l_nagg && (summask & (16u << a))) {
+                        if (mmf[a] != ~0ull) {
+                            uint64_t* st = (uint64_t*)(ge + P.aggs[P.l_agg[a]].off);
+                            amin64(&st[0], (mmf[a] << 2) | 1u);
+                            num_extreme(&st[2], mmk[a], mmo[a], (summask & (256u << a)) != 0u);
+                        }
+                    } else if (a < P.l_nagg && sn[a]) {
                         atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 16), (unsigned long long)sn[a]);
                         atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 24), (unsigned long long)s3[a]);
                     }
