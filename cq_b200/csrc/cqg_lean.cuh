@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
 
     uint32_t rows = 0, count = 0;
     uint64_t first = ~0ull;
+    bool have_first = false;
     long long s3[4];
     uint32_t sn[4];
     uint64_t mmk[4], mmo[4], mmf[4];  // scalar MIN/MAX (MINMAX && !GROUPED): extreme key, its row, first non-NULL row
@@ -377,6 +378,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
         long long olo_l = (long long)P.own_lo - g0, ohi_l = (long long)P.own_hi - g0;
         const uint32_t olo = (uint32_t)(olo_l < G::PRE ? G::PRE : (olo_l > G::PRE + G::TILE ? G::PRE + G::TILE : olo_l));
         const uint32_t ohi = (uint32_t)(ohi_l < G::PRE ? G::PRE : (ohi_l > G::PRE + G::TILE ? G::PRE + G::TILE : ohi_l));
+        const bool partial_tile = olo > (uint32_t)G::PRE || ohi < (uint32_t)(G::PRE + G::TILE);
         const uint32_t w0 = G::PRE / 32 + tid * G::WPT;
         uint32_t handed = 0, myrows = 0;
         static_assert(G::WPT == 4, "the row walk below keeps four start words in registers");
@@ -389,9 +391,11 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                 const uint32_t t = lds32(s_tm + 4 * (w0 + j));
                 uint32_t s = ((t << 1) | (prev >> 31)) & ~t;  // row starts: a terminator, then a byte that is none
                 prev = t;
-                const uint32_t p0 = (w0 + j) * 32u;
-                if (olo > p0) s &= olo >= p0 + 32u ? 0u : (0xffffffffu << (olo - p0));
-                if (ohi < p0 + 32u) s &= ohi <= p0 ? 0u : (0xffffffffu >> (p0 + 32u - ohi));
+                if (partial_tile) {  // only the first and last tile of a shard own less than all of their bytes
+                    const uint32_t p0 = (w0 + j) * 32u;
+                    if (olo > p0) s &= olo >= p0 + 32u ? 0u : (0xffffffffu << (olo - p0));
+                    if (ohi < p0 + 32u) s &= ohi <= p0 ? 0u : (0xffffffffu >> (p0 + 32u - ohi));
+                }
                 S[j] = s;
             }
             S0 = S[0];
@@ -669,7 +673,11 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                     if (take) {
                         count++;
                         const uint64_t gabs = P.global_base + (uint64_t)(g0 + (long long)rs);
-                        if (gabs < first) first = gabs;
+                        // a thread meets its rows in increasing offset order (within a tile and from tile to tile)
+                        if (!have_first) {
+                            first = gabs;
+                            have_first = true;
+                        }
                         if (!ONELEAF && (addmask & 1u)) {
                             if (MINMAX && (summask & (16u << 0))) {
                                 const uint64_t ok_ = gabs << 16;
