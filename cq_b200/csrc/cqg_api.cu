@@ -26,6 +26,7 @@
 
 #include "cq_gpu.h"
 #include "cqg_lean.cuh"
+#include "cqg_lean2.cuh"
 
 using namespace cqg;
 
@@ -455,6 +456,37 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
     return CQG_OK;
 }
 
+template <class LG, int MINB, bool ONELEAF, int MM, int GAP0>
+static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    DevPlan P = P0;
+    if (P.own_hi > P.own_lo) {
+        P.first_tile = (int32_t)(P.own_lo / LG::TILE);
+        P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
+    }
+    if (P.n_tiles <= 0) return CQG_OK;
+    const int smem = Lean2Layout<LG>::TOTAL;
+    LaunchCfg& c = g_cfg[dev & 63];
+    if (!c.ready) {
+        CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+        c.ready = true;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2_kernel<LG, MINB, ONELEAF, MM, GAP0>, LG::THREADS, smem));
+    if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean2 kernel does not fit");
+    int grid = std::min(P.n_tiles, c.sms * per_sm);
+    lean2_kernel<LG, MINB, ONELEAF, MM, GAP0><<<grid, LG::THREADS, smem, st>>>(P);
+    g_launches++;
+    CU(cudaGetLastError());
+    return CQG_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 // the lean kernel hands tiles over by index: its tile size must be the general kernel's
 static int launch_lean(const DevPlan& P, cudaStream_t st) {
     if (P.simple == 2) {
@@ -469,6 +501,37 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
     }
     const bool oneleaf = P.l_nprog == 1 && P.l_nleaf == 1 && P.l_leaf[0].kind == 0 && P.l_leaf[0].slot == 0 && P.l_nagg == 0 &&
                          P.nwantL == 1;
+    bool mm0 = false;
+    for (int a = 0; a < P.l_nagg; a++) mm0 = mm0 || P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX;
+    const int lean2 = env_int("CQG_LEAN2", 1);  // 0: the round-1 lean kernel (A/B runs)
+    if (lean2 && !mm0) {
+        using LG = Geo<128, 16384, 1>;
+        using LS = Geo<128, 16384, 1, 224>;  // rows of 64 bytes and more are handed over anyway: a short overlap
+        if (oneleaf) {
+            const int var = env_int("CQG_L2_VAR", 1);
+            if (lean2 == 3) return launch_lean2_geo<LG, 9, true, 0, -1>(P, st);
+            if (var == 0) return launch_lean2_geo<LG, 9, true, 1, -1>(P, st);
+            if (var == 2) {
+                switch (P.gap[0]) {
+                    case 2: return launch_lean2_geo<LS, 10, true, 1, 2>(P, st);
+                    case 4: return launch_lean2_geo<LS, 10, true, 1, 4>(P, st);
+                    default: return launch_lean2_geo<LS, 10, true, 1, -1>(P, st);
+                }
+            }
+            switch (P.gap[0]) {
+                case 0: return launch_lean2_geo<LS, 9, true, 1, 0>(P, st);
+                case 1: return launch_lean2_geo<LS, 9, true, 1, 1>(P, st);
+                case 2: return launch_lean2_geo<LS, 9, true, 1, 2>(P, st);
+                case 3: return launch_lean2_geo<LS, 9, true, 1, 3>(P, st);
+                case 4: return launch_lean2_geo<LS, 9, true, 1, 4>(P, st);
+                case 5: return launch_lean2_geo<LS, 9, true, 1, 5>(P, st);
+                case 6: return launch_lean2_geo<LS, 9, true, 1, 6>(P, st);
+                case 7: return launch_lean2_geo<LS, 9, true, 1, 7>(P, st);
+                default: return launch_lean2_geo<LS, 9, true, 1, -1>(P, st);
+            }
+        }
+        return launch_lean2_geo<LS, 8, false, 1, -1>(P, st);
+    }
     if (oneleaf) {
         static int variant = -1;
         if (variant < 0) {

@@ -1,0 +1,567 @@
+// cqg_lean2.cuh — the scalar lean kernel: DevPlan::simple == 1 plans (no GROUP BY, no MIN/MAX):
+// COUNT / SUM / AVG over short decimals, WHERE empty or a postfix program of `column <op> decimal
+// literal` / `column = | != 'text'` leaves. Same tile pipeline as cqg_lean.cuh (1-D TMA tile -> SWAR
+// masks -> thread-owned row walk) with half the instructions per byte:
+//   * two byte classes only: T = "byte < 0x23" (every terminator, quote and blank) and D = delimiter.
+//     Whether a T byte really is '\n' is checked once per ROW (one byte load at the row's end), not
+//     once per byte; a tile where any row ends in something else, holds an empty line, or hands over
+//     too many rows is DIRTY and goes to the general kernel as a whole (src/csv_reader.c:404-427 row
+//     split, :278-338 field split, :195-240 typed decode are then reproduced exactly there);
+//   * T and D words interleaved (one 64-bit shared load gives both), a running cursor from row end to
+//     next row start (no row-start masks), fields <= 4 bytes decoded right-aligned with one byte-permute
+//     to drop the '.' and one dot product for the digits;
+//   * `mant * A[fd] <op> LB[fd]` (cqg_lean.cuh) is folded, per CTA, into an interval test on mant alone.
+// Results of a tile are committed only after the whole CTA found the tile clean.
+#pragma once
+#include "cqg_lean.cuh"
+
+namespace cqg {
+
+template <class G>
+struct Lean2Layout {
+    static constexpr int OFF_MSK = G::STAGES * G::BUF;           // (T word, D word) per 32 CSV bytes
+    static constexpr int OFF_CMP = OFF_MSK + G::MASKW * 8;       // kMaxLeanLeaf x 4 fd x {lo, width, negate, pad}
+    static constexpr int OFF_MISC = OFF_CMP + kMaxLeanLeaf * 64; // handed-row counters (2 x u32)
+    static constexpr int OFF_MBAR = OFF_MISC + 16;
+    static constexpr int TOTAL = OFF_MBAR + G::STAGES * 8;
+    static_assert(OFF_MSK % 16 == 0 && OFF_CMP % 16 == 0, "alignment");
+};
+
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t ctz32(uint32_t x) { return (uint32_t)__clz((int)__brev(x)); }
+__device__ __forceinline__ uint32_t ctz64(uint64_t x) { return (uint32_t)__clzll((long long)__brevll(x)); }
+__device__ __forceinline__ uint32_t bfind32(uint32_t x) {
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+// four 0x80-flag words -> 16-bit mask in byte order (flags_to_mask16b with the nibble merges as single LOP3s)
+__device__ __forceinline__ uint32_t lean2_mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    const uint32_t h0 = __umulhi(f0, 0x02040810u), h1 = __umulhi(f1, 0x20408100u);
+    const uint32_t h2 = __umulhi(f2, 0x02040810u), h3 = __umulhi(f3, 0x20408100u);
+    uint32_t lo, hi;
+    asm("lop3.b32 %0, %1, %2, 0xf, 0xE4;" : "=r"(lo) : "r"(h0), "r"(h1));  // (h0 & 0xf) | (h1 & ~0xf)
+    asm("lop3.b32 %0, %1, %2, 0xf, 0xE4;" : "=r"(hi) : "r"(h2), "r"(h3));
+    return __byte_perm(lo, hi, 0x7740);
+}
+
+// `mant * A <op> LB` over mant in [0, 2^32) as an interval: pass = ((mant - lo) <= width) ^ negate
+__device__ inline void lean2_interval(const LeanLeaf& L, int fd, uint32_t& lo, uint32_t& width, uint32_t& negate) {
+    const unsigned long long A = L.A[fd] ? L.A[fd] : 1u;
+    const long long LB = L.LB[fd];
+    const unsigned long long top = 0xfffffffeull;
+    lo = 0u;
+    width = 0xffffffffu;
+    negate = 0u;
+    if (L.lop == 0) {  // mant * A > LB
+        if (LB >= 0) {
+            const unsigned long long q = (unsigned long long)LB / A;
+            if (q >= top) {
+                negate = 1u;
+            } else {
+                lo = (uint32_t)q + 1u;
+                width = 0xffffffffu - lo;
+            }
+        }
+    } else if (L.lop == 1) {  // mant * A < LB
+        if (LB <= 0) {
+            negate = 1u;
+        } else {
+            const unsigned long long q = ((unsigned long long)LB + A - 1ull) / A;  // mant <= q - 1
+            if (q - 1ull < top) width = (uint32_t)(q - 1ull);
+        }
+    } else {  // == / !=
+        const bool hit = LB >= 0 && (unsigned long long)LB % A == 0ull && (unsigned long long)LB / A <= top;
+        if (hit) {
+            lo = (uint32_t)((unsigned long long)LB / A);
+            width = 0u;
+            negate = L.lop == 3 ? 1u : 0u;
+        } else {
+            negate = L.lop == 2 ? 1u : 0u;
+        }
+    }
+}
+
+// unsigned decimal of 1..4 bytes ENDING at shared address `fe` (exclusive): mant / 10^(fd16/16).
+// false: not one (sign, exponent, text, two dots, a lone '.').
+__device__ __forceinline__ bool lean2_dec4(uint32_t fe, uint32_t len, uint32_t& mant, uint32_t& fd16) {
+    const uint32_t a = fe & ~3u;
+    const uint32_t w0 = lds32(a - 4u), w1 = lds32(a);
+    uint32_t t = __funnelshift_r(w0, w1, fe << 3) ^ 0x30303030u;  // bytes [fe-4, fe): the last character on top
+    t &= 0xffffffffu << (32u - 8u * len);                          // what precedes the field reads as leading zeros
+    const uint32_t x = ((t ^ 0x1e1e1e1eu) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    const uint32_t dotf = ~(x | t) & 0x80808080u;                  // 0x80 where the byte is '.'
+    fd16 = 0u;
+    if (dotf) {
+        if ((dotf & (dotf - 1u)) || len == 1u) return false;
+        // fd = 3 - (byte index of the dot), as fd * 0x11: nibble 0 picks the low selector byte, nibble 1 the high one
+        const uint32_t r = __umulhi(dotf, 0x66442200u);
+        fd16 = r & 0x30u;
+        const uint32_t sel = __byte_perm(0x14040404u, 0x32323121u, (r & 0x33u) | 0x40u);
+        t = __byte_perm(t, 0u, sel);                               // drop the dot, shift the integer digits down
+    }
+    if (((t + 0x76767676u) | t) & 0x80808080u) return false;      // a byte that is not a digit
+    mant = __dp4a(t, 0x010a6400u, (t & 0xffu) * 1000u);
+    return true;
+}
+
+// first terminator bit at or after bit `q` of the tile buffer; `limit` when there is none below it
+__device__ __noinline__ uint32_t lean2_next_term(uint32_t s_msk, uint32_t q, uint32_t limit) {
+    uint32_t w = q >> 5;
+    uint32_t t = lds32(s_msk + 8u * w) & (0xffffffffu << (q & 31u));
+    while (t == 0u && (w + 1u) * 32u < limit) {
+        w++;
+        t = lds32(s_msk + 8u * w);
+    }
+    const uint32_t e = w * 32u + ctz32(t);
+    return (t != 0u && e < limit) ? e : limit;
+}
+
+// field positions of one row out of its stop bits (delimiters below the terminator, and the terminator):
+// start (relative to the row) and length of wanted field K; a field the row does not have reads as empty
+template <typename W>
+struct Lean2Stops {
+    W st;
+    uint32_t sp;
+    bool missing;
+    __device__ __forceinline__ void field(int gap, uint32_t& off, uint32_t& len) {
+        if (gap > 0) {
+#pragma unroll 1
+            for (int i = 1; i < gap; i++) st &= st - 1;
+            missing = missing || st == 0;
+            sp = sizeof(W) == 8 ? (uint32_t)__ffsll((long long)st) : (uint32_t)__ffs((int)st);
+            st &= st - 1;
+        }
+        missing = missing || st == 0;
+        const uint32_t ep = sizeof(W) == 8 ? ctz64((uint64_t)st) : ctz32((uint32_t)st);
+        off = sp;
+        len = missing ? 0u : ep - sp;
+    }
+    // the same with the skip count known at compile time
+    template <int GAP>
+    __device__ __forceinline__ void field_c(uint32_t& off, uint32_t& len) {
+        if (GAP > 0) {
+#pragma unroll
+            for (int i = 1; i < GAP; i++) st &= st - 1;
+            sp = sizeof(W) == 8 ? (uint32_t)__ffsll((long long)st) : (uint32_t)__ffs((int)st);
+            st &= st - 1;
+        }
+        missing = st == 0;  // (no stop behind the field: the skipped ones were missing too)
+        const uint32_t ep = sizeof(W) == 8 ? ctz64((uint64_t)st) : ctz32((uint32_t)st);
+        off = sp;
+        len = missing ? 0u : ep - sp;
+    }
+};
+
+// unsigned decimal of 5..7 bytes (rare next to the 4-byte route: kept out of line)
+// returns mant (< 10^7) | fd16 << 24 | ok << 31
+__device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
+    uint32_t mant, fd;
+    bool hd;
+    const bool ok = lean_decimal(fa, len, mant, fd, hd);
+    return ok ? (0x80000000u | (fd << 28) | mant) : 0u;
+}
+#define CQG_L2_DEC7(FA, LEN, DEC, MANT, FD16)        \
+    {                                                \
+        const uint32_t r7 = lean2_dec7(FA, LEN);     \
+        DEC = (r7 >> 31) != 0u;                      \
+        MANT = r7 & 0x00ffffffu;                     \
+        FD16 = (r7 >> 24) & 0x30u;                   \
+    }
+
+// GAP0: the wanted column index of ONELEAF plans when it is below 8 (the delimiter skips unroll), else -1
+template <class G, int MINB, bool ONELEAF, int MM, int GAP0>
+__global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_constant__ DevPlan P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    static_assert(G::STAGES == 1 && G::TILE == G::THREADS * 128, "one stage, 128 bytes per thread");
+    using LL = Lean2Layout<G>;
+    uint32_t sbase;
+    asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));  // once: not to be rematerialised per row
+    const uint32_t s_buf = sbase + G::OFF_BUF, s_msk = sbase + LL::OFF_MSK, s_cmp = sbase + LL::OFF_CMP;
+    uint64_t* mbar = (uint64_t*)(smem + LL::OFF_MBAR);
+    unsigned* s_handed = (unsigned*)(smem + LL::OFF_MISC);
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_handed[0] = 0u;
+        s_handed[1] = 0u;
+    }
+    for (int w = G::BUF / 32 + tid; w < G::MASKW; w += G::THREADS) {  // behind the buffer: all terminators
+        sts32(s_msk + 8 * w, 0xffffffffu);
+        sts32(s_msk + 8 * w + 4, 0u);
+    }
+    if (tid < P.l_nleaf * 4 && P.l_leaf[tid >> 2].kind == 0) {
+        uint32_t lo, width, negate;
+        lean2_interval(P.l_leaf[tid >> 2], tid & 3, lo, width, negate);
+        sts128(s_cmp + 16 * tid, lo, width, negate, 0u);
+    }
+    __syncthreads();
+
+    // running totals of clean tiles
+    uint32_t rows = 0, count = 0;
+    uint64_t first = ~0ull;
+    bool have_first = false;
+    long long s3[4];
+    uint32_t sn[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        s3[a] = 0;
+        sn[a] = 0;
+    }
+    const uint64_t size = P.size;
+    const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
+    const uint32_t one = (uint32_t)P.simple;  // == 1, but not to the compiler: a + c as IMAD (FMA pipe), see add_fma
+    const int nwant = P.nwantL;
+    const int gap0 = GAP0 >= 0 ? GAP0 : P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
+    const int nprog = P.l_nprog;
+    uint32_t summask = 0;
+    int aslot[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        aslot[a] = 0;
+        if (!ONELEAF && a < P.l_nagg) {
+            summask |= 1u << a;
+            aslot[a] = P.aggs[P.l_agg[a]].slot;
+        }
+    }
+
+    const int my_tiles = (P.n_tiles > (int)blockIdx.x) ? (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    for (int it = 0; it < my_tiles; it++) {
+        const long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
+        const long long g0 = tile * (long long)G::TILE - G::PRE;
+        const bool edge = g0 < 0 || g0 + G::BUF > (long long)size;  // edge tiles are handed over, not loaded
+        if (tid == 0) {
+            if (!edge) {
+                mbar_expect_tx(&mbar[0], G::BUF);
+                tma_load_1d(smem + G::OFF_BUF, P.data + g0, G::BUF, &mbar[0]);
+            } else {
+                mbar_expect_tx(&mbar[0], 0);
+            }
+            s_handed[it & 1] = 0u;  // last read two tiles ago, at least one barrier back
+        }
+        mbar_wait(&mbar[0], (uint32_t)it & 1u);
+        if (edge) {
+            if (tid == 0) {
+                unsigned long long k = atomicAdd(P.def_tile_count, 1ull);
+                P.def_tiles[k] = (int32_t)tile;
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- phase 1: T ("< 0x23") and D (delimiter) masks, 16 bytes per thread and step ----
+        {
+            uint32_t ca = s_buf + 16u * tid;
+            uint32_t ma = s_msk + (((uint32_t)tid >> 1) << 3) + (((uint32_t)tid & 1u) << 1);
+#pragma unroll 2
+            for (int c = tid; c < G::CHUNKS; c += G::THREADS, ca += 16u * G::THREADS, ma += 4u * G::THREADS) {
+                const uint4 v = lds128(ca);
+                const uint32_t a0 = ~(add_fma(v.x & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.x) & 0x80808080u;
+                const uint32_t a1 = ~(add_fma(v.y & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.y) & 0x80808080u;
+                const uint32_t a2 = ~(add_fma(v.z & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.z) & 0x80808080u;
+                const uint32_t a3 = ~(add_fma(v.w & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.w) & 0x80808080u;
+                const uint32_t d0 = ~(add_fma((v.x ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.x) & 0x80808080u;
+                const uint32_t d1 = ~(add_fma((v.y ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.y) & 0x80808080u;
+                const uint32_t d2 = ~(add_fma((v.z ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.z) & 0x80808080u;
+                const uint32_t d3 = ~(add_fma((v.w ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.w) & 0x80808080u;
+                if (MM == 1) {
+                    // flags are 0x80 per byte: four dot products leave mask << 7
+                    uint32_t ra = __dp4a(a2, 0x08040201u, 0u);
+                    ra = __dp4a(a3, 0x80402010u, ra) * 256u;
+                    ra = __dp4a(a0, 0x08040201u, ra);
+                    ra = __dp4a(a1, 0x80402010u, ra);
+                    uint32_t rd = __dp4a(d2, 0x08040201u, 0u);
+                    rd = __dp4a(d3, 0x80402010u, rd) * 256u;
+                    rd = __dp4a(d0, 0x08040201u, rd);
+                    rd = __dp4a(d1, 0x80402010u, rd);
+                    sts16(ma, ra >> 7);
+                    sts16(ma + 4u, rd >> 7);
+                } else {
+                    sts16(ma, lean2_mask16(a0, a1, a2, a3));
+                    sts16(ma + 4u, lean2_mask16(d0, d1, d2, d3));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: every thread walks the rows that START in its own 128 bytes ----
+        uint32_t lo = (uint32_t)G::PRE + 128u * (uint32_t)tid, hi = lo + 128u;
+        {
+            const long long olo_l = (long long)P.own_lo - g0, ohi_l = (long long)P.own_hi - g0;
+            if (olo_l > (long long)G::PRE || ohi_l < (long long)(G::PRE + G::TILE)) {  // first / last tile of a shard
+                const uint32_t olo = (uint32_t)(olo_l < G::PRE ? G::PRE : (olo_l > G::PRE + G::TILE ? G::PRE + G::TILE : olo_l));
+                const uint32_t ohi = (uint32_t)(ohi_l < G::PRE ? G::PRE : (ohi_l > G::PRE + G::TILE ? G::PRE + G::TILE : ohi_l));
+                lo = lo > olo ? lo : olo;
+                hi = hi < ohi ? hi : ohi;
+            }
+        }
+        uint32_t tcnt = 0, trows = 0, tfirst = 0xffffffffu, seen = 0, dirty = 0, nh = 0, hpos = 0;
+        long long ts3[4];
+        uint32_t tsn[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            ts3[a] = 0;
+            tsn[a] = 0;
+        }
+        if (lo < hi) {
+            const uint32_t e0 = lean2_next_term(s_msk, lo - 1u, (uint32_t)G::BUF);
+            uint32_t pos = e0 + 1u;
+            if (pos < hi) {
+                dirty |= lds8(s_buf + e0) != 0x0au ? 1u : 0u;
+                do {
+                    const uint32_t ma = s_msk + ((pos >> 2) & ~7u);
+                    const uint2 m0 = lds64(ma), m1 = lds64(ma + 8u);
+                    const uint32_t tw = __funnelshift_r(m0.x, m1.x, pos);
+                    const uint32_t dw = __funnelshift_r(m0.y, m1.y, pos);
+                    bool ok = true, pass = true;
+                    uint32_t et;
+                    uint32_t off0 = 0, off1 = 0, off2 = 0, off3 = 0, len0 = 0, len1 = 0, len2 = 0, len3 = 0;
+                    if (tw != 0u) {
+                        // the row ends inside a 32-bit window
+                        seen |= tw;
+                        const uint32_t below = tw ^ (tw - 1u);  // up to and including the terminator
+                        et = bfind32(below);
+                        Lean2Stops<uint32_t> S{(dw | tw) & below, 0u, false};
+                        if (GAP0 >= 0) S.template field_c<(GAP0 >= 0 ? GAP0 : 0)>(off0, len0);
+                        else S.field(gap0, off0, len0);
+                        if (!ONELEAF) {
+                            if (nwant > 1) S.field(gap1, off1, len1);
+                            if (nwant > 2) S.field(gap2, off2, len2);
+                            if (nwant > 3) S.field(gap3, off3, len3);
+                        }
+                    } else {
+                        const uint32_t t2 = lds32(ma + 16u);
+                        const uint32_t tw2 = __funnelshift_r(m1.x, t2, pos);
+                        if (tw2 != 0u) {
+                            const uint32_t d2 = lds32(ma + 20u);
+                            const uint64_t tw64 = (uint64_t)tw2 << 32;
+                            const uint64_t dw64 = ((uint64_t)__funnelshift_r(m1.y, d2, pos) << 32) | dw;
+                            const uint64_t below = tw64 ^ (tw64 - 1ull);
+                            et = 32u + bfind32((uint32_t)(below >> 32));
+                            Lean2Stops<uint64_t> S{(dw64 | tw64) & below, 0u, false};
+                            if (GAP0 >= 0) S.template field_c<(GAP0 >= 0 ? GAP0 : 0)>(off0, len0);
+                            else S.field(gap0, off0, len0);
+                            if (!ONELEAF) {
+                                if (nwant > 1) S.field(gap1, off1, len1);
+                                if (nwant > 2) S.field(gap2, off2, len2);
+                                if (nwant > 3) S.field(gap3, off3, len3);
+                            }
+                        } else {
+                            // 64 bytes or more: find the end, hand the row over
+                            const uint32_t e = lean2_next_term(s_msk, pos + 64u, (uint32_t)G::BUF);
+                            if (e >= (uint32_t)G::BUF) dirty = 1u;
+                            et = e - pos;
+                            ok = false;
+                        }
+                    }
+                    const uint32_t rbase = s_buf + pos;
+                    unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
+                    uint32_t addmask = 0;
+                    if (ONELEAF) {
+                        uint32_t mant = 0, fd16 = 0;
+                        bool dec = false;
+                        if (ok) {
+                            if (len0 - 1u < 4u) {
+                                dec = lean2_dec4(rbase + off0 + len0, len0, mant, fd16);
+                            } else if (len0 - 1u < 7u) {
+                                CQG_L2_DEC7(rbase + off0, len0, dec, mant, fd16)
+                            }
+                        }
+                        ok = ok && dec;
+                        const uint4 iv = lds128(s_cmp + fd16);
+                        pass = ((mant - iv.x <= iv.y) ? 1u : 0u) != iv.z;
+                    } else if (ok) {
+#define CQG_L2_SLOT(SL, O, L)                                                    \
+    const uint32_t O = SL == 0 ? off0 : SL == 1 ? off1 : SL == 2 ? off2 : off3; \
+    const uint32_t L = SL == 0 ? len0 : SL == 1 ? len1 : SL == 2 ? len2 : len3;
+                        if (nprog) {
+                            uint32_t bs = 0;
+                            for (int pc = 0; pc < nprog; pc++) {
+                                const int c = P.l_prog[pc];
+                                if (c >= 0) {
+                                    const int sl = P.l_leaf[c].slot, kind = P.l_leaf[c].kind;
+                                    CQG_L2_SLOT(sl, o, l)
+                                    bool bv = false;
+                                    if (kind == 0) {
+                                        uint32_t mant = 0, fd16 = 0;
+                                        bool dec = false;
+                                        if (l - 1u < 4u) {
+                                            dec = lean2_dec4(rbase + o + l, l, mant, fd16);
+                                        } else if (l - 1u < 7u) {
+                                            CQG_L2_DEC7(rbase + o, l, dec, mant, fd16)
+                                        }
+                                        if (dec) {
+                                            const uint4 iv = lds128(s_cmp + 64u * (uint32_t)c + fd16);
+                                            bv = ((mant - iv.x <= iv.y) ? 1u : 0u) != iv.z;
+                                        } else {
+                                            ok = false;  // NULL, text, date, signed or long number: general kernel
+                                        }
+                                    } else {
+                                        // text equality (see cqg_lean.cuh: a number or date against text is handed over)
+                                        uint32_t tag;
+                                        uint64_t w0, w1;
+                                        if (l == 0u) {
+                                            bv = kind == 2;
+                                        } else if (l > 16u) {
+                                            const uint32_t c0 = lds8(rbase + o);
+                                            const bool ns = (c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.';
+                                            if (ns) ok = false;
+                                            bv = kind == 2;
+                                        } else if (lean_key_part(rbase + o, l, tag, w0, w1) && (tag == KT_STR || tag == KT_NULL)) {
+                                            if (tag == KT_NULL) {
+                                                w0 = 0x4c4c554eull;
+                                                w1 = 0;
+                                            }
+                                            const bool eq = (uint32_t)P.l_leaf[c].slen == l && w0 == P.l_leaf[c].w0 && w1 == P.l_leaf[c].w1;
+                                            bv = kind == 1 ? eq : !eq;
+                                        } else {
+                                            ok = false;
+                                        }
+                                    }
+                                    bs = (bs << 1) | (bv ? 1u : 0u);
+                                } else if (c == -1) {
+                                    bs = ((bs >> 1) & ~1u) | ((bs >> 1) & bs & 1u);
+                                } else if (c == -2) {
+                                    bs = ((bs >> 1) & ~1u) | (((bs >> 1) | bs) & 1u);
+                                } else {
+                                    bs ^= 1u;
+                                }
+                            }
+                            pass = (bs & 1u) != 0u;
+                        }
+                        if (ok && pass && summask) {
+#define CQG_L2_AGG(A, ADD)                                                                               \
+    if (summask & (1u << A)) {                                                                           \
+        const int sl = aslot[A];                                                                         \
+        CQG_L2_SLOT(sl, o, l)                                                                            \
+        uint32_t mant = 0, fd16 = 0;                                                                     \
+        bool dec = false;                                                                                \
+        if (l - 1u < 4u) {                                                                               \
+            dec = lean2_dec4(rbase + o + l, l, mant, fd16);                                              \
+        } else if (l - 1u < 7u) {                                                                        \
+            CQG_L2_DEC7(rbase + o, l, dec, mant, fd16)                                                \
+        }                                                                                                \
+        if (dec) {                                                                                       \
+            ADD = (unsigned long long)mant * (fd16 == 0u ? 1000u : fd16 == 16u ? 100u : fd16 == 32u ? 10u : 1u); \
+            addmask |= 1u << A;                                                                          \
+        } else if (l != 0u) {                                                                            \
+            ok = false; /* a value this kernel does not decode (NULL is simply not summed) */           \
+        }                                                                                                \
+    }
+                            CQG_L2_AGG(0, add0)
+                            CQG_L2_AGG(1, add1)
+                            CQG_L2_AGG(2, add2)
+                            CQG_L2_AGG(3, add3)
+#undef CQG_L2_AGG
+                        }
+#undef CQG_L2_SLOT
+                    }
+                    if (ok) {
+                        trows++;
+                        if (pass) {
+                            tcnt++;
+                            tfirst = tfirst < pos ? tfirst : pos;
+                            if (!ONELEAF) {
+                                if (addmask & 1u) {
+                                    ts3[0] += (long long)add0;
+                                    tsn[0]++;
+                                }
+                                if (addmask & 2u) {
+                                    ts3[1] += (long long)add1;
+                                    tsn[1]++;
+                                }
+                                if (addmask & 4u) {
+                                    ts3[2] += (long long)add2;
+                                    tsn[2]++;
+                                }
+                                if (addmask & 8u) {
+                                    ts3[3] += (long long)add3;
+                                    tsn[3]++;
+                                }
+                            }
+                        }
+                    } else {
+                        hpos = hpos * 65536u + pos;  // the last two rows handed over (pos < 2^16)
+                        nh++;
+                    }
+                    // the row must end in '\n' (anything else below 0x23 is not this kernel's business)
+                    dirty |= lds8(rbase + et) != 0x0au ? 1u : 0u;
+                    pos += et + 1u;
+                } while (pos < hi);
+                dirty |= seen & 1u;  // a row start that is a terminator: an empty line
+            }
+        }
+        if (nh > 2u) dirty = 1u;
+        if (nh != 0u && dirty == 0u) atomicAdd(&s_handed[it & 1], nh);
+        int bad = __syncthreads_or((int)dirty);
+        // (this barrier also ends every read of the tile and its masks)
+        if (s_handed[it & 1] > 32u) bad = 1;
+        if (!bad) {
+            rows += trows;
+            count += tcnt;
+            if (tcnt != 0u && !have_first) {
+                first = P.global_base + (uint64_t)(g0 + (long long)tfirst);
+                have_first = true;
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                s3[a] += ts3[a];
+                sn[a] += tsn[a];
+            }
+            if (nh != 0u) {
+                const unsigned long long k = atomicAdd(P.def_row_count, (unsigned long long)nh);
+                if (k < P.def_row_cap) P.def_rows[k] = (uint64_t)(g0 + (long long)(hpos & 0xffffu));
+                if (nh > 1u && k + 1ull < P.def_row_cap) P.def_rows[k + 1ull] = (uint64_t)(g0 + (long long)(hpos >> 16));
+            }
+        } else if (tid == 0) {
+            unsigned long long k = atomicAdd(P.def_tile_count, 1ull);
+            P.def_tiles[k] = (int32_t)tile;
+        }
+    }
+
+    // ---- epilogue: fold the registers into the single group `_all_` ----
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        rows += __shfl_xor_sync(0xffffffffu, rows, d);
+        count += __shfl_xor_sync(0xffffffffu, count, d);
+        const uint64_t of = __shfl_xor_sync(0xffffffffu, first, d);
+        first = of < first ? of : first;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            if (!ONELEAF) {
+                s3[a] += __shfl_xor_sync(0xffffffffu, s3[a], d);
+                sn[a] += __shfl_xor_sync(0xffffffffu, sn[a], d);
+            }
+        }
+    }
+    if (lane == 0 && rows) atomicAdd(P.rows_scanned, (unsigned long long)rows);
+    if (lane == 0 && count) {
+        unsigned err = 0;
+        const uint64_t h = key_hash_final(0x243F6A8885A308D3ull);
+        uint8_t* ge = global_entry_for(P, h, 0u, nullptr, err);
+        if (ge) {
+            atomicAdd((unsigned long long*)(ge + kOffCount), (unsigned long long)count);
+            amin64((uint64_t*)(ge + kOffFirst), first << 16);
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                if (!ONELEAF && a < P.l_nagg && sn[a]) {
+                    atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 16), (unsigned long long)sn[a]);
+                    atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 24), (unsigned long long)s3[a]);
+                }
+            }
+        }
+        if (err) atomicOr(P.errflags, err);
+    }
+}
+
+}  // namespace cqg

@@ -23,11 +23,11 @@ namespace cqg {
 // ------------------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------------------
-template <int THREADS_, int TILE_, int STAGES_>
+template <int THREADS_, int TILE_, int STAGES_, int OVER_ = 992>
 struct Geo {
     static constexpr int THREADS = THREADS_, TILE = TILE_, STAGES = STAGES_;
     static constexpr int PRE = 32;                 // bytes kept in front of the tile (>= 1 needed)
-    static constexpr int OVER = 992;               // bytes after the tile a row may run into
+    static constexpr int OVER = OVER_;             // bytes after the tile a row may run into
     static constexpr int BUF = PRE + TILE + OVER;  // multiple of 32
     static constexpr int CHUNKS = BUF / 16;
     static constexpr int MASKW = BUF / 32 + 4;     // mask words incl. padding for 64-bit windows

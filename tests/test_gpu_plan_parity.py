@@ -376,3 +376,68 @@ def test_partial_aggregates_merge_with_join():
         lib.partial_free(merged)
         for p in parts:
             lib.partial_free(p)
+
+
+def _sparse_anomaly_table(n, seed, kind):
+    """A table the scalar lean kernel covers, with ONE kind of byte it does not classify sprinkled in every few
+    hundred rows: the tile holding it must come out exactly as the reference reads it (handed to the general
+    kernel whole), its neighbours untouched."""
+    rnd = random.Random(seed)
+    rows = ["name,age,score,tag"]
+    for i in range(n):
+        name = rnd.choice(["ann", "bob", "carla", "dmitri", "eve"])
+        age = str(rnd.randint(0, 120))
+        score = rnd.choice(["1.5", "2", "0.25", "10.5", "99", "7.", ".5", "100", "1234", "12345", "3.125"])
+        tag = rnd.choice(["x", "yy", "zzz"])
+        if i % 397 == 5:
+            if kind == "blank_in_field":
+                name = "new york"
+            elif kind == "blank_number":
+                age = " " + age
+            elif kind == "quoted":
+                name = '"o,k"'
+            elif kind == "tab":
+                tag = "t\tt"
+            elif kind == "empty_line":
+                rows.append("")
+            elif kind == "cr":
+                tag = tag + "\r"
+            elif kind == "ragged":
+                rows.append(name)
+                continue
+            elif kind == "long_row":
+                tag = "L" * rnd.choice([40, 64, 200, 1500])
+            elif kind == "signed":
+                age = "-" + age
+            elif kind == "bang":
+                tag = "!" + tag
+        rows.append(f"{name},{age},{score},{tag}")
+    return ("\n".join(rows) + "\n").encode()
+
+
+@pytest.mark.parametrize("kind", ["none", "blank_in_field", "blank_number", "quoted", "tab", "empty_line", "cr", "ragged",
+                                  "long_row", "signed", "bang"])
+def test_scalar_lean_kernel_dirty_tiles(kind):
+    data = _sparse_anomaly_table(50_000, 3, kind)
+    NAME_, AGE_, SCORE_, TAG_ = range(4)
+    specs = [
+        dict(where=(">", ("col", AGE_), ("const", 40)), aggs=[(A.AGG_COUNT_STAR, -1)]),
+        dict(where=("<=", ("col", SCORE_), ("const", 2.5)), aggs=[(A.AGG_COUNT_STAR, -1)]),
+        dict(where=("=", ("col", SCORE_), ("const", 7)), aggs=[(A.AGG_COUNT_STAR, -1)]),
+        dict(where=("!=", ("col", AGE_), ("const", 33.5)), aggs=[(A.AGG_COUNT_STAR, -1)]),
+        dict(where=("<", ("col", NAME_), ("const", 3)), aggs=[(A.AGG_COUNT_STAR, -1)]),
+        dict(where=("and", (">=", ("col", AGE_), ("const", 18)), ("=", ("col", TAG_), ("const", "yy"))),
+             aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, SCORE_), (A.AGG_AVG, AGE_), (A.AGG_COUNT, NAME_)]),
+        dict(aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE_), (A.AGG_AVG, SCORE_)], out_cols=[NAME_, TAG_]),
+        dict(where=("or", ("<", ("col", SCORE_), ("const", 1)), ("not", ("!=", ("col", NAME_), ("const", "eve")))),
+             aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE_)]),
+    ]
+    with Table.from_bytes(data, lib=gpu()) as tg, Table.from_bytes(data, lib=oracle()) as to:
+        assert tg.row_count() == to.row_count()
+        for spec in specs:
+            pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
+        for i in range(4):
+            tg.set_shard(i, 4)
+            to.set_shard(i, 4)
+            for spec in (specs[0], specs[5]):
+                pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
