@@ -456,7 +456,7 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
     return CQG_OK;
 }
 
-template <class LG, int MINB, bool ONELEAF, int MM, int GAP0>
+template <class LG, int MINB, bool ONELEAF, int MM, int GAP0, bool PF = true, bool SWP = true>
 static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
@@ -466,17 +466,17 @@ static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
         P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
     }
     if (P.n_tiles <= 0) return CQG_OK;
-    const int smem = Lean2Layout<LG>::TOTAL;
+    const int smem = Lean2Layout<LG>::TOTAL;  // tile + padded masks + interval table
     LaunchCfg& c = g_cfg[dev & 63];
     if (!c.ready) {
         CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
         c.ready = true;
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2_kernel<LG, MINB, ONELEAF, MM, GAP0>, LG::THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2_kernel<LG, MINB, ONELEAF, MM, GAP0, PF, SWP>, LG::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean2 kernel does not fit");
     int grid = std::min(P.n_tiles, c.sms * per_sm);
-    lean2_kernel<LG, MINB, ONELEAF, MM, GAP0><<<grid, LG::THREADS, smem, st>>>(P);
+    lean2_kernel<LG, MINB, ONELEAF, MM, GAP0, PF, SWP><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
     CU(cudaGetLastError());
     return CQG_OK;
@@ -516,6 +516,14 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
                     case 2: return launch_lean2_geo<LS, 10, true, 1, 2>(P, st);
                     case 4: return launch_lean2_geo<LS, 10, true, 1, 4>(P, st);
                     default: return launch_lean2_geo<LS, 10, true, 1, -1>(P, st);
+                }
+            }
+            if (var == 4 && P.gap[0] == 2) return launch_lean2_geo<LS, 9, true, 1, 2, true, false>(P, st);
+            if (var == 5 && P.gap[0] == 2) return launch_lean2_geo<LS, 9, true, 1, 2, false, false>(P, st);
+            if (var == 3) {  // no L2 prefetch (A/B)
+                switch (P.gap[0]) {
+                    case 2: return launch_lean2_geo<LS, 9, true, 1, 2, false>(P, st);
+                    default: return launch_lean2_geo<LS, 9, true, 1, -1, false>(P, st);
                 }
             }
             switch (P.gap[0]) {

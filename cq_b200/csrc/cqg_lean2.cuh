@@ -20,7 +20,7 @@ namespace cqg {
 template <class G>
 struct Lean2Layout {
     static constexpr int OFF_MSK = G::STAGES * G::BUF;           // (T word, D word) per 32 CSV bytes
-    static constexpr int OFF_CMP = OFF_MSK + G::MASKW * 8;       // kMaxLeanLeaf x 4 fd x {lo, width, negate, pad}
+    static constexpr int OFF_CMP = OFF_MSK + G::MASKW * 8;       // kMaxLeanLeaf x 4 fd x {lo, width, code lo, code width}
     static constexpr int OFF_MISC = OFF_CMP + kMaxLeanLeaf * 64; // handed-row counters (2 x u32)
     static constexpr int OFF_MBAR = OFF_MISC + 16;
     static constexpr int TOTAL = OFF_MBAR + G::STAGES * 8;
@@ -32,8 +32,8 @@ __device__ __forceinline__ uint2 lds64(uint32_t a) {
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
-__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ uint32_t ctz32(uint32_t x) { return (uint32_t)__clz((int)__brev(x)); }
 __device__ __forceinline__ uint32_t ctz64(uint64_t x) { return (uint32_t)__clzll((long long)__brevll(x)); }
@@ -53,8 +53,28 @@ __device__ __forceinline__ uint32_t lean2_mask16(uint32_t f0, uint32_t f1, uint3
     return __byte_perm(lo, hi, 0x7740);
 }
 
-// `mant * A <op> LB` over mant in [0, 2^32) as an interval: pass = ((mant - lo) <= width) ^ negate
-__device__ inline void lean2_interval(const LeanLeaf& L, int fd, uint32_t& lo, uint32_t& width, uint32_t& negate) {
+// A decimal of <= 4 digits as its digit bytes, most significant on top (d3 << 24 | d2 << 16 | d1 << 8 | d0):
+// monotone in the value, so intervals of values are intervals of codes and no multiply is needed.
+__host__ __device__ __forceinline__ uint32_t lean2_code(uint32_t v) {  // v <= 9999
+    return ((v / 1000u) << 24) | (((v / 100u) % 10u) << 16) | (((v / 10u) % 10u) << 8) | (v % 10u);
+}
+
+// the complement of the modular interval {lo, width} (v - lo <= width, unsigned): again one
+__host__ __device__ __forceinline__ void lean2_negate(uint32_t& lo, uint32_t& width) {
+    if (width == 0xffffffffu) {  // always -> never
+        lo = 0xffffffffu;
+        width = 0u;
+    } else {
+        lo = lo + width + 1u;
+        width = 0xfffffffeu - width;
+    }
+}
+
+// `mant * A <op> LB` over mant in [0, 2^24) as a modular interval: pass = (mant - lo) <= width (unsigned).
+// "never" is {0xffffffff, 0}, "always" {0, 0xffffffff}; != is the complement of the == interval.
+// Also the same test over digit codes (lean2_code) of values <= 9999: {clo, cwidth}.
+__device__ inline void lean2_interval(const LeanLeaf& L, int fd, uint32_t& lo, uint32_t& width, uint32_t& clo, uint32_t& cwidth) {
+    uint32_t negate;
     const unsigned long long A = L.A[fd] ? L.A[fd] : 1u;
     const long long LB = L.LB[fd];
     const unsigned long long top = 0xfffffffeull;
@@ -87,6 +107,29 @@ __device__ inline void lean2_interval(const LeanLeaf& L, int fd, uint32_t& lo, u
         } else {
             negate = L.lop == 2 ? 1u : 0u;
         }
+    }
+    if (negate && L.lop != 3) {
+        // (only whole-range intervals are negated here: "never")
+        lo = 0xffffffffu;
+        width = 0u;
+        negate = 0u;
+    }
+    if (L.lop == 3 && !negate) {  // != without an exact hit: always true
+        lo = 0u;
+        width = 0xffffffffu;
+    }
+    // codes: [lo, lo + width] cut to 0..9999
+    clo = 0xffffffffu;
+    cwidth = 0u;
+    if (lo <= 9999u) {
+        const uint32_t hi_v = (width >= 9999u - lo) ? 9999u : lo + width;
+        clo = lean2_code(lo);
+        cwidth = lean2_code(hi_v) - clo;
+        if (lo == 0u && hi_v == 9999u) cwidth = 0xffffffffu;
+    }
+    if (L.lop == 3 && negate) {  // != with an exact hit: the complement of {E, 0}
+        lean2_negate(lo, width);
+        lean2_negate(clo, cwidth);
     }
 }
 
@@ -161,6 +204,55 @@ struct Lean2Stops {
     }
 };
 
+
+// ---- ONELEAF helpers ----
+// lean2_dec4 with the digit code (lean2_code) instead of the value (the byte permute that drops the '.' also reverses the bytes)
+// Returns 0 when the field is such a decimal, anything else when not (sign, exponent, text, two dots, a lone '.').
+__device__ __forceinline__ uint32_t lean2_dec4c(uint32_t fe, uint32_t len, uint32_t& code, uint32_t& fd16) {
+    const uint32_t a = fe & ~3u;
+    const uint32_t w0 = lds32(a - 4u), w1 = lds32(a);
+    uint32_t t = __funnelshift_r(w0, w1, fe << 3) ^ 0x30303030u;  // bytes [fe-4, fe): the last character on top
+    t &= 0xffffffffu << (32u - 8u * len);                          // what precedes the field reads as leading zeros
+    const uint32_t x = ((t ^ 0x1e1e1e1eu) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    const uint32_t dotf = ~(x | t) & 0x80808080u;                  // 0x80 where the byte is '.'
+    fd16 = 0u;
+    uint32_t sel = 0x0123u, bad = 0u;
+    if (dotf) {
+        bad = (dotf & (dotf - 1u)) | (len == 1u ? 1u : 0u);
+        const uint32_t r = __umulhi(dotf, 0x66442200u);            // fd * 0x11 (see lean2_dec4)
+        fd16 = r & 0x30u;
+        sel = __byte_perm(0x23231312u, 0x41404040u, (r & 0x33u) | 0x40u);
+    }
+    t = __byte_perm(t, 0u, sel);
+    bad |= ((t + 0x76767676u) | t) & 0x80808080u;                 // a byte that is not a digit
+    code = t;
+    return bad;
+}
+// A row that does not end inside the 32-bit window (ONELEAF): 32..63 bytes on 64-bit masks, longer ones are
+// found and handed over. Returns et | sp << 16 | flen << 24 | dirty << 31 (flen 0: hand the row over).
+__device__ __noinline__ uint32_t lean2_wide_row(uint32_t s_msk, uint32_t pos, int gap, uint32_t limit) {
+    const uint32_t ma = s_msk + ((pos >> 2) & ~7u);
+    const uint2 m0 = lds64(ma), m1 = lds64(ma + 8u), m2 = lds64(ma + 16u);
+    const uint32_t tw2 = __funnelshift_r(m1.x, m2.x, pos);
+    if (tw2 == 0u) {
+        const uint32_t e = lean2_next_term(s_msk, pos + 64u, limit);
+        return (e - pos) | (e >= limit ? 0x80000000u : 0u);
+    }
+    const uint64_t tw64 = (uint64_t)tw2 << 32;
+    const uint64_t dw64 = ((uint64_t)__funnelshift_r(m1.y, m2.y, pos) << 32) | __funnelshift_r(m0.y, m1.y, pos);
+    const uint64_t below = tw64 ^ (tw64 - 1ull);
+    const uint32_t et = 32u + bfind32((uint32_t)(below >> 32));
+    uint64_t st = (dw64 | tw64) & below;
+    uint32_t sp = 0;
+    if (gap > 0) {
+        for (int i = 1; i < gap; i++) st &= st - 1ull;
+        sp = (uint32_t)__ffsll((long long)st);
+        st &= st - 1ull;
+    }
+    const uint32_t flen = st ? ctz64(st) - sp : 0u;
+    return et | (sp << 16) | ((flen > 63u ? 0u : flen) << 24);
+}
+
 // unsigned decimal of 5..7 bytes (rare next to the 4-byte route: kept out of line)
 // returns mant (< 10^7) | fd16 << 24 | ok << 31
 __device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
@@ -178,7 +270,7 @@ __device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
     }
 
 // GAP0: the wanted column index of ONELEAF plans when it is below 8 (the delimiter skips unroll), else -1
-template <class G, int MINB, bool ONELEAF, int MM, int GAP0>
+template <class G, int MINB, bool ONELEAF, int MM, int GAP0, bool PF, bool SWP>
 __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     static_assert(G::STAGES == 1 && G::TILE == G::THREADS * 128, "one stage, 128 bytes per thread");
@@ -201,9 +293,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
         sts32(s_msk + 8 * w + 4, 0u);
     }
     if (tid < P.l_nleaf * 4 && P.l_leaf[tid >> 2].kind == 0) {
-        uint32_t lo, width, negate;
-        lean2_interval(P.l_leaf[tid >> 2], tid & 3, lo, width, negate);
-        sts128(s_cmp + 16 * tid, lo, width, negate, 0u);
+        uint32_t lo, width, clo, cwidth;
+        lean2_interval(P.l_leaf[tid >> 2], tid & 3, lo, width, clo, cwidth);
+        sts64(s_cmp + 16 * tid, lo, width);
+        sts64(s_cmp + 16 * tid + 8, clo, cwidth);
     }
     __syncthreads();
 
@@ -247,6 +340,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
             } else {
                 mbar_expect_tx(&mbar[0], 0);
             }
+            // this CTA's next tile: on its way into L2 while this one is worked on (one stage of shared memory only)
+            const long long gn = g0 + (long long)gridDim.x * G::TILE;
+            if (PF && it + 1 < my_tiles && gn + G::BUF <= (long long)size)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.data + gn), "r"((uint32_t)G::BUF) : "memory");
             s_handed[it & 1] = 0u;  // last read two tiles ago, at least one barrier back
         }
         mbar_wait(&mbar[0], (uint32_t)it & 1u);
@@ -318,9 +415,91 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
             uint32_t pos = e0 + 1u;
             if (pos < hi) {
                 dirty |= lds8(s_buf + e0) != 0x0au ? 1u : 0u;
+                uint32_t ma = s_msk + ((pos >> 2) & ~7u);
+                uint2 m0 = lds64(ma), m1 = lds64(ma + 8u);
+                if constexpr (ONELEAF) {
+                    // ---- COUNT(*) WHERE column <op> literal: the row loop written out for this shape alone ----
+                    uint32_t iters = 0, nlacc = 0;
+                    do {
+                        const uint32_t tw = __funnelshift_r(m0.x, m1.x, pos);
+                        const uint32_t dw = __funnelshift_r(m0.y, m1.y, pos);
+                        uint32_t et, sp = 0, flen;
+                        if (tw != 0u) {
+                            seen |= tw;
+                            const uint32_t below = tw ^ (tw - 1u);  // up to and including the terminator
+                            et = bfind32(below);
+                            // stops of the row: its delimiters, its terminator, and every bit above as a sentinel, so that
+                            // a field the row does not have comes out with length 0
+                            uint32_t st = dw | tw | ~below;
+                            if (GAP0 > 0) {
+#pragma unroll
+                                for (int i = 1; i < GAP0; i++) st &= st - 1u;
+                                sp = (uint32_t)__ffs((int)st);
+                                st &= st - 1u;
+                            } else if (GAP0 < 0 && gap0 > 0) {
+#pragma unroll 1
+                                for (int i = 1; i < gap0; i++) st &= st - 1u;
+                                sp = (uint32_t)__ffs((int)st);
+                                st &= st - 1u;
+                            }
+                            flen = ctz32(st) - sp;  // st == 0 (terminator on bit 31, field missing): 32 - sp, 0 or far too long
+                        } else {
+                            const uint32_t r = lean2_wide_row(s_msk, pos, gap0, (uint32_t)G::BUF);
+                            et = r & 0xffffu;
+                            sp = (r >> 16) & 0xffu;
+                            flen = (r >> 24) & 0x7fu;
+                            dirty |= r >> 31;
+                        }
+                        const uint32_t rbase = s_buf + pos;
+                        const uint32_t npos = pos + et + 1u;
+                        const uint32_t nma = s_msk + ((npos >> 2) & ~7u);
+                        uint2 n0, n1;
+                        uint32_t lastb;
+                        if (SWP) {
+                            n0 = lds64(nma);
+                            n1 = lds64(nma + 8u);
+                            lastb = lds8(rbase + et);
+                        }
+                        uint32_t val = 0, fd16 = 0, tab = 8u, bad = 1u;
+                        if (flen - 1u < 4u) {
+                            bad = lean2_dec4c(rbase + sp + flen, flen, val, fd16);
+                        } else if (flen - 1u < 7u) {
+                            bool dec;
+                            CQG_L2_DEC7(rbase + sp, flen, dec, val, fd16)
+                            bad = dec ? 0u : 1u;
+                            tab = 0u;
+                        }
+                        const uint2 iv = lds64(s_cmp + fd16 + tab);
+                        // count the row, keep the first one, or note it for the general kernel (the last two: pos < 2^16)
+                        asm("{\n\t"
+                            ".reg .pred good, take;\n\t"
+                            ".reg .u32 d;\n\t"
+                            "setp.eq.u32 good, %4, 0;\n\t"
+                            "sub.u32 d, %5, %6;\n\t"
+                            "setp.le.and.u32 take, d, %7, good;\n\t"
+                            "@take add.u32 %0, %0, 1;\n\t"
+                            "@take min.u32 %1, %1, %8;\n\t"
+                            "@!good mad.lo.u32 %2, %2, 65536, %8;\n\t"
+                            "@!good add.u32 %3, %3, 1;\n\t"
+                            "}"
+                            : "+r"(tcnt), "+r"(tfirst), "+r"(hpos), "+r"(nh)
+                            : "r"(bad), "r"(val), "r"(iv.x), "r"(iv.y), "r"(pos));
+                        if (!SWP) {
+                            n0 = lds64(nma);
+                            n1 = lds64(nma + 8u);
+                            lastb = lds8(rbase + et);
+                        }
+                        nlacc |= lastb ^ 0x0au;  // the row must end in '\n'
+                        iters++;
+                        pos = npos;
+                        ma = nma;
+                        m0 = n0;
+                        m1 = n1;
+                    } while (pos < hi);
+                    trows = iters - nh;
+                    dirty |= nlacc != 0u ? 1u : 0u;
+                } else
                 do {
-                    const uint32_t ma = s_msk + ((pos >> 2) & ~7u);
-                    const uint2 m0 = lds64(ma), m1 = lds64(ma + 8u);
                     const uint32_t tw = __funnelshift_r(m0.x, m1.x, pos);
                     const uint32_t dw = __funnelshift_r(m0.y, m1.y, pos);
                     bool ok = true, pass = true;
@@ -365,22 +544,19 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                         }
                     }
                     const uint32_t rbase = s_buf + pos;
+                    // the next row's mask words and this row's last byte: asked for now, used after the decode
+                    const uint32_t npos = pos + et + 1u;
+                    const uint32_t nma = s_msk + ((npos >> 2) & ~7u);
+                    uint2 n0, n1;
+                    uint32_t lastb;
+                    if (SWP) {
+                        n0 = lds64(nma);
+                        n1 = lds64(nma + 8u);
+                        lastb = lds8(rbase + et);
+                    }
                     unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
                     uint32_t addmask = 0;
-                    if (ONELEAF) {
-                        uint32_t mant = 0, fd16 = 0;
-                        bool dec = false;
-                        if (ok) {
-                            if (len0 - 1u < 4u) {
-                                dec = lean2_dec4(rbase + off0 + len0, len0, mant, fd16);
-                            } else if (len0 - 1u < 7u) {
-                                CQG_L2_DEC7(rbase + off0, len0, dec, mant, fd16)
-                            }
-                        }
-                        ok = ok && dec;
-                        const uint4 iv = lds128(s_cmp + fd16);
-                        pass = ((mant - iv.x <= iv.y) ? 1u : 0u) != iv.z;
-                    } else if (ok) {
+                    if (ok) {
 #define CQG_L2_SLOT(SL, O, L)                                                    \
     const uint32_t O = SL == 0 ? off0 : SL == 1 ? off1 : SL == 2 ? off2 : off3; \
     const uint32_t L = SL == 0 ? len0 : SL == 1 ? len1 : SL == 2 ? len2 : len3;
@@ -401,8 +577,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                                             CQG_L2_DEC7(rbase + o, l, dec, mant, fd16)
                                         }
                                         if (dec) {
-                                            const uint4 iv = lds128(s_cmp + 64u * (uint32_t)c + fd16);
-                                            bv = ((mant - iv.x <= iv.y) ? 1u : 0u) != iv.z;
+                                            const uint2 iv = lds64(s_cmp + 64u * (uint32_t)c + fd16);
+                                            bv = mant - iv.x <= iv.y;
                                         } else {
                                             ok = false;  // NULL, text, date, signed or long number: general kernel
                                         }
@@ -495,8 +671,16 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                         nh++;
                     }
                     // the row must end in '\n' (anything else below 0x23 is not this kernel's business)
-                    dirty |= lds8(rbase + et) != 0x0au ? 1u : 0u;
-                    pos += et + 1u;
+                    if (!SWP) {
+                        n0 = lds64(nma);
+                        n1 = lds64(nma + 8u);
+                        lastb = lds8(rbase + et);
+                    }
+                    dirty |= lastb != 0x0au ? 1u : 0u;
+                    pos = npos;
+                    ma = nma;
+                    m0 = n0;
+                    m1 = n1;
                 } while (pos < hi);
                 dirty |= seen & 1u;  // a row start that is a terminator: an empty line
             }
