@@ -354,7 +354,7 @@ def main():
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "cqg::lean_kernel (simple plans; cqg::scan_kernel for what it hands over)", "kernel_ms": kernel_avg,
+                    "traffic": traffic, "kernel": "cqg::lean2_kernel (scalar lean plans; cqg::scan_kernel for the tiles and rows it hands over)", "kernel_ms": kernel_avg,
                     "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                     "frac_of_nominal_8TBs": achieved / 8000.0}
         if world == 1:

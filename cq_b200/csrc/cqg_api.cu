@@ -456,7 +456,7 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
     return CQG_OK;
 }
 
-template <class LG, int MINB, bool ONELEAF, int MM, int GAP0, bool PF = true, bool SWP = true>
+template <class LG, int MINB, bool ONELEAF, int GAP0>
 static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
@@ -473,10 +473,10 @@ static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
         c.ready = true;
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2_kernel<LG, MINB, ONELEAF, MM, GAP0, PF, SWP>, LG::THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2_kernel<LG, MINB, ONELEAF, GAP0>, LG::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean2 kernel does not fit");
     int grid = std::min(P.n_tiles, c.sms * per_sm);
-    lean2_kernel<LG, MINB, ONELEAF, MM, GAP0, PF, SWP><<<grid, LG::THREADS, smem, st>>>(P);
+    lean2_kernel<LG, MINB, ONELEAF, GAP0><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
     CU(cudaGetLastError());
     return CQG_OK;
@@ -503,42 +503,23 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
                          P.nwantL == 1;
     bool mm0 = false;
     for (int a = 0; a < P.l_nagg; a++) mm0 = mm0 || P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX;
-    const int lean2 = env_int("CQG_LEAN2", 1);  // 0: the round-1 lean kernel (A/B runs)
+    const int lean2 = env_int("CQG_LEAN2", 1);  // 0: the first lean kernel (A/B runs)
     if (lean2 && !mm0) {
-        using LG = Geo<128, 16384, 1>;
         using LS = Geo<128, 16384, 1, 224>;  // rows of 64 bytes and more are handed over anyway: a short overlap
         if (oneleaf) {
-            const int var = env_int("CQG_L2_VAR", 1);
-            if (lean2 == 3) return launch_lean2_geo<LG, 9, true, 0, -1>(P, st);
-            if (var == 0) return launch_lean2_geo<LG, 9, true, 1, -1>(P, st);
-            if (var == 2) {
-                switch (P.gap[0]) {
-                    case 2: return launch_lean2_geo<LS, 10, true, 1, 2>(P, st);
-                    case 4: return launch_lean2_geo<LS, 10, true, 1, 4>(P, st);
-                    default: return launch_lean2_geo<LS, 10, true, 1, -1>(P, st);
-                }
-            }
-            if (var == 4 && P.gap[0] == 2) return launch_lean2_geo<LS, 9, true, 1, 2, true, false>(P, st);
-            if (var == 5 && P.gap[0] == 2) return launch_lean2_geo<LS, 9, true, 1, 2, false, false>(P, st);
-            if (var == 3) {  // no L2 prefetch (A/B)
-                switch (P.gap[0]) {
-                    case 2: return launch_lean2_geo<LS, 9, true, 1, 2, false>(P, st);
-                    default: return launch_lean2_geo<LS, 9, true, 1, -1, false>(P, st);
-                }
-            }
             switch (P.gap[0]) {
-                case 0: return launch_lean2_geo<LS, 9, true, 1, 0>(P, st);
-                case 1: return launch_lean2_geo<LS, 9, true, 1, 1>(P, st);
-                case 2: return launch_lean2_geo<LS, 9, true, 1, 2>(P, st);
-                case 3: return launch_lean2_geo<LS, 9, true, 1, 3>(P, st);
-                case 4: return launch_lean2_geo<LS, 9, true, 1, 4>(P, st);
-                case 5: return launch_lean2_geo<LS, 9, true, 1, 5>(P, st);
-                case 6: return launch_lean2_geo<LS, 9, true, 1, 6>(P, st);
-                case 7: return launch_lean2_geo<LS, 9, true, 1, 7>(P, st);
-                default: return launch_lean2_geo<LS, 9, true, 1, -1>(P, st);
+                case 0: return launch_lean2_geo<LS, 9, true, 0>(P, st);
+                case 1: return launch_lean2_geo<LS, 9, true, 1>(P, st);
+                case 2: return launch_lean2_geo<LS, 9, true, 2>(P, st);
+                case 3: return launch_lean2_geo<LS, 9, true, 3>(P, st);
+                case 4: return launch_lean2_geo<LS, 9, true, 4>(P, st);
+                case 5: return launch_lean2_geo<LS, 9, true, 5>(P, st);
+                case 6: return launch_lean2_geo<LS, 9, true, 6>(P, st);
+                case 7: return launch_lean2_geo<LS, 9, true, 7>(P, st);
+                default: return launch_lean2_geo<LS, 9, true, -1>(P, st);
             }
         }
-        return launch_lean2_geo<LS, 8, false, 1, -1>(P, st);
+        return launch_lean2_geo<LS, 6, false, -1>(P, st);
     }
     if (oneleaf) {
         static int variant = -1;

@@ -7,10 +7,14 @@
 //     once per byte; a tile where any row ends in something else, holds an empty line, or hands over
 //     too many rows is DIRTY and goes to the general kernel as a whole (src/csv_reader.c:404-427 row
 //     split, :278-338 field split, :195-240 typed decode are then reproduced exactly there);
+//   * byte flags become mask bits through dot products (IDP.4A runs at twice the rate of IMAD.HI on sm_100a,
+//     tools/micro/pipe_bench.cu), adds are issued as IMAD so that the ALU and FMA pipes share the work;
 //   * T and D words interleaved (one 64-bit shared load gives both), a running cursor from row end to
-//     next row start (no row-start masks), fields <= 4 bytes decoded right-aligned with one byte-permute
-//     to drop the '.' and one dot product for the digits;
-//   * `mant * A[fd] <op> LB[fd]` (cqg_lean.cuh) is folded, per CTA, into an interval test on mant alone.
+//     next row start (no row-start masks, the next row's mask words asked for before the decode), fields
+//     <= 4 bytes decoded right-aligned with one byte-permute that drops the '.';
+//   * `mant * A[fd] <op> LB[fd]` (cqg_lean.cuh) is folded, per CTA, into ONE modular interval test
+//     (v - lo <= width, != included); the COUNT(*)-WHERE shape compares digit bytes, no multiply at all;
+//   * the CTA's next tile is prefetched into L2 while the current one is worked on.
 // Results of a tile are committed only after the whole CTA found the tile clean.
 #pragma once
 #include "cqg_lean.cuh"
@@ -41,16 +45,6 @@ __device__ __forceinline__ uint32_t bfind32(uint32_t x) {
     uint32_t r;
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
     return r;
-}
-
-// four 0x80-flag words -> 16-bit mask in byte order (flags_to_mask16b with the nibble merges as single LOP3s)
-__device__ __forceinline__ uint32_t lean2_mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
-    const uint32_t h0 = __umulhi(f0, 0x02040810u), h1 = __umulhi(f1, 0x20408100u);
-    const uint32_t h2 = __umulhi(f2, 0x02040810u), h3 = __umulhi(f3, 0x20408100u);
-    uint32_t lo, hi;
-    asm("lop3.b32 %0, %1, %2, 0xf, 0xE4;" : "=r"(lo) : "r"(h0), "r"(h1));  // (h0 & 0xf) | (h1 & ~0xf)
-    asm("lop3.b32 %0, %1, %2, 0xf, 0xE4;" : "=r"(hi) : "r"(h2), "r"(h3));
-    return __byte_perm(lo, hi, 0x7740);
 }
 
 // A decimal of <= 4 digits as its digit bytes, most significant on top (d3 << 24 | d2 << 16 | d1 << 8 | d0):
@@ -139,7 +133,7 @@ __device__ __forceinline__ bool lean2_dec4(uint32_t fe, uint32_t len, uint32_t& 
     const uint32_t a = fe & ~3u;
     const uint32_t w0 = lds32(a - 4u), w1 = lds32(a);
     uint32_t t = __funnelshift_r(w0, w1, fe << 3) ^ 0x30303030u;  // bytes [fe-4, fe): the last character on top
-    t &= 0xffffffffu << (32u - 8u * len);                          // what precedes the field reads as leading zeros
+    t &= ~(0x00ffffffu >> (8u * len - 8u));                        // what precedes the field reads as leading zeros
     const uint32_t x = ((t ^ 0x1e1e1e1eu) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
     const uint32_t dotf = ~(x | t) & 0x80808080u;                  // 0x80 where the byte is '.'
     fd16 = 0u;
@@ -212,7 +206,7 @@ __device__ __forceinline__ uint32_t lean2_dec4c(uint32_t fe, uint32_t len, uint3
     const uint32_t a = fe & ~3u;
     const uint32_t w0 = lds32(a - 4u), w1 = lds32(a);
     uint32_t t = __funnelshift_r(w0, w1, fe << 3) ^ 0x30303030u;  // bytes [fe-4, fe): the last character on top
-    t &= 0xffffffffu << (32u - 8u * len);                          // what precedes the field reads as leading zeros
+    t &= ~(0x00ffffffu >> (8u * len - 8u));                        // what precedes the field reads as leading zeros
     const uint32_t x = ((t ^ 0x1e1e1e1eu) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
     const uint32_t dotf = ~(x | t) & 0x80808080u;                  // 0x80 where the byte is '.'
     fd16 = 0u;
@@ -270,7 +264,7 @@ __device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
     }
 
 // GAP0: the wanted column index of ONELEAF plans when it is below 8 (the delimiter skips unroll), else -1
-template <class G, int MINB, bool ONELEAF, int MM, int GAP0, bool PF, bool SWP>
+template <class G, int MINB, bool ONELEAF, int GAP0>
 __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     static_assert(G::STAGES == 1 && G::TILE == G::THREADS * 128, "one stage, 128 bytes per thread");
@@ -342,7 +336,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
             }
             // this CTA's next tile: on its way into L2 while this one is worked on (one stage of shared memory only)
             const long long gn = g0 + (long long)gridDim.x * G::TILE;
-            if (PF && it + 1 < my_tiles && gn + G::BUF <= (long long)size)
+            if (it + 1 < my_tiles && gn + G::BUF <= (long long)size)
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.data + gn), "r"((uint32_t)G::BUF) : "memory");
             s_handed[it & 1] = 0u;  // last read two tiles ago, at least one barrier back
         }
@@ -358,10 +352,9 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
 
         // ---- phase 1: T ("< 0x23") and D (delimiter) masks, 16 bytes per thread and step ----
         {
-            uint32_t ca = s_buf + 16u * tid;
-            uint32_t ma = s_msk + (((uint32_t)tid >> 1) << 3) + (((uint32_t)tid & 1u) << 1);
-#pragma unroll 2
-            for (int c = tid; c < G::CHUNKS; c += G::THREADS, ca += 16u * G::THREADS, ma += 4u * G::THREADS) {
+            const uint32_t ca = s_buf + 16u * tid;
+            const uint32_t ma = s_msk + (((uint32_t)tid >> 1) << 3) + (((uint32_t)tid & 1u) << 1);
+            auto chunk = [&](uint32_t ca, uint32_t ma) {
                 const uint4 v = lds128(ca);
                 const uint32_t a0 = ~(add_fma(v.x & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.x) & 0x80808080u;
                 const uint32_t a1 = ~(add_fma(v.y & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.y) & 0x80808080u;
@@ -371,23 +364,22 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                 const uint32_t d1 = ~(add_fma((v.y ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.y) & 0x80808080u;
                 const uint32_t d2 = ~(add_fma((v.z ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.z) & 0x80808080u;
                 const uint32_t d3 = ~(add_fma((v.w ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.w) & 0x80808080u;
-                if (MM == 1) {
-                    // flags are 0x80 per byte: four dot products leave mask << 7
-                    uint32_t ra = __dp4a(a2, 0x08040201u, 0u);
-                    ra = __dp4a(a3, 0x80402010u, ra) * 256u;
-                    ra = __dp4a(a0, 0x08040201u, ra);
-                    ra = __dp4a(a1, 0x80402010u, ra);
-                    uint32_t rd = __dp4a(d2, 0x08040201u, 0u);
-                    rd = __dp4a(d3, 0x80402010u, rd) * 256u;
-                    rd = __dp4a(d0, 0x08040201u, rd);
-                    rd = __dp4a(d1, 0x80402010u, rd);
-                    sts16(ma, ra >> 7);
-                    sts16(ma + 4u, rd >> 7);
-                } else {
-                    sts16(ma, lean2_mask16(a0, a1, a2, a3));
-                    sts16(ma + 4u, lean2_mask16(d0, d1, d2, d3));
-                }
-            }
+                // flags are 0x80 per byte: four dot products leave mask << 7
+                uint32_t ra = __dp4a(a2, 0x08040201u, 0u);
+                ra = __dp4a(a3, 0x80402010u, ra) * 256u;
+                ra = __dp4a(a0, 0x08040201u, ra);
+                ra = __dp4a(a1, 0x80402010u, ra);
+                uint32_t rd = __dp4a(d2, 0x08040201u, 0u);
+                rd = __dp4a(d3, 0x80402010u, rd) * 256u;
+                rd = __dp4a(d0, 0x08040201u, rd);
+                rd = __dp4a(d1, 0x80402010u, rd);
+                sts16(ma, ra >> 7);
+                sts16(ma + 4u, rd >> 7);
+            };
+            constexpr int kFull = G::CHUNKS / G::THREADS;  // steps every thread takes
+#pragma unroll
+            for (int k = 0; k < kFull; k++) chunk(ca + 16u * G::THREADS * k, ma + 4u * G::THREADS * k);
+            if (tid < G::CHUNKS - kFull * G::THREADS) chunk(ca + 16u * G::THREADS * kFull, ma + 4u * G::THREADS * kFull);
         }
         __syncthreads();
 
@@ -455,11 +447,9 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                         const uint32_t nma = s_msk + ((npos >> 2) & ~7u);
                         uint2 n0, n1;
                         uint32_t lastb;
-                        if (SWP) {
-                            n0 = lds64(nma);
-                            n1 = lds64(nma + 8u);
-                            lastb = lds8(rbase + et);
-                        }
+                        n0 = lds64(nma);  // (asked for before the decode, used after it)
+                        n1 = lds64(nma + 8u);
+                        lastb = lds8(rbase + et);
                         uint32_t val = 0, fd16 = 0, tab = 8u, bad = 1u;
                         if (flen - 1u < 4u) {
                             bad = lean2_dec4c(rbase + sp + flen, flen, val, fd16);
@@ -484,11 +474,6 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                             "}"
                             : "+r"(tcnt), "+r"(tfirst), "+r"(hpos), "+r"(nh)
                             : "r"(bad), "r"(val), "r"(iv.x), "r"(iv.y), "r"(pos));
-                        if (!SWP) {
-                            n0 = lds64(nma);
-                            n1 = lds64(nma + 8u);
-                            lastb = lds8(rbase + et);
-                        }
                         nlacc |= lastb ^ 0x0au;  // the row must end in '\n'
                         iters++;
                         pos = npos;
@@ -549,11 +534,9 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                     const uint32_t nma = s_msk + ((npos >> 2) & ~7u);
                     uint2 n0, n1;
                     uint32_t lastb;
-                    if (SWP) {
-                        n0 = lds64(nma);
-                        n1 = lds64(nma + 8u);
-                        lastb = lds8(rbase + et);
-                    }
+                    n0 = lds64(nma);
+                    n1 = lds64(nma + 8u);
+                    lastb = lds8(rbase + et);
                     unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
                     uint32_t addmask = 0;
                     if (ok) {
@@ -671,11 +654,6 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                         nh++;
                     }
                     // the row must end in '\n' (anything else below 0x23 is not this kernel's business)
-                    if (!SWP) {
-                        n0 = lds64(nma);
-                        n1 = lds64(nma + 8u);
-                        lastb = lds8(rbase + et);
-                    }
                     dirty |= lastb != 0x0au ? 1u : 0u;
                     pos = npos;
                     ma = nma;

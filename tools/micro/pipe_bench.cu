@@ -24,7 +24,11 @@ __device__ __forceinline__ uint32_t step(uint32_t x, uint32_t k, uint32_t one) {
     else if (OP == 10) asm volatile("add.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(k));
     else if (OP == 11) asm volatile("vabsdiff4.u32.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(k), "r"(one));
     else if (OP == 12) asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(k));
-    else d = x;
+    else if (OP == 13) {
+        unsigned long long w;
+        asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(x), "r"(k), "l"(((unsigned long long)k << 32) | x));
+        d = (uint32_t)w ^ (uint32_t)(w >> 32);
+    } else d = x;
     return d;
 }
 
@@ -86,6 +90,7 @@ int main() {
     run<8, -1>("FLO", out, cyc, sms);
     run<9, -1>("POPC", out, cyc, sms);
     run<11, -1>("VABSDIFF4", out, cyc, sms);
+    run<13, -1>("IMAD.WIDE (+LOP3)", out, cyc, sms);
     run<0, 1>("LOP3 + add imm", out, cyc, sms);
     run<0, 10>("LOP3 + add reg", out, cyc, sms);
     run<0, 2>("LOP3 + IMAD", out, cyc, sms);

@@ -54,7 +54,7 @@ if os.path.exists(rep):
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
     vals = {}
     with open(os.path.join(OUT, f"{R}_lean_kernel_ncu.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:lean_kernel : CQ_BENCH_BYTES=2e9 python bench.py --steps 2 --warmup 3 --no-extra\n")
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:lean2_kernel : CQ_BENCH_BYTES=2e9 python bench.py --steps 2 --warmup 3 --no-extra\n")
         for i, k in enumerate(h):
             if k in keep or (k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio")):
                 f.write(f"{k} = {v[i]} {u[i]}\n")
