@@ -519,7 +519,7 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
                 default: return launch_lean2_geo<LS, 9, true, -1>(P, st);
             }
         }
-        return launch_lean2_geo<LS, 6, false, -1>(P, st);
+        return launch_lean2_geo<LS, 8, false, -1>(P, st);
     }
     if (oneleaf) {
         static int variant = -1;
