@@ -202,12 +202,12 @@ struct Lean2Stops {
 // ---- ONELEAF helpers ----
 // lean2_dec4 with the digit code (lean2_code) instead of the value (the byte permute that drops the '.' also reverses the bytes)
 // Returns 0 when the field is such a decimal, anything else when not (sign, exponent, text, two dots, a lone '.').
-__device__ __forceinline__ uint32_t lean2_dec4c(uint32_t fe, uint32_t len, uint32_t& code, uint32_t& fd16) {
+__device__ __forceinline__ uint32_t lean2_dec4c(uint32_t fe, uint32_t len, uint32_t kdot, uint32_t& code, uint32_t& fd16) {
     const uint32_t a = fe & ~3u;
     const uint32_t w0 = lds32(a - 4u), w1 = lds32(a);
     uint32_t t = __funnelshift_r(w0, w1, fe << 3) ^ 0x30303030u;  // bytes [fe-4, fe): the last character on top
     t &= ~(0x00ffffffu >> (8u * len - 8u));                        // what precedes the field reads as leading zeros
-    const uint32_t x = ((t ^ 0x1e1e1e1eu) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    const uint32_t x = ((t ^ kdot) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
     const uint32_t dotf = ~(x | t) & 0x80808080u;                  // 0x80 where the byte is '.'
     fd16 = 0u;
     uint32_t sel = 0x0123u, bad = 0u;
@@ -403,7 +403,13 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
             tsn[a] = 0;
         }
         if (lo < hi) {
-            const uint32_t e0 = lean2_next_term(s_msk, lo - 1u, (uint32_t)G::BUF);
+            uint32_t e0;
+            {
+                const uint32_t q = lo - 1u;
+                const uint32_t qa = s_msk + ((q >> 2) & ~7u);
+                const uint32_t fw = __funnelshift_r(lds32(qa), lds32(qa + 8u), q);
+                e0 = fw != 0u ? q + ctz32(fw) : lean2_next_term(s_msk, q + 32u, (uint32_t)G::BUF);
+            }
             uint32_t pos = e0 + 1u;
             if (pos < hi) {
                 dirty |= lds8(s_buf + e0) != 0x0au ? 1u : 0u;
@@ -412,6 +418,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                 if constexpr (ONELEAF) {
                     // ---- COUNT(*) WHERE column <op> literal: the row loop written out for this shape alone ----
                     uint32_t iters = 0, nlacc = 0;
+                    uint32_t kdot;  // '.' ^ '0' in every byte, pinned in a register (a second LOP3 immediate otherwise)
+                    asm volatile("mov.u32 %0, 0x1e1e1e1e;" : "=r"(kdot));
                     do {
                         const uint32_t tw = __funnelshift_r(m0.x, m1.x, pos);
                         const uint32_t dw = __funnelshift_r(m0.y, m1.y, pos);
@@ -452,7 +460,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                         lastb = lds8(rbase + et);
                         uint32_t val = 0, fd16 = 0, tab = 8u, bad = 1u;
                         if (flen - 1u < 4u) {
-                            bad = lean2_dec4c(rbase + sp + flen, flen, val, fd16);
+                            bad = lean2_dec4c(rbase + sp + flen, flen, kdot, val, fd16);
                         } else if (flen - 1u < 7u) {
                             bool dec;
                             CQG_L2_DEC7(rbase + sp, flen, dec, val, fd16)
