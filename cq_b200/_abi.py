@@ -128,6 +128,13 @@ PROTOTYPES = {
     "partial_merge": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64]),
     "partial_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(Result))]),
     "partial_free": (None, [C.c_void_p]),
+    "partition_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "rowlist_device_ptr": (C.c_uint64, [C.c_void_p]),
+    "rowlist_counts": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
+    "rowlist_copy": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64]),
+    "rowlist_free": (None, [C.c_void_p]),
+    "execute_partial_rows": (C.c_int, [C.c_void_p, C.POINTER(Query), C.c_uint64, C.c_int64, C.c_uint64, C.c_int64,
+                                       C.POINTER(C.c_void_p)]),
     "generate_bigdata": (C.c_int, [C.c_uint64, C.c_size_t, C.c_int64, C.c_uint64, C.c_int64, C.POINTER(C.c_size_t)]),
     "generate_bigdata_bound": (C.c_size_t, [C.c_int64, C.c_int64]),
     "total_kernel_launches": (C.c_int64, []),

@@ -1077,6 +1077,7 @@ static const char* flag_text(unsigned f) {
 struct JoinState {
     DevBuf slots, row_off, row_next, scalars;
     uint64_t cap = 0, rows = 0;
+    unsigned flags = 0, key_classes = 0;  // what the build wrote into the probe plan's scalar block (the scan clears it)
 };
 
 static int count_rows_device(const cqg_table* t, bool whole, cudaStream_t st, int64_t* out) {
@@ -1103,9 +1104,12 @@ static int count_rows_device(const cqg_table* t, bool whole, cudaStream_t st, in
     return CQG_OK;
 }
 
-static int build_join(HostPlan& probe, JoinState& js, const cqg_table* rt, int right_col, cudaStream_t st) {
-    int64_t nrows = 0;
-    int rc = count_rows_device(rt, true, st, &nrows);
+// rows != nullptr: the build side is exactly these `n_rows` rows of the right file (offsets in device memory,
+// the rows this rank owns in a hash-partitioned join) instead of the whole right table.
+static int build_join(HostPlan& probe, JoinState& js, const cqg_table* rt, int right_col, cudaStream_t st,
+                      const uint64_t* rows = nullptr, int64_t n_rows = 0) {
+    int64_t nrows = n_rows;
+    int rc = rows ? CQG_OK : count_rows_device(rt, true, st, &nrows);
     if (rc) return rc;
     js.rows = (uint64_t)nrows;
     uint64_t cap = 1024;
@@ -1145,9 +1149,22 @@ static int build_join(HostPlan& probe, JoinState& js, const cqg_table* rt, int r
     B.jrow_next = js.row_next.as<uint32_t>();
     B.jrow_cap = js.rows;
     if (js.rows >= 0xfffffff0ull) return fail(CQG_ERR_UNSUPPORTED, "right table has too many rows");
-    if (right_col >= 0) {
+    if (right_col >= 0 && !rows) {
         rc = launch_scan(B, 0, st);
         if (rc) return rc;
+    } else if (right_col >= 0 && n_rows > 0) {
+        int grid = (int)std::min<uint64_t>(((uint64_t)n_rows + 127) / 128, 148 * 8);
+        deferred_rows_kernel<<<grid, 128, 0, st>>>(B, rows, (uint64_t)n_rows);
+        g_launches++;
+        CU(cudaGetLastError());
+    }
+    {
+        // the probe scan starts from a cleared scalar block: keep the build's error flags and key classes
+        ScalarBlock hb{};
+        CU(cudaMemcpyAsync(&hb, probe.d_scalars.p, sizeof hb, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        js.flags = hb.errflags & kFatalMask;
+        js.key_classes = hb.jclass[1];
     }
     DevPlan& P = probe.P;
     P.jslots = B.jslots;
@@ -1892,6 +1909,8 @@ CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t
         GroupTable gt;
         ScalarBlock hs{};
         if ((rc = run_aggregate_scan(hp, gt, st, hs, &ms))) return rc;
+        hs.errflags |= js.flags;
+        hs.jclass[1] |= js.key_classes;
         if ((rc = check_flags(hs, hp.P.join != 0))) return rc;
         DevBuf entries;
         uint64_t G = 0;
@@ -1978,7 +1997,9 @@ CQG_API void cqg_value_release(cqg_value_t* v) {
 struct cqg_partial {
     HostPlan hp;
     GroupTable gt;
-    JoinState js;  // build side of an equi-join (whole right table, replicated on every rank)
+    JoinState js;  // build side of an equi-join (whole right table, or the rows this rank owns)
+    JoinState js_finish;  // hash-partitioned joins: the whole right table again, built by the rank that finishes
+    bool owned_rows_only = false;  // js covers only the keys one rank owns
     cqg_query_t q{};
     int64_t rows_scanned = 0;
     double kernel_ms = 0;
@@ -2008,6 +2029,8 @@ CQG_API int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_
         return rc;
     }
     rc = run_aggregate_scan(p->hp, p->gt, 0, hs, &ms);
+    hs.errflags |= p->js.flags;
+    hs.jclass[1] |= p->js.key_classes;
     if (rc == CQG_OK) rc = check_flags(hs, q->join.right != nullptr);
     if (rc != CQG_OK) {
         delete p;
@@ -2015,6 +2038,174 @@ CQG_API int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_
     }
     p->rows_scanned = (int64_t)hs.rows_scanned;
     p->kernel_ms = ms;
+    *out = p;
+    return CQG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// hash-partitioned equi-join across ranks: row offsets split by key owner, exchanged by the
+// caller (NCCL all-to-all), then build + probe + aggregate over exactly the rows a rank owns
+// ------------------------------------------------------------------------------------------
+struct cqg_rowlist {
+    DevBuf list;
+    std::vector<int64_t> counts;
+};
+
+CQG_API int cqg_partition_rows(const cqg_table_t* t, int key_col, int world, cqg_rowlist_t** out) {
+    if (!t || !out || world < 1 || world > 4096) return fail(CQG_ERR_ARG, "bad argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    cqg_rowlist* rl = new cqg_rowlist();
+    rl->counts.assign((size_t)world, 0);
+    const int ncols = (int)t->names.size();
+    if (key_col < 0 || key_col >= ncols) {  // resolve_column -> NULL: the ON condition is false for every row (joins.c:54)
+        *out = rl;
+        return CQG_OK;
+    }
+    HostPlan hp;
+    DevPlan& P = hp.P;
+    set_file(P, t, false);
+    P.mode = SCAN_PARTITION;
+    for (int c = 0; c < kMaxQueryCols; c++) P.colslot[c] = -1;
+    P.n_left_cols = ncols;
+    P.n_cols_total = ncols;
+    P.jr_col = key_col;
+    P.wantL[0] = (int16_t)key_col;
+    P.nwantL = 1;
+    P.colslot[key_col] = 0;
+    P.part_world = world;
+    DevBuf d_counts, d_base;
+    auto fail_free = [&](int code) {
+        delete rl;
+        return code;
+    };
+    if (hp.d_scalars.alloc(sizeof(ScalarBlock), st) != cudaSuccess || d_counts.alloc((size_t)world * 8, st) != cudaSuccess ||
+        d_base.alloc((size_t)world * 8, st) != cudaSuccess)
+        return fail_free(fail(CQG_ERR_NOMEM, "partition buffers"));
+    ScalarBlock* sb = hp.d_scalars.as<ScalarBlock>();
+    cudaMemsetAsync(sb, 0, sizeof(ScalarBlock), st);
+    P.errflags = &sb->errflags;
+    P.rows_scanned = &sb->rows_scanned;
+    P.jclass = sb->jclass;
+    P.gcount = &sb->gcount;
+    P.sel_count = &sb->sel_count;
+    P.jrow_count = &sb->jrow_count;
+    P.part_counts = d_counts.as<unsigned long long>();
+    P.part_base = d_base.as<uint64_t>();
+    P.part_list = nullptr;
+    // pass 1: rows per owner
+    cudaMemsetAsync(d_counts.p, 0, (size_t)world * 8, st);
+    if ((rc = launch_scan(P, 0, st))) return fail_free(rc);
+    std::vector<uint64_t> cnt((size_t)world), base((size_t)world);
+    if (cudaMemcpyAsync(cnt.data(), d_counts.p, (size_t)world * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+        return fail_free(fail(CQG_ERR_CUDA, "partition count: %s", cudaGetErrorString(cudaGetLastError())));
+    uint64_t total = 0;
+    for (int o = 0; o < world; o++) {
+        base[(size_t)o] = total;
+        total += cnt[(size_t)o];
+        rl->counts[(size_t)o] = (int64_t)cnt[(size_t)o];
+    }
+    // pass 2: the offsets, every owner's segment dense
+    if (rl->list.alloc((total + 1) * 8, st) != cudaSuccess) return fail_free(fail(CQG_ERR_NOMEM, "partition list"));
+    cudaMemcpyAsync(d_base.p, base.data(), (size_t)world * 8, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(d_counts.p, 0, (size_t)world * 8, st);
+    P.part_list = rl->list.as<uint64_t>();
+    if ((rc = launch_scan(P, 0, st))) return fail_free(rc);
+    ScalarBlock h{};
+    if (cudaMemcpyAsync(&h, sb, sizeof h, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+        return fail_free(fail(CQG_ERR_CUDA, "partition scan: %s", cudaGetErrorString(cudaGetLastError())));
+    if (h.errflags & kFatalMask) return fail_free(fail(CQG_ERR_UNSUPPORTED, "%s", flag_text(h.errflags & kFatalMask)));
+    *out = rl;
+    return CQG_OK;
+}
+CQG_API uint64_t cqg_rowlist_device_ptr(const cqg_rowlist_t* rl) { return rl ? (uint64_t)(uintptr_t)rl->list.p : 0; }
+CQG_API int cqg_rowlist_counts(const cqg_rowlist_t* rl, int world, int64_t* counts) {
+    if (!rl || !counts || world != (int)rl->counts.size()) return fail(CQG_ERR_ARG, "bad argument");
+    for (int o = 0; o < world; o++) counts[o] = rl->counts[(size_t)o];
+    return CQG_OK;
+}
+CQG_API int cqg_rowlist_copy(const cqg_rowlist_t* rl, uint64_t dst_device_ptr, int64_t capacity) {
+    if (!rl) return fail(CQG_ERR_ARG, "null argument");
+    int64_t total = 0;
+    for (int64_t c : rl->counts) total += c;
+    if (capacity < total) return fail(CQG_ERR_ARG, "row list holds %lld offsets", (long long)total);
+    if (total) {
+        CU(cudaMemcpyAsync((void*)(uintptr_t)dst_device_ptr, rl->list.p, (size_t)total * 8, cudaMemcpyDeviceToDevice, 0));
+        CU(cudaStreamSynchronize(0));
+    }
+    return CQG_OK;
+}
+CQG_API void cqg_rowlist_free(cqg_rowlist_t* rl) { delete rl; }
+
+// the aggregate of `q` (an equi-join) over `n_left` rows of the left file against `n_right` rows of the right one
+CQG_API int cqg_execute_partial_rows(const cqg_table_t* t, const cqg_query_t* q, uint64_t left_rows_device_ptr, int64_t n_left,
+                                     uint64_t right_rows_device_ptr, int64_t n_right, cqg_partial_t** out) {
+    if (!t || !q || !out || n_left < 0 || n_right < 0) return fail(CQG_ERR_ARG, "bad argument");
+    if (!partial_query_ok(q) || !q->join.right) return fail(CQG_ERR_UNSUPPORTED, "row-list partials cover aggregates over an equi-join");
+    if (t->global_base != 0 || q->join.right->global_base != 0)
+        return fail(CQG_ERR_UNSUPPORTED, "row-list partials read whole files: global offset must be 0");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    cqg_partial* p = new cqg_partial();
+    p->q = *q;
+    p->q.where.code = nullptr;
+    p->q.where.consts = nullptr;
+    p->q.where.n_code = p->q.where.n_consts = 0;
+    auto bail = [&](int code) {
+        delete p;
+        return code;
+    };
+    if ((rc = build_plan(p->hp, t, q, st))) return bail(rc);
+    const uint64_t* lrows = (const uint64_t*)(uintptr_t)left_rows_device_ptr;
+    const uint64_t* rrows = (const uint64_t*)(uintptr_t)right_rows_device_ptr;
+    if ((rc = build_join(p->hp, p->js, q->join.right, q->join.right_col, st, rrows ? rrows : (const uint64_t*)8, n_right))) return bail(rc);  // (any non-null pointer with n_right == 0: an empty build side)
+    DevPlan& P = p->hp.P;
+    ScalarBlock hs{};
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return bail(fail(CQG_ERR_CUDA, "events"));
+    float ms_total = 0;
+    uint64_t cap = P.ngc == 0 ? 16 : 1 << 12;
+    while (P.ngc && cap < (uint64_t)n_left / 4 && cap < (1ull << 22)) cap <<= 1;
+    for (int attempt = 0; attempt < 12; attempt++) {
+        if ((rc = alloc_group_table(p->hp, p->gt, cap, st))) break;
+        cudaMemsetAsync(p->hp.d_scalars.p, 0, sizeof(ScalarBlock), st);
+        cudaEventRecord(e0, st);
+        if (n_left > 0) {
+            DevPlan R = P;
+            R.simple = 0;
+            R.scalar_regs = 0;
+            R.smem_cap = 0;
+            int grid = (int)std::min<uint64_t>(((uint64_t)n_left + 127) / 128, 148 * 8);
+            deferred_rows_kernel<<<grid, 128, 0, st>>>(R, lrows, (uint64_t)n_left);
+            g_launches++;
+        }
+        cudaEventRecord(e1, st);
+        if ((rc = read_scalars(p->hp, hs, st))) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms_total += ms;
+        if (hs.errflags & KERR_TABLE_FULL) {
+            cap *= 4;
+            if (cap > (1ull << 32)) {
+                rc = fail(CQG_ERR_NOMEM, "group table beyond 2^32 entries");
+                break;
+            }
+            continue;
+        }
+        break;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    hs.errflags |= p->js.flags;
+    hs.jclass[1] |= p->js.key_classes;
+    if (rc == CQG_OK) rc = check_flags(hs, true);
+    if (rc != CQG_OK) return bail(rc);
+    p->rows_scanned = (int64_t)hs.rows_scanned;
+    p->kernel_ms = ms_total;
+    p->owned_rows_only = true;
     *out = p;
     return CQG_OK;
 }
@@ -2065,6 +2256,7 @@ CQG_API int cqg_partial_new_like(const cqg_partial_t* like, cqg_partial_t** out)
     if (!like || !out) return fail(CQG_ERR_ARG, "null argument");
     cqg_partial* p = new cqg_partial();
     p->q = like->q;
+    p->owned_rows_only = like->owned_rows_only;
     p->hp.P = like->hp.P;
     p->hp.entry_init = like->hp.entry_init;
     p->hp.table_smem_bytes = like->hp.table_smem_bytes;
@@ -2103,16 +2295,12 @@ CQG_API int cqg_partial_merge(cqg_partial_t* p, uint64_t src_device_ptr, int64_t
     if (!p || n < 0) return fail(CQG_ERR_ARG, "bad argument");
     if (n == 0) return CQG_OK;
     DevPlan& P = p->hp.P;
-    for (int attempt = 0; attempt < 12; attempt++) {
-        CU(cudaMemsetAsync(P.errflags, 0, 4, 0));
-        int grid = (int)std::min<int64_t>((n + 127) / 128, 148 * 8);
-        merge_entries_kernel<<<grid, 128>>>(P, (const uint8_t*)src_device_ptr, (uint64_t)n);
-        g_launches++;
-        CU(cudaGetLastError());
-        unsigned f = 0;
-        CU(cudaMemcpy(&f, P.errflags, 4, cudaMemcpyDeviceToHost));
-        if (!(f & KERR_TABLE_FULL)) return CQG_OK;
-        // grow: re-insert what is there into a table four times the size, then try again
+    // room first: every record may be a new group, and a batch that overflowed half way could not be retried
+    // (the records already folded in would be added twice)
+    unsigned long long have = 0;
+    CU(cudaMemcpy(&have, P.gcount, 8, cudaMemcpyDeviceToHost));
+    while ((have + (unsigned long long)n) * 2ull > p->gt.cap) {
+        if (p->gt.cap > (1ull << 32)) return fail(CQG_ERR_NOMEM, "merge table beyond 2^32 entries");
         DevBuf old_entries;
         uint64_t G = 0;
         int rc = compact_groups(p->hp, p->gt, 0, 1, old_entries, &G, 0);
@@ -2130,7 +2318,15 @@ CQG_API int cqg_partial_merge(cqg_partial_t* p, uint64_t src_device_ptr, int64_t
             CU(cudaDeviceSynchronize());
         }
     }
-    return fail(CQG_ERR_NOMEM, "merge table kept overflowing");
+    CU(cudaMemsetAsync(P.errflags, 0, 4, 0));
+    int grid = (int)std::min<int64_t>((n + 127) / 128, 148 * 8);
+    merge_entries_kernel<<<grid, 128>>>(P, (const uint8_t*)src_device_ptr, (uint64_t)n);
+    g_launches++;
+    CU(cudaGetLastError());
+    unsigned f = 0;
+    CU(cudaMemcpy(&f, P.errflags, 4, cudaMemcpyDeviceToHost));
+    if (f & KERR_TABLE_FULL) return fail(CQG_ERR_NOMEM, "merge table overflowed");
+    return CQG_OK;
 }
 
 CQG_API int cqg_partial_finish(const cqg_partial_t* pc, const cqg_table_t* t, cqg_result_t** out) {
@@ -2144,6 +2340,17 @@ CQG_API int cqg_partial_finish(const cqg_partial_t* pc, const cqg_table_t* t, cq
     p->hp.P.data = t->d_data;
     p->hp.P.size = t->size;
     p->hp.P.global_base = t->global_base;
+    if (p->owned_rows_only && p->q.join.right) {
+        // the groups' representative rows (bare columns, numeric MIN/MAX of right columns) are looked up by
+        // (left row, rank of the match): that needs the matches of ANY key, i.e. a table over the whole right file
+        bool need = p->q.n_out_cols > 0;
+        for (int a = 0; a < p->q.n_aggs; a++)
+            need = need || ((p->q.aggs[a].func == CQG_AGG_MIN || p->q.aggs[a].func == CQG_AGG_MAX) && p->q.aggs[a].col >= p->hp.P.n_left_cols);
+        if (need) {
+            if ((rc = build_join(p->hp, p->js_finish, p->q.join.right, p->q.join.right_col, 0))) return rc;
+            p->owned_rows_only = false;
+        }
+    }
     rc = finish_aggregate(p->hp, t, p->q.join.right, &p->q, entries.as<uint8_t>(), G, true, p->rows_scanned, out, 0);
     if (rc == CQG_OK) {
         (*out)->kernel_ms = p->kernel_ms;

@@ -174,6 +174,13 @@ struct DevPlan {
     unsigned* jclass;   // [2] OR of (1 << class) over left / right key values
     int32_t need_right_fields;
 
+    // ---- partition (SCAN_PARTITION): this scan's row offsets split by owner = join-key hash % part_world ----
+    int32_t part_world;
+    int32_t part_pad;
+    unsigned long long* part_counts;  // [world] rows per owner (first pass) / write cursors (second pass)
+    const uint64_t* part_base;        // [world] first index of an owner's segment in part_list
+    uint64_t* part_list;              // global row offsets; nullptr: count only
+
     // ---- select ----
     uint64_t* sel_okey;
     uint64_t* sel_roff;
@@ -189,7 +196,8 @@ enum ScanMode : int {
     SCAN_AGG = 0,
     SCAN_SELECT = 1,
     SCAN_COUNT_ROWS = 2,  // only rows_scanned
-    SCAN_JOIN_BUILD = 3   // insert (key, row offset) of every row into the join table
+    SCAN_JOIN_BUILD = 3,  // insert (key, row offset) of every row into the join table
+    SCAN_PARTITION = 4    // split the row offsets by owner of the join key (hash-partitioned join)
 };
 
 }  // namespace cqg

@@ -836,6 +836,21 @@ __device__ inline void join_build_row(const DevPlan& P, const RowView& rv, uint6
     P.jrow_next[idx] = atomicExch(&s->head, (uint32_t)idx + 1u);
 }
 
+// owner rank of a join key in a hash-partitioned join: bits of the hash the slot index does not use first
+__device__ __forceinline__ uint32_t join_owner(uint64_t h, int world) { return (uint32_t)((h >> 33) % (uint64_t)world); }
+
+// SCAN_PARTITION: the row's offset goes on the list of the rank that owns its key (both sides of the join
+// canonicalise and hash the key the same way, so equal keys meet on one rank; NULL = NULL included)
+__device__ inline void partition_row(const DevPlan& P, const RowView& rv, uint64_t goff, unsigned& err) {
+    DVal v = row_value(rv, P.jr_col, err);
+    uint32_t tag;
+    uint64_t w0, w1, h;
+    join_key_of(v, err, tag, w0, w1, h);
+    const uint32_t o = join_owner(h, P.part_world);
+    const unsigned long long idx = atomicAdd(&P.part_counts[o], 1ull);
+    if (P.part_list) P.part_list[P.part_base[o] + idx] = P.global_base + goff;
+}
+
 // right row at file offset roff: find its end, split the wanted right columns
 __device__ inline void split_right_row(const DevPlan& P, uint64_t roff, uint32_t* foff, uint32_t* flen) {
     const uint8_t* b = P.rdata + roff;
@@ -867,6 +882,10 @@ __device__ __noinline__ void process_row_slow(const DevPlan& P, const CtaState& 
     uint64_t okey = gabs << 16;
     if (P.mode == SCAN_JOIN_BUILD) {
         join_build_row(P, rv, goff, acc.err);
+        return;
+    }
+    if (P.mode == SCAN_PARTITION) {
+        partition_row(P, rv, goff, acc.err);
         return;
     }
     if (!P.join) {

@@ -307,6 +307,30 @@ int cqg_partial_merge(cqg_partial_t* p, uint64_t src_device_ptr, int64_t n);
 int cqg_partial_finish(const cqg_partial_t* p, const cqg_table_t* t, cqg_result_t** out);
 void cqg_partial_free(cqg_partial_t* p);
 
+/* ---- hash-partitioned equi-join across ranks (replaces the O(L*R) loop of perform_join,
+ * src/evaluator/evaluator_joins.c:96-140, on N GPUs) ----
+ * Every rank holds both files whole in HBM (they are read in place: a join moves row REFERENCES, not rows).
+ * The work is split by key: rank r scans its byte-range shard of each file and splits the row offsets by
+ * owner = hash(canonical join key) % world (cqg_partition_rows); the ranks exchange the lists (NCCL
+ * all-to-all of 8-byte global offsets over NVLink); every rank then builds the join table over the RIGHT
+ * rows it owns, probes it with the LEFT rows it owns and aggregates (cqg_execute_partial_rows). Equal keys
+ * meet on exactly one rank (NULL = NULL and 1 = 1.0 included: both sides canonicalise the key the way
+ * value_compare, src/csv_reader.c:98-130, equates them), so the partials merge like any others
+ * (cqg_partial_export / _merge / _finish). Row order (first appearance, ties) rests on global offsets. */
+typedef struct cqg_rowlist cqg_rowlist_t;
+/* offsets of the data rows of this table's shard, split by owner of the key in column `key_col`:
+ * `world` dense segments in device memory, segment o = counts[o] offsets (uint64, global file offsets). */
+int cqg_partition_rows(const cqg_table_t* t, int key_col, int world, cqg_rowlist_t** out);
+uint64_t cqg_rowlist_device_ptr(const cqg_rowlist_t* rl);
+int cqg_rowlist_counts(const cqg_rowlist_t* rl, int world, int64_t* counts);
+/* all segments, in owner order, into caller-owned device memory (capacity in offsets) */
+int cqg_rowlist_copy(const cqg_rowlist_t* rl, uint64_t dst_device_ptr, int64_t capacity);
+void cqg_rowlist_free(cqg_rowlist_t* rl);
+/* cqg_execute_partial for an equi-join query restricted to `n_left` rows of `t` and `n_right` rows of
+ * q->join.right (device arrays of file offsets; both tables must view their whole file at offset 0). */
+int cqg_execute_partial_rows(const cqg_table_t* t, const cqg_query_t* q, uint64_t left_rows_device_ptr, int64_t n_left,
+                             uint64_t right_rows_device_ptr, int64_t n_right, cqg_partial_t** out);
+
 /* ---- synthetic data: seeded restatement of utils/generate_big_dataset.py:9-19 ----
  * Fills device memory with header + rows `name,surname,age,gender,height\n`; returns
  * the byte size. key_card>0 appends an integer column `uid` ~ U{0..key_card-1}.

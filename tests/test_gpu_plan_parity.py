@@ -441,3 +441,50 @@ def test_scalar_lean_kernel_dirty_tiles(kind):
             to.set_shard(i, 4)
             for spec in (specs[0], specs[5]):
                 pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_hash_partitioned_join(world):
+    """BASELINE config 5 on one device: `world` simulated ranks split the row offsets of their shards by key
+    owner (cqg_partition_rows), the lists are regrouped as the NCCL all-to-all regroups them, every owner builds
+    and probes over its own rows (cqg_execute_partial_rows), the partials merge. Must equal the single join."""
+    from cq_b200 import partitioned_join as pj
+    od, cd = _join_tables(20000, 3000, 17)
+    # keys the reference equates across spellings, NULL keys on both sides, keys without a partner
+    od += b"90001,1.00,0.10,1,\n90002,2.00,0.20,2,7.0\n90003,3.00,0.30,3,0007\n90004,4.00,0.40,4,999999\n"
+    cd += b",nokey,none@example.com,1999\n7.00,seven,s@example.com,1998\n"
+    lib_g, lib_o = gpu(), oracle()
+    with Table.from_bytes(od, lib=lib_g) as og, Table.from_bytes(cd, lib=lib_g) as cg, \
+            Table.from_bytes(od, lib=lib_o) as oo, Table.from_bytes(cd, lib=lib_o) as co:
+        specs = [
+            dict(aggs=[(A.AGG_COUNT_STAR, -1)]),
+            dict(aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 1), (A.AGG_MIN, 6), (A.AGG_MAX, 1)],
+                 where=(">", ("col", 1), ("const", 500))),
+            dict(group_by=[8], out_cols=[8, 6, 0], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 1), (A.AGG_MAX, 7)]),
+            dict(group_by=[6], out_cols=[6], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_AVG, 3)],
+                 where=("like", ("col", 6), ("const", "cust1%"))),
+            dict(group_by=[4], out_cols=[4, 5], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_MIN, 0)]),
+        ]
+        for spec in specs:
+            got = pj.join_aggregate(lib_g, og, cg, pc.build(spec, join=(cg, 4, 0)), world=world)
+            want = oo.execute(pc.build(spec, join=(co, 4, 0)))
+            got.pop("stats")
+            pc.compare_results(got, want)
+        # the lists partition the rows: every row on exactly one owner's list
+        rows, counts = pj.partition(lib_g, og, 4, world)
+        assert sum(counts) == og.row_count() and len(set(rows.tolist())) == sum(counts)
+        # an unresolved key column never matches (evaluator_joins.c:54)
+        got = pj.join_aggregate(lib_g, og, cg, pc.build(specs[0], join=(cg, -1, 0)), world=world)
+        assert got["groups"][0]["count"] == 0
+
+
+def test_join_keys_of_different_classes_are_declined():
+    """value_compare is 0 ("equal") across type classes (src/csv_reader.c:98-130): a numeric key column joined to
+    a text one matches every pair in the reference. The hash join cannot reproduce that and must say so, also
+    when each side on its own is of one class."""
+    left = b"k,v\n1,a\n2,b\n"
+    right = b"k,w\nx,1\ny,2\n"
+    with Table.from_bytes(left, lib=gpu()) as lg, Table.from_bytes(right, lib=gpu()) as rg:
+        with pytest.raises(CqError) as ei:
+            lg.execute(Plan(aggs=[(A.AGG_COUNT_STAR, -1)], join=(rg, 0, 0)))
+        assert ei.value.code == A.ERR_UNSUPPORTED
