@@ -106,3 +106,108 @@ def test_two_rank_shards_merge_to_the_whole_answer():
                 assert abs(x[1] - y[1]) <= 1e-12 * max(abs(x[1]), abs(y[1]))
             else:
                 assert x == y
+
+
+# ---------------------------------------------------------------------------------------------
+# hash-partitioned join: the exchange the GPU ranks do with cqg_partition_rows + NCCL all-to-all
+# ---------------------------------------------------------------------------------------------
+def _key_owner(text, world):
+    """owner of a join key: equal under value_compare (src/csv_reader.c:98-130) => same owner"""
+    t = text.strip()
+    try:
+        k = ("n", float(t))
+    except ValueError:
+        k = ("s", t)
+    if t == "":
+        k = ("null",)
+    import zlib
+    return zlib.crc32(repr(k).encode()) % world
+
+
+def _shard_rows(data, rank, world):
+    """data rows (bytes, without the header) whose first byte lies in this rank's byte range"""
+    lo, hi = len(data) * rank // world, len(data) * (rank + 1) // world
+    return [ln for ln, p in _rows_with_pos(data) if (lo <= p or rank == 0) and p < hi]
+
+
+def _rows_with_pos(data):
+    header_end = data.index(b"\n") + 1
+    pos = header_end
+    for line in data[header_end:].split(b"\n"):
+        if line:
+            yield line, pos
+        pos += len(line) + 1
+
+
+def _join_worker(rank, world, port, orders, customers, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oh, ch = orders[:orders.index(b"\n") + 1], customers[:customers.index(b"\n") + 1]
+        # partition this rank's shard of both sides by key owner
+        send_l = [[] for _ in range(world)]
+        send_r = [[] for _ in range(world)]
+        for line in _shard_rows(orders, rank, world):
+            send_l[_key_owner(line.split(b",")[4].decode(), world)].append(line)
+        for line in _shard_rows(customers, rank, world):
+            send_r[_key_owner(line.split(b",")[0].decode(), world)].append(line)
+        # all-to-all (gloo: as an all-gather of the send lists, each rank keeps its own column)
+        all_l, all_r = [None] * world, [None] * world
+        dist.all_gather_object(all_l, send_l)
+        dist.all_gather_object(all_r, send_r)
+        mine_l = [ln for src in all_l for ln in src[rank]]
+        mine_r = [ln for src in all_r for ln in src[rank]]
+        # local build + probe + aggregate over the owned rows
+        spec = dict(group_by=[8], out_cols=[8], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 1)])
+        with Table.from_bytes(oh + b"\n".join(mine_l) + b"\n", lib=oracle()) as lt, \
+                Table.from_bytes(ch + b"\n".join(mine_r) + b"\n", lib=oracle()) as rt:
+            part = lt.execute(pc.build(spec, join=(rt, 4, 0)))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (part, len(mine_l), len(mine_r)))
+        if rank == 0:
+            q.put(gathered)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_hash_partitioned_join_equals_the_whole_join():
+    import random
+    rnd = random.Random(3)
+    orders = ["id,price,tax,quantity,customer_id"]
+    for i in range(3000):
+        key = rnd.choice([str(rnd.randint(1, 450)), f"{rnd.randint(1, 450)}.0", "", f"00{rnd.randint(1, 9)}"])
+        orders.append(f"{i + 1},{rnd.randint(100, 9999) / 100:.2f},0.5,{rnd.randint(1, 9)},{key}")
+    customers = ["id,name,email,since"]
+    for i in range(400):
+        customers.append(f"{i + 1},c{i % 7},e{i}@x.org,{2015 + i % 5}")
+    customers += ["7.0,dup,d@x.org,1999", ",nokey,n@x.org,1998"]
+    orders = ("\n".join(orders) + "\n").encode()
+    customers = ("\n".join(customers) + "\n").encode()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_join_worker, args=(r, world, port, orders, customers, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    spec = dict(group_by=[8], out_cols=[8], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 1)])
+    with Table.from_bytes(orders, lib=oracle()) as lt, Table.from_bytes(customers, lib=oracle()) as rt:
+        whole = lt.execute(pc.build(spec, join=(rt, 4, 0)))
+    assert sum(g[1] for g in gathered) == 3000 and sum(g[2] for g in gathered) == 402  # every row on exactly one rank
+    got = {}
+    for part, _, _ in gathered:
+        for g in part["groups"]:
+            m = got.setdefault(tuple(g["out"]), [0, 0.0])
+            m[0] += g["count"]
+            m[1] += g["sum"][1]
+    want = {tuple(g["out"]): (g["count"], g["sum"][1]) for g in whole["groups"]}
+    assert set(got) == set(want)
+    for k, (c, s) in want.items():
+        assert got[k][0] == c
+        assert abs(got[k][1] - s) <= 1e-12 * max(abs(s), 1.0)
