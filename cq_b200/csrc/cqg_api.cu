@@ -19,6 +19,7 @@
 #include <ctime>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -948,8 +949,8 @@ static int compile_predicate(HostPlan& hp, const cqg_predicate_t& w, cudaStream_
         P.pred.n_code = w.n_code;
         P.pred_kind = 2;
     }
-    // the host vectors must outlive the async copies
-    CU(cudaStreamSynchronize(st));
+    // (sources are pageable host memory: cudaMemcpyAsync has staged them when it returns, so the vectors may go;
+    //  the copies themselves are ordered before the scan on the same stream)
     return CQG_OK;
 }
 
@@ -1244,6 +1245,29 @@ CQG_API void cqg_result_free(cqg_result_t* r) {
     free(r);
 }
 
+// host loops over millions of result cells (the finish of a ~2 M group result): split over a few threads.
+// fn(chunk, lo, hi); chunks are contiguous and in order, so per-chunk outputs concatenate deterministically.
+static unsigned par_chunk_count(size_t n) {
+    if (n < (1u << 16)) return 1;
+    unsigned hw = std::thread::hardware_concurrency();
+    return std::min<unsigned>(std::max(1u, hw), 16u);
+}
+template <class F>
+static void par_chunks(size_t n, unsigned T, F&& fn) {
+    if (T <= 1 || n == 0) {
+        fn(0u, (size_t)0, n);
+        return;
+    }
+    const size_t per = (n + T - 1) / T;
+    std::vector<std::thread> th;
+    for (unsigned k = 0; k < T; k++) {
+        const size_t lo = (size_t)k * per, hi = std::min(n, lo + per);
+        if (lo >= hi) break;
+        th.emplace_back([&fn, k, lo, hi] { fn(k, lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+
 // turn OutCells into cqg_value_t, pulling string bytes from the host view when there is one,
 // else gathering them on the device
 static int cells_to_values(const cqg_table* t, const cqg_table* rt, const std::vector<OutCell>& cells, cqg_value_t* out,
@@ -1254,39 +1278,75 @@ static int cells_to_values(const cqg_table* t, const cqg_table* rt, const std::v
     std::vector<uint64_t> offs;
     std::vector<size_t> which;
     uint64_t total = 0;
-    for (size_t i = 0; i < n; i++) {
-        const OutCell& c = cells[i];
-        cqg_value_t v;
-        memset(&v, 0, sizeof v);
-        v.type = c.type;
-        switch (c.type) {
-            case CQG_TYPE_INTEGER: v.int_value = (long long)c.payload; break;
-            case CQG_TYPE_DOUBLE: memcpy(&v.double_value, &c.payload, 8); break;
-            case CQG_TYPE_DATE:
-                v.date_value.year = (int)(c.payload >> 16);
-                v.date_value.month = (int)((c.payload >> 8) & 0xff);
-                v.date_value.day = (int)(c.payload & 0xff);
-                break;
-            case CQG_TYPE_STRING: {
-                bool right = (c.payload >> 63) != 0;
-                uint64_t off = c.payload & 0x7fffffffffffffffull;
-                const cqg_table* src = right ? rt : t;
-                char* s = (char*)arena->alloc((size_t)c.len + 1);
-                v.string_value = s;
-                if (src && src->h_data) {
-                    memcpy(s, src->h_data + off, c.len);
-                } else {
-                    refs.push_back(c.payload);
-                    lens.push_back(c.len);
-                    offs.push_back(total);
-                    which.push_back(i);
-                    total += c.len;
+    const unsigned T = par_chunk_count(n);
+    struct Chunk {
+        std::vector<uint64_t> refs;
+        std::vector<uint32_t> lens;
+        std::vector<uint64_t> offs;  // chunk-local
+        std::vector<size_t> which;
+        uint64_t total = 0;
+        size_t str_bytes = 0;
+        char* block = nullptr;
+    };
+    std::vector<Chunk> ch(T);
+    // pass 1: string storage each chunk needs (one arena block per chunk: the arena itself is not thread safe)
+    par_chunks(n, T, [&](unsigned k, size_t lo, size_t hi) {
+        size_t bytes = 0;
+        for (size_t i = lo; i < hi; i++)
+            if (cells[i].type == CQG_TYPE_STRING) bytes += ((size_t)cells[i].len + 1 + 15) & ~(size_t)15;
+        ch[k].str_bytes = bytes;
+    });
+    for (unsigned k = 0; k < T; k++)
+        if (ch[k].str_bytes) ch[k].block = (char*)arena->alloc(ch[k].str_bytes);
+    // pass 2: the values
+    par_chunks(n, T, [&](unsigned k, size_t lo, size_t hi) {
+        Chunk& c_ = ch[k];
+        char* cur = c_.block;
+        for (size_t i = lo; i < hi; i++) {
+            const OutCell& c = cells[i];
+            cqg_value_t v;
+            memset(&v, 0, sizeof v);
+            v.type = c.type;
+            switch (c.type) {
+                case CQG_TYPE_INTEGER: v.int_value = (long long)c.payload; break;
+                case CQG_TYPE_DOUBLE: memcpy(&v.double_value, &c.payload, 8); break;
+                case CQG_TYPE_DATE:
+                    v.date_value.year = (int)(c.payload >> 16);
+                    v.date_value.month = (int)((c.payload >> 8) & 0xff);
+                    v.date_value.day = (int)(c.payload & 0xff);
+                    break;
+                case CQG_TYPE_STRING: {
+                    bool right = (c.payload >> 63) != 0;
+                    uint64_t off = c.payload & 0x7fffffffffffffffull;
+                    const cqg_table* src = right ? rt : t;
+                    char* s = cur;
+                    cur += ((size_t)c.len + 1 + 15) & ~(size_t)15;
+                    s[c.len] = 0;
+                    v.string_value = s;
+                    if (src && src->h_data) {
+                        memcpy(s, src->h_data + off, c.len);
+                    } else {
+                        c_.refs.push_back(c.payload);
+                        c_.lens.push_back(c.len);
+                        c_.offs.push_back(c_.total);
+                        c_.which.push_back(i);
+                        c_.total += c.len;
+                    }
+                    break;
                 }
-                break;
+                default: v.type = CQG_TYPE_NULL; break;
             }
-            default: v.type = CQG_TYPE_NULL; break;
+            out[i] = v;
         }
-        out[i] = v;
+    });
+    for (unsigned k = 0; k < T; k++) {
+        for (size_t j = 0; j < ch[k].refs.size(); j++) {
+            refs.push_back(ch[k].refs[j]);
+            lens.push_back(ch[k].lens[j]);
+            offs.push_back(total + ch[k].offs[j]);
+            which.push_back(ch[k].which[j]);
+        }
+        total += ch[k].total;
     }
     if (!refs.empty()) {
         DevBuf d_refs, d_lens, d_offs, d_dst;
@@ -1305,7 +1365,9 @@ static int cells_to_values(const cqg_table* t, const cqg_table* rt, const std::v
         std::vector<uint8_t> bytes(total + 8);
         CU(cudaMemcpyAsync(bytes.data(), d_dst.p, total, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        for (size_t k = 0; k < which.size(); k++) memcpy(out[which[k]].string_value, bytes.data() + offs[k], lens[k]);
+        par_chunks(which.size(), par_chunk_count(which.size()), [&](unsigned, size_t lo, size_t hi) {
+            for (size_t k = lo; k < hi; k++) memcpy((char*)out[which[k]].string_value, bytes.data() + offs[k], lens[k]);
+        });
     }
     return CQG_OK;
 }
@@ -1474,7 +1536,21 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
     std::vector<OutCell> strcells;  // MIN/MAX string results
     std::vector<size_t> strdst;
     unsigned host_flags = 0;
-    for (uint64_t gi = 0; gi < G; gi++) {
+    const unsigned TF = par_chunk_count((size_t)G);
+    struct FinChunk {
+        std::vector<std::pair<uint64_t, uint64_t>> numfetch[CQG_MAX_AGGS];
+        std::vector<OutCell> strcells;
+        std::vector<size_t> strdst;
+        unsigned host_flags = 0;
+    };
+    std::vector<FinChunk> fch(TF);
+    par_chunks((size_t)G, TF, [&](unsigned chunk_k, size_t gi_lo, size_t gi_hi) {
+    auto& numfetch = fch[chunk_k].numfetch;
+    auto& strcells = fch[chunk_k].strcells;
+    auto& strdst = fch[chunk_k].strdst;
+    unsigned& host_flags = fch[chunk_k].host_flags;
+    (void)host_flags;
+    for (uint64_t gi = gi_lo; gi < gi_hi; gi++) {
         const uint8_t* e = entp + (size_t)order[gi] * eb;
         uint64_t first = *(const uint64_t*)(e + kOffFirst);
         int64_t count = (int64_t) * (const uint64_t*)(e + kOffCount);
@@ -1532,6 +1608,13 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
             }
             r->value[ix] = v;
         }
+    }
+    });
+    for (unsigned k = 0; k < TF; k++) {
+        for (int a = 0; a < CQG_MAX_AGGS; a++) numfetch[a].insert(numfetch[a].end(), fch[k].numfetch[a].begin(), fch[k].numfetch[a].end());
+        strcells.insert(strcells.end(), fch[k].strcells.begin(), fch[k].strcells.end());
+        strdst.insert(strdst.end(), fch[k].strdst.begin(), fch[k].strdst.end());
+        host_flags |= fch[k].host_flags;
     }
     if (host_flags) {
         cqg_result_free(r);
@@ -1601,8 +1684,10 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
         if (rc == CQG_OK) {
             // cells are [group][col]; the result wants [col][group]
             std::vector<OutCell> tr(cells.size());
-            for (uint64_t gi = 0; gi < G; gi++)
-                for (int c = 0; c < q->n_out_cols; c++) tr[(size_t)c * G + gi] = cells[(size_t)gi * q->n_out_cols + c];
+            par_chunks((size_t)G, par_chunk_count((size_t)G), [&](unsigned, size_t lo, size_t hi) {
+                for (uint64_t gi = lo; gi < hi; gi++)
+                    for (int c = 0; c < q->n_out_cols; c++) tr[(size_t)c * G + gi] = cells[(size_t)gi * q->n_out_cols + c];
+            });
             rc = cells_to_values(t, rt, tr, r->out, arena, st);
         }
     }
@@ -1774,11 +1859,15 @@ static int check_flags(const ScalarBlock& hs, bool join) {
     return CQG_OK;
 }
 
-static int compact_groups(HostPlan& hp, const GroupTable& gt, int owner, int world, DevBuf& out, uint64_t* n_out, cudaStream_t st) {
+// known_occupied >= 0: the table's entry count as the scan's scalar block already reported it (saves a round trip)
+static int compact_groups(HostPlan& hp, const GroupTable& gt, int owner, int world, DevBuf& out, uint64_t* n_out, cudaStream_t st,
+                          long long known_occupied = -1) {
     DevPlan& P = hp.P;
-    unsigned long long occupied = 0;
-    CU(cudaMemcpyAsync(&occupied, P.gcount, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    unsigned long long occupied = (unsigned long long)known_occupied;
+    if (known_occupied < 0) {
+        CU(cudaMemcpyAsync(&occupied, P.gcount, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     CU(out.alloc((occupied + 1) * (uint64_t)P.entry_bytes, st));
     DevBuf cnt;
     CU(cnt.alloc(8, st));
@@ -1788,6 +1877,10 @@ static int compact_groups(HostPlan& hp, const GroupTable& gt, int owner, int wor
                                                cnt.as<unsigned long long>(), owner, world);
     g_launches++;
     CU(cudaGetLastError());
+    if (world <= 1) {  // no owner filter: every occupied entry is written
+        *n_out = occupied;
+        return CQG_OK;
+    }
     unsigned long long n = 0;
     CU(cudaMemcpyAsync(&n, cnt.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1914,9 +2007,10 @@ CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t
         if ((rc = check_flags(hs, hp.P.join != 0))) return rc;
         DevBuf entries;
         uint64_t G = 0;
-        if ((rc = compact_groups(hp, gt, 0, 1, entries, &G, st))) return rc;
+        if ((rc = compact_groups(hp, gt, 0, 1, entries, &G, st, (long long)hs.gcount))) return rc;
+        const long long launches_before_finish = g_launches.load();
         rc = finish_aggregate(hp, t, rt, q, entries.as<uint8_t>(), G, true, (int64_t)hs.rows_scanned, out, st);
-        if (rc == CQG_OK) {
+        if (rc == CQG_OK && g_launches.load() != launches_before_finish) {  // the finish ran kernels that can raise flags
             unsigned f = 0;
             CU(cudaMemcpy(&f, hp.P.errflags, 4, cudaMemcpyDeviceToHost));
             if (f & kFatalMask) {

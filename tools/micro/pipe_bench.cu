@@ -28,6 +28,16 @@ __device__ __forceinline__ uint32_t step(uint32_t x, uint32_t k, uint32_t one) {
         unsigned long long w;
         asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(x), "r"(k), "l"(((unsigned long long)k << 32) | x));
         d = (uint32_t)w ^ (uint32_t)(w >> 32);
+    } else if (OP == 14) asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(d) : "r"(x));
+    else if (OP == 15) asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(d) : "r"(x));
+    else if (OP == 16) {
+        asm volatile("{.reg .pred p; setp.ne.u32 p, %1, %2; vote.sync.ballot.b32 %0, p, 0xffffffff;}" : "=r"(d) : "r"(x), "r"(k));
+    } else if (OP == 17) asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(d) : "r"(x), "r"(one));
+    else if (OP == 18) asm volatile("match.any.sync.b32 %0, %1, 0xffffffff;" : "=r"(d) : "r"(x & 15u));
+    else if (OP == 19) {
+        // shared-memory atomic add, addresses spread over 16 words per warp
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(d) : "r"((x & 15u) * 4u), "r"(one) : "memory");
+        d ^= x;
     } else d = x;
     return d;
 }
@@ -35,6 +45,8 @@ __device__ __forceinline__ uint32_t step(uint32_t x, uint32_t k, uint32_t one) {
 // A, B: the two instruction kinds interleaved 1:1 (B = -1: A only)
 template <int A, int B>
 __global__ void __launch_bounds__(1024, 1) bench(uint32_t* out, long long* cycles, uint32_t one, uint32_t k) {
+    __shared__ uint32_t sm_atom[64];
+    if (threadIdx.x < 64) sm_atom[threadIdx.x] = 0;
     uint32_t x[CHAINS];
 #pragma unroll
     for (int c = 0; c < CHAINS; c++) x[c] = threadIdx.x * 2654435761u + c;
@@ -91,6 +103,13 @@ int main() {
     run<9, -1>("POPC", out, cyc, sms);
     run<11, -1>("VABSDIFF4", out, cyc, sms);
     run<13, -1>("IMAD.WIDE (+LOP3)", out, cyc, sms);
+    run<14, -1>("REDUX.SUM", out, cyc, sms);
+    run<15, -1>("REDUX.MIN", out, cyc, sms);
+    run<16, -1>("ISETP + VOTE.ballot", out, cyc, sms);
+    run<17, -1>("SHFL.IDX", out, cyc, sms);
+    run<18, -1>("MATCH.ANY", out, cyc, sms);
+    run<19, -1>("ATOMS.ADD (16 addresses)", out, cyc, sms);
+    run<0, 14>("LOP3 + REDUX.SUM", out, cyc, sms);
     run<0, 1>("LOP3 + add imm", out, cyc, sms);
     run<0, 10>("LOP3 + add reg", out, cyc, sms);
     run<0, 2>("LOP3 + IMAD", out, cyc, sms);
