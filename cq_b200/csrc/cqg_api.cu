@@ -28,6 +28,7 @@
 #include "cq_gpu.h"
 #include "cqg_lean.cuh"
 #include "cqg_lean2.cuh"
+#include "cqg_lean2g.cuh"
 
 using namespace cqg;
 
@@ -483,6 +484,32 @@ static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
     return CQG_OK;
 }
 
+template <class LG, int MINB>
+static int launch_lean2g_geo(const DevPlan& P0, cudaStream_t st) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    DevPlan P = P0;
+    if (P.own_hi > P.own_lo) {
+        P.first_tile = (int32_t)(P.own_lo / LG::TILE);
+        P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
+    }
+    if (P.n_tiles <= 0) return CQG_OK;
+    const int smem = Lean2GLayout<LG>::TOTAL;  // tile + masks + interval table + dictionary + per-warp accumulators
+    LaunchCfg& c = g_cfg[dev & 63];
+    if (!c.ready) {
+        CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+        c.ready = true;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2g_kernel<LG, MINB>, LG::THREADS, smem));
+    if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean2g kernel does not fit");
+    int grid = std::min(P.n_tiles, c.sms * per_sm);
+    lean2g_kernel<LG, MINB><<<grid, LG::THREADS, smem, st>>>(P);
+    g_launches++;
+    CU(cudaGetLastError());
+    return CQG_OK;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -498,6 +525,7 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
             return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false, true>(P, st);
         }
         if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 4, true, false, true, false>(P, st);
+        if (env_int("CQG_LEAN2", 1)) return launch_lean2g_geo<Geo<128, 16384, 1, 224>, 6>(P, st);  // few groups, COUNT/SUM/AVG
         return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false, false>(P, st);
     }
     const bool oneleaf = P.l_nprog == 1 && P.l_nleaf == 1 && P.l_leaf[0].kind == 0 && P.l_leaf[0].slot == 0 && P.l_nagg == 0 &&
