@@ -21,7 +21,7 @@ constexpr int kL2Groups = 32;     // groups a CTA numbers
 constexpr int kL2DictCap = 1024;  // slots: 0 empty, 2 being written, (hash & ~0x7f) | gid << 1 | 1 ready (gid 63: overflow)
 constexpr int kL2KeyRec = 80;     // tags 4 | tile of insertion 4 | first okey 8 | 4 x key part 16
 constexpr uint32_t kL2Lock = 2u;
-// per-warp accumulators: count u32[G] | 4 x { lo[G] hi[G] n[G] }
+// per-warp accumulators: count u32[G] | 4 x { lo[G] hi[G] nulls[G] } (values summed = count - nulls)
 constexpr int kL2AggBlock = kL2Groups * 12;
 constexpr int kL2WarpAcc = kL2Groups * 4 + 4 * kL2AggBlock;
 
@@ -33,11 +33,39 @@ struct Lean2GLayout {
     static constexpr int OFF_DICT = (OFF_MBAR + G::STAGES * 8 + 15) / 16 * 16;
     static constexpr int OFF_KEYS = OFF_DICT + kL2DictCap * 4;
     static constexpr int OFF_NG = OFF_KEYS + kL2Groups * kL2KeyRec;
-    static constexpr int OFF_ACC = OFF_NG + 16;
+    static constexpr int OFF_KMASK = OFF_NG + 16;   // [17][4] words: the first `len` bytes of 16
+    static constexpr int OFF_ACC = OFF_KMASK + 17 * 16;
     static constexpr int TOTAL = OFF_ACC + G::NWARPS * kL2WarpAcc;
 };
 
 __device__ __forceinline__ uint32_t l2g_hash_word(uint32_t h, uint32_t x) { return (h ^ x) * 0x9E3779B1u; }
+
+// lean_key_part (cqg_lean.cuh) with the text case done on 32-bit words and a byte-mask table in shared memory
+// (`s_kmask`); numbers as keys take lean_key_part itself. Same (tag, w0, w1) as canon_part<true> builds.
+__device__ __forceinline__ bool l2g_key_part(uint32_t fa, uint32_t len, uint32_t s_kmask, uint32_t& tag, uint64_t& w0, uint64_t& w1) {
+    w0 = 0;
+    w1 = 0;
+    if (len == 0u) {
+        tag = KT_NULL;
+        return true;
+    }
+    const uint32_t c0 = lds8(fa);
+    if ((c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.') return lean_key_part(fa, len, tag, w0, w1);
+    if (len > 16u) return false;
+    const uint32_t a = fa & ~3u, sh = fa << 3;
+    const uint32_t x0 = lds32(a), x1 = lds32(a + 4), x2 = lds32(a + 8), x3 = lds32(a + 12), x4 = lds32(a + 16);
+    const uint4 m = lds128(s_kmask + 16u * len);
+    const uint32_t y0 = __funnelshift_r(x0, x1, sh) & m.x, y1 = __funnelshift_r(x1, x2, sh) & m.y;
+    const uint32_t y2 = __funnelshift_r(x2, x3, sh) & m.z, y3 = __funnelshift_r(x3, x4, sh) & m.w;
+    if (len == 4u && y0 == 0x4c4c554eu) {  // the text NULL is the NULL group
+        tag = KT_NULL;
+        return true;
+    }
+    tag = KT_STR;
+    w0 = ((uint64_t)y1 << 32) | y0;
+    w1 = ((uint64_t)y3 << 32) | y2;
+    return true;
+}
 
 template <class G, int MINB>
 __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_constant__ DevPlan P) {
@@ -72,6 +100,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
         for (int k = tid; k < words; k += G::THREADS) ((uint32_t*)dict)[k] = 0u;
     }
     __syncthreads();
+    if (tid < 17 * 4) {
+        const int nb = (tid >> 2) - 4 * (tid & 3);  // bytes of word (tid & 3) inside a text of (tid >> 2) bytes
+        ((uint32_t*)(smem + LL::OFF_KMASK))[tid] = nb >= 4 ? 0xffffffffu : (nb <= 0 ? 0u : (1u << (8 * nb)) - 1u);
+    }
     for (int k = tid; k < kL2Groups; k += G::THREADS) *(uint64_t*)(keys + k * kL2KeyRec + 8) = ~0ull;  // first okey
     __syncthreads();
 
@@ -316,7 +348,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
                             uint32_t tag = KT_NULL;
                             if (sl >= 0) {
                                 CQG_L2G_SLOT(sl, o, l)
-                                ok = lean_key_part(rbase + o, l, tag, kw[2 * g], kw[2 * g + 1]);
+                                ok = l2g_key_part(rbase + o, l, sbase + LL::OFF_KMASK, tag, kw[2 * g], kw[2 * g + 1]);
                             }
                             tags |= tag << (4 * g);
                             h32 = l2g_hash_word(h32, (uint32_t)kw[2 * g] + tag);
@@ -405,7 +437,9 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
         const uint32_t old = atomicAdd((unsigned int*)(b + 4 * gid), vlo);                 \
         const uint32_t up = vhi + ((old + vlo) < old ? 1u : 0u);                           \
         if (up) atomicAdd((unsigned int*)(b + kL2Groups * 4 + 4 * gid), up);               \
-        atomicAdd((unsigned int*)(b + kL2Groups * 8 + 4 * gid), 1u);                       \
+    } else if ((summask >> A) & 1u) {                                                      \
+        /* a NULL field: the rows that do NOT count towards this aggregate are the rare ones */ \
+        atomicAdd((unsigned int*)(wacc + kL2Groups * 4 + A * kL2AggBlock + kL2Groups * 8 + 4 * gid), 1u); \
     }
                         CQG_L2G_SUM(0, add0)
                         CQG_L2G_SUM(1, add1)
@@ -457,6 +491,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
                     t3 += ((unsigned long long)*(const uint32_t*)(b + kL2Groups * 4 + 4 * gid) << 32) + *(const uint32_t*)(b + 4 * gid);
                     tn += *(const uint32_t*)(b + kL2Groups * 8 + 4 * gid);
                 }
+                tn = c - tn;  // rows of the group minus those whose field was NULL
                 if (tn) {
                     atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 16), tn);
                     atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 24), t3);
