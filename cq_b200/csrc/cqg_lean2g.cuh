@@ -40,6 +40,38 @@ struct Lean2GLayout {
 
 __device__ __forceinline__ uint32_t l2g_hash_word(uint32_t h, uint32_t x) { return (h ^ x) * 0x9E3779B1u; }
 
+// cold paths, kept out of the row loop's instruction footprint
+struct L2GKey {
+    uint64_t w0, w1;
+    uint32_t tag, ok;
+};
+__device__ __noinline__ L2GKey l2g_key_part_number(uint32_t fa, uint32_t len) {
+    L2GKey k;
+    k.ok = lean_key_part(fa, len, k.tag, k.w0, k.w1) ? 1u : 0u;
+    return k;
+}
+// fields of a row of 32..63 bytes on 64-bit masks: (off | len << 8) of wanted field k in byte pair k, et on top
+struct L2GWide {
+    uint64_t fields;
+    uint32_t et;
+};
+__device__ __noinline__ L2GWide l2g_wide_fields(uint32_t tw2, uint32_t dlo, uint32_t dhi, int nwant, int gap0, int gap1, int gap2,
+                                               int gap3) {
+    const uint64_t tw64 = (uint64_t)tw2 << 32;
+    const uint64_t dw64 = ((uint64_t)dhi << 32) | dlo;
+    const uint64_t below = tw64 ^ (tw64 - 1ull);
+    L2GWide r;
+    r.et = 32u + bfind32((uint32_t)(below >> 32));
+    Lean2Stops<uint64_t> S{(dw64 | tw64) & below, 0u, false};
+    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0, l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+    S.field(gap0, o0, l0);
+    if (nwant > 1) S.field(gap1, o1, l1);
+    if (nwant > 2) S.field(gap2, o2, l2);
+    if (nwant > 3) S.field(gap3, o3, l3);
+    r.fields = (uint64_t)(o0 | (l0 << 8) | (o1 << 16) | (l1 << 24)) | ((uint64_t)(o2 | (l2 << 8) | (o3 << 16) | (l3 << 24)) << 32);
+    return r;
+}
+
 // lean_key_part (cqg_lean.cuh) with the text case done on 32-bit words and a byte-mask table in shared memory
 // (`s_kmask`); numbers as keys take lean_key_part itself. Same (tag, w0, w1) as canon_part<true> builds.
 __device__ __forceinline__ bool l2g_key_part(uint32_t fa, uint32_t len, uint32_t s_kmask, uint32_t& tag, uint64_t& w0, uint64_t& w1) {
@@ -50,7 +82,13 @@ __device__ __forceinline__ bool l2g_key_part(uint32_t fa, uint32_t len, uint32_t
         return true;
     }
     const uint32_t c0 = lds8(fa);
-    if ((c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.') return lean_key_part(fa, len, tag, w0, w1);
+    if ((c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.') {
+        const L2GKey k = l2g_key_part_number(fa, len);
+        tag = k.tag;
+        w0 = k.w0;
+        w1 = k.w1;
+        return k.ok != 0u;
+    }
     if (len > 16u) return false;
     const uint32_t a = fa & ~3u, sh = fa << 3;
     const uint32_t x0 = lds32(a), x1 = lds32(a + 4), x2 = lds32(a + 8), x3 = lds32(a + 12), x4 = lds32(a + 16);
@@ -230,16 +268,16 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
                     const uint32_t t2 = lds32(ma + 16u);
                     const uint32_t tw2 = __funnelshift_r(m1.x, t2, pos);
                     if (tw2 != 0u) {
-                        const uint32_t d2 = lds32(ma + 20u);
-                        const uint64_t tw64 = (uint64_t)tw2 << 32;
-                        const uint64_t dw64 = ((uint64_t)__funnelshift_r(m1.y, d2, pos) << 32) | dw;
-                        const uint64_t below = tw64 ^ (tw64 - 1ull);
-                        et = 32u + bfind32((uint32_t)(below >> 32));
-                        Lean2Stops<uint64_t> S{(dw64 | tw64) & below, 0u, false};
-                        S.field(gap0, off0, len0);
-                        if (nwant > 1) S.field(gap1, off1, len1);
-                        if (nwant > 2) S.field(gap2, off2, len2);
-                        if (nwant > 3) S.field(gap3, off3, len3);
+                        const L2GWide wr = l2g_wide_fields(tw2, dw, __funnelshift_r(m1.y, lds32(ma + 20u), pos), nwant, gap0, gap1, gap2, gap3);
+                        et = wr.et;
+                        off0 = (uint32_t)wr.fields & 0xffu;
+                        len0 = ((uint32_t)wr.fields >> 8) & 0xffu;
+                        off1 = ((uint32_t)wr.fields >> 16) & 0xffu;
+                        len1 = (uint32_t)wr.fields >> 24;
+                        off2 = (uint32_t)(wr.fields >> 32) & 0xffu;
+                        len2 = ((uint32_t)(wr.fields >> 32) >> 8) & 0xffu;
+                        off3 = ((uint32_t)(wr.fields >> 32) >> 16) & 0xffu;
+                        len3 = (uint32_t)(wr.fields >> 32) >> 24;
                     } else {
                         // 64 bytes or more: hand the row over; its end is where the walk goes on
                         const uint32_t e = lean2_next_term(s_msk, pos + 64u, (uint32_t)G::BUF);
@@ -287,7 +325,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
                                     const bool ns = (c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.';
                                     if (ns) ok = false;
                                     bv = kind == 2;
-                                } else if (lean_key_part(rbase + o, l, tag, w0, w1) && (tag == KT_STR || tag == KT_NULL)) {
+                                } else if (l2g_key_part(rbase + o, l, sbase + LL::OFF_KMASK, tag, w0, w1) && (tag == KT_STR || tag == KT_NULL)) {
                                     if (tag == KT_NULL) {
                                         w0 = 0x4c4c554eull;
                                         w1 = 0;
