@@ -1,6 +1,7 @@
 // cqg_api.cu — host side of libcqgpu: the C-ABI of include/cq_gpu.h over the sm_100a kernels
 // of cqg_scan.cuh. Plain CUDA runtime; no torch, no CPU operator fallback: every query either
 // runs on the device or fails with an error code.
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -17,6 +18,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <map>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -458,6 +461,175 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
     return CQG_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// kernels compiled per query (NVRTC): the lean kernels with the plan's shape as compile-time constants
+// ------------------------------------------------------------------------------------------
+// The ahead-of-time lean kernels interpret the plan's shape per row (which columns, how many delimiters between
+// them, which leaf reads which slot, ...). cqg_jit compiles the SAME source once per distinct shape with the
+// shape as macros (cqg_lean2.cuh: CQG_SPEC), caches the cubin in the process, and launches it through the
+// runtime's library API. Anything that goes wrong (no libnvrtc, sources not next to the library, a compile
+// error) falls back to the ahead-of-time kernel of the same source: same results, only slower. CQG_JIT=0 turns
+// it off.
+namespace cqg_jit {
+
+typedef int (*nvrtcCreateProgram_t)(void**, const char*, const char*, int, const char* const*, const char* const*);
+typedef int (*nvrtcProg1_t)(void**);
+typedef int (*nvrtcAddName_t)(void*, const char*);
+typedef int (*nvrtcCompile_t)(void*, int, const char* const*);
+typedef int (*nvrtcLowered_t)(void*, const char*, const char**);
+typedef int (*nvrtcSize_t)(void*, size_t*);
+typedef int (*nvrtcGet_t)(void*, char*);
+
+struct Api {
+    void* h = nullptr;
+    nvrtcCreateProgram_t create = nullptr;
+    nvrtcProg1_t destroy = nullptr;
+    nvrtcAddName_t add_name = nullptr;
+    nvrtcCompile_t compile = nullptr;
+    nvrtcLowered_t lowered = nullptr;
+    nvrtcSize_t cubin_size = nullptr, log_size = nullptr;
+    nvrtcGet_t cubin = nullptr, log = nullptr;
+    bool ok = false;
+};
+
+static Api& api() {
+    static Api a;
+    static bool tried = false;
+    if (tried) return a;
+    tried = true;
+    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"}) {
+        a.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+        if (a.h) break;
+    }
+    if (!a.h) return a;
+    a.create = (nvrtcCreateProgram_t)dlsym(a.h, "nvrtcCreateProgram");
+    a.destroy = (nvrtcProg1_t)dlsym(a.h, "nvrtcDestroyProgram");
+    a.add_name = (nvrtcAddName_t)dlsym(a.h, "nvrtcAddNameExpression");
+    a.compile = (nvrtcCompile_t)dlsym(a.h, "nvrtcCompileProgram");
+    a.lowered = (nvrtcLowered_t)dlsym(a.h, "nvrtcGetLoweredName");
+    a.cubin_size = (nvrtcSize_t)dlsym(a.h, "nvrtcGetCUBINSize");
+    a.cubin = (nvrtcGet_t)dlsym(a.h, "nvrtcGetCUBIN");
+    a.log_size = (nvrtcSize_t)dlsym(a.h, "nvrtcGetProgramLogSize");
+    a.log = (nvrtcGet_t)dlsym(a.h, "nvrtcGetProgramLog");
+    a.ok = a.create && a.destroy && a.add_name && a.compile && a.lowered && a.cubin_size && a.cubin && a.log_size && a.log;
+    return a;
+}
+
+// <dir of libcqgpu.so>/csrc and <that dir>/../include (the in-tree layout); CQG_JIT_SRC / CQG_JIT_INCLUDE override
+static void source_dirs(std::string& csrc, std::string& inc) {
+    const char* e1 = getenv("CQG_JIT_SRC");
+    const char* e2 = getenv("CQG_JIT_INCLUDE");
+    std::string base;
+    Dl_info info;
+    if (dladdr((void*)&source_dirs, &info) && info.dli_fname) {
+        base = info.dli_fname;
+        size_t k = base.rfind('/');
+        base = k == std::string::npos ? "." : base.substr(0, k);
+    }
+    csrc = e1 ? e1 : base + "/csrc";
+    inc = e2 ? e2 : base + "/../include";
+}
+
+struct Kernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t fn = nullptr;
+    bool failed = false;
+};
+
+static std::mutex g_mu;
+static std::map<std::string, Kernel> g_cache;
+
+static bool enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("CQG_JIT");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+// defs: the #define block of the shape; header: the file that holds the kernel template; name: its instantiation
+static cudaKernel_t get(const std::string& defs, const char* header, const char* name) {
+    if (!enabled()) return nullptr;
+    std::lock_guard<std::mutex> lock(g_mu);
+    const std::string key = std::string(name) + "\n" + defs;
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) return it->second.failed ? nullptr : it->second.fn;
+    Kernel& k = g_cache[key];
+    k.failed = true;
+    Api& a = api();
+    if (!a.ok) return nullptr;
+    std::string csrc, inc;
+    source_dirs(csrc, inc);
+    const std::string src = "#define CQG_JIT 1\n" + defs + "#include \"" + header + "\"\n";
+    void* prog = nullptr;
+    if (a.create(&prog, src.c_str(), "cqg_jit.cu", 0, nullptr, nullptr) != 0) return nullptr;
+    const std::string i1 = "-I" + csrc, i2 = "-I" + inc;
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device", "-lineinfo", i1.c_str(), i2.c_str(),
+                          "-I/usr/local/cuda/include"};
+    bool ok = a.add_name(prog, name) == 0 && a.compile(prog, (int)(sizeof opts / sizeof opts[0]), opts) == 0;
+    if (!ok && getenv("CQG_JIT_VERBOSE")) {
+        size_t n = 0;
+        a.log_size(prog, &n);
+        std::string log(n + 1, 0);
+        a.log(prog, &log[0]);
+        fprintf(stderr, "[cqg jit] compile failed:\n%s\n", log.c_str());
+    }
+    const char* low = nullptr;
+    size_t n = 0;
+    std::vector<char> cubin;
+    if (ok) ok = a.lowered(prog, name, &low) == 0 && low && a.cubin_size(prog, &n) == 0 && n > 0;
+    std::string lowered = ok ? low : "";
+    if (ok) {
+        cubin.resize(n);
+        ok = a.cubin(prog, cubin.data()) == 0;
+    }
+    a.destroy(&prog);
+    if (!ok) return nullptr;
+    if (cudaLibraryLoadData(&k.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+        cudaLibraryGetKernel(&k.fn, k.lib, lowered.c_str()) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    k.failed = false;
+    if (getenv("CQG_JIT_VERBOSE")) fprintf(stderr, "[cqg jit] compiled %s (%zu bytes)\n", name, n);
+    return k.fn;
+}
+
+// the shape of a lean plan as the macros cqg_lean2.cuh / cqg_lean2g.cuh read
+static std::string lean_shape_defs(const cqg::DevPlan& P) {
+    char b[256];
+    std::string d;
+    auto def = [&](const char* name, long long v) {
+        snprintf(b, sizeof b, "#define CQG_JIT_%s %lld\n", name, v);
+        d += b;
+    };
+    auto def_at = [&](const char* name, int n, auto value) {
+        std::string m = std::string("#define CQG_JIT_") + name + "(i) (";
+        for (int i = 0; i < n; i++) {
+            snprintf(b, sizeof b, "(i)==%d?%lld:", i, (long long)value(i));
+            m += b;
+        }
+        d += m + "0)\n";
+    };
+    def("NWANT", P.nwantL);
+    def("GAP0", P.gap[0]);
+    def("GAP1", P.gap[1]);
+    def("GAP2", P.gap[2]);
+    def("GAP3", P.gap[3]);
+    def("NPROG", P.l_nprog);
+    def("NGC", P.ngc);
+    def("NAGG", P.l_nagg);
+    def_at("PROG", P.l_nprog, [&](int i) { return (int)P.l_prog[i]; });
+    def_at("LEAFSLOT", P.l_nleaf, [&](int i) { return P.l_leaf[i].slot; });
+    def_at("LEAFKIND", P.l_nleaf, [&](int i) { return P.l_leaf[i].kind; });
+    def_at("GSLOT", P.ngc, [&](int i) { return (int)P.gslot[i]; });
+    def_at("ASLOT", P.l_nagg, [&](int i) { return P.aggs[P.l_agg[i]].slot; });
+    return d;
+}
+
+}  // namespace cqg_jit
+
 template <class LG, int MINB, bool ONELEAF, int GAP0>
 static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
     int dev = 0;
@@ -478,11 +650,26 @@ static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2_kernel<LG, MINB, ONELEAF, GAP0>, LG::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean2 kernel does not fit");
     int grid = std::min(P.n_tiles, c.sms * per_sm);
+    if (!ONELEAF) {
+        // the general instantiation interprets the plan's shape per row: compiled for this query when possible
+        char name[160];
+        snprintf(name, sizeof name, "cqg::lean2_kernel<cqg::Geo<%d, %d, %d, %d>, %d, false, -1>", LG::THREADS, LG::TILE, LG::STAGES,
+                 LG::OVER, MINB);
+        if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean2.cuh", name)) {
+            void* args[] = {(void*)&P};
+            if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
+                g_launches++;
+                return CQG_OK;
+            }
+            cudaGetLastError();
+        }
+    }
     lean2_kernel<LG, MINB, ONELEAF, GAP0><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
     CU(cudaGetLastError());
     return CQG_OK;
 }
+
 
 template <class LG, int MINB>
 static int launch_lean2g_geo(const DevPlan& P0, cudaStream_t st) {
@@ -504,6 +691,17 @@ static int launch_lean2g_geo(const DevPlan& P0, cudaStream_t st) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2g_kernel<LG, MINB>, LG::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean2g kernel does not fit");
     int grid = std::min(P.n_tiles, c.sms * per_sm);
+    // the same kernel compiled for this query's shape, when the run-time compiler is there (else the generic one)
+    char name[160];
+    snprintf(name, sizeof name, "cqg::lean2g_kernel<cqg::Geo<%d, %d, %d, %d>, %d>", LG::THREADS, LG::TILE, LG::STAGES, LG::OVER, MINB);
+    if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean2g.cuh", name)) {
+        void* args[] = {(void*)&P};
+        if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
+            g_launches++;
+            return CQG_OK;
+        }
+        cudaGetLastError();
+    }
     lean2g_kernel<LG, MINB><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
     CU(cudaGetLastError());

@@ -3,8 +3,11 @@
 // no libc on this side, so every libc call of the reference (strtoll / strtod / sscanf /
 // isspace / tolower / strcmp) is restated here and cited.
 #pragma once
+#include "cqg_rtc.h"
+#ifndef __CUDACC_RTC__
 #include <cstdint>
 #include <cuda_runtime.h>
+#endif
 
 #include "cq_gpu.h"
 

@@ -897,6 +897,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     }
 }
 
+#ifndef CQG_JIT
 // rows handed over one by one: each is found and split straight from HBM by the general operators
 __global__ void deferred_rows_kernel(const __grid_constant__ DevPlan P, const uint64_t* rows, uint64_t n) {
     CtaState cs;
@@ -920,5 +921,7 @@ __global__ void deferred_rows_kernel(const __grid_constant__ DevPlan P, const ui
     if (acc.rows) atomicAdd(P.rows_scanned, (unsigned long long)acc.rows);
     if (acc.err) atomicOr(P.errflags, acc.err);
 }
+
+#endif  // CQG_JIT
 
 }  // namespace cqg

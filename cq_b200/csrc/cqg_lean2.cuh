@@ -19,6 +19,21 @@
 #pragma once
 #include "cqg_lean.cuh"
 
+// ---- per-query specialisation (cqg_jit in cqg_api.cu) ----
+// Compiled ahead of time the lean kernels read the plan's SHAPE (wanted columns and the delimiters between
+// them, the leaf program, key and aggregate slots) from the kernel parameter. Compiled at run time for one
+// query (NVRTC, -DCQG_JIT) the same source gets the shape as macros: loops unroll, slot selects and leaf-kind
+// branches fold away. Values (literals, intervals, offsets) stay in the parameter either way.
+#ifdef CQG_JIT
+#define CQG_SPEC(NAME, RUNTIME) (CQG_JIT_##NAME)
+#define CQG_SPEC_AT(NAME, I, RUNTIME) (CQG_JIT_##NAME(I))
+#define CQG_SPEC_UNROLL _Pragma("unroll")
+#else
+#define CQG_SPEC(NAME, RUNTIME) (RUNTIME)
+#define CQG_SPEC_AT(NAME, I, RUNTIME) (RUNTIME)
+#define CQG_SPEC_UNROLL _Pragma("unroll 1")
+#endif
+
 namespace cqg {
 
 template <class G>
@@ -171,7 +186,7 @@ struct Lean2Stops {
     bool missing;
     __device__ __forceinline__ void field(int gap, uint32_t& off, uint32_t& len) {
         if (gap > 0) {
-#pragma unroll 1
+            CQG_SPEC_UNROLL
             for (int i = 1; i < gap; i++) st &= st - 1;
             missing = missing || st == 0;
             sp = sizeof(W) == 8 ? (uint32_t)__ffsll((long long)st) : (uint32_t)__ffs((int)st);
@@ -308,17 +323,19 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
     const uint32_t one = (uint32_t)P.simple;  // == 1, but not to the compiler: a + c as IMAD (FMA pipe), see add_fma
-    const int nwant = P.nwantL;
-    const int gap0 = GAP0 >= 0 ? GAP0 : P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
-    const int nprog = P.l_nprog;
+    const int nwant = CQG_SPEC(NWANT, P.nwantL);
+    const int gap0 = GAP0 >= 0 ? GAP0 : CQG_SPEC(GAP0, P.gap[0]), gap1 = CQG_SPEC(GAP1, P.gap[1]), gap2 = CQG_SPEC(GAP2, P.gap[2]),
+              gap3 = CQG_SPEC(GAP3, P.gap[3]);
+    const int nprog = CQG_SPEC(NPROG, P.l_nprog);
+    const int nagg = CQG_SPEC(NAGG, P.l_nagg);
     uint32_t summask = 0;
     int aslot[4];
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         aslot[a] = 0;
-        if (!ONELEAF && a < P.l_nagg) {
+        if (!ONELEAF && a < nagg) {
             summask |= 1u << a;
-            aslot[a] = P.aggs[P.l_agg[a]].slot;
+            aslot[a] = CQG_SPEC_AT(ASLOT, a, P.aggs[P.l_agg[a]].slot);
         }
     }
 
@@ -553,10 +570,11 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
     const uint32_t L = SL == 0 ? len0 : SL == 1 ? len1 : SL == 2 ? len2 : len3;
                         if (nprog) {
                             uint32_t bs = 0;
+                            CQG_SPEC_UNROLL
                             for (int pc = 0; pc < nprog; pc++) {
-                                const int c = P.l_prog[pc];
+                                const int c = CQG_SPEC_AT(PROG, pc, P.l_prog[pc]);
                                 if (c >= 0) {
-                                    const int sl = P.l_leaf[c].slot, kind = P.l_leaf[c].kind;
+                                    const int sl = CQG_SPEC_AT(LEAFSLOT, c, P.l_leaf[c].slot), kind = CQG_SPEC_AT(LEAFKIND, c, P.l_leaf[c].kind);
                                     CQG_L2_SLOT(sl, o, l)
                                     bool bv = false;
                                     if (kind == 0) {
@@ -724,7 +742,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
             amin64((uint64_t*)(ge + kOffFirst), first << 16);
 #pragma unroll
             for (int a = 0; a < 4; a++) {
-                if (!ONELEAF && a < P.l_nagg && sn[a]) {
+                if (!ONELEAF && a < nagg && sn[a]) {
                     atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 16), (unsigned long long)sn[a]);
                     atomicAdd((unsigned long long*)(ge + P.aggs[P.l_agg[a]].off + 24), (unsigned long long)s3[a]);
                 }

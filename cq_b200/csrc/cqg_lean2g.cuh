@@ -149,18 +149,20 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
     const uint32_t one = (uint32_t)P.simple >> 1;  // simple == 2 here: 1, but not to the compiler (IMAD adds)
-    const int nwant = P.nwantL;
-    const int gap0 = P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
-    const int nprog = P.l_nprog;
-    const int ngc = P.ngc;
+    const int nwant = CQG_SPEC(NWANT, P.nwantL);
+    const int gap0 = CQG_SPEC(GAP0, P.gap[0]), gap1 = CQG_SPEC(GAP1, P.gap[1]), gap2 = CQG_SPEC(GAP2, P.gap[2]),
+              gap3 = CQG_SPEC(GAP3, P.gap[3]);
+    const int nprog = CQG_SPEC(NPROG, P.l_nprog);
+    const int ngc = CQG_SPEC(NGC, P.ngc);
+    const int nagg = CQG_SPEC(NAGG, P.l_nagg);
     uint32_t summask = 0;
     int aslot[4];
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         aslot[a] = 0;
-        if (a < P.l_nagg) {
+        if (a < nagg) {
             summask |= 1u << a;
-            aslot[a] = P.aggs[P.l_agg[a]].slot;
+            aslot[a] = CQG_SPEC_AT(ASLOT, a, P.aggs[P.l_agg[a]].slot);
         }
     }
 
@@ -295,10 +297,11 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
                 // ---- WHERE ----
                 if (ok && nprog) {
                     uint32_t bs = 0;
+                    CQG_SPEC_UNROLL
                     for (int pc = 0; pc < nprog; pc++) {
-                        const int c = P.l_prog[pc];
+                        const int c = CQG_SPEC_AT(PROG, pc, P.l_prog[pc]);
                         if (c >= 0) {
-                            const int sl = P.l_leaf[c].slot, kind = P.l_leaf[c].kind;
+                            const int sl = CQG_SPEC_AT(LEAFSLOT, c, P.l_leaf[c].slot), kind = CQG_SPEC_AT(LEAFKIND, c, P.l_leaf[c].kind);
                             CQG_L2G_SLOT(sl, o, l)
                             bool bv = false;
                             if (kind == 0) {
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
                         kw[2 * g] = 0;
                         kw[2 * g + 1] = 0;
                         if (g < ngc && ok) {
-                            const int sl = P.gslot[g];
+                            const int sl = CQG_SPEC_AT(GSLOT, g, P.gslot[g]);
                             uint32_t tag = KT_NULL;
                             if (sl >= 0) {
                                 CQG_L2G_SLOT(sl, o, l)
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
         atomicAdd((unsigned long long*)(ge + kOffCount), c);
         amin64((uint64_t*)(ge + kOffFirst), *(const uint64_t*)(e + 8));
         for (int a = 0; a < 4; a++) {
-            if (a < P.l_nagg) {
+            if (a < nagg) {
                 unsigned long long t3 = 0, tn = 0;
                 for (int w = 0; w < G::NWARPS; w++) {
                     const uint8_t* b = smem + LL::OFF_ACC + w * kL2WarpAcc + kL2Groups * 4 + a * kL2AggBlock;

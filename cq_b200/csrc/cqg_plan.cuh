@@ -2,7 +2,10 @@
 // to the scan kernel by value. Layout of group-table entries lives here too because the
 // host sizes and initialises tables with it.
 #pragma once
+#include "cqg_rtc.h"
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 #include "cq_gpu.h"
 #include "cqg_device.cuh"

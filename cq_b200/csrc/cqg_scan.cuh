@@ -13,8 +13,11 @@
 // evaluator_aggregates.c:108-176, evaluate_aggregate :263-326, perform_join
 // evaluator_joins.c:96-140.
 #pragma once
+#include "cqg_rtc.h"
+#ifndef __CUDACC_RTC__
 #include <cstdint>
 #include <cuda_runtime.h>
+#endif
 
 #include "cqg_plan.cuh"
 
@@ -1376,6 +1379,7 @@ __global__ void __launch_bounds__(G::THREADS, 4) scan_kernel(const __grid_consta
     if (acc.err) atomicOr(P.errflags, acc.err);
 }
 
+#ifndef CQG_JIT  // a kernel compiled at run time for one query (cqg_jit) needs none of the kernels below
 // ------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------
@@ -1663,5 +1667,7 @@ __global__ void gen_write_kernel(uint8_t* out, long long rows, uint64_t seed, lo
         }
     }
 }
+
+#endif  // CQG_JIT
 
 }  // namespace cqg

@@ -19,8 +19,10 @@
 #ifndef CQ_GPU_H
 #define CQ_GPU_H
 
+#ifndef __CUDACC_RTC__ /* (kernels compiled at run time get these types from cqg_rtc.h) */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
