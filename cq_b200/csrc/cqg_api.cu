@@ -429,38 +429,6 @@ static int launch_scan_nw(const DevPlan& P, int smem, int dev, cudaStream_t st) 
     return CQG_OK;
 }
 
-template <class LG, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX, bool GLOBAL>
-static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
-    int dev = 0;
-    CU(cudaGetDevice(&dev));
-    DevPlan P = P0;
-    // tiles of this geometry covering the same ownership range
-    if (P.own_hi > P.own_lo) {
-        P.first_tile = (int32_t)(P.own_lo / LG::TILE);
-        P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
-    }
-    if (P.n_tiles <= 0) return CQG_OK;
-    const int smem = LeanLayout<LG>::OFF_TABLE + ((GROUPED && !GLOBAL) ? kLeanDictCap * kLeanDictEntry + 16 + LG::NWARPS * lean_warp_acc(MINMAX) : 0);
-    static bool attr_set[64];
-    if (!attr_set[dev & 63]) {
-        CU(cudaFuncSetAttribute(lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[dev & 63] = true;
-    }
-    LaunchCfg& c = g_cfg[dev & 63];
-    if (!c.ready) {
-        CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
-        c.ready = true;
-    }
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL>, LG::THREADS, smem));
-    if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean kernel does not fit");
-    int grid = std::min(P.n_tiles, c.sms * per_sm);
-    lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL><<<grid, LG::THREADS, smem, st>>>(P);
-    g_launches++;
-    CU(cudaGetLastError());
-    return CQG_OK;
-}
-
 // ------------------------------------------------------------------------------------------
 // kernels compiled per query (NVRTC): the lean kernels with the plan's shape as compile-time constants
 // ------------------------------------------------------------------------------------------
@@ -625,10 +593,60 @@ static std::string lean_shape_defs(const cqg::DevPlan& P) {
     def_at("LEAFKIND", P.l_nleaf, [&](int i) { return P.l_leaf[i].kind; });
     def_at("GSLOT", P.ngc, [&](int i) { return (int)P.gslot[i]; });
     def_at("ASLOT", P.l_nagg, [&](int i) { return P.aggs[P.l_agg[i]].slot; });
+    def_at("AFUNC", P.l_nagg, [&](int i) { return P.aggs[P.l_agg[i]].func; });
     return d;
 }
 
 }  // namespace cqg_jit
+
+template <class LG, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX, bool GLOBAL>
+static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    DevPlan P = P0;
+    // tiles of this geometry covering the same ownership range
+    if (P.own_hi > P.own_lo) {
+        P.first_tile = (int32_t)(P.own_lo / LG::TILE);
+        P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
+    }
+    if (P.n_tiles <= 0) return CQG_OK;
+    const int smem = LeanLayout<LG>::OFF_TABLE + ((GROUPED && !GLOBAL) ? kLeanDictCap * kLeanDictEntry + 16 + LG::NWARPS * lean_warp_acc(MINMAX) : 0);
+    static bool attr_set[64];
+    if (!attr_set[dev & 63]) {
+        CU(cudaFuncSetAttribute(lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev & 63] = true;
+    }
+    LaunchCfg& c = g_cfg[dev & 63];
+    if (!c.ready) {
+        CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+        c.ready = true;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL>, LG::THREADS, smem));
+    if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean kernel does not fit");
+    int grid = std::min(P.n_tiles, c.sms * per_sm);
+    {
+        // compiled for this query's shape when the run-time compiler is there (cqg_jit), else the generic kernel below
+        char name[200];
+        snprintf(name, sizeof name, "cqg::lean_kernel<cqg::Geo<%d, %d, %d, %d>, %d, %s, %s, %s, %s>", LG::THREADS, LG::TILE, LG::STAGES,
+                 LG::OVER, MINB, GROUPED ? "true" : "false", ONELEAF ? "true" : "false", MINMAX ? "true" : "false",
+                 GLOBAL ? "true" : "false");
+        if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean.cuh", name)) {
+            void* args[] = {(void*)&P};
+            if (cudaFuncSetAttribute((const void*)jk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+                cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
+                g_launches++;
+                return CQG_OK;
+            }
+            cudaGetLastError();
+        }
+    }
+    lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL><<<grid, LG::THREADS, smem, st>>>(P);
+    g_launches++;
+    CU(cudaGetLastError());
+    return CQG_OK;
+}
+
 
 template <class LG, int MINB, bool ONELEAF, int GAP0>
 static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {

@@ -13,6 +13,21 @@
 #pragma once
 #include "cqg_scan.cuh"
 
+// ---- per-query specialisation (cqg_jit in cqg_api.cu) ----
+// Compiled ahead of time the lean kernels read the plan's SHAPE (wanted columns and the delimiters between
+// them, the leaf program, key and aggregate slots) from the kernel parameter. Compiled at run time for one
+// query (NVRTC, -DCQG_JIT) the same source gets the shape as macros: loops unroll, slot selects and leaf-kind
+// branches fold away. Values (literals, intervals, offsets) stay in the parameter either way.
+#ifdef CQG_JIT
+#define CQG_SPEC(NAME, RUNTIME) (CQG_JIT_##NAME)
+#define CQG_SPEC_AT(NAME, I, RUNTIME) (CQG_JIT_##NAME(I))
+#define CQG_SPEC_UNROLL _Pragma("unroll")
+#else
+#define CQG_SPEC(NAME, RUNTIME) (RUNTIME)
+#define CQG_SPEC_AT(NAME, I, RUNTIME) (RUNTIME)
+#define CQG_SPEC_UNROLL _Pragma("unroll 1")
+#endif
+
 namespace cqg {
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
@@ -292,24 +307,27 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     asm volatile("mov.u32 %0, 1;" : "=r"(one));
     asm volatile("mov.u32 %0, 0x0a0a0a0a;" : "=r"(patN));
     asm volatile("mov.u32 %0, %1;" : "=r"(patDv) : "r"(patD));
-    const int nwant = P.nwantL;
-    const int gap0 = P.gap[0], gap1 = P.gap[1], gap2 = P.gap[2], gap3 = P.gap[3];
-    const int nprog = P.l_nprog;
+    const int nwant = CQG_SPEC(NWANT, P.nwantL);
+    const int gap0 = CQG_SPEC(GAP0, P.gap[0]), gap1 = CQG_SPEC(GAP1, P.gap[1]), gap2 = CQG_SPEC(GAP2, P.gap[2]),
+              gap3 = CQG_SPEC(GAP3, P.gap[3]);
+    const int nprog = CQG_SPEC(NPROG, P.l_nprog);
+    const int nagg = CQG_SPEC(NAGG, P.l_nagg);
     const int leaf0_lop = P.l_leaf[0].lop;
-    const int ngc = GROUPED ? P.ngc : 0;
+    const int ngc = GROUPED ? CQG_SPEC(NGC, P.ngc) : 0;
     constexpr bool lean_global = GROUPED && GLOBAL;
     uint32_t summask = 0;  // aggregates that read a column: SUM/AVG, and (bits 4..7) those that are MIN/MAX, (8..11) MIN
     int aslot[4];
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         aslot[a] = 0;
-        if (a < P.l_nagg) {
+        if (a < nagg) {
             const AggSpec sp = P.aggs[P.l_agg[a]];
+            const int func = CQG_SPEC_AT(AFUNC, a, sp.func);
             summask |= 1u << a;
-            if (sp.func == CQG_AGG_MIN || sp.func == CQG_AGG_MAX) summask |= 16u << a;
-            if (sp.func == CQG_AGG_MIN) summask |= 256u << a;
-            aslot[a] = sp.slot;
-            if (sp.func == CQG_AGG_MIN) mmk[a] = ~0ull;
+            if (func == CQG_AGG_MIN || func == CQG_AGG_MAX) summask |= 16u << a;
+            if (func == CQG_AGG_MIN) summask |= 256u << a;
+            aslot[a] = CQG_SPEC_AT(ASLOT, a, sp.slot);
+            if (func == CQG_AGG_MIN) mmk[a] = ~0ull;
         }
     }
 
@@ -499,10 +517,11 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                         }
                     } else if (ok && nprog) {
                         uint32_t bs = 0;
+                        CQG_SPEC_UNROLL
                         for (int pc = 0; pc < nprog; pc++) {
-                            const int c = P.l_prog[pc];
+                            const int c = CQG_SPEC_AT(PROG, pc, P.l_prog[pc]);
                             if (c >= 0) {
-                                const int sl = P.l_leaf[c].slot, kind = P.l_leaf[c].kind;
+                                const int sl = CQG_SPEC_AT(LEAFSLOT, c, P.l_leaf[c].slot), kind = CQG_SPEC_AT(LEAFKIND, c, P.l_leaf[c].kind);
                                 CQG_LEAN_SLOT(sl, o, l)
                                 bool bv = false;
                                 if (kind == 0) {
@@ -588,7 +607,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                             kw[2 * g] = 0;
                             kw[2 * g + 1] = 0;
                             if (g < ngc && ok) {
-                                const int sl = P.gslot[g];
+                                const int sl = CQG_SPEC_AT(GSLOT, g, P.gslot[g]);
                                 uint32_t tag = KT_NULL;
                                 if (sl >= 0) {
                                     CQG_LEAN_SLOT(sl, o, l)

@@ -19,21 +19,6 @@
 #pragma once
 #include "cqg_lean.cuh"
 
-// ---- per-query specialisation (cqg_jit in cqg_api.cu) ----
-// Compiled ahead of time the lean kernels read the plan's SHAPE (wanted columns and the delimiters between
-// them, the leaf program, key and aggregate slots) from the kernel parameter. Compiled at run time for one
-// query (NVRTC, -DCQG_JIT) the same source gets the shape as macros: loops unroll, slot selects and leaf-kind
-// branches fold away. Values (literals, intervals, offsets) stay in the parameter either way.
-#ifdef CQG_JIT
-#define CQG_SPEC(NAME, RUNTIME) (CQG_JIT_##NAME)
-#define CQG_SPEC_AT(NAME, I, RUNTIME) (CQG_JIT_##NAME(I))
-#define CQG_SPEC_UNROLL _Pragma("unroll")
-#else
-#define CQG_SPEC(NAME, RUNTIME) (RUNTIME)
-#define CQG_SPEC_AT(NAME, I, RUNTIME) (RUNTIME)
-#define CQG_SPEC_UNROLL _Pragma("unroll 1")
-#endif
-
 namespace cqg {
 
 template <class G>
