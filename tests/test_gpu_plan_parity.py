@@ -488,3 +488,17 @@ def test_join_keys_of_different_classes_are_declined():
         with pytest.raises(CqError) as ei:
             lg.execute(Plan(aggs=[(A.AGG_COUNT_STAR, -1)], join=(rg, 0, 0)))
         assert ei.value.code == A.ERR_UNSUPPORTED
+
+
+def test_ahead_of_time_lean_kernels_without_the_run_time_compiler():
+    """CQG_JIT=0: the same plans on the ahead-of-time (generic) lean kernels, in a fresh process (the switch is
+    read once). Every other test of this file runs the kernels compiled per query shape."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CQG_JIT="0")
+    sel = "test_plan_parity and (group_name or filter_not or scalar_aggs or count_age or lean_group or group_high_card)"
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-x", "-k", sel], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
