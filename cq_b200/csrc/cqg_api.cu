@@ -516,15 +516,61 @@ static bool enabled() {
     return on == 1;
 }
 
+// a compile costs about a second: only scans big enough to win it back within a few queries get one
+// (CQG_JIT_MIN_BYTES, default 64 MB of owned bytes; read every time so that tests can change it)
+static bool worth_it(uint64_t scan_bytes) {
+    const char* e = getenv("CQG_JIT_MIN_BYTES");
+    const uint64_t min_bytes = e ? strtoull(e, nullptr, 10) : (64ull << 20);
+    return scan_bytes >= min_bytes;
+}
+
+// cubins persist across processes: $CQG_JIT_CACHE, else $HOME/.cache/cqg_jit, else /tmp/cqg_jit (best effort)
+static std::string cache_path(const std::string& key) {
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : key) h = (h ^ c) * 1099511628211ull;
+    for (const char* c = "sm_100a|v1|" __DATE__ " " __TIME__; *c; c++) h = (h ^ (unsigned char)*c) * 1099511628211ull;
+    const char* e = getenv("CQG_JIT_CACHE");
+    std::string dir;
+    if (e) dir = e;
+    else if (const char* home = getenv("HOME")) dir = std::string(home) + "/.cache/cqg_jit";
+    else dir = "/tmp/cqg_jit";
+    mkdir(dir.substr(0, dir.rfind('/')).c_str(), 0700);
+    mkdir(dir.c_str(), 0700);
+    char name[40];
+    snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)h);
+    return dir + name;
+}
+
 // defs: the #define block of the shape; header: the file that holds the kernel template; name: its instantiation
-static cudaKernel_t get(const std::string& defs, const char* header, const char* name) {
-    if (!enabled()) return nullptr;
+static cudaKernel_t get(const std::string& defs, const char* header, const char* name, uint64_t scan_bytes) {
+    if (!enabled() || !worth_it(scan_bytes)) return nullptr;
     std::lock_guard<std::mutex> lock(g_mu);
     const std::string key = std::string(name) + "\n" + defs;
     auto it = g_cache.find(key);
     if (it != g_cache.end()) return it->second.failed ? nullptr : it->second.fn;
     Kernel& k = g_cache[key];
     k.failed = true;
+    // a cubin of this shape from an earlier process? (file = lowered name, NUL, cubin)
+    const std::string path = cache_path(key);
+    {
+        std::vector<char> blob;
+        if (FILE* f = fopen(path.c_str(), "rb")) {
+            char buf[65536];
+            size_t n;
+            while ((n = fread(buf, 1, sizeof buf, f)) > 0) blob.insert(blob.end(), buf, buf + n);
+            fclose(f);
+        }
+        const void* nul = blob.empty() ? nullptr : memchr(blob.data(), 0, blob.size());
+        if (nul) {
+            const size_t off = (const char*)nul - blob.data() + 1;
+            if (off < blob.size() && cudaLibraryLoadData(&k.lib, blob.data() + off, nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+                cudaLibraryGetKernel(&k.fn, k.lib, blob.data()) == cudaSuccess) {
+                k.failed = false;
+                return k.fn;
+            }
+            cudaGetLastError();
+        }
+    }
     Api& a = api();
     if (!a.ok) return nullptr;
     std::string csrc, inc;
@@ -561,6 +607,14 @@ static cudaKernel_t get(const std::string& defs, const char* header, const char*
     }
     k.failed = false;
     if (getenv("CQG_JIT_VERBOSE")) fprintf(stderr, "[cqg jit] compiled %s (%zu bytes)\n", name, n);
+    {
+        const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+        if (FILE* f = fopen(tmp.c_str(), "wb")) {
+            const bool w = fwrite(lowered.c_str(), 1, lowered.size() + 1, f) == lowered.size() + 1 && fwrite(cubin.data(), 1, n, f) == n;
+            fclose(f);
+            if (!w || rename(tmp.c_str(), path.c_str()) != 0) unlink(tmp.c_str());
+        }
+    }
     return k.fn;
 }
 
@@ -631,7 +685,7 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
         snprintf(name, sizeof name, "cqg::lean_kernel<cqg::Geo<%d, %d, %d, %d>, %d, %s, %s, %s, %s>", LG::THREADS, LG::TILE, LG::STAGES,
                  LG::OVER, MINB, GROUPED ? "true" : "false", ONELEAF ? "true" : "false", MINMAX ? "true" : "false",
                  GLOBAL ? "true" : "false");
-        if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean.cuh", name)) {
+        if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean.cuh", name, P.own_hi - P.own_lo)) {
             void* args[] = {(void*)&P};
             if (cudaFuncSetAttribute((const void*)jk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
                 cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
@@ -673,7 +727,7 @@ static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
         char name[160];
         snprintf(name, sizeof name, "cqg::lean2_kernel<cqg::Geo<%d, %d, %d, %d>, %d, false, -1>", LG::THREADS, LG::TILE, LG::STAGES,
                  LG::OVER, MINB);
-        if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean2.cuh", name)) {
+        if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean2.cuh", name, P.own_hi - P.own_lo)) {
             void* args[] = {(void*)&P};
             if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
                 g_launches++;
@@ -712,7 +766,7 @@ static int launch_lean2g_geo(const DevPlan& P0, cudaStream_t st) {
     // the same kernel compiled for this query's shape, when the run-time compiler is there (else the generic one)
     char name[160];
     snprintf(name, sizeof name, "cqg::lean2g_kernel<cqg::Geo<%d, %d, %d, %d>, %d>", LG::THREADS, LG::TILE, LG::STAGES, LG::OVER, MINB);
-    if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean2g.cuh", name)) {
+    if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean2g.cuh", name, P.own_hi - P.own_lo)) {
         void* args[] = {(void*)&P};
         if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
             g_launches++;

@@ -13,6 +13,20 @@ from oracle_lib import generate_bigdata, oracle
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _compile_kernels_per_query_shape():
+    """The tables of this file are far below the size at which the library compiles a kernel for a query's shape
+    (CQG_JIT_MIN_BYTES, 64 MB): lower the bar so that the plan-level parity tests run those kernels."""
+    import os
+    old = os.environ.get("CQG_JIT_MIN_BYTES")
+    os.environ["CQG_JIT_MIN_BYTES"] = "0"
+    yield
+    if old is None:
+        os.environ.pop("CQG_JIT_MIN_BYTES", None)
+    else:
+        os.environ["CQG_JIT_MIN_BYTES"] = old
+
+
 @pytest.fixture(scope="module")
 def big():
     data = generate_bigdata(200_000, seed=1)
