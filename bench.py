@@ -236,7 +236,8 @@ def main():
         counts = torch.tensor([n], device="cuda", dtype=torch.int64)
         allc = torch.empty(world, device="cuda", dtype=torch.int64)
         dist.all_gather_into_tensor(allc, counts)
-        nmax = int(allc.max().item())
+        ac = allc.tolist()
+        nmax = max(ac)
         send = torch.zeros(max(nmax, 1) * rec, dtype=torch.uint8, device="cuda")
         got = C.c_int64()
         _check(lib, lib.partial_export(p, 0, 1, send.data_ptr(), nmax, C.byref(got)))
@@ -244,10 +245,13 @@ def main():
         dist.all_gather_into_tensor(recv, send)
         m = C.c_void_p()
         _check(lib, lib.partial_new_like(p, C.byref(m)))
-        ac = allc.tolist()
-        for r in range(world):
-            if ac[r]:
-                _check(lib, lib.partial_merge(m, recv.data_ptr() + r * max(nmax, 1) * rec, ac[r]))
+        if nmax and all(a == nmax for a in ac):
+            # every rank sent the same number of records: the gathered buffer is dense, one merge launch
+            _check(lib, lib.partial_merge(m, recv.data_ptr(), nmax * world))
+        else:
+            for r in range(world):
+                if ac[r]:
+                    _check(lib, lib.partial_merge(m, recv.data_ptr() + r * max(nmax, 1) * rec, ac[r]))
         res = C.POINTER(A.Result)()
         _check(lib, lib.partial_finish(m, table.handle, C.byref(res)))
         out = {"count0": res.contents.count[0] if res.contents.n_groups else 0, "kernel_ms": lib.partial_kernel_ms(p),
