@@ -1482,6 +1482,7 @@ struct Arena {
     std::vector<void*> blocks;
     char* cur = nullptr;
     size_t left = 0;
+    size_t next_block = 16u << 10;  // blocks grow 16 KB -> 4 MB: a one-group result must not cost a 4 MB calloc
     void* alloc(size_t n) {
         n = (n + 15) & ~(size_t)15;
         if (n == 0) n = 16;
@@ -1491,7 +1492,9 @@ struct Arena {
             return p;
         }
         if (n > left) {
-            size_t sz = 4u << 20;
+            size_t sz = next_block;
+            while (sz < n) sz <<= 1;
+            if (next_block < (4u << 20)) next_block <<= 2;
             cur = (char*)calloc(1, sz);
             blocks.push_back(cur);
             left = sz;
@@ -2036,13 +2039,16 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
         if (!P.dec_table) return fail(CQG_ERR_CUDA, "decimal table allocation failed");
     }
     uint64_t cap = P.ngc == 0 ? 16 : (1u << 14);
+    PhaseTimer pt;
     for (int attempt = 0; attempt < 14; attempt++) {
         if ((rc = alloc_group_table(hp, gt, cap, st))) return rc;
         CU(cudaMemsetAsync(sb, 0, sizeof(ScalarBlock), st));
+        pt.lap("lean: buffers");
         cudaEventRecord(e0, st);
         if ((rc = launch_lean(P, st))) return rc;
         cudaEventRecord(e1, st);
         if ((rc = read_scalars(hp, hs, st))) return rc;
+        pt.lap("lean: kernel + flags");
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         *ms_out += ms;
@@ -2090,6 +2096,7 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
             float ms = 0;
             cudaEventElapsedTime(&ms, e0, e1);
             *ms_out += ms;
+            pt.lap("lean: handed-over tiles and rows");
             hs.errflags |= h2.errflags & ~KERR_TABLE_FULL;
             hs.rows_scanned = h2.rows_scanned;
             hs.gcount = h2.gcount;
@@ -2288,7 +2295,9 @@ CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t
     if (rc) return rc;
     cudaStream_t st = 0;
     HostPlan hp;
+    PhaseTimer pt;
     if ((rc = build_plan(hp, t, q, st))) return rc;
+    pt.lap("execute: plan");
     const cqg_table* rt = q->join.right;
     JoinState js;
     float ms = 0;
@@ -2300,12 +2309,14 @@ CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t
         GroupTable gt;
         ScalarBlock hs{};
         if ((rc = run_aggregate_scan(hp, gt, st, hs, &ms))) return rc;
+        pt.lap("execute: scan");
         hs.errflags |= js.flags;
         hs.jclass[1] |= js.key_classes;
         if ((rc = check_flags(hs, hp.P.join != 0))) return rc;
         DevBuf entries;
         uint64_t G = 0;
         if ((rc = compact_groups(hp, gt, 0, 1, entries, &G, st, (long long)hs.gcount))) return rc;
+        pt.lap("execute: compact");
         const long long launches_before_finish = g_launches.load();
         rc = finish_aggregate(hp, t, rt, q, entries.as<uint8_t>(), G, true, (int64_t)hs.rows_scanned, out, st);
         if (rc == CQG_OK && g_launches.load() != launches_before_finish) {  // the finish ran kernels that can raise flags
