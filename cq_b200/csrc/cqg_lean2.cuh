@@ -67,7 +67,7 @@ __host__ __device__ __forceinline__ void lean2_negate(uint32_t& lo, uint32_t& wi
 // `mant * A <op> LB` over mant in [0, 2^24) as a modular interval: pass = (mant - lo) <= width (unsigned).
 // "never" is {0xffffffff, 0}, "always" {0, 0xffffffff}; != is the complement of the == interval.
 // Also the same test over digit codes (lean2_code) of values <= 9999: {clo, cwidth}.
-__device__ inline void lean2_interval(const LeanLeaf& L, int fd, uint32_t& lo, uint32_t& width, uint32_t& clo, uint32_t& cwidth) {
+__host__ __device__ inline void lean2_interval(const LeanLeaf& L, int fd, uint32_t& lo, uint32_t& width, uint32_t& clo, uint32_t& cwidth) {
     uint32_t negate;
     const unsigned long long A = L.A[fd] ? L.A[fd] : 1u;
     const long long LB = L.LB[fd];

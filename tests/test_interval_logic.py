@@ -1,0 +1,26 @@
+"""The scalar lean kernels never multiply or convert to compare `column <op> literal`: per CTA the comparison is
+folded into one modular interval test on the field's mantissa, or on its digit bytes (cqg_lean2.cuh:
+lean2_interval, lean2_code). tests/native/interval_check.cu checks that folding exhaustively against the scaled
+integer comparison it replaces (all six operators, literals with 0..3 fraction digits, mantissas 0..12000 and a
+sweep up to 10^7 - 1). Compiled for the HOST by nvcc: no GPU needed."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.mark.timeout(300)
+def test_interval_folding_equals_scaled_integer_compare(tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    exe = str(tmp_path / "interval_check")
+    src = os.path.join(ROOT, "tests", "native", "interval_check.cu")
+    subprocess.run([nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "cq_b200", "csrc"), "-o", exe, src], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.startswith("ok ")
