@@ -127,12 +127,37 @@ __host__ __device__ inline void lean2_interval(const LeanLeaf& L, int fd, uint32
     }
 }
 
-// unsigned decimal of 1..4 bytes ENDING at shared address `fe` (exclusive): mant / 10^(fd16/16).
-// false: not one (sign, exponent, text, two dots, a lone '.').
-__device__ __forceinline__ bool lean2_dec4(uint32_t fe, uint32_t len, uint32_t& mant, uint32_t& fd16) {
-    const uint32_t a = fe & ~3u;
-    const uint32_t w0 = lds32(a - 4u), w1 = lds32(a);
-    uint32_t t = __funnelshift_r(w0, w1, fe << 3) ^ 0x30303030u;  // bytes [fe-4, fe): the last character on top
+// the three integer intrinsics of the decode, with host stand-ins so that tests/native can run the same arithmetic
+__host__ __device__ __forceinline__ uint32_t l2_prmt(uint32_t a, uint32_t b, uint32_t s) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, b, s);
+#else
+    const unsigned long long pool = ((unsigned long long)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((pool >> (8 * ((s >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t l2_umulhi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((unsigned long long)a * b) >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t l2_dp4a(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+    return __dp4a(a, b, c);
+#else
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+    return c;
+#endif
+}
+
+// unsigned decimal of 1..4 bytes given as the 4 bytes ENDING at the field's end (`w`: last character on top,
+// whatever precedes the field below): mant / 10^(fd16/16). false: not one (sign, exponent, text, two dots, a lone '.').
+__host__ __device__ __forceinline__ bool lean2_dec4_word(uint32_t w, uint32_t len, uint32_t& mant, uint32_t& fd16) {
+    uint32_t t = w ^ 0x30303030u;
     t &= ~(0x00ffffffu >> (8u * len - 8u));                        // what precedes the field reads as leading zeros
     const uint32_t x = ((t ^ 0x1e1e1e1eu) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
     const uint32_t dotf = ~(x | t) & 0x80808080u;                  // 0x80 where the byte is '.'
@@ -140,16 +165,47 @@ __device__ __forceinline__ bool lean2_dec4(uint32_t fe, uint32_t len, uint32_t& 
     if (dotf) {
         if ((dotf & (dotf - 1u)) || len == 1u) return false;
         // fd = 3 - (byte index of the dot), as fd * 0x11: nibble 0 picks the low selector byte, nibble 1 the high one
-        const uint32_t r = __umulhi(dotf, 0x66442200u);
+        const uint32_t r = l2_umulhi(dotf, 0x66442200u);
         fd16 = r & 0x30u;
-        const uint32_t sel = __byte_perm(0x14040404u, 0x32323121u, (r & 0x33u) | 0x40u);
-        t = __byte_perm(t, 0u, sel);                               // drop the dot, shift the integer digits down
+        const uint32_t sel = l2_prmt(0x14040404u, 0x32323121u, (r & 0x33u) | 0x40u);
+        t = l2_prmt(t, 0u, sel);                                   // drop the dot, shift the integer digits down
     }
     if (((t + 0x76767676u) | t) & 0x80808080u) return false;      // a byte that is not a digit
-    mant = __dp4a(t, 0x010a6400u, (t & 0xffu) * 1000u);
+    mant = l2_dp4a(t, 0x010a6400u, (t & 0xffu) * 1000u);
     return true;
 }
-
+// the field ENDS at shared address `fe` (exclusive)
+__device__ __forceinline__ bool lean2_dec4(uint32_t fe, uint32_t len, uint32_t& mant, uint32_t& fd16) {
+    const uint32_t a = fe & ~3u;
+    const uint32_t w0 = lds32(a - 4u), w1 = lds32(a);
+    return lean2_dec4_word(__funnelshift_r(w0, w1, fe << 3), len, mant, fd16);  // bytes [fe-4, fe)
+}
+// lean2_dec4_word with the digit code (lean2_code) instead of the value (the byte permute that drops the '.' also
+// reverses the bytes). Returns 0 when the field is such a decimal, anything else when not. `kdot` = 0x1e1e1e1e
+// ('.' ^ '0' in every byte), handed in so that the kernel can pin it in a register.
+__host__ __device__ __forceinline__ uint32_t lean2_dec4c_word(uint32_t w, uint32_t len, uint32_t kdot, uint32_t& code, uint32_t& fd16) {
+    uint32_t t = w ^ 0x30303030u;
+    t &= ~(0x00ffffffu >> (8u * len - 8u));
+    const uint32_t x = ((t ^ kdot) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    const uint32_t dotf = ~(x | t) & 0x80808080u;
+    fd16 = 0u;
+    uint32_t sel = 0x0123u, bad = 0u;
+    if (dotf) {
+        bad = (dotf & (dotf - 1u)) | (len == 1u ? 1u : 0u);
+        const uint32_t r = l2_umulhi(dotf, 0x66442200u);           // fd * 0x11 (see lean2_dec4_word)
+        fd16 = r & 0x30u;
+        sel = l2_prmt(0x23231312u, 0x41404040u, (r & 0x33u) | 0x40u);
+    }
+    t = l2_prmt(t, 0u, sel);
+    bad |= ((t + 0x76767676u) | t) & 0x80808080u;                 // a byte that is not a digit
+    code = t;
+    return bad;
+}
+__device__ __forceinline__ uint32_t lean2_dec4c(uint32_t fe, uint32_t len, uint32_t kdot, uint32_t& code, uint32_t& fd16) {
+    const uint32_t a = fe & ~3u;
+    const uint32_t w0 = lds32(a - 4u), w1 = lds32(a);
+    return lean2_dec4c_word(__funnelshift_r(w0, w1, fe << 3), len, kdot, code, fd16);
+}
 // first terminator bit at or after bit `q` of the tile buffer; `limit` when there is none below it
 __device__ __noinline__ uint32_t lean2_next_term(uint32_t s_msk, uint32_t q, uint32_t limit) {
     uint32_t w = q >> 5;
@@ -199,29 +255,6 @@ struct Lean2Stops {
 };
 
 
-// ---- ONELEAF helpers ----
-// lean2_dec4 with the digit code (lean2_code) instead of the value (the byte permute that drops the '.' also reverses the bytes)
-// Returns 0 when the field is such a decimal, anything else when not (sign, exponent, text, two dots, a lone '.').
-__device__ __forceinline__ uint32_t lean2_dec4c(uint32_t fe, uint32_t len, uint32_t kdot, uint32_t& code, uint32_t& fd16) {
-    const uint32_t a = fe & ~3u;
-    const uint32_t w0 = lds32(a - 4u), w1 = lds32(a);
-    uint32_t t = __funnelshift_r(w0, w1, fe << 3) ^ 0x30303030u;  // bytes [fe-4, fe): the last character on top
-    t &= ~(0x00ffffffu >> (8u * len - 8u));                        // what precedes the field reads as leading zeros
-    const uint32_t x = ((t ^ kdot) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-    const uint32_t dotf = ~(x | t) & 0x80808080u;                  // 0x80 where the byte is '.'
-    fd16 = 0u;
-    uint32_t sel = 0x0123u, bad = 0u;
-    if (dotf) {
-        bad = (dotf & (dotf - 1u)) | (len == 1u ? 1u : 0u);
-        const uint32_t r = __umulhi(dotf, 0x66442200u);            // fd * 0x11 (see lean2_dec4)
-        fd16 = r & 0x30u;
-        sel = __byte_perm(0x23231312u, 0x41404040u, (r & 0x33u) | 0x40u);
-    }
-    t = __byte_perm(t, 0u, sel);
-    bad |= ((t + 0x76767676u) | t) & 0x80808080u;                 // a byte that is not a digit
-    code = t;
-    return bad;
-}
 // A row that does not end inside the 32-bit window (ONELEAF): 32..63 bytes on 64-bit masks, longer ones are
 // found and handed over. Returns et | sp << 16 | flen << 24 | dirty << 31 (flen 0: hand the row over).
 __device__ __noinline__ uint32_t lean2_wide_row(uint32_t s_msk, uint32_t pos, int gap, uint32_t limit) {

@@ -24,3 +24,20 @@ def test_interval_folding_equals_scaled_integer_compare(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert r.stdout.startswith("ok ")
+
+
+@pytest.mark.timeout(300)
+def test_four_byte_decimal_decode_is_exact(tmp_path):
+    """tests/native/decimal_check.cu: every field of 1..4 characters over digits, '.', signs, exponent letters,
+    blanks, quotes, newline, a UTF-8 lead byte — with every kind of byte in front of it — decodes to the reference's
+    value or is declined (lean2_dec4_word / lean2_dec4c_word, the kernels' own arithmetic compiled for the host)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    exe = str(tmp_path / "decimal_check")
+    src = os.path.join(ROOT, "tests", "native", "decimal_check.cu")
+    subprocess.run([nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "cq_b200", "csrc"), "-o", exe, src], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.startswith("ok ")
