@@ -964,8 +964,6 @@ static bool make_lean_leaf(DevPlan& P, const FInsn& in, LeanLeaf& L) {
     if (c.type == CQG_TYPE_STRING) {
         if (op != CQG_OP_EQ && op != CQG_OP_NE) return false;
         if (c.len < 1 || c.len > 16) return false;
-        const uint8_t* sp = nullptr;
-        (void)sp;
         return false;  // filled by the caller, which owns the host copy of the string pool
     }
     long long cm;
@@ -1007,9 +1005,6 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
         if (P.aggs[a].slot < 0 || P.aggs[a].slot >= 4 || P.l_nagg >= 4) return;
         P.l_agg[P.l_nagg++] = a;
     }
-    bool scalar_minmax = false;  // no GROUP BY but MIN/MAX: the grouped kernel with a one-group dictionary
-    for (int a = 0; a < P.naggs; a++)
-        if ((P.aggs[a].func == CQG_AGG_MIN || P.aggs[a].func == CQG_AGG_MAX) && P.aggs[a].off >= 0 && P.ngc == 0) scalar_minmax = true;
     if (P.pred_kind == 2) return;
     if (P.pred_kind == 1) {
         for (int k = 0; k < P.n_fcode; k++) {
@@ -1032,7 +1027,6 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
                     if ((op != CQG_OP_EQ && op != CQG_OP_NE) || c.len < 1 || c.len > 16) return;
                     if ((size_t)c.bits + c.len > pool.size()) return;
                     const uint8_t* sp = pool.data() + c.bits;
-                    unsigned c0 = sp[0];
                     // a literal that could be typed as a number/date is not a STRING const; blanks cannot
                     // occur in a clean tile's field, so such a literal simply never matches there
                     memset(&L, 0, sizeof L);
@@ -1043,7 +1037,6 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
                         if (i < 8) L.w0 |= (uint64_t)sp[i] << (8 * i);
                         else L.w1 |= (uint64_t)sp[i] << (8 * (i - 8));
                     }
-                    (void)c0;
                 }
                 P.l_prog[P.l_nprog++] = (int8_t)P.l_nleaf;
                 P.l_nleaf++;
@@ -1052,7 +1045,6 @@ static void plan_simple_route(DevPlan& P, const std::vector<uint8_t>& pool) {
             }
         }
     }
-    (void)scalar_minmax;
     P.simple = P.ngc == 0 ? 1 : 2;  // 2: lean GROUP BY (per-CTA dictionary, up to 64 groups per CTA)
 }
 
@@ -1885,8 +1877,6 @@ static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* r
                 v.double_value = f == CQG_AGG_SUM ? sum : ((int)n > 0 ? sum / (double)(int)n : 0.0);
             } else {
                 const uint64_t* s = (const uint64_t*)(e + sp.off);
-                bool is_min = f == CQG_AGG_MIN;
-                uint64_t empty = is_min ? ~0ull : 0ull;
                 uint32_t cls = s[0] == ~0ull ? 0u : (uint32_t)(s[0] & 3u);
                 if (cls == 1) {
                     // type and bits of the extreme come from the row that holds it

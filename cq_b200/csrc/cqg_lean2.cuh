@@ -238,20 +238,6 @@ struct Lean2Stops {
         off = sp;
         len = missing ? 0u : ep - sp;
     }
-    // the same with the skip count known at compile time
-    template <int GAP>
-    __device__ __forceinline__ void field_c(uint32_t& off, uint32_t& len) {
-        if (GAP > 0) {
-#pragma unroll
-            for (int i = 1; i < GAP; i++) st &= st - 1;
-            sp = sizeof(W) == 8 ? (uint32_t)__ffsll((long long)st) : (uint32_t)__ffs((int)st);
-            st &= st - 1;
-        }
-        missing = st == 0;  // (no stop behind the field: the skipped ones were missing too)
-        const uint32_t ep = sizeof(W) == 8 ? ctz64((uint64_t)st) : ctz32((uint32_t)st);
-        off = sp;
-        len = missing ? 0u : ep - sp;
-    }
 };
 
 
@@ -539,13 +525,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                         const uint32_t below = tw ^ (tw - 1u);  // up to and including the terminator
                         et = bfind32(below);
                         Lean2Stops<uint32_t> S{(dw | tw) & below, 0u, false};
-                        if (GAP0 >= 0) S.template field_c<(GAP0 >= 0 ? GAP0 : 0)>(off0, len0);
-                        else S.field(gap0, off0, len0);
-                        if (!ONELEAF) {
-                            if (nwant > 1) S.field(gap1, off1, len1);
-                            if (nwant > 2) S.field(gap2, off2, len2);
-                            if (nwant > 3) S.field(gap3, off3, len3);
-                        }
+                        S.field(gap0, off0, len0);
+                        if (nwant > 1) S.field(gap1, off1, len1);
+                        if (nwant > 2) S.field(gap2, off2, len2);
+                        if (nwant > 3) S.field(gap3, off3, len3);
                     } else {
                         const uint32_t t2 = lds32(ma + 16u);
                         const uint32_t tw2 = __funnelshift_r(m1.x, t2, pos);
@@ -556,13 +539,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                             const uint64_t below = tw64 ^ (tw64 - 1ull);
                             et = 32u + bfind32((uint32_t)(below >> 32));
                             Lean2Stops<uint64_t> S{(dw64 | tw64) & below, 0u, false};
-                            if (GAP0 >= 0) S.template field_c<(GAP0 >= 0 ? GAP0 : 0)>(off0, len0);
-                            else S.field(gap0, off0, len0);
-                            if (!ONELEAF) {
-                                if (nwant > 1) S.field(gap1, off1, len1);
-                                if (nwant > 2) S.field(gap2, off2, len2);
-                                if (nwant > 3) S.field(gap3, off3, len3);
-                            }
+                            S.field(gap0, off0, len0);
+                            if (nwant > 1) S.field(gap1, off1, len1);
+                            if (nwant > 2) S.field(gap2, off2, len2);
+                            if (nwant > 3) S.field(gap3, off3, len3);
                         } else {
                             // 64 bytes or more: find the end, hand the row over
                             const uint32_t e = lean2_next_term(s_msk, pos + 64u, (uint32_t)G::BUF);
