@@ -282,6 +282,40 @@ __device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
         FD16 = (r7 >> 24) & 0x30u;                   \
     }
 
+// decimal of the field in slot SL (1..7 bytes; DEC stays false otherwise). A kernel compiled for one query knows
+// its slots, so a column read by a leaf AND an aggregate (`WHERE age > 25 ... AVG(age)`) is decoded once per row.
+#ifdef CQG_JIT
+#define CQG_L2_DECODE_STATE uint32_t dcache_mant[4] = {0u, 0u, 0u, 0u}, dcache_fd[4] = {0u, 0u, 0u, 0u}, dcache_state = 0u;
+#define CQG_L2_DECODE(SL, RB, O, L, DEC, MANT, FD16)                                        \
+    {                                                                                       \
+        const uint32_t st_ = (dcache_state >> (2 * (SL))) & 3u;                             \
+        if (st_ != 0u) {                                                                    \
+            DEC = st_ == 1u;                                                                \
+            MANT = dcache_mant[SL];                                                         \
+            FD16 = dcache_fd[SL];                                                           \
+        } else {                                                                            \
+            if ((L) - 1u < 4u) {                                                            \
+                DEC = lean2_dec4((RB) + (O) + (L), L, MANT, FD16);                          \
+            } else if ((L) - 1u < 7u) {                                                     \
+                CQG_L2_DEC7((RB) + (O), L, DEC, MANT, FD16)                                 \
+            }                                                                               \
+            dcache_mant[SL] = MANT;                                                         \
+            dcache_fd[SL] = FD16;                                                           \
+            dcache_state |= (DEC ? 1u : 2u) << (2 * (SL));                                  \
+        }                                                                                   \
+    }
+#else
+#define CQG_L2_DECODE_STATE
+#define CQG_L2_DECODE(SL, RB, O, L, DEC, MANT, FD16)                                        \
+    {                                                                                       \
+        if ((L) - 1u < 4u) {                                                                \
+            DEC = lean2_dec4((RB) + (O) + (L), L, MANT, FD16);                              \
+        } else if ((L) - 1u < 7u) {                                                         \
+            CQG_L2_DEC7((RB) + (O), L, DEC, MANT, FD16)                                     \
+        }                                                                                   \
+    }
+#endif
+
 // GAP0: the wanted column index of ONELEAF plans when it is below 8 (the delimiter skips unroll), else -1
 template <class G, int MINB, bool ONELEAF, int GAP0>
 __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_constant__ DevPlan P) {
@@ -562,6 +596,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                     lastb = lds8(rbase + et);
                     unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
                     uint32_t addmask = 0;
+                    CQG_L2_DECODE_STATE
                     if (ok) {
 #define CQG_L2_SLOT(SL, O, L)                                                    \
     const uint32_t O = SL == 0 ? off0 : SL == 1 ? off1 : SL == 2 ? off2 : off3; \
@@ -578,11 +613,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                                     if (kind == 0) {
                                         uint32_t mant = 0, fd16 = 0;
                                         bool dec = false;
-                                        if (l - 1u < 4u) {
-                                            dec = lean2_dec4(rbase + o + l, l, mant, fd16);
-                                        } else if (l - 1u < 7u) {
-                                            CQG_L2_DEC7(rbase + o, l, dec, mant, fd16)
-                                        }
+                                        CQG_L2_DECODE(sl, rbase, o, l, dec, mant, fd16)
                                         if (dec) {
                                             const uint2 iv = lds64(s_cmp + 64u * (uint32_t)c + fd16);
                                             bv = mant - iv.x <= iv.y;
@@ -629,11 +660,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
         CQG_L2_SLOT(sl, o, l)                                                                            \
         uint32_t mant = 0, fd16 = 0;                                                                     \
         bool dec = false;                                                                                \
-        if (l - 1u < 4u) {                                                                               \
-            dec = lean2_dec4(rbase + o + l, l, mant, fd16);                                              \
-        } else if (l - 1u < 7u) {                                                                        \
-            CQG_L2_DEC7(rbase + o, l, dec, mant, fd16)                                                \
-        }                                                                                                \
+        CQG_L2_DECODE(sl, rbase, o, l, dec, mant, fd16) \
         if (dec) {                                                                                       \
             ADD = (unsigned long long)mant * (fd16 == 0u ? 1000u : fd16 == 16u ? 100u : fd16 == 32u ? 10u : 1u); \
             addmask |= 1u << A;                                                                          \

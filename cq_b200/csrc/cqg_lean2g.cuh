@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
                 const uint32_t rbase = s_buf + pos;
                 unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
                 uint32_t addmask = 0, gid = 0xffffffffu;
+                CQG_L2_DECODE_STATE
 #define CQG_L2G_SLOT(SL, O, L)                                                   \
     const uint32_t O = SL == 0 ? off0 : SL == 1 ? off1 : SL == 2 ? off2 : off3; \
     const uint32_t L = SL == 0 ? len0 : SL == 1 ? len1 : SL == 2 ? len2 : len3;
@@ -307,11 +308,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
                             if (kind == 0) {
                                 uint32_t mant = 0, fd16 = 0;
                                 bool dec = false;
-                                if (l - 1u < 4u) {
-                                    dec = lean2_dec4(rbase + o + l, l, mant, fd16);
-                                } else if (l - 1u < 7u) {
-                                    CQG_L2_DEC7(rbase + o, l, dec, mant, fd16)
-                                }
+                                CQG_L2_DECODE(sl, rbase, o, l, dec, mant, fd16)
                                 if (dec) {
                                     const uint2 iv = lds64(s_cmp + 64u * (uint32_t)c + fd16);
                                     bv = mant - iv.x <= iv.y;
@@ -358,11 +355,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
         CQG_L2G_SLOT(sl, o, l)                                                                           \
         uint32_t mant = 0, fd16 = 0;                                                                     \
         bool dec = false;                                                                                \
-        if (l - 1u < 4u) {                                                                               \
-            dec = lean2_dec4(rbase + o + l, l, mant, fd16);                                              \
-        } else if (l - 1u < 7u) {                                                                        \
-            CQG_L2_DEC7(rbase + o, l, dec, mant, fd16)                                                   \
-        }                                                                                                \
+        CQG_L2_DECODE(sl, rbase, o, l, dec, mant, fd16) \
         if (dec) {                                                                                       \
             ADD = (unsigned long long)mant * (fd16 == 0u ? 1000u : fd16 == 16u ? 100u : fd16 == 32u ? 10u : 1u); \
             addmask |= 1u << A;                                                                          \
