@@ -39,8 +39,36 @@ __device__ __forceinline__ uint2 lds64(uint32_t a) {
 __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
-__device__ __forceinline__ uint32_t ctz32(uint32_t x) { return (uint32_t)__clz((int)__brev(x)); }
-__device__ __forceinline__ uint32_t ctz64(uint64_t x) { return (uint32_t)__clzll((long long)__brevll(x)); }
+// bit scans: the device intrinsics, with host stand-ins so that tests/native can run the field split on the CPU
+// (ctz of 0 is the word width, ffs of 0 is 0, as on the device)
+__host__ __device__ __forceinline__ uint32_t ctz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__clz((int)__brev(x));
+#else
+    return x ? (uint32_t)__builtin_ctz(x) : 32u;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t ctz64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__clzll((long long)__brevll(x));
+#else
+    return x ? (uint32_t)__builtin_ctzll(x) : 64u;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t l2_ffs32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)x);
+#else
+    return x ? (uint32_t)__builtin_ctz(x) + 1u : 0u;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t l2_ffs64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffsll((long long)x);
+#else
+    return x ? (uint32_t)__builtin_ctzll(x) + 1u : 0u;
+#endif
+}
 __device__ __forceinline__ uint32_t bfind32(uint32_t x) {
     uint32_t r;
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
@@ -225,12 +253,12 @@ struct Lean2Stops {
     W st;
     uint32_t sp;
     bool missing;
-    __device__ __forceinline__ void field(int gap, uint32_t& off, uint32_t& len) {
+    __host__ __device__ __forceinline__ void field(int gap, uint32_t& off, uint32_t& len) {
         if (gap > 0) {
             CQG_SPEC_UNROLL
             for (int i = 1; i < gap; i++) st &= st - 1;
             missing = missing || st == 0;
-            sp = sizeof(W) == 8 ? (uint32_t)__ffsll((long long)st) : (uint32_t)__ffs((int)st);
+            sp = sizeof(W) == 8 ? l2_ffs64((uint64_t)st) : l2_ffs32((uint32_t)st);
             st &= st - 1;
         }
         missing = missing || st == 0;
