@@ -69,10 +69,14 @@ __host__ __device__ __forceinline__ uint32_t l2_ffs64(uint64_t x) {
     return x ? (uint32_t)__builtin_ctzll(x) + 1u : 0u;
 #endif
 }
-__device__ __forceinline__ uint32_t bfind32(uint32_t x) {
+__host__ __device__ __forceinline__ uint32_t bfind32(uint32_t x) {  // index of the highest set bit
+#ifdef __CUDA_ARCH__
     uint32_t r;
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
     return r;
+#else
+    return x ? 31u - (uint32_t)__builtin_clz(x) : 0xffffffffu;
+#endif
 }
 
 // A decimal of <= 4 digits as its digit bytes, most significant on top (d3 << 24 | d2 << 16 | d1 << 8 | d0):
@@ -268,6 +272,29 @@ struct Lean2Stops {
     }
 };
 
+
+// One wanted field (column GAP0, or gap0 when GAP0 < 0) of a row that ends inside its 32-bit window: tw / dw = the
+// terminator / delimiter bits from the row's first byte on. et = index of the terminator, sp = start of the field,
+// flen = its length. The stops are the row's delimiters, its terminator, and every bit above it as a sentinel, so
+// that a field the row does not have comes out with length 0 (terminator on bit 31: 32 - sp, 0 or far too long).
+template <int GAP0>
+__host__ __device__ __forceinline__ void lean2_oneleaf_field(uint32_t tw, uint32_t dw, int gap0, uint32_t& et, uint32_t& sp, uint32_t& flen) {
+    const uint32_t below = tw ^ (tw - 1u);  // up to and including the terminator
+    et = bfind32(below);
+    uint32_t st = dw | tw | ~below;
+    if (GAP0 > 0) {
+#pragma unroll
+        for (int i = 1; i < GAP0; i++) st &= st - 1u;
+        sp = l2_ffs32(st);
+        st &= st - 1u;
+    } else if (GAP0 < 0 && gap0 > 0) {
+#pragma unroll 1
+        for (int i = 1; i < gap0; i++) st &= st - 1u;
+        sp = l2_ffs32(st);
+        st &= st - 1u;
+    }
+    flen = ctz32(st) - sp;
+}
 
 // A row that does not end inside the 32-bit window (ONELEAF): 32..63 bytes on 64-bit masks, longer ones are
 // found and handed over. Returns et | sp << 16 | flen << 24 | dirty << 31 (flen 0: hand the row over).
@@ -509,23 +536,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                         uint32_t et, sp = 0, flen;
                         if (tw != 0u) {
                             seen |= tw;
-                            const uint32_t below = tw ^ (tw - 1u);  // up to and including the terminator
-                            et = bfind32(below);
-                            // stops of the row: its delimiters, its terminator, and every bit above as a sentinel, so that
-                            // a field the row does not have comes out with length 0
-                            uint32_t st = dw | tw | ~below;
-                            if (GAP0 > 0) {
-#pragma unroll
-                                for (int i = 1; i < GAP0; i++) st &= st - 1u;
-                                sp = (uint32_t)__ffs((int)st);
-                                st &= st - 1u;
-                            } else if (GAP0 < 0 && gap0 > 0) {
-#pragma unroll 1
-                                for (int i = 1; i < gap0; i++) st &= st - 1u;
-                                sp = (uint32_t)__ffs((int)st);
-                                st &= st - 1u;
-                            }
-                            flen = ctz32(st) - sp;  // st == 0 (terminator on bit 31, field missing): 32 - sp, 0 or far too long
+                            lean2_oneleaf_field<GAP0>(tw, dw, gap0, et, sp, flen);
                         } else {
                             const uint32_t r = lean2_wide_row(s_msk, pos, gap0, (uint32_t)G::BUF);
                             et = r & 0xffffu;

@@ -70,9 +70,56 @@ static long long run(int max_len, int rows) {
     return checked;
 }
 
+// the COUNT(*)-WHERE kernel's own single-field version (stops with sentinel bits, compile-time or run-time column)
+template <int GAP0>
+static long long run_oneleaf(int rows, int gap_runtime) {
+    long long checked = 0;
+    const int col = GAP0 >= 0 ? GAP0 : gap_runtime;
+    for (int r = 0; r < rows; r++) {
+        const int nf = 1 + (int)(rnd() % 11);
+        std::vector<int> flen(nf), start(nf);
+        int total = nf - 1;
+        for (int f = 0; f < nf; f++) {
+            flen[f] = (rnd() % 4 == 0) ? 0 : (int)(rnd() % 6);
+            total += flen[f];
+        }
+        if (total + 1 > 32) continue;
+        uint32_t dw = 0, tw = 0;
+        int pos = 0;
+        for (int f = 0; f < nf; f++) {
+            start[f] = pos;
+            pos += flen[f];
+            if (f + 1 < nf) dw |= 1u << pos++;
+        }
+        tw |= 1u << pos;
+        for (int i = pos + 1; i < 32; i++) {
+            const uint32_t x = rnd() % 8;
+            if (x == 0) dw |= 1u << i;
+            if (x == 1) tw |= 1u << i;
+        }
+        uint32_t et = 0, sp = 0, fl = 0;
+        lean2_oneleaf_field<GAP0>(tw, dw, gap_runtime, et, sp, fl);
+        const bool have = col < nf;
+        // a missing field must not look like a decimal of 1..7 bytes (the kernel hands such rows over)
+        const bool bad = et != (uint32_t)pos || (have ? (fl != (uint32_t)flen[col] || (fl && sp != (uint32_t)start[col])) : (fl - 1u < 7u));
+        if (bad) {
+            printf("MISMATCH oneleaf column %d of %d fields: et %u sp %u len %u, expected et %d start %d len %d\n", col, nf, et, sp, fl, pos,
+                   have ? start[col] : -1, have ? flen[col] : -1);
+            exit(1);
+        }
+        checked++;
+    }
+    return checked;
+}
+
 int main() {
+    long long o = 0;
+    o += run_oneleaf<0>(100000, 0) + run_oneleaf<1>(100000, 1) + run_oneleaf<2>(100000, 2) + run_oneleaf<3>(100000, 3);
+    o += run_oneleaf<5>(100000, 5) + run_oneleaf<7>(100000, 7);
+    for (int g = 0; g < 12; g++) o += run_oneleaf<-1>(50000, g);
+    printf("ok %lld single-field rows; ", o);
     const long long a = run<uint32_t>(32, 400000);
     const long long b = run<uint64_t>(64, 400000);
-    printf("ok %lld fields on 32-bit masks, %lld on 64-bit masks\n", a, b);
+    printf("%lld fields on 32-bit masks, %lld on 64-bit masks\n", a, b);
     return 0;
 }
