@@ -159,6 +159,14 @@ __host__ __device__ inline void lean2_interval(const LeanLeaf& L, int fd, uint32
     }
 }
 
+// a + c as an IMAD on the device (add_fma, cqg_lean.cuh), plainly on the host
+__host__ __device__ __forceinline__ uint32_t l2_add(uint32_t a, uint32_t one, uint32_t c) {
+#ifdef __CUDA_ARCH__
+    return add_fma(a, one, c);
+#else
+    return a * one + c;
+#endif
+}
 // the three integer intrinsics of the decode, with host stand-ins so that tests/native can run the same arithmetic
 __host__ __device__ __forceinline__ uint32_t l2_prmt(uint32_t a, uint32_t b, uint32_t s) {
 #ifdef __CUDA_ARCH__
@@ -184,6 +192,32 @@ __host__ __device__ __forceinline__ uint32_t l2_dp4a(uint32_t a, uint32_t b, uin
     for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
     return c;
 #endif
+}
+
+// phase 1 of the scalar lean kernel on one 16-byte chunk: bit i of `t16` = byte i is below 0x23 (every terminator,
+// quote, blank, control byte), bit i of `d16` = byte i is the delimiter (patD = it, in every byte). Bytes with
+// bit 7 set (UTF-8) are neither. 3 instructions per word and class, then the 0x80 flags become mask bits
+// through four dot products per class (weights 1,2,4,8 | 16..128 leave mask << 7).
+__host__ __device__ __forceinline__ void lean2_masks16(uint32_t vx, uint32_t vy, uint32_t vz, uint32_t vw, uint32_t patD, uint32_t one,
+                                                       uint32_t& t16, uint32_t& d16) {
+    const uint32_t a0 = ~(l2_add(vx & 0x7f7f7f7fu, one, 0x5d5d5d5du) | vx) & 0x80808080u;
+    const uint32_t a1 = ~(l2_add(vy & 0x7f7f7f7fu, one, 0x5d5d5d5du) | vy) & 0x80808080u;
+    const uint32_t a2 = ~(l2_add(vz & 0x7f7f7f7fu, one, 0x5d5d5d5du) | vz) & 0x80808080u;
+    const uint32_t a3 = ~(l2_add(vw & 0x7f7f7f7fu, one, 0x5d5d5d5du) | vw) & 0x80808080u;
+    const uint32_t d0 = ~(l2_add((vx ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vx) & 0x80808080u;
+    const uint32_t d1 = ~(l2_add((vy ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vy) & 0x80808080u;
+    const uint32_t d2 = ~(l2_add((vz ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vz) & 0x80808080u;
+    const uint32_t d3 = ~(l2_add((vw ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vw) & 0x80808080u;
+    uint32_t ra = l2_dp4a(a2, 0x08040201u, 0u);
+    ra = l2_dp4a(a3, 0x80402010u, ra) * 256u;
+    ra = l2_dp4a(a0, 0x08040201u, ra);
+    ra = l2_dp4a(a1, 0x80402010u, ra);
+    uint32_t rd = l2_dp4a(d2, 0x08040201u, 0u);
+    rd = l2_dp4a(d3, 0x80402010u, rd) * 256u;
+    rd = l2_dp4a(d0, 0x08040201u, rd);
+    rd = l2_dp4a(d1, 0x80402010u, rd);
+    t16 = ra >> 7;
+    d16 = rd >> 7;
 }
 
 // unsigned decimal of 1..4 bytes given as the 4 bytes ENDING at the field's end (`w`: last character on top,
@@ -466,25 +500,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
             const uint32_t ma = s_msk + (((uint32_t)tid >> 1) << 3) + (((uint32_t)tid & 1u) << 1);
             auto chunk = [&](uint32_t ca, uint32_t ma) {
                 const uint4 v = lds128(ca);
-                const uint32_t a0 = ~(add_fma(v.x & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.x) & 0x80808080u;
-                const uint32_t a1 = ~(add_fma(v.y & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.y) & 0x80808080u;
-                const uint32_t a2 = ~(add_fma(v.z & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.z) & 0x80808080u;
-                const uint32_t a3 = ~(add_fma(v.w & 0x7f7f7f7fu, one, 0x5d5d5d5du) | v.w) & 0x80808080u;
-                const uint32_t d0 = ~(add_fma((v.x ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.x) & 0x80808080u;
-                const uint32_t d1 = ~(add_fma((v.y ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.y) & 0x80808080u;
-                const uint32_t d2 = ~(add_fma((v.z ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.z) & 0x80808080u;
-                const uint32_t d3 = ~(add_fma((v.w ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.w) & 0x80808080u;
-                // flags are 0x80 per byte: four dot products leave mask << 7
-                uint32_t ra = __dp4a(a2, 0x08040201u, 0u);
-                ra = __dp4a(a3, 0x80402010u, ra) * 256u;
-                ra = __dp4a(a0, 0x08040201u, ra);
-                ra = __dp4a(a1, 0x80402010u, ra);
-                uint32_t rd = __dp4a(d2, 0x08040201u, 0u);
-                rd = __dp4a(d3, 0x80402010u, rd) * 256u;
-                rd = __dp4a(d0, 0x08040201u, rd);
-                rd = __dp4a(d1, 0x80402010u, rd);
-                sts16(ma, ra >> 7);
-                sts16(ma + 4u, rd >> 7);
+                uint32_t ra, rd;
+                lean2_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd);
+                sts16(ma, ra);
+                sts16(ma + 4u, rd);
             };
             constexpr int kFull = G::CHUNKS / G::THREADS;  // steps every thread takes
 #pragma unroll

@@ -57,3 +57,19 @@ def test_field_split_on_bitmasks_equals_byte_split(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert r.stdout.startswith("ok ")
+
+
+@pytest.mark.timeout(300)
+def test_byte_classification_masks_are_exact(tmp_path):
+    """tests/native/masks_check.cu: lean2_masks16 (phase 1 of the scalar lean kernel: SWAR classes + dot-product
+    movemask) against a byte loop, all byte-value pairs at all positions and 1.8 M random chunks, six delimiters."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    exe = str(tmp_path / "masks_check")
+    src = os.path.join(ROOT, "tests", "native", "masks_check.cu")
+    subprocess.run([nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "cq_b200", "csrc"), "-o", exe, src], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.startswith("ok ")
