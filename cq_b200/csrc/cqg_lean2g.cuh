@@ -40,6 +40,36 @@ struct Lean2GLayout {
 
 __device__ __forceinline__ uint32_t l2g_hash_word(uint32_t h, uint32_t x) { return (h ^ x) * 0x9E3779B1u; }
 
+// phase 1 on one 16-byte chunk: bit i of `n16` = byte i is '\n', of `d16` = byte i is the delimiter; the return value
+// has a 0x80 bit set when the chunk holds any OTHER byte below 0x23 (CR, quote, blank, NUL ...: the tile is then left
+// to the general kernel). x - 0x23 per byte borrows into bit 7 exactly where the byte is below 0x23 and bit 7 clear
+// ('\n' bytes are lifted out of the way first); a borrow that crosses into the next byte can only ADD a flag.
+__host__ __device__ __forceinline__ uint32_t l2g_masks16(uint32_t vx, uint32_t vy, uint32_t vz, uint32_t vw, uint32_t patD, uint32_t one,
+                                                         uint32_t& n16, uint32_t& d16) {
+    const uint32_t f0 = ~(l2_add((vx ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vx) & 0x80808080u;
+    const uint32_t f1 = ~(l2_add((vy ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vy) & 0x80808080u;
+    const uint32_t f2 = ~(l2_add((vz ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vz) & 0x80808080u;
+    const uint32_t f3 = ~(l2_add((vw ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vw) & 0x80808080u;
+    const uint32_t d0 = ~(l2_add((vx ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vx) & 0x80808080u;
+    const uint32_t d1 = ~(l2_add((vy ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vy) & 0x80808080u;
+    const uint32_t d2 = ~(l2_add((vz ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vz) & 0x80808080u;
+    const uint32_t d3 = ~(l2_add((vw ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vw) & 0x80808080u;
+    const uint32_t x0 = vx | f0, x1 = vy | f1, x2 = vz | f2, x3 = vw | f3;
+    const uint32_t spec = (l2_add(x0, one, 0xdcdcdcddu) & ~x0) | (l2_add(x1, one, 0xdcdcdcddu) & ~x1) |
+                          (l2_add(x2, one, 0xdcdcdcddu) & ~x2) | (l2_add(x3, one, 0xdcdcdcddu) & ~x3);
+    uint32_t ra = l2_dp4a(f2, 0x08040201u, 0u);
+    ra = l2_dp4a(f3, 0x80402010u, ra) * 256u;
+    ra = l2_dp4a(f0, 0x08040201u, ra);
+    ra = l2_dp4a(f1, 0x80402010u, ra);
+    uint32_t rd = l2_dp4a(d2, 0x08040201u, 0u);
+    rd = l2_dp4a(d3, 0x80402010u, rd) * 256u;
+    rd = l2_dp4a(d0, 0x08040201u, rd);
+    rd = l2_dp4a(d1, 0x80402010u, rd);
+    n16 = ra >> 7;
+    d16 = rd >> 7;
+    return spec;
+}
+
 // cold paths, kept out of the row loop's instruction footprint
 struct L2GKey {
     uint64_t w0, w1;
@@ -192,28 +222,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
             const uint32_t ma0 = s_msk + (((uint32_t)tid >> 1) << 3) + (((uint32_t)tid & 1u) << 1);
             auto chunk = [&](uint32_t ca, uint32_t ma) {
                 const uint4 v = lds128(ca);
-                const uint32_t f0 = ~(add_fma((v.x ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.x) & 0x80808080u;
-                const uint32_t f1 = ~(add_fma((v.y ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.y) & 0x80808080u;
-                const uint32_t f2 = ~(add_fma((v.z ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.z) & 0x80808080u;
-                const uint32_t f3 = ~(add_fma((v.w ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.w) & 0x80808080u;
-                const uint32_t d0 = ~(add_fma((v.x ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.x) & 0x80808080u;
-                const uint32_t d1 = ~(add_fma((v.y ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.y) & 0x80808080u;
-                const uint32_t d2 = ~(add_fma((v.z ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.z) & 0x80808080u;
-                const uint32_t d3 = ~(add_fma((v.w ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.w) & 0x80808080u;
-                // a byte below 0x23 that is not '\n' (x - 0x23 borrows into bit 7 where bit 7 was clear)
-                const uint32_t x0 = v.x | f0, x1 = v.y | f1, x2 = v.z | f2, x3 = v.w | f3;
-                spec |= (add_fma(x0, one, 0xdcdcdcddu) & ~x0) | (add_fma(x1, one, 0xdcdcdcddu) & ~x1) |
-                        (add_fma(x2, one, 0xdcdcdcddu) & ~x2) | (add_fma(x3, one, 0xdcdcdcddu) & ~x3);
-                uint32_t ra = __dp4a(f2, 0x08040201u, 0u);
-                ra = __dp4a(f3, 0x80402010u, ra) * 256u;
-                ra = __dp4a(f0, 0x08040201u, ra);
-                ra = __dp4a(f1, 0x80402010u, ra);
-                uint32_t rd = __dp4a(d2, 0x08040201u, 0u);
-                rd = __dp4a(d3, 0x80402010u, rd) * 256u;
-                rd = __dp4a(d0, 0x08040201u, rd);
-                rd = __dp4a(d1, 0x80402010u, rd);
-                sts16(ma, ra >> 7);
-                sts16(ma + 4u, rd >> 7);
+                uint32_t ra, rd;
+                spec |= l2g_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd);
+                sts16(ma, ra);
+                sts16(ma + 4u, rd);
             };
             constexpr int kFull = G::CHUNKS / G::THREADS;
 #pragma unroll
