@@ -10,6 +10,9 @@ sys.path.insert(0, ROOT)
 FIX = os.path.join(ROOT, "tests", "fixtures")
 GOLDEN = os.path.join(ROOT, "tests", "golden", "sql_golden.json")
 REF_ROOT = os.environ.get("CQ_REF", "/root/reference")
+# the reference's shipped fixtures the "refdata" golden cases read (data/users.csv is BASELINE configs[0]):
+# copied under tests/golden/ so that those cases also run where /root/reference does not exist (the GPU box)
+REFDATA_ROOT = os.path.join(ROOT, "tests", "golden", "refdata")
 
 
 def pytest_configure(config):
@@ -99,7 +102,7 @@ def dumps_equal(got, want, rel=0.0):
 
 
 def run_dump(binary, case, env=None):
-    cwd = FIX if case["kind"] == "fix" else REF_ROOT
+    cwd = FIX if case["kind"] == "fix" else REFDATA_ROOT
     e = dict(os.environ)
     if env:
         e.update(env)

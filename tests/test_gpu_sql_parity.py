@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import REF_ROOT, ROOT, dumps_equal, load_golden, parse_dump, run_dump
+from conftest import ROOT, dumps_equal, load_golden, parse_dump, run_dump
 
 pytestmark = pytest.mark.gpu
 GPU_DUMP = os.path.join(ROOT, "build", "cq_gpu_dump")
@@ -18,8 +18,6 @@ CASES = load_golden()
 def test_sql_matches_reference_golden(case):
     if not os.path.exists(GPU_DUMP):
         pytest.skip("build/cq_gpu_dump not built (needs the reference sources at build time)")
-    if case["kind"] == "refdata" and not os.path.isdir(os.path.join(REF_ROOT, "data")):
-        pytest.skip("reference data directory not present")
     rc, out, err = run_dump(GPU_DUMP, case, env={"CQ_GPU_TRACE": "1"})
     ok, why = dumps_equal(parse_dump(out), parse_dump(case["expected"]), rel=1e-12)
     assert ok, f"{case['sql']}: {why}\n--- got\n{out}\n--- want\n{case['expected']}\n{err}"
