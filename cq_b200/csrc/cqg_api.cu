@@ -32,6 +32,7 @@
 #include "cqg_lean.cuh"
 #include "cqg_lean2.cuh"
 #include "cqg_lean2g.cuh"
+#include "cqg_leanhc.cuh"
 
 using namespace cqg;
 
@@ -137,6 +138,8 @@ struct cqg_table {
     int shard_index = 0, shard_count = 1;
     uint64_t global_base = 0;
     int64_t row_count = -1;
+    mutable std::vector<uint8_t> sample;  // first bytes after the header (layout guesses only), fetched on first use
+    mutable bool sample_ready = false;
 };
 
 static inline bool host_is_space(unsigned c) { return c == 32u || (c - 9u) <= 4u; }
@@ -648,12 +651,20 @@ static std::string lean_shape_defs(const cqg::DevPlan& P) {
     def_at("GSLOT", P.ngc, [&](int i) { return (int)P.gslot[i]; });
     def_at("ASLOT", P.l_nagg, [&](int i) { return P.aggs[P.l_agg[i]].slot; });
     def_at("AFUNC", P.l_nagg, [&](int i) { return P.aggs[P.l_agg[i]].func; });
+    // packed lines of the lean GROUP BY in global mode (PackedLayout)
+    def("PKIDW", P.pk.id_words);
+    def("PKBYTES", P.pk.entry_bytes);
+    def("PKCOUNT", P.pk.count_off);
+    def_at("PKKEYWORD", P.ngc, [&](int i) { return (int)P.pk.key_word[i]; });
+    def_at("PKKEYWIDE", P.ngc, [&](int i) { return (int)P.pk.key_wide[i]; });
+    def_at("PKAGGOFF", P.l_nagg, [&](int i) { return (int)P.pk.agg_off[i]; });
+    def_at("PKAGGKEY", P.l_nagg, [&](int i) { return (int)P.pk.agg_key[i]; });
     return d;
 }
 
 }  // namespace cqg_jit
 
-template <class LG, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX, bool GLOBAL>
+template <class LG, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX>
 static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
@@ -664,10 +675,10 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
         P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
     }
     if (P.n_tiles <= 0) return CQG_OK;
-    const int smem = LeanLayout<LG>::OFF_TABLE + ((GROUPED && !GLOBAL) ? kLeanDictCap * kLeanDictEntry + 16 + LG::NWARPS * lean_warp_acc(MINMAX) : 0);
+    const int smem = LeanLayout<LG>::OFF_TABLE + (GROUPED ? kLeanDictCap * kLeanDictEntry + 16 + LG::NWARPS * lean_warp_acc(MINMAX) : 0);
     static bool attr_set[64];
     if (!attr_set[dev & 63]) {
-        CU(cudaFuncSetAttribute(lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev & 63] = true;
     }
     LaunchCfg& c = g_cfg[dev & 63];
@@ -676,15 +687,14 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
         c.ready = true;
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL>, LG::THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX>, LG::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean kernel does not fit");
     int grid = std::min(P.n_tiles, c.sms * per_sm);
     {
         // compiled for this query's shape when the run-time compiler is there (cqg_jit), else the generic kernel below
         char name[200];
-        snprintf(name, sizeof name, "cqg::lean_kernel<cqg::Geo<%d, %d, %d, %d>, %d, %s, %s, %s, %s>", LG::THREADS, LG::TILE, LG::STAGES,
-                 LG::OVER, MINB, GROUPED ? "true" : "false", ONELEAF ? "true" : "false", MINMAX ? "true" : "false",
-                 GLOBAL ? "true" : "false");
+        snprintf(name, sizeof name, "cqg::lean_kernel<cqg::Geo<%d, %d, %d, %d>, %d, %s, %s, %s>", LG::THREADS, LG::TILE, LG::STAGES,
+                 LG::OVER, MINB, GROUPED ? "true" : "false", ONELEAF ? "true" : "false", MINMAX ? "true" : "false");
         if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean.cuh", name, P.own_hi - P.own_lo)) {
             void* args[] = {(void*)&P};
             if (cudaFuncSetAttribute((const void*)jk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
@@ -695,7 +705,7 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
             cudaGetLastError();
         }
     }
-    lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX, GLOBAL><<<grid, LG::THREADS, smem, st>>>(P);
+    lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
     CU(cudaGetLastError());
     return CQG_OK;
@@ -780,6 +790,47 @@ static int launch_lean2g_geo(const DevPlan& P0, cudaStream_t st) {
     return CQG_OK;
 }
 
+template <class LG, int MINB>
+static int launch_leanhc_geo(const DevPlan& P0, cudaStream_t st) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    DevPlan P = P0;
+    if (P.own_hi > P.own_lo) {
+        P.first_tile = (int32_t)(P.own_lo / LG::TILE);
+        P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
+    }
+    if (P.n_tiles <= 0) return CQG_OK;
+    const int smem = LeanHCLayout<LG>::TOTAL;
+    LaunchCfg& c = g_cfg[dev & 63];
+    if (!c.ready) {
+        CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+        c.ready = true;
+    }
+    // the same kernel compiled for this query's shape, when the run-time compiler is there (else the generic one)
+    char name[160];
+    snprintf(name, sizeof name, "cqg::leanhc_kernel<cqg::Geo<%d, %d, %d, %d>, %d>", LG::THREADS, LG::TILE, LG::STAGES, LG::OVER, MINB);
+    if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_leanhc.cuh", name, P.own_hi - P.own_lo)) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)jk, LG::THREADS, smem) == cudaSuccess && per_sm >= 1) {
+            const int grid = std::min(P.n_tiles, c.sms * per_sm);
+            void* args[] = {(void*)&P};
+            if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
+                g_launches++;
+                return CQG_OK;
+            }
+        }
+        cudaGetLastError();
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leanhc_kernel<LG, MINB>, LG::THREADS, smem));
+    if (per_sm < 1) return fail(CQG_ERR_CUDA, "leanhc kernel does not fit");
+    const int grid = std::min(P.n_tiles, c.sms * per_sm);
+    leanhc_kernel<LG, MINB><<<grid, LG::THREADS, smem, st>>>(P);
+    g_launches++;
+    CU(cudaGetLastError());
+    return CQG_OK;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -790,13 +841,10 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
     if (P.simple == 2) {
         bool mm = false;
         for (int a = 0; a < P.l_nagg; a++) mm = mm || P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX;
-        if (P.lean_global) {
-            if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, true, true>(P, st);
-            return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false, true>(P, st);
-        }
-        if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 4, true, false, true, false>(P, st);
+        if (P.lean_global) return launch_leanhc_geo<Geo<128, 16384, 1, 224>, 6>(P, st);  // many groups: packed global table
+        if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 4, true, false, true>(P, st);
         if (env_int("CQG_LEAN2", 1)) return launch_lean2g_geo<Geo<128, 16384, 1, 224>, 6>(P, st);  // few groups, COUNT/SUM/AVG
-        return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false, false>(P, st);
+        return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false>(P, st);
     }
     const bool oneleaf = P.l_nprog == 1 && P.l_nleaf == 1 && P.l_leaf[0].kind == 0 && P.l_leaf[0].slot == 0 && P.l_nagg == 0 &&
                          P.nwantL == 1;
@@ -826,14 +874,14 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
             const char* e = getenv("CQG_LEAN_GEO");
             variant = e ? atoi(e) : 0;
         }
-        if (variant == 1) return launch_lean_geo<Geo<128, 16384, 2>, 6, false, true, false, false>(P, st);
-        if (variant == 2) return launch_lean_geo<Geo<128, 16384, 1>, 12, false, true, false, false>(P, st);
-        return launch_lean_geo<Geo<128, 16384, 1>, 9, false, true, false, false>(P, st);
+        if (variant == 1) return launch_lean_geo<Geo<128, 16384, 2>, 6, false, true, false>(P, st);
+        if (variant == 2) return launch_lean_geo<Geo<128, 16384, 1>, 12, false, true, false>(P, st);
+        return launch_lean_geo<Geo<128, 16384, 1>, 9, false, true, false>(P, st);
     }
     bool mm = false;
     for (int a = 0; a < P.l_nagg; a++) mm = mm || P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX;
-    if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 6, false, false, true, false>(P, st);
-    return launch_lean_geo<Geo<128, 16384, 1>, 8, false, false, false, false>(P, st);
+    if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 6, false, false, true>(P, st);
+    return launch_lean_geo<Geo<128, 16384, 1>, 8, false, false, false>(P, st);
 }
 
 // [4][10000] doubles: mant / 10^fd, correctly rounded (one IEEE division each), per device
@@ -872,13 +920,15 @@ struct HostPlan {
     DevBuf d_entry_init, d_code, d_consts, d_pool;
     DevBuf d_scalars;  // errflags, rows_scanned, gcount, sel_count, jrow_count, jclass[2]
     int table_smem_bytes = 0;
+    std::vector<uint8_t> packed_init;  // image of an empty packed line (lean GROUP BY, global mode)
+    DevBuf d_packed_init;
 };
 
 struct ScalarBlock {
     unsigned errflags;
     unsigned jclass[2];
     unsigned pad;
-    unsigned long long rows_scanned, gcount, sel_count, jrow_count, def_tile_count, def_row_count;
+    unsigned long long rows_scanned, gcount, sel_count, jrow_count, def_tile_count, def_row_count, pcount, n_dense;
 };
 
 static void shard_range(const cqg_table* t, uint64_t& lo, uint64_t& hi) {
@@ -1276,6 +1326,114 @@ static void layout_entry(HostPlan& hp) {
     }
 }
 
+// the first bytes after the header line, for layout guesses (never for results)
+static const std::vector<uint8_t>& table_sample(const cqg_table* t) {
+    if (!t->sample_ready) {
+        t->sample_ready = true;
+        const size_t lo = t->data_start, n = t->size > lo ? std::min<size_t>(t->size - lo, 4096) : 0;
+        t->sample.resize(n);
+        if (n) {
+            if (t->h_data) memcpy(t->sample.data(), t->h_data + lo, n);
+            else if (cudaMemcpy(t->sample.data(), t->d_data + lo, n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                cudaGetLastError();
+                t->sample.clear();
+            }
+        }
+    }
+    return t->sample;
+}
+
+// PackedLayout (cqg_plan.cuh) of a lean GROUP BY plan. Key columns whose sampled fields all read as unsigned
+// decimals (or are empty) get a narrow 8-byte slot; a text met there later is handed over, so the guess only
+// costs speed, never a result.
+static void layout_packed(HostPlan& hp, const cqg_table* t) {
+    DevPlan& P = hp.P;
+    memset(&P.pk, 0, sizeof P.pk);
+    if (P.simple != 2 || P.ngc < 1 || P.ngc > 4 || P.l_nagg > 4) return;
+    bool narrow[4] = {false, false, false, false};
+    {
+        const std::vector<uint8_t>& sm = table_sample(t);
+        int seen[4] = {0, 0, 0, 0};
+        bool numeric[4] = {true, true, true, true};
+        size_t pos = 0;
+        int rows = 0;
+        while (pos < sm.size() && rows < 16) {
+            size_t eol = pos;
+            while (eol < sm.size() && sm[eol] != '\n' && sm[eol] != '\r') eol++;
+            if (eol == sm.size()) break;  // incomplete last line of the sample
+            if (eol > pos) {
+                rows++;
+                int col = 0;
+                size_t fs = pos;
+                for (size_t k = pos; k <= eol; k++) {
+                    if (k == eol || sm[k] == (uint8_t)t->cfg.delimiter) {
+                        for (int g = 0; g < P.ngc; g++) {
+                            if (P.gcol[g] == col) {
+                                seen[g]++;
+                                for (size_t j = fs; j < k; j++)
+                                    if (!((sm[j] >= '0' && sm[j] <= '9') || sm[j] == '.')) numeric[g] = false;
+                                if (k - fs > 7) numeric[g] = false;
+                            }
+                        }
+                        col++;
+                        fs = k + 1;
+                    }
+                }
+            }
+            pos = eol + 1;
+        }
+        for (int g = 0; g < P.ngc; g++) narrow[g] = seen[g] > 0 && numeric[g];
+    }
+    int w = 2;  // words 0, 1: hash, first okey | tags
+    for (int g = 0; g < P.ngc; g++) {
+        P.pk.key_word[g] = (int16_t)w;
+        P.pk.key_wide[g] = narrow[g] ? 0 : 1;
+        w += narrow[g] ? 1 : 2;
+    }
+    P.pk.id_words = w;
+    int off = 8 * w;
+    P.pk.count_off = off;
+    off += 8;
+    for (int a = 0; a < 4; a++) {
+        P.pk.agg_off[a] = -1;
+        P.pk.agg_key[a] = -1;
+    }
+    for (int a = 0; a < P.l_nagg; a++) {
+        // an aggregate over a GROUP BY column is a function of the key and the count: no state
+        const AggSpec& sp = P.aggs[P.l_agg[a]];
+        for (int g = 0; g < P.ngc; g++)
+            if (sp.slot >= 0 && P.gslot[g] == sp.slot) P.pk.agg_key[a] = (int16_t)g;
+        if (getenv("CQG_HC_NO_DERIVED")) P.pk.agg_key[a] = -1;  // (measurement: keep a state for every aggregate)
+    }
+    for (int a = 0; a < P.l_nagg; a++) {
+        const int f = P.aggs[P.l_agg[a]].func;
+        if (P.pk.agg_key[a] < 0 && (f == CQG_AGG_SUM || f == CQG_AGG_AVG)) {
+            P.pk.agg_off[a] = (int16_t)off;
+            off += 8;
+        }
+    }
+    off = (off + 15) / 16 * 16;
+    for (int a = 0; a < P.l_nagg; a++) {
+        const int f = P.aggs[P.l_agg[a]].func;
+        if (P.pk.agg_key[a] < 0 && (f == CQG_AGG_MIN || f == CQG_AGG_MAX)) {
+            P.pk.agg_off[a] = (int16_t)off;
+            off += 16;
+        }
+    }
+    P.pk.entry_bytes = (off + 31) / 32 * 32;  // whole 32-byte chunks (sectors); at most 2 + 8 + 1 + 4 words + 4 pairs = 184 -> 192
+    hp.packed_init.assign((size_t)P.pk.entry_bytes, 0);
+    const uint64_t ones = ~0ull;
+    memcpy(hp.packed_init.data() + 8, &ones, 8);
+    for (int a = 0; a < P.l_nagg; a++) {
+        const int f = P.aggs[P.l_agg[a]].func;
+        if (P.pk.agg_off[a] >= 0 && (f == CQG_AGG_MIN || f == CQG_AGG_MAX)) {
+            uint64_t* st = (uint64_t*)(hp.packed_init.data() + P.pk.agg_off[a]);
+            st[0] = f == CQG_AGG_MIN ? ~0ull : 0ull;
+            st[1] = ~0ull;
+        }
+    }
+}
+
 // common part of a plan over table t (left) [+ right]
 static int build_plan(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, cudaStream_t st) {
     DevPlan& P = hp.P;
@@ -1335,6 +1493,7 @@ static int build_plan(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, cu
         P.entry_init = hp.d_entry_init.as<uint8_t>();
     }
     if ((rc = number_slots(P, hp.pool))) return rc;
+    layout_packed(hp, t);
     P.need_right_fields = P.nwantR > 0;
     CU(hp.d_scalars.alloc(sizeof(ScalarBlock), st));
     CU(cudaMemsetAsync(hp.d_scalars.p, 0, sizeof(ScalarBlock), st));
@@ -1345,6 +1504,7 @@ static int build_plan(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, cu
     P.gcount = &sb->gcount;
     P.sel_count = &sb->sel_count;
     P.jrow_count = &sb->jrow_count;
+    P.pcount = &sb->pcount;
     return CQG_OK;
 }
 
@@ -1705,11 +1865,14 @@ static int run_fetch(const cqg_table* t, const cqg_table* rt, const int32_t* col
 struct GroupTable {
     DevBuf tab;
     uint64_t cap = 0;
+    bool dense = false;  // `tab` is a dense array of `cap` occupied entries (no empty slots, not probeable)
+    DevBuf packed;       // lean GROUP BY, global mode: the packed table the scan updated
 };
 
 static int alloc_group_table(HostPlan& hp, GroupTable& gt, uint64_t cap, cudaStream_t st) {
     DevPlan& P = hp.P;
     gt.cap = cap;
+    gt.dense = false;
     CU(gt.tab.alloc(cap * (uint64_t)P.entry_bytes, st));
     int grid = (int)std::min<uint64_t>((cap * (uint64_t)(P.entry_bytes / 8) + 255) / 256, 148 * 8);
     init_table_kernel<<<grid, 256, 0, st>>>(gt.tab.as<uint8_t>(), cap, P.entry_bytes, P.entry_init);
@@ -2001,10 +2164,39 @@ static int read_scalars(HostPlan& hp, ScalarBlock& hs, cudaStream_t st) {
     return CQG_OK;
 }
 
+static void swap_buf(DevBuf& a, DevBuf& b) {
+    std::swap(a.p, b.p);
+    std::swap(a.n, b.n);
+    std::swap(a.s, b.s);
+}
+
+// the packed table of the lean GROUP BY in global mode: `cap` empty lines
+static int alloc_packed_table(HostPlan& hp, GroupTable& gt, uint64_t cap, cudaStream_t st) {
+    DevPlan& P = hp.P;
+    const int pb = P.pk.entry_bytes;
+    if (!hp.d_packed_init.p) {
+        CU(hp.d_packed_init.alloc(hp.packed_init.size(), st));
+        CU(cudaMemcpyAsync(hp.d_packed_init.p, hp.packed_init.data(), hp.packed_init.size(), cudaMemcpyHostToDevice, st));
+    }
+    CU(gt.packed.alloc(cap * (uint64_t)pb, st));
+    int grid = (int)std::min<uint64_t>((cap * (uint64_t)(pb / 8) + 255) / 256, 148 * 8);
+    init_table_kernel<<<grid, 256, 0, st>>>(gt.packed.as<uint8_t>(), cap, pb, hp.d_packed_init.as<uint8_t>());
+    g_launches++;
+    CU(cudaGetLastError());
+    P.ptab = gt.packed.as<uint8_t>();
+    P.pcap = cap;
+    return CQG_OK;
+}
+
+static int compact_groups(HostPlan& hp, GroupTable& gt, int owner, int world, DevBuf& out, uint64_t* n_out, cudaStream_t st,
+                          long long known_occupied = -1, bool may_steal = false);
+
 // DevPlan::simple plans: the lean kernel, then the general kernel on whatever it handed over.
-// GROUP BY first numbers groups per CTA (shared-memory dictionary, <= 64 groups per CTA); when a CTA
-// meets more, the lean kernel is rerun updating the global table directly. *done = 0: the caller must
-// run the general scan instead.
+// GROUP BY first numbers groups per CTA (shared-memory dictionary, <= 32/64 groups per CTA); when a CTA meets
+// more, the lean kernel is rerun in GLOBAL mode: find-or-insert in a table of packed 64/128-byte lines
+// (PackedLayout), the general kernel builds general entries for the handed-over tiles and rows in a table of
+// its own, and the two are brought together as one dense array of general entries (gt.dense).
+// *done = 0: the caller must run the general scan instead.
 static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBlock& hs, float* ms_out, cudaEvent_t e0,
                          cudaEvent_t e1, int* done) {
     DevPlan& P = hp.P;
@@ -2022,6 +2214,9 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     P.def_row_cap = row_cap;
     P.tile_list = nullptr;
     P.lean_global = 0;
+    P.ptab = nullptr;
+    P.pcap = 0;
+    P.hc_debug = env_int("CQG_HC_DEBUG", 0);
     {
         int dev = 0;
         CU(cudaGetDevice(&dev));
@@ -2031,7 +2226,11 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     uint64_t cap = P.ngc == 0 ? 16 : (1u << 14);
     PhaseTimer pt;
     for (int attempt = 0; attempt < 14; attempt++) {
-        if ((rc = alloc_group_table(hp, gt, cap, st))) return rc;
+        if (P.lean_global) {
+            if ((rc = alloc_packed_table(hp, gt, cap, st))) return rc;
+        } else {
+            if ((rc = alloc_group_table(hp, gt, cap, st))) return rc;
+        }
         CU(cudaMemsetAsync(sb, 0, sizeof(ScalarBlock), st));
         pt.lap("lean: buffers");
         cudaEventRecord(e0, st);
@@ -2042,7 +2241,7 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         *ms_out += ms;
-        if ((hs.errflags & KERR_LEAN_GROUPS) && !P.lean_global) {
+        if ((hs.errflags & KERR_LEAN_GROUPS) && !P.lean_global && P.pk.entry_bytes) {
             P.lean_global = 1;  // too many groups for per-CTA numbering
             cap = initial_group_cap(P);
             continue;
@@ -2057,10 +2256,21 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     if ((hs.errflags & (KERR_LEAN_ABORT | KERR_TABLE_FULL)) || hs.def_row_count > row_cap) {
         P.simple = 0;  // the data is not what the lean kernel is for
         P.lean_global = 0;
+        P.ptab = nullptr;
+        P.pcap = 0;
+        gt.packed.release();
         return CQG_OK;
     }
+    const unsigned long long rows_after_lean = hs.rows_scanned;
+    ScalarBlock h2{};
     if (hs.def_tile_count || hs.def_row_count) {
+        uint64_t st_cap = 1u << 12;
         for (int attempt = 0; attempt < 12; attempt++) {
+            if (P.lean_global) {
+                // the general kernel's own table; sized by what was handed over, grown on overflow
+                if ((rc = alloc_group_table(hp, gt, st_cap, st))) return rc;
+                CU(cudaMemcpyAsync(&sb->rows_scanned, &rows_after_lean, 8, cudaMemcpyHostToDevice, st));
+            }
             cudaEventRecord(e0, st);
             CU(cudaMemsetAsync(&sb->errflags, 0, 4, st));
             if (hs.def_tile_count) {
@@ -2081,23 +2291,70 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
                 CU(cudaGetLastError());
             }
             cudaEventRecord(e1, st);
-            ScalarBlock h2{};
             if ((rc = read_scalars(hp, h2, st))) return rc;
             float ms = 0;
             cudaEventElapsedTime(&ms, e0, e1);
             *ms_out += ms;
             pt.lap("lean: handed-over tiles and rows");
-            hs.errflags |= h2.errflags & ~KERR_TABLE_FULL;
-            hs.rows_scanned = h2.rows_scanned;
-            hs.gcount = h2.gcount;
             if (h2.errflags & KERR_TABLE_FULL) {
+                if (P.lean_global) {
+                    st_cap *= 4;
+                    if (st_cap > (1ull << 32)) return fail(CQG_ERR_NOMEM, "group table beyond 2^32 entries");
+                    continue;
+                }
                 // the handed-over part overflowed the table the lean pass sized: start over on the general kernel
                 P.simple = 0;
                 P.lean_global = 0;
                 return CQG_OK;
             }
+            hs.errflags |= h2.errflags & ~KERR_TABLE_FULL;
+            hs.rows_scanned = h2.rows_scanned;
+            hs.gcount = h2.gcount;
             break;
         }
+    }
+    if (P.lean_global) {
+        // packed lines -> general entries, then the general kernel's entries folded in
+        const uint64_t g_pt = hs.pcount, g_st = (hs.def_tile_count || hs.def_row_count) ? h2.gcount : 0;
+        const uint64_t dense_cap = g_pt + g_st + 1;
+        DevBuf dense, strecs;
+        CU(dense.alloc(dense_cap * (uint64_t)P.entry_bytes, st));
+        cudaEventRecord(e0, st);
+        CU(cudaMemsetAsync(&sb->n_dense, 0, 8, st));
+        {
+            int grid = (int)std::min<uint64_t>((P.pcap + 255) / 256, 148 * 16);
+            expand_packed_kernel<<<grid, 256, 0, st>>>(P, dense.as<uint8_t>(), dense_cap, &sb->n_dense);
+            g_launches++;
+            CU(cudaGetLastError());
+        }
+        if (g_st) {
+            uint64_t n = 0;
+            if ((rc = compact_groups(hp, gt, 0, 1, strecs, &n, st, (long long)g_st))) return rc;
+            int grid = (int)std::min<uint64_t>((n + 127) / 128, 148 * 8);
+            merge_general_into_dense_kernel<<<grid, 128, 0, st>>>(P, strecs.as<uint8_t>(), n, dense.as<uint8_t>(), dense_cap, &sb->n_dense);
+            g_launches++;
+            CU(cudaGetLastError());
+        }
+        cudaEventRecord(e1, st);
+        ScalarBlock h3{};
+        if ((rc = read_scalars(hp, h3, st))) return rc;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out += ms;
+        if (h3.n_dense > dense_cap) return fail(CQG_ERR_CUDA, "expanded group entries overflowed their buffer");
+        hs.errflags |= h3.errflags & ~KERR_TABLE_FULL;
+        swap_buf(gt.tab, dense);
+        gt.cap = h3.n_dense;
+        gt.dense = true;
+        gt.packed.release();
+        P.ptab = nullptr;
+        P.pcap = 0;
+        P.gtab = gt.tab.as<uint8_t>();
+        P.gcap = gt.cap;
+        hs.gcount = h3.n_dense;
+        CU(cudaMemcpyAsync(P.gcount, &hs.gcount, 8, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // (&hs.gcount is caller memory: the copy has left it when this returns)
+        pt.lap("lean: packed lines -> entries");
     }
     *done = 1;
     return CQG_OK;
@@ -2154,10 +2411,22 @@ static int check_flags(const ScalarBlock& hs, bool join) {
     return CQG_OK;
 }
 
-// known_occupied >= 0: the table's entry count as the scan's scalar block already reported it (saves a round trip)
-static int compact_groups(HostPlan& hp, const GroupTable& gt, int owner, int world, DevBuf& out, uint64_t* n_out, cudaStream_t st,
-                          long long known_occupied = -1) {
+// known_occupied >= 0: the table's entry count as the scan's scalar block already reported it (saves a round trip).
+// A dense table (gt.dense) already is the list of its entries: it is handed over (may_steal) or copied.
+static int compact_groups(HostPlan& hp, GroupTable& gt, int owner, int world, DevBuf& out, uint64_t* n_out, cudaStream_t st,
+                          long long known_occupied, bool may_steal) {
     DevPlan& P = hp.P;
+    if (gt.dense && world <= 1) {
+        *n_out = gt.cap;
+        if (may_steal) {
+            swap_buf(out, gt.tab);
+            gt.cap = 0;
+        } else {
+            CU(out.alloc((gt.cap + 1) * (uint64_t)P.entry_bytes, st));
+            CU(cudaMemcpyAsync(out.p, gt.tab.p, gt.cap * (uint64_t)P.entry_bytes, cudaMemcpyDeviceToDevice, st));
+        }
+        return CQG_OK;
+    }
     unsigned long long occupied = (unsigned long long)known_occupied;
     if (known_occupied < 0) {
         CU(cudaMemcpyAsync(&occupied, P.gcount, 8, cudaMemcpyDeviceToHost, st));
@@ -2168,8 +2437,9 @@ static int compact_groups(HostPlan& hp, const GroupTable& gt, int owner, int wor
     CU(cnt.alloc(8, st));
     CU(cudaMemsetAsync(cnt.p, 0, 8, st));
     int grid = (int)std::min<uint64_t>((gt.cap + 255) / 256, 148 * 8);
-    compact_table_kernel<<<grid, 256, 0, st>>>(gt.tab.as<uint8_t>(), gt.cap, P.entry_bytes, out.as<uint8_t>(), occupied + 1,
-                                               cnt.as<unsigned long long>(), owner, world);
+    if (gt.cap)
+        compact_table_kernel<<<grid, 256, 0, st>>>(gt.tab.as<uint8_t>(), gt.cap, P.entry_bytes, out.as<uint8_t>(), occupied + 1,
+                                                   cnt.as<unsigned long long>(), owner, world);
     g_launches++;
     CU(cudaGetLastError());
     if (world <= 1) {  // no owner filter: every occupied entry is written
@@ -2305,7 +2575,7 @@ CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t
         if ((rc = check_flags(hs, hp.P.join != 0))) return rc;
         DevBuf entries;
         uint64_t G = 0;
-        if ((rc = compact_groups(hp, gt, 0, 1, entries, &G, st, (long long)hs.gcount))) return rc;
+        if ((rc = compact_groups(hp, gt, 0, 1, entries, &G, st, (long long)hs.gcount, true))) return rc;
         pt.lap("execute: compact");
         const long long launches_before_finish = g_launches.load();
         rc = finish_aggregate(hp, t, rt, q, entries.as<uint8_t>(), G, true, (int64_t)hs.rows_scanned, out, st);
@@ -2619,7 +2889,7 @@ CQG_API int cqg_partial_owner_counts(const cqg_partial_t* p, int world, int64_t*
     DevBuf d;
     CU(d.alloc(8 * (size_t)world, 0));
     CU(cudaMemsetAsync(d.p, 0, 8 * (size_t)world, 0));
-    int grid = (int)std::min<uint64_t>((p->gt.cap + 255) / 256, 148 * 8);
+    int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((p->gt.cap + 255) / 256, 148 * 8));
     owner_count_kernel<<<grid, 256>>>(p->gt.tab.as<uint8_t>(), p->gt.cap, p->hp.P.entry_bytes, world, d.as<unsigned long long>());
     g_launches++;
     CU(cudaGetLastError());
@@ -2633,7 +2903,7 @@ CQG_API int cqg_partial_export(const cqg_partial_t* p, int owner, int world, uin
     DevBuf cnt;
     CU(cnt.alloc(8, 0));
     CU(cudaMemsetAsync(cnt.p, 0, 8, 0));
-    int grid = (int)std::min<uint64_t>((p->gt.cap + 255) / 256, 148 * 8);
+    int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((p->gt.cap + 255) / 256, 148 * 8));
     compact_table_kernel<<<grid, 256>>>(p->gt.tab.as<uint8_t>(), p->gt.cap, p->hp.P.entry_bytes, (uint8_t*)dst_device_ptr,
                                         (uint64_t)capacity, cnt.as<unsigned long long>(), owner, world);
     g_launches++;
@@ -2674,7 +2944,12 @@ CQG_API int cqg_partial_new_like(const cqg_partial_t* like, cqg_partial_t** out)
         P.gcount = &sb->gcount;
         P.sel_count = &sb->sel_count;
         P.jrow_count = &sb->jrow_count;
-        rc = alloc_group_table(p->hp, p->gt, std::max<uint64_t>(like->gt.cap, 16), 0);
+        P.pcount = &sb->pcount;
+        P.ptab = nullptr;
+        P.pcap = 0;
+        uint64_t cap = 16;  // (a dense table's `cap` is its entry count, not a power of two)
+        while (cap < (like->gt.dense ? 2 * like->gt.cap : like->gt.cap)) cap <<= 1;
+        rc = alloc_group_table(p->hp, p->gt, cap, 0);
     } while (0);
     if (rc != CQG_OK) {
         delete p;

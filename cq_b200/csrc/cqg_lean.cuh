@@ -155,49 +155,140 @@ __device__ __forceinline__ bool lean_key_part(uint32_t fa, uint32_t len, uint32_
     return true;
 }
 
-// find-or-insert in the global table for the lean GROUP BY (<= 4 key parts). The steady state is a
-// lookup: one acquire load of the slot's hash word, then tags and key parts as independent 16-byte
-// loads (no dependent chain), compared without short-circuit.
+// ---- the PACKED global table of the lean GROUP BY in global mode (PackedLayout in cqg_plan.cuh) ----
+// Every access to a line that is not shared with other lines costs a round trip to L2 and, measured, ~1/80 G of a
+// second chip-wide whatever its width: the line is therefore read in 32-byte chunks (one 256-bit load each,
+// LDG.E.256) and a row sends as few atomics as it can.
 __device__ __forceinline__ uint64_t ld_acquire_u64(const void* p) {
     uint64_t v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint8_t* lean_global_find(const DevPlan& P, int ngc, uint64_t h, uint32_t tags, const uint64_t* kw) {
-    const uint64_t mask = P.gcap - 1;
+struct PkChunk {
+    uint64_t a, b, c, d;
+};
+__device__ __forceinline__ PkChunk pk_load(const void* p) {
+    PkChunk v;
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p) : "memory");
+    return v;
+}
+// word j (0..11) of a line read as three chunks; folds to one register when j is known at compile time
+__device__ __forceinline__ uint64_t pk_word(const PkChunk& c0, const PkChunk& c1, const PkChunk& c2, int j) {
+    switch (j) {
+        case 0: return c0.a;
+        case 1: return c0.b;
+        case 2: return c0.c;
+        case 3: return c0.d;
+        case 4: return c1.a;
+        case 5: return c1.b;
+        case 6: return c1.c;
+        case 7: return c1.d;
+        case 8: return c2.a;
+        case 9: return c2.b;
+        case 10: return c2.c;
+        default: return c2.d;
+    }
+}
+
+// layout values: compile-time constants in a kernel compiled for one query (cqg_jit), plan reads otherwise
+#define CQG_PK_IDWORDS CQG_SPEC(PKIDW, P.pk.id_words)
+#define CQG_PK_KEYWORD(g) CQG_SPEC_AT(PKKEYWORD, g, P.pk.key_word[g])
+#define CQG_PK_KEYWIDE(g) CQG_SPEC_AT(PKKEYWIDE, g, P.pk.key_wide[g])
+#define CQG_PK_BYTES CQG_SPEC(PKBYTES, P.pk.entry_bytes)
+
+// hash of a group key for the packed table only (two 32-bit multiplicative lanes, one avalanche each): it places
+// lines and pre-filters probes, identity is always the key compare. Never 0, bit 63 (the lock bit) clear.
+__device__ __forceinline__ uint32_t packed_mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint64_t packed_hash(int ngc, uint32_t tags, const uint64_t* kw) {
+    uint32_t a = 0x85ebca6bu + tags, b = 0xc2b2ae35u ^ (uint32_t)ngc;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        if (g < ngc) {
+            a = (a ^ (uint32_t)kw[2 * g]) * 0x9E3779B1u;
+            b = (b ^ (uint32_t)(kw[2 * g] >> 32)) * 0x85EBCA77u;
+            a = (a ^ (uint32_t)kw[2 * g + 1]) * 0xC2B2AE3Du;
+            b = (b ^ (uint32_t)(kw[2 * g + 1] >> 32)) * 0x27D4EB2Fu;
+        }
+    }
+    const uint32_t x = packed_mix32(a ^ __funnelshift_l(b, b, 16));
+    const uint32_t y = packed_mix32(b + a * 0x9E3779B1u);
+    return ((((uint64_t)y << 32) | x) & 0x7fffffffffffffffull) | 1ull;
+}
+
+// the chunks a lookup needs, then tags and key words against (tags, kw), compared without short-circuit
+__device__ __forceinline__ bool packed_same_key(const DevPlan& P, int ngc, const uint8_t* e, uint32_t tags, const uint64_t* kw, uint64_t& hash_word,
+                                                uint64_t& first_word) {
+    const int idw = CQG_PK_IDWORDS;
+    const PkChunk c0 = pk_load(e);
+    PkChunk c1 = {0, 0, 0, 0}, c2 = {0, 0, 0, 0};
+    if (idw > 4) c1 = pk_load(e + 32);
+    if (idw > 8) c2 = pk_load(e + 64);
+    hash_word = c0.a;
+    first_word = c0.b;
+    bool same = (uint32_t)(c0.b & 0xffffull) == tags;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        if (g < ngc) {
+            const int j = CQG_PK_KEYWORD(g);
+            same &= pk_word(c0, c1, c2, j) == kw[2 * g];
+            if (CQG_PK_KEYWIDE(g)) same &= pk_word(c0, c1, c2, j + 1) == kw[2 * g + 1];
+        }
+    }
+    return same;
+}
+
+// find-or-insert. The steady state is a lookup: the chunks holding hash, first okey | tags and the key words are
+// requested together (one memory round trip). They are therefore speculative - the key words may be older than the
+// hash word they are compared under - so a mismatch under an equal 64-bit hash (otherwise next to impossible) is
+// re-checked after an acquire load of the hash word.
+// INSERT = false: lookup only (merge of the general kernel's entries into the expanded ones).
+// `first_word`: the line's first okey | tags as loaded (may be stale, i.e. too large: it only decides whether the
+// atomicMin can be skipped).
+template <bool INSERT>
+__device__ __forceinline__ uint8_t* packed_find(const DevPlan& P, int ngc, uint64_t h, uint32_t tags, const uint64_t* kw, uint64_t& first_word) {
+    const uint64_t mask = P.pcap - 1;
+    const uint32_t eb = (uint32_t)CQG_PK_BYTES;
     uint64_t i = (h >> 1) & mask;
-    for (uint64_t probes = 0; probes < P.gcap;) {
-        uint8_t* e = P.gtab + i * (uint64_t)P.entry_bytes;
-        unsigned long long cur = ld_acquire_u64(e);
+    for (uint64_t probes = 0; probes < P.pcap;) {
+        uint8_t* e = P.ptab + i * (uint64_t)eb;
+        uint64_t cur;
+        bool same = packed_same_key(P, ngc, e, tags, kw, cur, first_word);
         if (cur == 0ull) {
-            if (*(volatile unsigned long long*)P.gcount >= P.gcap / 2) return nullptr;
+            if (!INSERT) return nullptr;
+            if (*(volatile unsigned long long*)P.pcount >= P.pcap / 2) return nullptr;
             cur = atomicCAS((unsigned long long*)e, 0ull, (unsigned long long)(h | kLockBit));
             if (cur == 0ull) {
-                atomicAdd(P.gcount, 1ull);
-                *(uint32_t*)(e + kOffTags) = tags;
-                for (int g = 0; g < ngc; g++) {
-                    *(uint64_t*)(e + kOffKeys + 16 * g) = kw[2 * g];
-                    *(uint64_t*)(e + kOffKeys + 16 * g + 8) = kw[2 * g + 1];
+                atomicAdd(P.pcount, 1ull);
+                first_word = 0xffffffffffff0000ull | tags;
+                *(uint64_t*)(e + 8) = first_word;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    if (g < ngc) {
+                        const int j = CQG_PK_KEYWORD(g);
+                        *(uint64_t*)(e + 8 * j) = kw[2 * g];
+                        if (CQG_PK_KEYWIDE(g)) *(uint64_t*)(e + 8 * j + 8) = kw[2 * g + 1];
+                    }
                 }
                 __threadfence();
                 atomicExch((unsigned long long*)e, (unsigned long long)h);
                 return e;
             }
+            same = false;  // somebody else took the line meanwhile: what was loaded above is older than `cur`
         }
         if ((cur & ~kLockBit) == h) {
-            if (cur & kLockBit) continue;  // being initialised by another thread: look again
-            const uint32_t t = __ldcg((const uint32_t*)(e + kOffTags));
-            const uint4 k0 = __ldcg((const uint4*)(e + kOffKeys));
-            const uint4 k1 = ngc > 1 ? __ldcg((const uint4*)(e + kOffKeys + 16)) : make_uint4(0, 0, 0, 0);
-            const uint4 k2 = ngc > 2 ? __ldcg((const uint4*)(e + kOffKeys + 32)) : make_uint4(0, 0, 0, 0);
-            const uint4 k3 = ngc > 3 ? __ldcg((const uint4*)(e + kOffKeys + 48)) : make_uint4(0, 0, 0, 0);
-            auto lo = [](const uint4& k) { return ((uint64_t)k.y << 32) | k.x; };
-            auto hi = [](const uint4& k) { return ((uint64_t)k.w << 32) | k.z; };
-            bool same = t == tags;
-            same &= lo(k0) == kw[0] & hi(k0) == kw[1];
-            if (ngc > 1) same &= lo(k1) == kw[2] & hi(k1) == kw[3];
-            if (ngc > 2) same &= lo(k2) == kw[4] & hi(k2) == kw[5];
-            if (ngc > 3) same &= lo(k3) == kw[6] & hi(k3) == kw[7];
+            if (!same) {
+                // ordered re-check: wait until the inserting thread has published the keys, then compare again
+                while (ld_acquire_u64(e) & kLockBit) {
+                }
+                same = packed_same_key(P, ngc, e, tags, kw, cur, first_word);
+            }
             if (same) return e;
         }
         i = (i + 1) & mask;
@@ -244,7 +335,7 @@ struct LeanLayout {
 
 // ONELEAF: the commonest shape, `COUNT(*) ... WHERE column <op> decimal literal` (one wanted field, no
 // aggregate state): the WHERE program loop, slot selects and operand bookkeeping compile away.
-template <class G, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX, bool GLOBAL>
+template <class G, int MINB, bool GROUPED, bool ONELEAF, bool MINMAX>
 __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -265,7 +356,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
         sts32(s_tm + 4 * w, 0xffffffffu);
         sts32(s_dm + 4 * w, 0u);
     }
-    if (GROUPED && !GLOBAL) {
+    if (GROUPED) {
         const int words = (kLeanDictCap * kLeanDictEntry + 16 + G::NWARPS * kLeanWarpAcc) / 4;
         for (int k = tid; k < words; k += G::THREADS) ((uint32_t*)dict)[k] = 0u;
         __syncthreads();
@@ -314,7 +405,6 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
     const int nagg = CQG_SPEC(NAGG, P.l_nagg);
     const int leaf0_lop = P.l_leaf[0].lop;
     const int ngc = GROUPED ? CQG_SPEC(NGC, P.ngc) : 0;
-    constexpr bool lean_global = GROUPED && GLOBAL;
     uint32_t summask = 0;  // aggregates that read a column: SUM/AVG, and (bits 4..7) those that are MIN/MAX, (8..11) MIN
     int aslot[4];
 #pragma unroll
@@ -434,7 +524,6 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                 if (!has) break;
                 bool ok = true, pass = true;
                 uint32_t gid = 0xffffffffu, addmask = 0, rs = 0;
-                uint8_t* gentry = nullptr;
                 unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
                 if (has) {
                     const uint32_t bi = __ffs(s) - 1u;
@@ -617,17 +706,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                                 h = key_hash_step(h, tag, kw[2 * g], kw[2 * g + 1]);
                             }
                         }
-                        if (ok && lean_global) {
-                            // many groups: straight into the global table
-                            h = key_hash_final(h);
-                            gentry = lean_global_find(P, ngc, h, tags, kw);
-                            if (!gentry) {
-                                atomicOr(P.errflags, KERR_TABLE_FULL);
-                            } else {
-                                gid = 0;
-                                amin64((uint64_t*)(gentry + kOffFirst), (P.global_base + (uint64_t)(g0 + (long long)rs)) << 16);
-                            }
-                        } else if (ok) {
+                        if (ok) {
                             h = key_hash_final(h);
                             // find-or-insert in the CTA dictionary
                             uint32_t i = (uint32_t)(h >> 1) & (kLeanDictCap - 1);
@@ -758,25 +837,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                     // ---- group step: this warp's own accumulators in shared memory, native 32-bit
                     // atomics only; a 64-bit sum is (lo, hi) with the carry added by the lane that wrapped lo ----
                     const uint64_t okey_row = (P.global_base + (uint64_t)(g0 + (long long)rs)) << 16;
-                    if (take && gentry) {
-                        atomicAdd((unsigned long long*)(gentry + kOffCount), 1ull);
-#define CQG_LEAN_GSUMG(A, ADD)                                                                         \
-    if ((addmask >> A) & 1u) {                                                                         \
-        if (MINMAX && (summask & (16u << A))) {                                                        \
-            uint64_t* st = (uint64_t*)(gentry + P.aggs[P.l_agg[A]].off);                                        \
-            amin64(&st[0], (okey_row << 2) | 1u);                                                      \
-            num_extreme(&st[2], ADD, okey_row, (summask & (256u << A)) != 0u);                         \
-        } else {                                                                                       \
-            atomicAdd((unsigned long long*)(gentry + P.aggs[P.l_agg[A]].off + 24), (unsigned long long)ADD);    \
-            atomicAdd((unsigned long long*)(gentry + P.aggs[P.l_agg[A]].off + 16), 1ull);                       \
-        }                                                                                              \
-    }
-                        CQG_LEAN_GSUMG(0, add0)
-                        CQG_LEAN_GSUMG(1, add1)
-                        CQG_LEAN_GSUMG(2, add2)
-                        CQG_LEAN_GSUMG(3, add3)
-#undef CQG_LEAN_GSUMG
-                    } else if (take && gid != 0xffffffffu) {
+                    if (take && gid != 0xffffffffu) {
                         atomicAdd((unsigned int*)(wacc + 4 * gid), 1u);
 #define CQG_LEAN_GSUM(A, ADD)                                                                  \
     if ((addmask >> A) & 1u) {                                                                 \
@@ -865,7 +926,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
             }
             if (err) atomicOr(P.errflags, err);
         }
-    } else if (!GLOBAL) {
+    } else {
         // every dictionary entry: add up the warps' accumulators and fold them into the global table
         __syncthreads();
         unsigned err = 0;
@@ -939,6 +1000,107 @@ __global__ void deferred_rows_kernel(const __grid_constant__ DevPlan P, const ui
     }
     if (acc.rows) atomicAdd(P.rows_scanned, (unsigned long long)acc.rows);
     if (acc.err) atomicOr(P.errflags, acc.err);
+}
+
+// ---- packed table -> general entries ----
+// Every occupied line of the packed table becomes one general entry (DevPlan::entry_bytes, the image the host
+// finish path, the partial export and merge_entries_kernel read), written densely in arbitrary order; the
+// entry's index is left in the line's count word for merge_general_into_dense_kernel.
+__global__ void expand_packed_kernel(const __grid_constant__ DevPlan P, uint8_t* out, uint64_t out_cap, unsigned long long* n_out) {
+    const int eb = P.entry_bytes, pb = P.pk.entry_bytes;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P.pcap; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint8_t* e = P.ptab + i * (uint64_t)pb;
+        if (*(const uint64_t*)e == 0ull) continue;
+        const unsigned long long idx = atomicAdd(n_out, 1ull);
+        if (idx >= out_cap) continue;
+        uint8_t* o = out + idx * (uint64_t)eb;
+        copy_entry_init(o, P.entry_init, eb);
+        const uint64_t fw = *(const uint64_t*)(e + 8), count = *(const uint64_t*)(e + P.pk.count_off);
+        const uint64_t first = fw & ~0xffffull;
+        const uint32_t tags = (uint32_t)(fw & 0xffffull);
+        *(uint64_t*)(e + P.pk.count_off) = idx;
+        *(uint64_t*)(o + kOffFirst) = first;
+        *(uint64_t*)(o + kOffCount) = count;
+        *(uint32_t*)(o + kOffTags) = tags;
+        uint64_t h = 0x243F6A8885A308D3ull + (uint64_t)P.ngc;  // the general table's hash (agg_row, cqg_scan.cuh), once per group
+        uint64_t kw0[4] = {0, 0, 0, 0};
+        for (int g = 0; g < P.ngc && g < 4; g++) {
+            const uint64_t w0 = *(const uint64_t*)(e + 8 * P.pk.key_word[g]);
+            const uint64_t w1 = P.pk.key_wide[g] ? *(const uint64_t*)(e + 8 * P.pk.key_word[g] + 8) : 0ull;
+            kw0[g] = w0;
+            *(uint64_t*)(o + kOffKeys + 16 * g) = w0;
+            *(uint64_t*)(o + kOffKeys + 16 * g + 8) = w1;
+            h = key_hash_step(h, (tags >> (4 * g)) & 15u, w0, w1);
+        }
+        *(uint64_t*)(o + kOffHash) = key_hash_final(h);
+        for (int a = 0; a < P.l_nagg; a++) {
+            const AggSpec sp = P.aggs[P.l_agg[a]];
+            uint64_t* st = (uint64_t*)(o + sp.off);
+            const bool mm = sp.func == CQG_AGG_MIN || sp.func == CQG_AGG_MAX;
+            const int kg = P.pk.agg_key[a];
+            if (kg >= 0) {
+                // the aggregate's column is GROUP BY column kg: one value per group (INTEGER w0, or DOUBLE w0 / 10^6
+                // with w0 a multiple of 1000: rows whose part is anything else were handed over)
+                const bool is_int = ((tags >> (4 * kg)) & 15u) == KT_INT;
+                if (mm) {
+                    const double dv = is_int ? (double)kw0[kg] : __ddiv_rn((double)kw0[kg], 1000000.0);
+                    st[0] = (first << 2) | 1u;
+                    st[2] = num_key(dv);
+                    st[3] = first;  // every row of the group ties: the earliest one holds the value
+                } else {
+                    st[2] = count;
+                    st[3] = count * (is_int ? kw0[kg] * 1000ull : kw0[kg] / 1000ull);
+                }
+            } else {
+                const uint64_t* ps = (const uint64_t*)(e + P.pk.agg_off[a]);
+                if (mm) {
+                    st[0] = (first << 2) | 1u;  // every row of the line had a numeric operand: the earliest one is the group's first
+                    st[2] = ps[0];
+                    st[3] = ps[1];
+                } else {
+                    st[2] = count;  // values summed = rows (NULL operands never reach the packed table)
+                    st[3] = ps[0];  // sum of value * 1000
+                }
+            }
+        }
+    }
+}
+
+// Entries the general kernel built for the tiles and rows the lean kernel handed over (`recs`, compacted) are
+// folded into the expanded ones: a key the packed table holds is merged into its expanded entry, any other
+// is appended. Two records never share a key (they come out of one hash table).
+__global__ void merge_general_into_dense_kernel(const __grid_constant__ DevPlan P, const uint8_t* recs, uint64_t n, uint8_t* dense,
+                                                uint64_t dense_cap, unsigned long long* n_dense) {
+    const int eb = P.entry_bytes;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t* r = recs + i * (uint64_t)eb;
+        const uint32_t tags = *(const uint32_t*)(r + kOffTags);
+        uint64_t kw[8];
+        bool packable = P.pcap != 0 && P.ngc <= 4;
+        for (int g = 0; g < 4; g++) {
+            kw[2 * g] = kw[2 * g + 1] = 0;
+            if (g < P.ngc) {
+                kw[2 * g] = *(const uint64_t*)(r + kOffKeys + 16 * g);
+                kw[2 * g + 1] = *(const uint64_t*)(r + kOffKeys + 16 * g + 8);
+                // a narrow slot holds w0 only: a key with a second word is not in the packed table
+                if (!P.pk.key_wide[g] && kw[2 * g + 1] != 0ull) packable = false;
+            }
+        }
+        uint8_t* pe = nullptr;
+        if (packable) {
+            uint64_t first_word;
+            pe = packed_find<false>(P, P.ngc, packed_hash(P.ngc, tags, kw), tags, kw, first_word);
+        }
+        if (pe) {
+            entry_merge(P, dense + *(const uint64_t*)(pe + P.pk.count_off) * (uint64_t)eb, r);
+        } else {
+            const unsigned long long idx = atomicAdd(n_dense, 1ull);
+            if (idx < dense_cap) {
+                uint8_t* o = dense + idx * (uint64_t)eb;
+                for (int k = 0; k < eb; k += 8) *(uint64_t*)(o + k) = *(const uint64_t*)(r + k);
+            }
+        }
+    }
 }
 
 #endif  // CQG_JIT

@@ -88,6 +88,31 @@ constexpr uint64_t kLockBit = 0x8000000000000000ull;
 // key part tags
 enum : uint32_t { KT_NULL = 0, KT_INT = 1, KT_DBL_POS = 2, KT_DBL_NEG = 3, KT_STR = 4, KT_STR_HASH = 5, KT_DATE = 6, KT_DBL_BIG = 7 };
 
+// ---- packed group lines of the lean GROUP BY in global mode (cqg_leanhc.cuh, config-3 shape: ~10^6 groups) ----
+// One line of 32..192 bytes per group instead of the general entry (32 + 16*ngc + 32 per SUM/AVG + 48 per
+// MIN/MAX), laid out in 8-byte words so that what a row must READ comes first and in as few 32-byte chunks
+// (one 256-bit load each) as possible:
+//   word 0      hash of the key (0 empty, bit 63 = being written)
+//   word 1      first okey of the group; its low 16 bits (the join rank, always 0 here) hold the key tags
+//   words 2..   key part g: (w0, w1) in a wide slot, w0 alone in a narrow one (numbers and NULL only: a row whose
+//               part is text there is handed over to the general kernel)
+//   then        count; per SUM/AVG an int64 sum of value*1000 (values summed == count: rows with a NULL operand are
+//               handed over); then, 16-byte aligned, per MIN/MAX { ordered double image, okey of the earliest row
+//               holding it } (128-bit CAS, ties to the earliest row).
+// An aggregate over a GROUP BY column needs no state at all: inside one group that column has ONE value, so
+// SUM = count * value and MIN = MAX = the value of the group's first row (agg_key[a] = the key part).
+// expand_packed_kernel rewrites the occupied lines as general entries, so everything behind the scan is unchanged.
+struct PackedLayout {
+    int32_t entry_bytes;   // a multiple of 32 (whole sectors), at most 192; 0: this plan has no packed form
+    int32_t id_words;      // words a lookup compares: 2 + key words
+    int16_t key_word[4];   // first word of key part g
+    int16_t key_wide[4];
+    int16_t agg_off[4];    // byte offset of the state of lean aggregate a (index into l_agg[]); -1: derived from a key
+    int16_t agg_key[4];    // key part the aggregate's column is (-1: none)
+    int32_t count_off;     // byte offset of the row count (after expansion: the entry's index among the expanded ones)
+    int32_t pad;
+};
+
 struct JoinSlot {
     uint64_t h;  // 0 empty, bit 63 lock
     uint64_t w0, w1;
@@ -135,7 +160,7 @@ struct DevPlan {
     int32_t l_nleaf, l_nprog;
     LeanLeaf l_leaf[kMaxLeanLeaf];
     int8_t l_prog[16];
-    int32_t lean_global;  // lean GROUP BY updates the global table directly (any number of groups)
+    int32_t lean_global;  // lean GROUP BY updates the packed global table directly (any number of groups)
     int32_t l_nagg;       // aggregates with a state (SUM/AVG/MIN/MAX over a known column): at most 4 on the lean kernel
     int32_t l_agg[4];     // their indices in aggs[]
     int32_t l_pad;
@@ -147,6 +172,13 @@ struct DevPlan {
     unsigned long long* def_row_count;
     uint64_t def_row_cap;
     const int32_t* tile_list;           // general kernel: when set, tile i of this launch is tile_list[i]
+    // packed table of the lean GROUP BY in global mode
+    PackedLayout pk;
+    uint8_t* ptab;
+    uint64_t pcap;                      // power of two
+    unsigned long long* pcount;         // occupied lines
+    int32_t hc_debug;                   // CQG_HC_DEBUG (measurement only): 1 skip the updates, 2 skip the table altogether
+    int32_t hc_pad;
 
     // ---- aggregation ----
     int32_t ngc;

@@ -25,13 +25,21 @@ SHAPE = """#define CQG_JIT 1
 #define CQG_JIT_GSLOT(i) ((i)==0?0:0)
 #define CQG_JIT_ASLOT(i) ((i)==0?2:(i)==1?1:0)
 #define CQG_JIT_AFUNC(i) ((i)==0?3:(i)==1?2:0)
+#define CQG_JIT_PKIDW 4
+#define CQG_JIT_PKBYTES 64
+#define CQG_JIT_PKCOUNT 32
+#define CQG_JIT_PKKEYWORD(i) ((i)==0?2:0)
+#define CQG_JIT_PKKEYWIDE(i) ((i)==0?1:0)
+#define CQG_JIT_PKAGGOFF(i) ((i)==0?40:(i)==1?-1:0)
+#define CQG_JIT_PKAGGKEY(i) ((i)==0?-1:(i)==1?0:0)
 """
 
 KERNELS = [
     ("cqg_lean2.cuh", "cqg::lean2_kernel<cqg::Geo<128, 16384, 1, 224>, 8, false, -1>"),
     ("cqg_lean2g.cuh", "cqg::lean2g_kernel<cqg::Geo<128, 16384, 1, 224>, 6>"),
-    ("cqg_lean.cuh", "cqg::lean_kernel<cqg::Geo<128, 16384, 1, 992>, 5, true, false, false, true>"),
-    ("cqg_lean.cuh", "cqg::lean_kernel<cqg::Geo<128, 16384, 1, 992>, 6, false, false, true, false>"),
+    ("cqg_leanhc.cuh", "cqg::leanhc_kernel<cqg::Geo<128, 16384, 1, 224>, 6>"),
+    ("cqg_lean.cuh", "cqg::lean_kernel<cqg::Geo<128, 16384, 1, 992>, 5, true, false, false>"),
+    ("cqg_lean.cuh", "cqg::lean_kernel<cqg::Geo<128, 16384, 1, 992>, 6, false, false, true>"),
 ]
 
 
