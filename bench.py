@@ -1,21 +1,33 @@
 #!/usr/bin/env python
-"""bench.py — CSV GB/s of cq's scan + filter + aggregate hot path on B200.
+"""bench.py — CSV GB/s of cq's scan + filter + GROUP BY hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--bytes B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--bytes B] [--no-extra]
 
-One step = one pass of the hot path over one batch of synthetic CSV (the seeded restatement of
-the reference's utils/generate_big_dataset.py). Workload at N=1: BASELINE.json configs[1],
-`SELECT COUNT(*) FROM f WHERE age > 40` over a 10^10-byte file (≫ L2, so no flush needed).
-N>1 (torchrun, one rank per GPU): weak scaling — every rank scans its own 10^10-byte slice of
-one N×10 GB file, the partial aggregates are exchanged with NCCL (all_gather of fixed-size
-records) and merged on the device; value = all bytes / max-over-ranks time.
+One step = one pass of the hot path over one batch of synthetic CSV (the seeded restatement of the reference's
+utils/generate_big_dataset.py, generated on the device). The file is 10^10 bytes (far larger than the 126 MB L2,
+so nothing is flushed between steps).
 
-Prints ONE JSON line (rank 0). Keys beyond the base contract: roofline, cpu_baseline, extra.
+Headline (`value`, `roofline`, `e2e`, the reference arm): the metric's own shape, scan + filter + GROUP BY —
+BASELINE configs[0]'s query on the 10 GB file:
+    SELECT name, COUNT(*), AVG(height), SUM(age) FROM f WHERE age > 25 GROUP BY name
+Timed beside it in the same run, W warm-up + K timed steps each, with a roofline object each (`configs`):
+    configs[1]  SELECT COUNT(*) FROM f WHERE age > 40                                  (pure parse + filter)
+    configs[2]  GROUP BY name, surname, age, height (1 835 776 keys) + SUM/MIN/MAX/AVG (high cardinality)
+
+N = 1: `value` = bytes / CUDA-event time of K steps through cqg_execute on the resident table; `e2e` = the same query
+through cqg_table_open(path) on a page-cached file (mmap -> parallel pinned staging -> scan -> result on the host).
+N > 1 (torchrun, one rank per GPU): STRONG scaling — the same 10 GB file, every rank holds and scans 1/N of it
+(byte-range slices cut at row edges), the partial group records cross NVLink with one NCCL collective and are merged
+on the device (cq_b200/sharded.py); value = file bytes / max-over-ranks time. `weak` repeats the headline with 10 GB
+per rank. Results are asserted against the ranks' own single-scan answers.
+
+Prints ONE JSON line (rank 0). Keys beyond the base contract: roofline, cpu_baseline, configs, weak, extra.
 """
 import argparse
 import ctypes as C
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -27,8 +39,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "csv_scan_filter_groupby_throughput"
 UNIT = "GB/s"
-QUERY = "SELECT COUNT(*) FROM f WHERE age > 40"
-WORKLOAD = f"BASELINE configs[1]: 10 GB synthetic CSV (seeded restatement of utils/generate_big_dataset.py): {QUERY}"
+QUERY = "SELECT name, COUNT(*), AVG(height), SUM(age) FROM f WHERE age > 25 GROUP BY name"
+WORKLOAD = ("BASELINE configs[0] query shape (scan + filter + GROUP BY) on the 10 GB synthetic CSV of configs[1] "
+            f"(seeded restatement of utils/generate_big_dataset.py): {QUERY}")
+LEGS = {  # name -> (plan in tests/parity_cases.py, SQL text, kernel)
+    "groupby": ("group_name", QUERY, "cqg::lean2g_kernel (per-CTA dictionary, per-warp shared-memory accumulators)"),
+    "count_where": ("count_age_gt_40", "SELECT COUNT(*) FROM f WHERE age > 40", "cqg::lean2_kernel<ONELEAF>"),
+    "high_card": ("group_high_card",
+                  "SELECT name, surname, age, height, COUNT(*), SUM(age), MIN(height), MAX(height), AVG(height) FROM f "
+                  "GROUP BY name, surname, age, height",
+                  "cqg::leanhc_kernel (packed global table) + expand_packed_kernel"),
+}
 
 
 def parse_args():
@@ -112,7 +133,7 @@ def cpu_run_once(path):
     """Time the reference CLI (oracle/_ref/cq, compiled from the unmodified sources) on `path`;
     falls back to the CPU restatement when the compiled reference is not there."""
     ref_cq = os.path.join(ROOT, "oracle", "_ref", "cq")
-    sql = f"SELECT COUNT(*) FROM '{path}' WHERE age > 40"
+    sql = QUERY.replace(" f ", f" '{path}' ")
     if os.path.exists(ref_cq):
         t0 = time.perf_counter()
         p = subprocess.run([ref_cq, "-q", sql, "-p"], capture_output=True, timeout=3600)
@@ -124,18 +145,22 @@ def cpu_run_once(path):
     from cq_b200.engine import Table
     t0 = time.perf_counter()
     with Table.open(path, lib=oracle()) as t:
-        r = t.execute(pc.build(pc.plans()["count_age_gt_40"]))
+        r = t.execute(pc.build(pc.plans()["group_name"]))
     dt = time.perf_counter() - t0
-    return dt, "port", str(r["groups"][0]["count"])
+    return dt, "port", str(len(r["groups"]))
 
 
-def cpu_baseline(target_seconds=12.0):
+def cpu_rate_sample(seconds):
+    """(path, bytes, rows) of a sample the reference needs about `seconds` for (calibrated on 20 MB, <= 1 GB)."""
     path, n, rows = cpu_sample_file(20e6)
     dt, kind, _ = cpu_run_once(path)
     os.unlink(path)
-    rate = n / dt
-    nbytes = min(max(rate * target_seconds, 20e6), 400e6)
-    path, n, rows = cpu_sample_file(nbytes)
+    nbytes = min(max(n / dt * seconds, 20e6), 1e9)
+    return cpu_sample_file(nbytes)
+
+
+def cpu_baseline(target_seconds=12.0):
+    path, n, rows = cpu_rate_sample(target_seconds)
     dt, kind, _ = cpu_run_once(path)
     os.unlink(path)
     return {"value": n / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
@@ -147,13 +172,9 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    calib_path, n, rows = cpu_sample_file(20e6)
-    dt, kind, _ = cpu_run_once(calib_path)
-    os.unlink(calib_path)
     total = args.steps + args.warmup
-    per_step = max(2.0, min(20.0, 150.0 / max(total, 1)))
-    nbytes = min(max(n / dt * per_step, 20e6), 400e6)
-    path, n, rows = cpu_sample_file(nbytes)
+    per_step = max(2.0, min(25.0, 170.0 / max(total, 1)))
+    path, n, rows = cpu_rate_sample(per_step)
     times = []
     for i in range(total):
         dt, kind, _ = cpu_run_once(path)
@@ -164,7 +185,7 @@ def reference_arm(args):
     value = n / (ms / 1e3) / 1e9
     sample = f"first {rows} rows ({n / 1e6:.1f} MB) of the seeded file per step, {QUERY}, single thread"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "sample_bytes": n, "note": "the reference's CPU path on host cores; bounded sample per step"},
@@ -194,7 +215,8 @@ def main():
 
     import parity_cases as pc
     from cq_b200 import _abi as A
-    from cq_b200.engine import Table, _check, gpu
+    from cq_b200.engine import Plan, Table, _check, gpu
+    from cq_b200.sharded import GatherExchange, OwnerExchange
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -207,182 +229,357 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # ---- synthetic input, resident in HBM ----
-    rows = int(args.bytes / 29.89)
-    cap = lib.generate_bigdata_bound(rows, 0) + lib.device_padding()
-    buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
-    size = C.c_size_t()
-    _check(lib, lib.generate_bigdata(buf.data_ptr(), cap - lib.device_padding(), rows, 1 + rank, 0, C.byref(size)))
-    nbytes = size.value
-    table = Table.from_device(buf.data_ptr(), nbytes, lib=lib, keep=buf)
-    if world > 1:
-        sizes = [None] * world
-        dist.all_gather_object(sizes, nbytes)
-        table.set_global_offset(sum(sizes[:rank]))
-        total_bytes = sum(sizes)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))["hbm_gbs"]
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
-        total_bytes = nbytes
-    plan = pc.build(pc.plans()["count_age_gt_40"])
-
-    def step_single():
-        return table.execute_raw(plan)
-
-    def step_multi():
-        """scan own slice -> export the partial records -> NCCL all_gather -> merge -> finish"""
-        p = C.c_void_p()
-        _check(lib, lib.execute_partial(table.handle, C.byref(plan.q), C.byref(p)))
-        rec = lib.partial_record_size(p)
-        n = lib.partial_count(p)
-        counts = torch.tensor([n], device="cuda", dtype=torch.int64)
-        allc = torch.empty(world, device="cuda", dtype=torch.int64)
-        dist.all_gather_into_tensor(allc, counts)
-        ac = allc.tolist()
-        nmax = max(ac)
-        send = torch.zeros(max(nmax, 1) * rec, dtype=torch.uint8, device="cuda")
-        got = C.c_int64()
-        _check(lib, lib.partial_export(p, 0, 1, send.data_ptr(), nmax, C.byref(got)))
-        recv = torch.empty(world * max(nmax, 1) * rec, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(recv, send)
-        m = C.c_void_p()
-        _check(lib, lib.partial_new_like(p, C.byref(m)))
-        if nmax and all(a == nmax for a in ac):
-            # every rank sent the same number of records: the gathered buffer is dense, one merge launch
-            _check(lib, lib.partial_merge(m, recv.data_ptr(), nmax * world))
-        else:
-            for r in range(world):
-                if ac[r]:
-                    _check(lib, lib.partial_merge(m, recv.data_ptr() + r * max(nmax, 1) * rec, ac[r]))
-        res = C.POINTER(A.Result)()
-        _check(lib, lib.partial_finish(m, table.handle, C.byref(res)))
-        out = {"count0": res.contents.count[0] if res.contents.n_groups else 0, "kernel_ms": lib.partial_kernel_ms(p),
-               "rows_scanned": lib.partial_rows_scanned(p)}
-        lib.result_free(res)
-        lib.partial_free(m)
-        lib.partial_free(p)
-        return out
-
-    step = step_multi if world > 1 else step_single
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        last = step()
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    launches0 = lib.total_kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    e0.record()
-    for _ in range(args.steps):
-        last = step()
-        kernel_ms.append(last["kernel_ms"])
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = lib.total_kernel_launches() - launches0
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        k = torch.tensor([sum(kernel_ms) / len(kernel_ms)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(k, op=dist.ReduceOp.MAX)
-        kernel_avg = float(k.item())
-    else:
-        kernel_avg = sum(kernel_ms) / len(kernel_ms)
-    ms_per_step = ms_total / args.steps
-    value = total_bytes / (ms_per_step / 1e3) / 1e9
+        return float(t.item())
 
-    # ---- end to end: host buffer in, host result out, through the C-ABI ----
-    e2e = None
-    extra = {}
-    cpu = None
-    if True:
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def make_slice(total_rows, nslices, index, seed=1):
+        """rows [index*R/n, (index+1)*R/n) of the seeded file of `total_rows` rows, resident in HBM: a table whose
+        byte 0 sits at its global offset in that file (header only in slice 0; the others view data rows only)."""
+        r0 = total_rows * index // nslices
+        r1 = total_rows * (index + 1) // nslices
+        cap = lib.generate_bigdata_bound(r1 - r0, 0) + lib.device_padding()
+        buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        size = C.c_size_t()
+        _check(lib, lib.generate_bigdata_range(buf.data_ptr(), cap - lib.device_padding(), r0, r1 - r0, seed, 0,
+                                               1 if index == 0 else 0, C.byref(size)))
+        from cq_b200.engine import csv_config
+        t = Table.from_device(buf.data_ptr(), size.value, cfg=csv_config(has_header=(index == 0)), lib=lib, keep=buf)
+        return t, buf, size.value
+
+    def roofline_of(nbytes, kernel_ms, kernel):
+        ach = nbytes / (kernel_ms / 1e3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": ach / 8000.0,
+                "traffic_note": "dram__bytes per launch is in the ncu captures under profiles/ (r02_*), not re-measured here"}
+
+    total_rows = int(args.bytes / 29.89)
+
+    # =========================================================================================
+    # N = 1
+    # =========================================================================================
+    if world == 1:
+        table, buf, nbytes = make_slice(total_rows, 1, 0)
+        legs, clocks, launches = {}, None, 0
+        for leg, (plan_name, sql, kernel) in LEGS.items():
+            plan = pc.build(pc.plans()[plan_name])
+            for _ in range(args.warmup):
+                last = table.execute_raw(plan)
+            sampler = ClockSampler(local) if leg == "groupby" else None
+            torch.cuda.synchronize()
+            if sampler:
+                sampler.start()
+            l0 = lib.total_kernel_launches()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kms = []
+            e0.record()
+            for _ in range(args.steps):
+                last = table.execute_raw(plan)
+                kms.append(last["kernel_ms"])
+            e1.record()
+            torch.cuda.synchronize()
+            if sampler:
+                clocks = sampler.stop()
+                launches = lib.total_kernel_launches() - l0
+            ms = e0.elapsed_time(e1) / args.steps
+            kernel_ms = sum(kms) / len(kms)
+            legs[leg] = {"query": sql, "value": nbytes / (ms / 1e3) / 1e9, "unit": UNIT, "ms_per_step": ms,
+                         "rows_per_s": last["rows_scanned"] / (ms / 1e3), "groups": last["n_groups"],
+                         "first_group_count": int(last["count0"]), "steps": args.steps, "warmup": args.warmup,
+                         "roofline": roofline_of(nbytes, kernel_ms, kernel)}
+        head = legs["groupby"]
+
+        # ---- end to end through the reference-facing call: cqg_table_open(path) on a page-cached file ----
+        e2e, e2e_pinned = None, None
+        plan = pc.build(pc.plans()["group_name"])
+        n_e2e = max(2, min(args.steps, 3))
         pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         pinned.copy_(buf[:nbytes])
         torch.cuda.synchronize()
+
+        def timed(fn):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                r = fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / n_e2e, r
+
+        def step_pinned():
+            with Table.from_bytes((pinned.data_ptr(), nbytes), lib=lib, pinned=True) as t:
+                return t.execute_raw(plan)
+
+        dt, r = timed(step_pinned)
+        assert r["count0"] == head["first_group_count"] and r["n_groups"] == head["groups"]
+        e2e_pinned = {"value": nbytes / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
+                      "note": "cqg_table_open_buffer on an already page-locked host buffer (DMA in place) + cqg_execute + close"}
+        path = None
+        for d in ("/dev/shm", "/tmp"):
+            try:
+                if shutil.disk_usage(d).free > nbytes * 1.2:
+                    path = os.path.join(d, f"cq_bench_{os.getpid()}.csv")
+                    break
+            except OSError:
+                pass
+        if path:
+            try:
+                import numpy as np
+                with open(path, "wb") as f:
+                    view = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(pinned.data_ptr()))
+                    step = 256 << 20
+                    for o in range(0, nbytes, step):
+                        f.write(memoryview(view[o:o + step]))
+
+                def step_file():
+                    with Table.open(path, lib=lib) as t:
+                        return t.execute_raw(plan)
+
+                dt, r = timed(step_file)
+                assert r["count0"] == head["first_group_count"] and r["n_groups"] == head["groups"]
+                e2e = {"value": nbytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+                       "d2h_bytes_per_step": 24 * 16 * 4 + 64, "ms_per_step": dt * 1e3, "steps": n_e2e,
+                       "note": f"cqg_table_open('{os.path.dirname(path)}/...', page-cached file: mmap + parallel staging through "
+                               "page-locked bounce buffers) + cqg_execute + result on host + cqg_table_close per step"}
+            finally:
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
+        if e2e is None:
+            e2e = dict(e2e_pinned, h2d_bytes_per_step=nbytes, d2h_bytes_per_step=24 * 16 * 4 + 64, steps=n_e2e)
+        e2e["pinned_buffer_route"] = e2e_pinned
+        del pinned
+
+        extra = {}
+        if not args.no_extra:
+            for name in ["scalar_aggs", "lean_group_abort_many", "count_height_gt_1_5"]:
+                pl = pc.build(pc.plans()[name])
+                table.execute_raw(pl)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r = table.execute_raw(pl)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                extra[name] = {"scan_kernel_gbs": nbytes / (r["kernel_ms"] / 1e3) / 1e9, "query_gbs": nbytes / dt / 1e9,
+                               "groups": r["n_groups"], "kernel_ms": r["kernel_ms"], "query_ms": dt * 1e3}
+        try:
+            cpu = cpu_baseline()
+        except Exception as ex:  # the baseline must never sink the bench line
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(ex)}
+        line = {
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bytes_per_gpu": nbytes, "total_bytes": nbytes,
+                       "l2": "no flush: the 10 GB input is far larger than the 126 MB L2",
+                       "parallelism": "one GPU", "groups": head["groups"], "first_group_count": head["first_group_count"]},
+            "rows_per_s": head["rows_per_s"], "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": head["roofline"], "cpu_baseline": cpu,
+            "configs": {"configs[0]-shape groupby (headline)": legs["groupby"], "configs[1] count_where": legs["count_where"],
+                        "configs[2] high_card": legs["high_card"]},
+            "extra": extra,
+        }
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        return
+
+    # =========================================================================================
+    # N > 1: strong scaling of ONE file; weak scaling as a second figure
+    # =========================================================================================
+    def no_out(spec):  # merged groups' bare columns live on whichever rank holds their first row: not fetched here
+        s = dict(spec)
+        s["out_cols"] = []
+        return s
+
+    def truth_counts(table, spec):
+        """this rank's own single-scan answer, for the cross-check: {first-row key columns: (count, sums)}"""
+        r = table.execute(pc.build(spec))
+        return {tuple(g["out"]): (g["count"], g["first_offset"], list(g["sum"])) for g in r["groups"]}
+
+    def merged_truth(parts):
+        m = {}
+        for d in parts:
+            for k, (c, fo, sums) in d.items():
+                if k in m:
+                    m[k] = (m[k][0] + c, min(m[k][1], fo), [a + b for a, b in zip(m[k][2], sums)])
+                else:
+                    m[k] = (c, fo, sums)
+        return sorted(m.values(), key=lambda v: v[1])
+
+    def run_gather(table, spec, nbytes_total, label):
+        plan = pc.build(no_out(spec))
+        ex = GatherExchange(lib, dist)
+        for _ in range(args.warmup):
+            last = ex.step(table, plan)
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        l0 = lib.total_kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kms = []
+        e0.record()
+        for _ in range(args.steps):
+            last = ex.step(table, plan)
+            kms.append(last["kernel_ms"])
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        launches = lib.total_kernel_launches() - l0
+        ms = allmax(e0.elapsed_time(e1)) / args.steps
+        kernel_ms = allmax(sum(kms) / len(kms))
+        # results: the device-merged groups against the ranks' own answers merged on the host
+        parts = [None] * world
+        dist.all_gather_object(parts, truth_counts(table, spec))
+        want = merged_truth(parts)
+        assert last["n_groups"] == len(want), (last["n_groups"], len(want))
+        for g, (c, fo, sums) in enumerate(want):
+            assert last["count"][g] == c and last["first_offset"][g] == fo, (label, g, last["count"][g], c)
+            for a, s in enumerate(sums):
+                assert abs(last["sum"][a][g] - s) <= 1e-12 * max(abs(s), 1.0), (label, g, a, last["sum"][a][g], s)
+        rows = allsum(int(last["rows_scanned"]))
+        return {"value": nbytes_total / (ms / 1e3) / 1e9, "ms_per_step": ms, "kernel_ms_max_rank": kernel_ms, "groups": len(want),
+                "rows_per_s": rows / (ms / 1e3), "result_checked": "groups, first offsets, counts exact and sums within 1e-12 "
+                "against the ranks' own single-scan answers merged on the host", "clocks": clocks, "launches": int(launches)}
+
+    # ---- strong: rank r holds rows [r*R/N, (r+1)*R/N) of the one 10 GB file ----
+    table, buf, nbytes = make_slice(total_rows, world, rank)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, nbytes)
+    table.set_global_offset(sum(sizes[:rank]))
+    total_bytes = sum(sizes)
+    strong = {}
+    for leg in ("groupby", "count_where"):
+        strong[leg] = run_gather(table, pc.plans()[LEGS[leg][0]], total_bytes, leg)
+        strong[leg]["query"] = LEGS[leg][1]
+        strong[leg]["roofline_per_gpu"] = roofline_of(nbytes, strong[leg]["kernel_ms_max_rank"], LEGS[leg][2])
+    # config 3: all-to-all of the partial records by owner
+    hc = None
+    try:
+        plan = pc.build(no_out(pc.plans()["group_high_card"]))
+        ox = OwnerExchange(lib, dist)
+        for _ in range(max(1, args.warmup - 1)):
+            last = ox.step(table, plan)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        exch, kms, sent = [], [], 0
+        e0.record()
+        for _ in range(args.steps):
+            last = ox.step(table, plan)
+            exch.append(last["exchange_ms"])
+            kms.append(last["kernel_ms"])
+        e1.record()
+        barrier()
+        ms = allmax(e0.elapsed_time(e1)) / args.steps
+        groups = allsum(int(last["n_groups"]))
+        rows_in = allsum(int(last["rows_in_groups"]))
+        rows = allsum(int(last["rows_scanned"]))
+        assert rows_in == rows, (rows_in, rows)  # every row sits in exactly one owner's group
+        if abs(args.bytes - 1e10) < 1:
+            assert groups == 1835776, groups
+        hc = {"query": LEGS["high_card"][1], "value": total_bytes / (ms / 1e3) / 1e9, "ms_per_step": ms, "groups": groups,
+              "exchange_ms_max_rank": allmax(sum(exch) / len(exch)), "scan_kernel_ms_max_rank": allmax(sum(kms) / len(kms)),
+              "records_sent_per_rank": int(last["records_sent"]), "record_bytes": int(last["record_bytes"]),
+              "exchange": "all_to_all_single of the partial group records by owner = hash % world, then device merge + finish of "
+                          "the owned groups on every rank",
+              "result_checked": "sum of the owners' group counts == rows scanned over all ranks; distinct groups over all ranks"}
+    except Exception as ex:
+        hc = {"error": repr(ex)}
+    del table, buf
+    torch.cuda.empty_cache()
+
+    # ---- weak: 10 GB per rank (one N x 10 GB file) ----
+    weak = None
+    try:
+        wt, wbuf, wbytes = make_slice(total_rows * world, world, rank)
+        wsizes = [None] * world
+        dist.all_gather_object(wsizes, wbytes)
+        wt.set_global_offset(sum(wsizes[:rank]))
+        weak = run_gather(wt, pc.plans()["group_name"], sum(wsizes), "weak groupby")
+        weak["total_bytes"] = sum(wsizes)
+        weak["note"] = "weak scaling: every rank scans its own 10 GB slice of one N x 10 GB file"
+        del wt, wbuf
+    except Exception as ex:
+        weak = {"error": repr(ex)}
+
+    # ---- end to end at N GPUs: every rank stages its slice from page-locked host memory and scans it ----
+    e2e = None
+    try:
+        table, buf, nbytes = make_slice(total_rows, world, rank)
+        table.set_global_offset(sum(sizes[:rank]))
+        pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(buf[:nbytes])
+        del table, buf
+        torch.cuda.empty_cache()
+        from cq_b200.engine import csv_config
+        plan = pc.build(no_out(pc.plans()["group_name"]))
+        ex = GatherExchange(lib, dist)
         n_e2e = max(2, min(args.steps, 3))
 
         def e2e_step():
-            with Table.from_bytes((pinned.data_ptr(), nbytes), lib=lib, pinned=True) as t:
-                return t.execute_raw(plan)
+            with Table.from_bytes((pinned.data_ptr(), nbytes), cfg=csv_config(has_header=(rank == 0)), lib=lib, pinned=True) as t:
+                t.set_global_offset(sum(sizes[:rank]))
+                return ex.step(t, plan)
 
         e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             r = e2e_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / n_e2e
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": total_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 64,
+        barrier()
+        dt = allmax((time.perf_counter() - t0) / n_e2e)
+        assert r["n_groups"] == strong["groupby"]["groups"], (r["n_groups"], strong["groupby"]["groups"])
+        e2e = {"value": total_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 24 * 16 * 4 + 64,
                "ms_per_step": dt * 1e3, "steps": n_e2e,
-               "note": "cqg_table_open_buffer(pinned host CSV) + cqg_execute + result on host + cqg_table_close per step"}
-        assert r["count0"] == last["count0"] or world > 1
+               "note": "per rank and step: cqg_table_open_buffer(page-locked host slice) + cqg_execute_partial + NCCL all_gather + "
+                       "merge + result on host + close"}
         del pinned
-
-    # ---- the other BASELINE configs, device-resident, for the record (N=1 only) ----
-    if world == 1 and not args.no_extra:
-        for name in ["group_name", "scalar_aggs", "group_high_card"]:
-            pl = pc.build(pc.plans()[name])
-            r = table.execute_raw(pl)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            r = table.execute_raw(pl)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            extra[name] = {"scan_kernel_gbs": nbytes / (r["kernel_ms"] / 1e3) / 1e9, "query_gbs": nbytes / dt / 1e9,
-                           "groups": r["n_groups"], "kernel_ms": r["kernel_ms"], "query_ms": dt * 1e3}
+    except Exception as ex:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)}
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = json.load(open(peaks_path))["hbm_gbs"]
-            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = nbytes / (kernel_avg / 1e3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                tj = json.load(open(tpath))
-                traffic = tj["dram_bytes_per_input_byte"] * nbytes
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "cqg::lean2_kernel (scalar lean plans; cqg::scan_kernel for the tiles and rows it hands over)", "kernel_ms": kernel_avg,
-                    "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
-                    "frac_of_nominal_8TBs": achieved / 8000.0}
-        if world == 1:
-            try:
-                cpu = cpu_baseline()
-            except Exception as ex:  # the baseline must never sink the bench line
-                cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(ex)}
+        head = strong["groupby"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "bytes_per_gpu": nbytes, "rows_per_gpu": int(last["rows_scanned"]), "total_bytes": total_bytes,
-                       "l2": "no flush: the 10 GB input is far larger than the 126 MB L2",
-                       "parallelism": f"byte-range shards x{world}" + (", NCCL all_gather of partial aggregates" if world > 1 else ""),
-                       "result_count": int(last["count0"])},
-            "rows_per_s": int(last["rows_scanned"]) * world / (ms_per_step / 1e3),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "extra": extra,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bytes_per_gpu": nbytes, "total_bytes": total_bytes,
+                       "l2": "no flush: every rank's slice is far larger than the 126 MB L2",
+                       "parallelism": f"byte-range slices x{world} of one file, NCCL all_gather of fixed-capacity partial "
+                                      "group records, device merge", "groups": head["groups"],
+                       "result_checked": head["result_checked"]},
+            "rows_per_s": head["rows_per_s"], "e2e": e2e, "gpu_launches": head["launches"], "clocks": head["clocks"],
+            "roofline": strong["groupby"]["roofline_per_gpu"], "cpu_baseline": None,
+            "configs": {"configs[0]-shape groupby (headline)": strong["groupby"], "configs[1] count_where": strong["count_where"],
+                        "configs[2] high_card": hc},
+            "weak": weak,
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

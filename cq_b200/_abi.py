@@ -7,7 +7,7 @@ import ctypes as C
 
 # ---- enums (include/cq_gpu.h) ----
 TYPE_NULL, TYPE_INTEGER, TYPE_DOUBLE, TYPE_STRING, TYPE_DATE = 0, 1, 2, 3, 4
-OK, ERR_CUDA, ERR_IO, ERR_ARG, ERR_UNSUPPORTED, ERR_NOMEM = 0, 1, 2, 3, 4, 5
+OK, ERR_CUDA, ERR_IO, ERR_ARG, ERR_UNSUPPORTED, ERR_NOMEM, ERR_UNSUPPORTED_PLAN = 0, 1, 2, 3, 4, 5, 6
 
 OP_COL, OP_CONST = 1, 2
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_MOD, OP_BAND, OP_BOR, OP_BXOR, OP_NEG, OP_POS, OP_ARITH_NULL = range(10, 21)
@@ -130,12 +130,15 @@ PROTOTYPES = {
     "partial_free": (None, [C.c_void_p]),
     "partition_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "rowlist_device_ptr": (C.c_uint64, [C.c_void_p]),
+    "rowlist_key_classes": (C.c_uint, [C.c_void_p]),
     "rowlist_counts": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "rowlist_copy": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64]),
     "rowlist_free": (None, [C.c_void_p]),
     "execute_partial_rows": (C.c_int, [C.c_void_p, C.POINTER(Query), C.c_uint64, C.c_int64, C.c_uint64, C.c_int64,
                                        C.POINTER(C.c_void_p)]),
     "generate_bigdata": (C.c_int, [C.c_uint64, C.c_size_t, C.c_int64, C.c_uint64, C.c_int64, C.POINTER(C.c_size_t)]),
+    "generate_bigdata_range": (C.c_int, [C.c_uint64, C.c_size_t, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int,
+                                         C.POINTER(C.c_size_t)]),
     "generate_bigdata_bound": (C.c_size_t, [C.c_int64, C.c_int64]),
     "total_kernel_launches": (C.c_int64, []),
 }

@@ -27,6 +27,7 @@
 
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "cq_gpu.h"
 #include "cqg_lean.cuh"
@@ -140,6 +141,7 @@ struct cqg_table {
     int64_t row_count = -1;
     mutable std::vector<uint8_t> sample;  // first bytes after the header (layout guesses only), fetched on first use
     mutable bool sample_ready = false;
+    bool src_pinned = false;  // h_data is page-locked: DMA straight from it
 };
 
 static inline bool host_is_space(unsigned c) { return c == 32u || (c - 9u) <= 4u; }
@@ -243,9 +245,39 @@ static int check_dialect(cqg_csv_config_t cfg) {
     };
     // strtod / strtoll in the reference read on past the field into a delimiter that looks
     // numeric (src/csv_reader.c:207-210); such dialects are not reproduced here
-    if (bad(d) || bad(q)) return fail(CQG_ERR_UNSUPPORTED, "delimiter/quote character 0x%02x/0x%02x not supported", d, q);
+    if (bad(d) || bad(q)) return fail(CQG_ERR_UNSUPPORTED_PLAN, "delimiter/quote character 0x%02x/0x%02x not supported", d, q);
     return CQG_OK;
 }
+
+// Host bytes -> HBM. Page-locked sources are DMA'd in place. Pageable / mmap'ed sources (portable_mmap,
+// src/mmap.c:78-108) go through page-locked bounce buffers: several host threads, each with two buffers and a
+// stream of its own, fault their chunks in and hand them to the copy engines, so that the host memcpy of one
+// chunk overlaps the DMA of others (one thread tops out far below what PCIe Gen5 takes).
+struct StagePool {
+    static constexpr int kThreads = 8;
+    static constexpr size_t kChunk = 8u << 20;
+    uint8_t* bounce[kThreads][2] = {};
+    cudaStream_t stream[kThreads] = {};
+    cudaEvent_t ev[kThreads][2] = {};
+    int ready = 0;  // threads whose buffers exist
+    std::mutex mu;
+    int prepare(int want) {
+        for (; ready < want; ready++) {
+            for (int k = 0; k < 2; k++)
+                if (cudaMallocHost((void**)&bounce[ready][k], kChunk) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ev[ready][k], cudaEventDisableTiming) != cudaSuccess) {
+                    cudaGetLastError();
+                    return ready;
+                }
+            if (cudaStreamCreateWithFlags(&stream[ready], cudaStreamNonBlocking) != cudaSuccess) {
+                cudaGetLastError();
+                return ready;
+            }
+        }
+        return ready;
+    }
+};
+static StagePool g_stage[64];
 
 static int stage_to_device(cqg_table* t, const uint8_t* src, size_t size, bool pinned) {
     // stream-ordered allocation from the device pool (kept warm: release threshold is unlimited)
@@ -257,37 +289,48 @@ static int stage_to_device(cqg_table* t, const uint8_t* src, size_t size, bool p
         CU(cudaStreamSynchronize(0));
         return CQG_OK;
     }
-    // pageable / mmap'ed source: double-buffered pinned bounce, copy engine overlapped with the
-    // host memcpy that faults the pages in
-    const size_t chunk = 32u << 20;
-    uint8_t* bounce[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2];
-    for (int k = 0; k < 2; k++) {
-        CU(cudaMallocHost((void**)&bounce[k], chunk));
-        CU(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
-    }
-    int rc = CQG_OK;
-    size_t off = 0;
-    int k = 0;
-    while (off < size) {
-        size_t n = std::min(chunk, size - off);
-        cudaEventSynchronize(ev[k]);
-        memcpy(bounce[k], src + off, n);
-        cudaError_t e = cudaMemcpyAsync(t->d_data + off, bounce[k], n, cudaMemcpyHostToDevice, 0);
-        if (e != cudaSuccess) {
-            rc = fail(CQG_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
-            break;
+    CU(cudaStreamSynchronize(0));  // the allocation is ordered on stream 0, the copies run on streams of their own
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    StagePool& sp = g_stage[dev & 63];
+    std::lock_guard<std::mutex> lock(sp.mu);
+    constexpr size_t chunk = StagePool::kChunk;
+    const size_t nchunks = (size + chunk - 1) / chunk;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    int want = (int)std::min<size_t>(std::min<size_t>(StagePool::kThreads, hw), std::max<size_t>(1, nchunks / 2));
+    const int T = sp.prepare(want);
+    if (T < 1) return fail(CQG_ERR_CUDA, "page-locked staging buffers: allocation failed");
+    std::atomic<int> bad{0};
+    uint8_t* dst = t->d_data;
+    auto work = [&](int k) {
+        cudaSetDevice(dev);
+        int b = 0;
+        for (size_t c = (size_t)k; c < nchunks && !bad.load(); c += (size_t)T, b ^= 1) {
+            const size_t off = c * chunk, n = std::min(chunk, size - off);
+            if (cudaEventSynchronize(sp.ev[k][b]) != cudaSuccess) bad = 1;  // the copy that last used this buffer
+            memcpy(sp.bounce[k][b], src + off, n);
+            if (cudaMemcpyAsync(dst + off, sp.bounce[k][b], n, cudaMemcpyHostToDevice, sp.stream[k]) != cudaSuccess) bad = 1;
+            cudaEventRecord(sp.ev[k][b], sp.stream[k]);
         }
-        cudaEventRecord(ev[k], 0);
-        off += n;
-        k ^= 1;
+        if (cudaStreamSynchronize(sp.stream[k]) != cudaSuccess) bad = 1;
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < T; k++) th.emplace_back(work, k);
+        for (auto& x : th) x.join();
     }
-    cudaStreamSynchronize(0);
-    for (int j = 0; j < 2; j++) {
-        cudaFreeHost(bounce[j]);
-        cudaEventDestroy(ev[j]);
-    }
-    return rc;
+    if (bad.load()) return fail(CQG_ERR_CUDA, "host to device staging: %s", cudaGetErrorString(cudaGetLastError()));
+    return CQG_OK;
+}
+
+// tables opened from host bytes are uploaded when a query first needs them: a statement whose shape is then
+// declined (plan-time checks) or routed elsewhere never pays for the copy
+static int ensure_staged(const cqg_table* tc) {
+    cqg_table* t = const_cast<cqg_table*>(tc);
+    if (!t || t->d_data || !t->h_data) return CQG_OK;
+    return stage_to_device(t, t->h_data, t->size, t->src_pinned);
 }
 
 CQG_API int cqg_table_open_buffer(const void* data, size_t size, int pinned, cqg_csv_config_t cfg, cqg_table_t** out) {
@@ -299,8 +342,8 @@ CQG_API int cqg_table_open_buffer(const void* data, size_t size, int pinned, cqg
     t->cfg = cfg;
     t->size = size;
     t->h_data = (const uint8_t*)data;
-    rc = stage_to_device(t, (const uint8_t*)data, size, pinned != 0);
-    if (rc == CQG_OK) rc = finish_open(t);
+    t->src_pinned = pinned != 0;
+    rc = finish_open(t);
     if (rc != CQG_OK) {
         cqg_table_close(t);
         return rc;
@@ -332,8 +375,7 @@ CQG_API int cqg_table_open(const char* path, cqg_csv_config_t cfg, cqg_table_t**
     t->map = m;
     t->map_len = (size_t)sb.st_size;
     t->h_data = (const uint8_t*)m;
-    rc = stage_to_device(t, t->h_data, t->size, false);
-    if (rc == CQG_OK) rc = finish_open(t);
+    rc = finish_open(t);
     if (rc != CQG_OK) {
         cqg_table_close(t);
         return rc;
@@ -394,7 +436,10 @@ CQG_API int cqg_table_column_index(const cqg_table_t* t, const char* name) {
     return -1;
 }
 CQG_API size_t cqg_table_size(const cqg_table_t* t) { return t ? t->size : 0; }
-CQG_API uint64_t cqg_table_device_ptr(const cqg_table_t* t) { return t ? (uint64_t)t->d_data : 0; }
+CQG_API uint64_t cqg_table_device_ptr(const cqg_table_t* t) {
+    if (!t || ensure_staged(t) != CQG_OK) return 0;
+    return (uint64_t)t->d_data;
+}
 
 // ------------------------------------------------------------------------------------------
 // kernel configuration
@@ -922,6 +967,7 @@ struct HostPlan {
     int table_smem_bytes = 0;
     std::vector<uint8_t> packed_init;  // image of an empty packed line (lean GROUP BY, global mode)
     DevBuf d_packed_init;
+    bool start_global = false;  // the sampled rows already hold more distinct keys than a CTA dictionary numbers
 };
 
 struct ScalarBlock {
@@ -1357,7 +1403,8 @@ static void layout_packed(HostPlan& hp, const cqg_table* t) {
         bool numeric[4] = {true, true, true, true};
         size_t pos = 0;
         int rows = 0;
-        while (pos < sm.size() && rows < 16) {
+        std::vector<std::string> keys;
+        while (pos < sm.size() && rows < 256) {
             size_t eol = pos;
             while (eol < sm.size() && sm[eol] != '\n' && sm[eol] != '\r') eol++;
             if (eol == sm.size()) break;  // incomplete last line of the sample
@@ -1365,10 +1412,13 @@ static void layout_packed(HostPlan& hp, const cqg_table* t) {
                 rows++;
                 int col = 0;
                 size_t fs = pos;
+                std::string key;
                 for (size_t k = pos; k <= eol; k++) {
                     if (k == eol || sm[k] == (uint8_t)t->cfg.delimiter) {
                         for (int g = 0; g < P.ngc; g++) {
                             if (P.gcol[g] == col) {
+                                key.append((const char*)&sm[fs], k - fs);
+                                key.push_back('\0');
                                 seen[g]++;
                                 for (size_t j = fs; j < k; j++)
                                     if (!((sm[j] >= '0' && sm[j] <= '9') || sm[j] == '.')) numeric[g] = false;
@@ -1379,12 +1429,17 @@ static void layout_packed(HostPlan& hp, const cqg_table* t) {
                         fs = k + 1;
                     }
                 }
+                keys.push_back(key);
             }
             pos = eol + 1;
         }
         for (int g = 0; g < P.ngc; g++) narrow[g] = seen[g] > 0 && numeric[g];
+        // more distinct keys in the sample than a CTA dictionary numbers: start in global mode (a guess that costs
+        // or saves one aborted launch, nothing else)
+        std::sort(keys.begin(), keys.end());
+        hp.start_global = (size_t)(std::unique(keys.begin(), keys.end()) - keys.begin()) >= 48;
     }
-    int w = 2;  // words 0, 1: hash, first okey | tags
+    int w = 1;  // word 0: state / first okey | tags
     for (int g = 0; g < P.ngc; g++) {
         P.pk.key_word[g] = (int16_t)w;
         P.pk.key_wide[g] = narrow[g] ? 0 : 1;
@@ -1422,8 +1477,6 @@ static void layout_packed(HostPlan& hp, const cqg_table* t) {
     }
     P.pk.entry_bytes = (off + 31) / 32 * 32;  // whole 32-byte chunks (sectors); at most 2 + 8 + 1 + 4 words + 4 pairs = 184 -> 192
     hp.packed_init.assign((size_t)P.pk.entry_bytes, 0);
-    const uint64_t ones = ~0ull;
-    memcpy(hp.packed_init.data() + 8, &ones, 8);
     for (int a = 0; a < P.l_nagg; a++) {
         const int f = P.aggs[P.l_agg[a]].func;
         if (P.pk.agg_off[a] >= 0 && (f == CQG_AGG_MIN || f == CQG_AGG_MAX)) {
@@ -1656,6 +1709,7 @@ struct Arena {
         left -= n;
         return p;
     }
+    void adopt(void* p) { blocks.push_back(p); }  // a malloc'ed block the arena frees with the rest
     ~Arena() {
         for (void* p : blocks) free(p);
     }
@@ -1892,9 +1946,183 @@ static uint64_t initial_group_cap(const DevPlan& P) {
     return cap;
 }
 
+// device block -> pageable host memory through two page-locked bounce buffers: the copy of chunk k+1 runs while
+// host threads move chunk k to its place (first touch of fresh pages is what costs on the host side)
+static int copy_block_to_host(void* dst, const void* d_src, size_t n, cudaStream_t st) {
+    constexpr size_t kChunk = 32u << 20;
+    static void* bounce[2] = {nullptr, nullptr};
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int k = 0; k < 2; k++)
+        if (!bounce[k] && cudaMallocHost(&bounce[k], kChunk) != cudaSuccess) {
+            cudaGetLastError();
+            bounce[k] = nullptr;
+        }
+    if (!bounce[0] || !bounce[1]) {
+        CU(cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return CQG_OK;
+    }
+    cudaEvent_t ev[2];
+    CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    const size_t chunks = (n + kChunk - 1) / kChunk;
+    auto issue = [&](size_t k) {
+        const size_t lo = k * kChunk, len = std::min(kChunk, n - lo);
+        cudaMemcpyAsync(bounce[k & 1], (const char*)d_src + lo, len, cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(ev[k & 1], st);
+    };
+    if (chunks) issue(0);
+    int rc = CQG_OK;
+    for (size_t k = 0; k < chunks; k++) {
+        if (cudaEventSynchronize(ev[k & 1]) != cudaSuccess) {
+            rc = fail(CQG_ERR_CUDA, "result copy: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (k + 1 < chunks) issue(k + 1);  // (the other bounce buffer: its previous contents were moved in the last round)
+        const size_t lo = k * kChunk, len = std::min(kChunk, n - lo);
+        const char* src = (const char*)bounce[k & 1];
+        par_chunks(len, par_chunk_count(len), [&](unsigned, size_t a, size_t b) { memcpy((char*)dst + lo + a, src + a, b - a); });
+    }
+    cudaStreamSynchronize(st);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    return rc;
+}
+
+// finish of a result with many groups, on the device: order by first appearance (radix sort), aggregate values,
+// MIN/MAX rows and first-row columns decoded by one kernel, cqg_value_t records and strings written in their
+// final layout, one block to the host. Same results as the host path below (same IEEE operations for SUM/AVG).
+static int finish_aggregate_device(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, const uint8_t* d_entries, uint64_t G,
+                                   int64_t rows_scanned, cqg_result_t** out, cudaStream_t st) {
+    DevPlan& P = hp.P;
+    PhaseTimer pt;
+    const int eb = P.entry_bytes;
+    const int A = q->n_aggs, O = q->n_out_cols;
+    const uint64_t ncell = G * (uint64_t)(A + O);
+    DevBuf d_keys, d_keys2, d_idx, d_idx2, d_tmp;
+    CU(d_keys.alloc(G * 8, st));
+    CU(d_keys2.alloc(G * 8, st));
+    CU(d_idx.alloc(G * 4, st));
+    CU(d_idx2.alloc(G * 4, st));
+    int grid = (int)std::min<uint64_t>((G + 255) / 256, 148 * 8);
+    extract_first_kernel<<<grid, 256, 0, st>>>(d_entries, G, eb, d_keys.as<uint64_t>(), d_idx.as<uint32_t>());
+    g_launches++;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.as<uint64_t>(), d_keys2.as<uint64_t>(), d_idx.as<uint32_t>(),
+                                    d_idx2.as<uint32_t>(), (int)G, 16, 64, st);
+    CU(d_tmp.alloc(tmp_bytes, st));
+    cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys.as<uint64_t>(), d_keys2.as<uint64_t>(), d_idx.as<uint32_t>(),
+                                    d_idx2.as<uint32_t>(), (int)G, 16, 64, st);
+    g_launches += 4;
+    CU(cudaGetLastError());
+    // the host block and its device image: first_offset | count | sum | ncount | value | out | strings
+    const size_t gn = (size_t)G, an = (size_t)std::max(A, 1), on = (size_t)std::max(O, 1);
+    const size_t o_first = 0, o_count = o_first + 8 * gn, o_sum = o_count + 8 * gn, o_ncount = o_sum + 8 * gn * an,
+                 o_value = o_ncount + 8 * gn * an, o_out = o_value + 24 * gn * an, o_str = o_out + 24 * gn * on;
+    DevBuf d_cells, d_ssize, d_soff, d_scan_tmp, d_block;
+    CU(d_cells.alloc(std::max<uint64_t>(ncell, 1) * sizeof(OutCell), st));
+    CU(d_ssize.alloc((ncell + 1) * 8, st));
+    CU(d_soff.alloc((ncell + 1) * 8, st));
+    CU(d_block.alloc(o_str + 8, st));
+    if (A == 0) CU(cudaMemsetAsync((char*)d_block.p + o_sum, 0, o_out - o_sum, st));  // (placeholder arrays of a query without aggregates)
+    if (O == 0) CU(cudaMemsetAsync((char*)d_block.p + o_out, 0, o_str - o_out, st));
+    FinishParams F{};
+    F.entries = d_entries;
+    F.idx = d_idx2.as<uint32_t>();
+    F.G = G;
+    F.entry_bytes = eb;
+    F.n_aggs = A;
+    F.n_out = O;
+    for (int a = 0; a < A; a++) {
+        F.agg_func[a] = q->aggs[a].func;
+        F.agg_col[a] = P.aggs[a].col;
+        F.agg_off[a] = P.aggs[a].off;
+    }
+    for (int c = 0; c < O; c++) F.out_cols[c] = (int16_t)((q->out_cols[c] < 0 || q->out_cols[c] >= 0x7fff) ? -1 : q->out_cols[c]);
+    F.data = t->d_data;
+    F.size = t->size;
+    F.global_base = P.global_base;
+    F.delim = (uint8_t)t->cfg.delimiter;
+    F.quote = (uint8_t)t->cfg.quote;
+    F.first_offset = (uint64_t*)((char*)d_block.p + o_first);
+    F.count = (int64_t*)((char*)d_block.p + o_count);
+    F.sum = (double*)((char*)d_block.p + o_sum);
+    F.ncount = (int64_t*)((char*)d_block.p + o_ncount);
+    F.cells = d_cells.as<OutCell>();
+    F.str_size = d_ssize.as<uint64_t>();
+    F.errflags = P.errflags;
+    if (ncell) {
+        grid = (int)std::min<uint64_t>((ncell + 127) / 128, 148 * 16);
+        finish_cells_kernel<<<grid, 128, 0, st>>>(F);
+        g_launches++;
+        CU(cudaGetLastError());
+    } else {
+        return fail(CQG_ERR_ARG, "query without output columns");  // (the caller routes those to the host path)
+    }
+    CU(cudaMemsetAsync((char*)d_ssize.p + ncell * 8, 0, 8, st));
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_ssize.as<uint64_t>(), d_soff.as<uint64_t>(), (int64_t)(ncell + 1), st);
+    CU(d_scan_tmp.alloc(scan_bytes, st));
+    cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, scan_bytes, d_ssize.as<uint64_t>(), d_soff.as<uint64_t>(), (int64_t)(ncell + 1), st);
+    g_launches += 2;
+    CU(cudaGetLastError());
+    uint64_t str_total = 0;
+    CU(cudaMemcpyAsync(&str_total, d_soff.as<uint64_t>() + ncell, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    pt.lap("finish: sort, cells, string sizes");
+    const size_t block_bytes = o_str + (size_t)str_total;
+    // 2 MB aligned and advised for huge pages: first touch of ~10^5 small pages is what the copy below would wait for
+    char* block = nullptr;
+    if (posix_memalign((void**)&block, 2u << 20, (block_bytes + 16 + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1)) != 0) block = nullptr;
+    if (block) madvise(block, block_bytes + 16, MADV_HUGEPAGE);
+    if (!block) return fail(CQG_ERR_NOMEM, "result of %llu groups: out of host memory", (unsigned long long)G);
+    DevBuf d_full;  // the arrays written so far and the strings in one piece
+    CU(d_full.alloc(block_bytes + 16, st));
+    CU(cudaMemcpyAsync(d_full.p, d_block.p, o_value, cudaMemcpyDeviceToDevice, st));
+    {
+        grid = (int)std::min<uint64_t>((ncell + 127) / 128, 148 * 16);
+        // cells are [aggregate or column][group]: exactly the order of `value` followed by `out` (when A == 0 the
+        // placeholder value array of one column lies between: cells then start at `out`)
+        uint8_t* values = (uint8_t*)d_full.p + (A > 0 ? o_value : o_out);
+        if (A > 0 && O == 0) CU(cudaMemsetAsync((char*)d_full.p + o_out, 0, o_str - o_out, st));
+        if (A == 0) CU(cudaMemsetAsync((char*)d_full.p + o_value, 0, o_out - o_value, st));
+        finish_values_kernel<<<grid, 128, 0, st>>>(d_cells.as<OutCell>(), d_soff.as<uint64_t>(), ncell, t->d_data, values,
+                                                   (uint8_t*)d_full.p + o_str, (uint64_t)(uintptr_t)(block + o_str));
+        g_launches++;
+        CU(cudaGetLastError());
+    }
+    int rc = copy_block_to_host(block, d_full.p, block_bytes, st);
+    if (rc != CQG_OK) {
+        free(block);
+        return rc;
+    }
+    pt.lap("finish: values, block to host");
+    Arena* arena;
+    cqg_result_t* r = new_result(&arena);
+    arena->adopt(block);
+    r->n_groups = (int64_t)G;
+    r->n_aggs = A;
+    r->n_out_cols = O;
+    r->rows_scanned = rows_scanned;
+    r->first_offset = (uint64_t*)(block + o_first);
+    r->count = (int64_t*)(block + o_count);
+    r->sum = (double*)(block + o_sum);
+    r->ncount = (int64_t*)(block + o_ncount);
+    r->value = (cqg_value_t*)(block + o_value);
+    r->out = (cqg_value_t*)(block + o_out);
+    *out = r;
+    return CQG_OK;
+}
+
 static int finish_aggregate(HostPlan& hp, const cqg_table* t, const cqg_table* rt, const cqg_query_t* q, const uint8_t* d_entries,
                             uint64_t G, bool entries_on_device, int64_t rows_scanned, cqg_result_t** out, cudaStream_t st) {
     DevPlan& P = hp.P;
+    // many groups, no join: the whole finish runs on the device (CQG_FINISH=host keeps the path below for A/B runs)
+    if (G > 4096 && entries_on_device && !rt && !(q->n_group_cols == 1 && q->group_cols[0] < 0) && q->n_aggs + q->n_out_cols > 0) {
+        const char* fe = getenv("CQG_FINISH");
+        if (!(fe && fe[0] == 'h')) return finish_aggregate_device(hp, t, q, d_entries, G, rows_scanned, out, st);
+    }
     PhaseTimer pt;
     const int eb = P.entry_bytes;
     std::vector<uint8_t> ent;
@@ -2213,7 +2441,7 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     P.def_row_count = &sb->def_row_count;
     P.def_row_cap = row_cap;
     P.tile_list = nullptr;
-    P.lean_global = 0;
+    P.lean_global = (hp.start_global && P.pk.entry_bytes && env_int("CQG_START_GLOBAL", 1)) ? 1 : 0;
     P.ptab = nullptr;
     P.pcap = 0;
     P.hc_debug = env_int("CQG_HC_DEBUG", 0);
@@ -2223,7 +2451,7 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
         P.dec_table = decimal_table(dev);
         if (!P.dec_table) return fail(CQG_ERR_CUDA, "decimal table allocation failed");
     }
-    uint64_t cap = P.ngc == 0 ? 16 : (1u << 14);
+    uint64_t cap = P.ngc == 0 ? 16 : P.lean_global ? initial_group_cap(P) : (1u << 14);
     PhaseTimer pt;
     for (int attempt = 0; attempt < 14; attempt++) {
         if (P.lean_global) {
@@ -2556,9 +2784,15 @@ CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t
     cudaStream_t st = 0;
     HostPlan hp;
     PhaseTimer pt;
-    if ((rc = build_plan(hp, t, q, st))) return rc;
+    // the plan is built from the header alone: a shape the planner declines costs no upload (the caller keeps its own
+    // route for it: CQG_ERR_UNSUPPORTED_PLAN, as opposed to data the kernels met and could not reproduce)
+    if ((rc = build_plan(hp, t, q, st))) return rc == CQG_ERR_UNSUPPORTED ? CQG_ERR_UNSUPPORTED_PLAN : rc;
     pt.lap("execute: plan");
     const cqg_table* rt = q->join.right;
+    if ((rc = ensure_staged(t)) || (rc = ensure_staged(rt))) return rc;
+    hp.P.data = t->d_data;
+    if (rt) hp.P.rdata = rt->d_data;
+    pt.lap("execute: tables resident");
     JoinState js;
     float ms = 0;
     long long launches0 = g_launches.load();
@@ -2600,6 +2834,7 @@ CQG_API int cqg_table_row_count(const cqg_table_t* t, int64_t* out) {
     if (!t || !out) return fail(CQG_ERR_ARG, "null argument");
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = ensure_staged(t))) return rc;
     return count_rows_device(t, false, 0, out);
 }
 
@@ -2675,6 +2910,7 @@ CQG_API int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_
     if (!partial_query_ok(q)) return fail(CQG_ERR_UNSUPPORTED, "partials cover aggregates (with or without a join)");
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = ensure_staged(t)) || (rc = ensure_staged(q->join.right))) return rc;
     cqg_partial* p = new cqg_partial();
     p->q = *q;
     p->q.where.code = nullptr;  // the partial keeps no reference to caller memory
@@ -2712,12 +2948,14 @@ CQG_API int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_
 struct cqg_rowlist {
     DevBuf list;
     std::vector<int64_t> counts;
+    unsigned key_classes = 0;  // OR of (1 << comparison class) over the keys of this shard (bit 0: NULL)
 };
 
 CQG_API int cqg_partition_rows(const cqg_table_t* t, int key_col, int world, cqg_rowlist_t** out) {
     if (!t || !out || world < 1 || world > 4096) return fail(CQG_ERR_ARG, "bad argument");
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = ensure_staged(t))) return rc;
     cudaStream_t st = 0;
     cqg_rowlist* rl = new cqg_rowlist();
     rl->counts.assign((size_t)world, 0);
@@ -2780,9 +3018,11 @@ CQG_API int cqg_partition_rows(const cqg_table_t* t, int key_col, int world, cqg
     if (cudaMemcpyAsync(&h, sb, sizeof h, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
         return fail_free(fail(CQG_ERR_CUDA, "partition scan: %s", cudaGetErrorString(cudaGetLastError())));
     if (h.errflags & kFatalMask) return fail_free(fail(CQG_ERR_UNSUPPORTED, "%s", flag_text(h.errflags & kFatalMask)));
+    rl->key_classes = h.jclass[0];
     *out = rl;
     return CQG_OK;
 }
+CQG_API unsigned cqg_rowlist_key_classes(const cqg_rowlist_t* rl) { return rl ? rl->key_classes : 0u; }
 CQG_API uint64_t cqg_rowlist_device_ptr(const cqg_rowlist_t* rl) { return rl ? (uint64_t)(uintptr_t)rl->list.p : 0; }
 CQG_API int cqg_rowlist_counts(const cqg_rowlist_t* rl, int world, int64_t* counts) {
     if (!rl || !counts || world != (int)rl->counts.size()) return fail(CQG_ERR_ARG, "bad argument");
@@ -2811,6 +3051,7 @@ CQG_API int cqg_execute_partial_rows(const cqg_table_t* t, const cqg_query_t* q,
         return fail(CQG_ERR_UNSUPPORTED, "row-list partials read whole files: global offset must be 0");
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = ensure_staged(t)) || (rc = ensure_staged(q->join.right))) return rc;
     cudaStream_t st = 0;
     cqg_partial* p = new cqg_partial();
     p->q = *q;
@@ -3002,8 +3243,9 @@ CQG_API int cqg_partial_finish(const cqg_partial_t* pc, const cqg_table_t* t, cq
     cqg_partial* p = const_cast<cqg_partial*>(pc);
     DevBuf entries;
     uint64_t G = 0;
-    int rc = compact_groups(p->hp, p->gt, 0, 1, entries, &G, 0);
+    int rc = ensure_staged(t);
     if (rc) return rc;
+    if ((rc = compact_groups(p->hp, p->gt, 0, 1, entries, &G, 0))) return rc;
     // first-row decoding and string MIN/MAX read the file `t` views
     p->hp.P.data = t->d_data;
     p->hp.P.size = t->size;
@@ -3038,13 +3280,18 @@ CQG_API size_t cqg_generate_bigdata_bound(int64_t rows, int64_t key_card) {
 
 CQG_API int cqg_generate_bigdata(uint64_t device_ptr, size_t capacity, int64_t rows, uint64_t seed, int64_t key_card,
                                  size_t* size_out) {
-    if (!device_ptr || !size_out || rows < 0) return fail(CQG_ERR_ARG, "bad argument");
+    return cqg_generate_bigdata_range(device_ptr, capacity, 0, rows, seed, key_card, 1, size_out);
+}
+
+CQG_API int cqg_generate_bigdata_range(uint64_t device_ptr, size_t capacity, int64_t row_start, int64_t rows, uint64_t seed,
+                                       int64_t key_card, int with_header, size_t* size_out) {
+    if (!device_ptr || !size_out || rows < 0 || row_start < 0) return fail(CQG_ERR_ARG, "bad argument");
     int rc = ensure_device();
     if (rc) return rc;
     if (capacity < cqg_generate_bigdata_bound(rows, key_card)) return fail(CQG_ERR_ARG, "capacity below cqg_generate_bigdata_bound");
     const char* hdr = key_card > 0 ? "name,surname,age,gender,height,uid\n" : "name,surname,age,gender,height\n";
-    size_t hl = strlen(hdr);
-    CU(cudaMemcpy((void*)device_ptr, hdr, hl, cudaMemcpyHostToDevice));
+    size_t hl = with_header ? strlen(hdr) : 0;
+    if (hl) CU(cudaMemcpy((void*)device_ptr, hdr, hl, cudaMemcpyHostToDevice));
     int64_t nblocks = (rows + kGenRowsPerBlock - 1) / kGenRowsPerBlock;
     if (nblocks == 0) {
         *size_out = hl;
@@ -3053,7 +3300,7 @@ CQG_API int cqg_generate_bigdata(uint64_t device_ptr, size_t capacity, int64_t r
     if (nblocks > 0x7fffffff) return fail(CQG_ERR_ARG, "too many rows");
     DevBuf d_sizes;
     CU(d_sizes.alloc((size_t)nblocks * 8, 0));
-    gen_sizes_kernel<<<(unsigned)nblocks, 256>>>(rows, seed, key_card, d_sizes.as<unsigned long long>());
+    gen_sizes_kernel<<<(unsigned)nblocks, 256>>>(row_start, rows, seed, key_card, d_sizes.as<unsigned long long>());
     g_launches++;
     CU(cudaGetLastError());
     std::vector<unsigned long long> sizes((size_t)nblocks);
@@ -3066,7 +3313,7 @@ CQG_API int cqg_generate_bigdata(uint64_t device_ptr, size_t capacity, int64_t r
     }
     if (off > capacity) return fail(CQG_ERR_ARG, "capacity too small");
     CU(cudaMemcpy(d_sizes.p, sizes.data(), (size_t)nblocks * 8, cudaMemcpyHostToDevice));
-    gen_write_kernel<<<(unsigned)nblocks, 256>>>((uint8_t*)device_ptr, rows, seed, key_card, d_sizes.as<unsigned long long>());
+    gen_write_kernel<<<(unsigned)nblocks, 256>>>((uint8_t*)device_ptr, row_start, rows, seed, key_card, d_sizes.as<unsigned long long>());
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());

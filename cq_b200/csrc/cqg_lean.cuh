@@ -222,75 +222,96 @@ __device__ __forceinline__ uint64_t packed_hash(int ngc, uint32_t tags, const ui
     return ((((uint64_t)y << 32) | x) & 0x7fffffffffffffffull) | 1ull;
 }
 
-// the chunks a lookup needs, then tags and key words against (tags, kw), compared without short-circuit
-__device__ __forceinline__ bool packed_same_key(const DevPlan& P, int ngc, const uint8_t* e, uint32_t tags, const uint64_t* kw, uint64_t& hash_word,
-                                                uint64_t& first_word) {
+// word 0 of a line: 0 = empty, kPkBusy = being written, else (first okey + kPkOkeyBias) | tags (never below 2^16)
+constexpr uint64_t kPkBusy = 1ull;
+constexpr uint64_t kPkOkeyBias = 1ull << 16;  // okeys are (row offset << 16): + one offset unit keeps word 0 away from 0 / busy
+// Key words are stored XOR this constant, so that the image of a key word is never the 0 an unwritten word reads as
+// (except for the one key word equal to the constant itself, which takes the ordered path below).
+constexpr uint64_t kPkKeyMask = 0xA5A5A5A55A5A5A5Bull;
+
+// The chunks a lookup needs, then tags and key words against (tags, kw), compared without short-circuit.
+// The loads are not ordered among themselves: a key word may have been read before the inserting thread wrote it,
+// and then reads 0. `unsure`: the outcome rests on such a word - a mismatch against a 0, or (for the one key word
+// whose image is 0) a match with one - and must be confirmed with ordered loads.
+__device__ __forceinline__ bool packed_same_key(const DevPlan& P, int ngc, const uint8_t* e, uint32_t tags, const uint64_t* kw,
+                                                uint64_t& word0, bool& unsure) {
     const int idw = CQG_PK_IDWORDS;
     const PkChunk c0 = pk_load(e);
     PkChunk c1 = {0, 0, 0, 0}, c2 = {0, 0, 0, 0};
     if (idw > 4) c1 = pk_load(e + 32);
     if (idw > 8) c2 = pk_load(e + 64);
-    hash_word = c0.a;
-    first_word = c0.b;
-    bool same = (uint32_t)(c0.b & 0xffffull) == tags;
+    word0 = c0.a;
+    bool same = (uint32_t)(c0.a & 0xffffull) == tags;
+    bool zero_miss = false, zero_image = false;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
         if (g < ngc) {
             const int j = CQG_PK_KEYWORD(g);
-            same &= pk_word(c0, c1, c2, j) == kw[2 * g];
-            if (CQG_PK_KEYWIDE(g)) same &= pk_word(c0, c1, c2, j + 1) == kw[2 * g + 1];
+            const uint64_t i0 = kw[2 * g] ^ kPkKeyMask, l0 = pk_word(c0, c1, c2, j);
+            same &= l0 == i0;
+            zero_miss |= (l0 == 0ull) & (i0 != 0ull);
+            zero_image |= i0 == 0ull;
+            if (CQG_PK_KEYWIDE(g)) {
+                const uint64_t i1 = kw[2 * g + 1] ^ kPkKeyMask, l1 = pk_word(c0, c1, c2, j + 1);
+                same &= l1 == i1;
+                zero_miss |= (l1 == 0ull) & (i1 != 0ull);
+                zero_image |= i1 == 0ull;
+            }
         }
     }
+    unsure = same ? zero_image : zero_miss;
     return same;
 }
 
-// find-or-insert. The steady state is a lookup: the chunks holding hash, first okey | tags and the key words are
-// requested together (one memory round trip). They are therefore speculative - the key words may be older than the
-// hash word they are compared under - so a mismatch under an equal 64-bit hash (otherwise next to impossible) is
-// re-checked after an acquire load of the hash word.
+// find-or-insert. The steady state is a lookup: the chunks holding word 0 (first okey | tags) and the key words are
+// requested together (one memory round trip). A line is claimed by CAS 0 -> busy on word 0, its key words are
+// written (each line once per query, over the 0 the table is initialised with), and it is published by storing
+// (no first row yet) | tags over `busy` after a fence. A published word 0 with all key images equal is this key:
+// every image is nonzero, so every word compared had been written. Anything resting on a word that read 0 is
+// confirmed after an acquire load of word 0.
 // INSERT = false: lookup only (merge of the general kernel's entries into the expanded ones).
-// `first_word`: the line's first okey | tags as loaded (may be stale, i.e. too large: it only decides whether the
-// atomicMin can be skipped).
+// `word0`: as loaded (may be stale, i.e. too large: it only decides whether the atomicMin can be skipped).
 template <bool INSERT>
-__device__ __forceinline__ uint8_t* packed_find(const DevPlan& P, int ngc, uint64_t h, uint32_t tags, const uint64_t* kw, uint64_t& first_word) {
+__device__ __forceinline__ uint8_t* packed_find(const DevPlan& P, int ngc, uint64_t h, uint32_t tags, const uint64_t* kw, uint64_t& word0) {
     const uint64_t mask = P.pcap - 1;
     const uint32_t eb = (uint32_t)CQG_PK_BYTES;
     uint64_t i = (h >> 1) & mask;
     for (uint64_t probes = 0; probes < P.pcap;) {
         uint8_t* e = P.ptab + i * (uint64_t)eb;
-        uint64_t cur;
-        bool same = packed_same_key(P, ngc, e, tags, kw, cur, first_word);
-        if (cur == 0ull) {
+        bool unsure;
+        bool same = packed_same_key(P, ngc, e, tags, kw, word0, unsure);
+        bool recheck = unsure;
+        if (word0 == 0ull) {
             if (!INSERT) return nullptr;
             if (*(volatile unsigned long long*)P.pcount >= P.pcap / 2) return nullptr;
-            cur = atomicCAS((unsigned long long*)e, 0ull, (unsigned long long)(h | kLockBit));
-            if (cur == 0ull) {
+            word0 = atomicCAS((unsigned long long*)e, 0ull, (unsigned long long)kPkBusy);
+            if (word0 == 0ull) {
                 atomicAdd(P.pcount, 1ull);
-                first_word = 0xffffffffffff0000ull | tags;
-                *(uint64_t*)(e + 8) = first_word;
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     if (g < ngc) {
                         const int j = CQG_PK_KEYWORD(g);
-                        *(uint64_t*)(e + 8 * j) = kw[2 * g];
-                        if (CQG_PK_KEYWIDE(g)) *(uint64_t*)(e + 8 * j + 8) = kw[2 * g + 1];
+                        *(uint64_t*)(e + 8 * j) = kw[2 * g] ^ kPkKeyMask;
+                        if (CQG_PK_KEYWIDE(g)) *(uint64_t*)(e + 8 * j + 8) = kw[2 * g + 1] ^ kPkKeyMask;
                     }
                 }
                 __threadfence();
-                atomicExch((unsigned long long*)e, (unsigned long long)h);
+                word0 = 0xffffffffffff0000ull | tags;
+                atomicExch((unsigned long long*)e, (unsigned long long)word0);
                 return e;
             }
-            same = false;  // somebody else took the line meanwhile: what was loaded above is older than `cur`
+            recheck = true;  // somebody else claimed the line meanwhile: what was loaded above is older than that
         }
-        if ((cur & ~kLockBit) == h) {
-            if (!same) {
-                // ordered re-check: wait until the inserting thread has published the keys, then compare again
-                while (ld_acquire_u64(e) & kLockBit) {
-                }
-                same = packed_same_key(P, ngc, e, tags, kw, cur, first_word);
+        if (word0 == kPkBusy) {
+            while (ld_acquire_u64(e) == kPkBusy) {
             }
-            if (same) return e;
+            recheck = true;
         }
+        if (recheck) {
+            (void)ld_acquire_u64(e);  // word 0 is published: loads behind this one see the key words
+            same = packed_same_key(P, ngc, e, tags, kw, word0, unsure);
+        }
+        if (same) return e;
         i = (i + 1) & mask;
         probes++;
     }
@@ -1015,8 +1036,8 @@ __global__ void expand_packed_kernel(const __grid_constant__ DevPlan P, uint8_t*
         if (idx >= out_cap) continue;
         uint8_t* o = out + idx * (uint64_t)eb;
         copy_entry_init(o, P.entry_init, eb);
-        const uint64_t fw = *(const uint64_t*)(e + 8), count = *(const uint64_t*)(e + P.pk.count_off);
-        const uint64_t first = fw & ~0xffffull;
+        const uint64_t fw = *(const uint64_t*)e, count = *(const uint64_t*)(e + P.pk.count_off);
+        const uint64_t first = (fw & ~0xffffull) - kPkOkeyBias;
         const uint32_t tags = (uint32_t)(fw & 0xffffull);
         *(uint64_t*)(e + P.pk.count_off) = idx;
         *(uint64_t*)(o + kOffFirst) = first;
@@ -1025,8 +1046,8 @@ __global__ void expand_packed_kernel(const __grid_constant__ DevPlan P, uint8_t*
         uint64_t h = 0x243F6A8885A308D3ull + (uint64_t)P.ngc;  // the general table's hash (agg_row, cqg_scan.cuh), once per group
         uint64_t kw0[4] = {0, 0, 0, 0};
         for (int g = 0; g < P.ngc && g < 4; g++) {
-            const uint64_t w0 = *(const uint64_t*)(e + 8 * P.pk.key_word[g]);
-            const uint64_t w1 = P.pk.key_wide[g] ? *(const uint64_t*)(e + 8 * P.pk.key_word[g] + 8) : 0ull;
+            const uint64_t w0 = *(const uint64_t*)(e + 8 * P.pk.key_word[g]) ^ kPkKeyMask;
+            const uint64_t w1 = P.pk.key_wide[g] ? *(const uint64_t*)(e + 8 * P.pk.key_word[g] + 8) ^ kPkKeyMask : 0ull;
             kw0[g] = w0;
             *(uint64_t*)(o + kOffKeys + 16 * g) = w0;
             *(uint64_t*)(o + kOffKeys + 16 * g + 8) = w1;
@@ -1088,8 +1109,8 @@ __global__ void merge_general_into_dense_kernel(const __grid_constant__ DevPlan 
         }
         uint8_t* pe = nullptr;
         if (packable) {
-            uint64_t first_word;
-            pe = packed_find<false>(P, P.ngc, packed_hash(P.ngc, tags, kw), tags, kw, first_word);
+            uint64_t word0;
+            pe = packed_find<false>(P, P.ngc, packed_hash(P.ngc, tags, kw), tags, kw, word0);
         }
         if (pe) {
             entry_merge(P, dense + *(const uint64_t*)(pe + P.pk.count_off) * (uint64_t)eb, r);

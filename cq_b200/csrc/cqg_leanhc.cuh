@@ -395,14 +395,15 @@ __global__ void __launch_bounds__(G::THREADS, MINB) leanhc_kernel(const __grid_c
                         rows += (uint32_t)(packed_hash(ngc, tags, kw) == 77ull);
                     } else if (ok) {
                         const uint64_t h = packed_hash(ngc, tags, kw);
-                        uint64_t first_word;
-                        gentry = packed_find<true>(P, ngc, h, tags, kw, first_word);
+                        uint64_t word0;
+                        gentry = packed_find<true>(P, ngc, h, tags, kw, word0);
                         if (!gentry) {
                             atomicOr(P.errflags, KERR_TABLE_FULL);
                         } else {
                             okey = (P.global_base + (uint64_t)(g0 + (long long)pos)) << 16;
-                            // (the low 16 bits of the line's first-okey word are the key tags: the same in every candidate)
-                            if ((okey | tags) < first_word) atomicMin((unsigned long long*)(gentry + 8), (unsigned long long)(okey | tags));
+                            // word 0 = (first okey + bias) | tags: the low 16 bits are the same in every candidate
+                            const uint64_t cand = (okey + kPkOkeyBias) | tags;
+                            if (cand < word0) atomicMin((unsigned long long*)gentry, (unsigned long long)cand);
                         }
                     }
                 }

@@ -92,9 +92,9 @@ enum : uint32_t { KT_NULL = 0, KT_INT = 1, KT_DBL_POS = 2, KT_DBL_NEG = 3, KT_ST
 // One line of 32..192 bytes per group instead of the general entry (32 + 16*ngc + 32 per SUM/AVG + 48 per
 // MIN/MAX), laid out in 8-byte words so that what a row must READ comes first and in as few 32-byte chunks
 // (one 256-bit load each) as possible:
-//   word 0      hash of the key (0 empty, bit 63 = being written)
-//   word 1      first okey of the group; its low 16 bits (the join rank, always 0 here) hold the key tags
-//   words 2..   key part g: (w0, w1) in a wide slot, w0 alone in a narrow one (numbers and NULL only: a row whose
+//   word 0      0 empty, 1 being written, else the group's first okey (+ 2^16, so that it is never 0 or 1); its low
+//               16 bits (the join rank, always 0 here) hold the key tags. No hash is stored: the key words decide.
+//   words 1..   key part g: (w0, w1) in a wide slot, w0 alone in a narrow one (numbers and NULL only: a row whose
 //               part is text there is handed over to the general kernel)
 //   then        count; per SUM/AVG an int64 sum of value*1000 (values summed == count: rows with a NULL operand are
 //               handed over); then, 16-byte aligned, per MIN/MAX { ordered double image, okey of the earliest row
@@ -104,7 +104,7 @@ enum : uint32_t { KT_NULL = 0, KT_INT = 1, KT_DBL_POS = 2, KT_DBL_NEG = 3, KT_ST
 // expand_packed_kernel rewrites the occupied lines as general entries, so everything behind the scan is unchanged.
 struct PackedLayout {
     int32_t entry_bytes;   // a multiple of 32 (whole sectors), at most 192; 0: this plan has no packed form
-    int32_t id_words;      // words a lookup compares: 2 + key words
+    int32_t id_words;      // words a lookup reads: 1 + key words
     int16_t key_word[4];   // first word of key part g
     int16_t key_wide[4];
     int16_t agg_off[4];    // byte offset of the state of lean aggregate a (index into l_agg[]); -1: derived from a key

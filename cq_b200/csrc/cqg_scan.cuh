@@ -849,6 +849,12 @@ __device__ inline void partition_row(const DevPlan& P, const RowView& rv, uint64
     uint32_t tag;
     uint64_t w0, w1, h;
     join_key_of(v, err, tag, w0, w1, h);
+    // comparison classes of the keys this shard holds (first pass only): the caller ORs them over all ranks and both
+    // sides, since a stray key of another class may land on a rank that owns no other key of the join
+    if (!P.part_list) {
+        const unsigned bit = 1u << join_class(v);
+        if (!(*(volatile unsigned*)&P.jclass[0] & bit)) atomicOr(&P.jclass[0], bit);
+    }
     const uint32_t o = join_owner(h, P.part_world);
     const unsigned long long idx = atomicAdd(&P.part_counts[o], 1ull);
     if (P.part_list) P.part_list[P.part_base[o] + idx] = P.global_base + goff;
@@ -1437,6 +1443,7 @@ __global__ void merge_entries_kernel(const __grid_constant__ DevPlan P, const ui
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint8_t* e = recs + i * (uint64_t)P.entry_bytes;
         uint64_t h = *(const uint64_t*)(e + kOffHash);
+        if (h == 0ull) continue;  // an unused record of a fixed-capacity exchange buffer (a key's hash is never 0)
         uint64_t kw[2 * CQG_MAX_GROUP_COLS];
         for (int g = 0; g < P.ngc; g++) {
             kw[2 * g] = *(const uint64_t*)(e + kOffKeys + 16 * g);
@@ -1518,6 +1525,128 @@ __global__ void fetch_kernel(const __grid_constant__ FetchParams F) {
         F.out[i] = oc;
     }
     if (err) atomicOr(F.errflags, err);
+}
+
+// ------------------------------------------------------------------------------------------
+// finish on the device (results of many groups, build_aggregated_result evaluator_aggregates.c:533-696): the
+// result arrays of cqg_result_t are written in their final layout into one device block that goes to the host
+// in one piece. `idx` orders the dense entries by first appearance.
+// ------------------------------------------------------------------------------------------
+struct FinishParams {
+    const uint8_t* entries;  // dense general entries
+    const uint32_t* idx;     // [G] entry of output row gi
+    uint64_t G;
+    int32_t entry_bytes;
+    int32_t n_aggs, n_out;
+    int32_t agg_func[CQG_MAX_AGGS], agg_col[CQG_MAX_AGGS], agg_off[CQG_MAX_AGGS];
+    int16_t out_cols[CQG_MAX_OUT_COLS];
+    const uint8_t* data;     // the (left) file
+    uint64_t size;
+    uint64_t global_base;
+    uint8_t delim, quote;
+    // outputs (device block laid out like the host block)
+    uint64_t* first_offset;  // [G]
+    int64_t* count;          // [G]
+    double* sum;             // [n_aggs][G]
+    int64_t* ncount;         // [n_aggs][G]
+    OutCell* cells;          // [n_aggs + n_out][G]
+    uint64_t* str_size;      // [n_aggs + n_out][G]: bytes the cell's string takes (len + 1; 0: not a string)
+    unsigned* errflags;
+};
+
+__global__ void finish_cells_kernel(const __grid_constant__ FinishParams F) {
+    unsigned err = 0;
+    const uint64_t total = F.G * (uint64_t)(F.n_aggs + F.n_out);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int cell = (int)(i / F.G);
+        const uint64_t gi = i % F.G;
+        const uint8_t* e = F.entries + (uint64_t)F.idx[gi] * (uint64_t)F.entry_bytes;
+        const uint64_t first = *(const uint64_t*)(e + kOffFirst);
+        const long long count = (long long)*(const uint64_t*)(e + kOffCount);
+        OutCell oc;
+        oc.type = T_NULL;
+        oc.len = 0;
+        oc.payload = 0;
+        if (cell == 0) {
+            F.first_offset[gi] = first == ~0ull ? 0ull : (first >> 16);
+            F.count[gi] = count;
+        }
+        if (cell < F.n_aggs) {
+            const int f = F.agg_func[cell], off = F.agg_off[cell];
+            double sum = 0.0;
+            long long n = 0;
+            if (f == CQG_AGG_COUNT_STAR || (f == CQG_AGG_COUNT && F.agg_col[cell] >= 0)) {
+                oc.type = T_INT;
+                oc.payload = (uint64_t)(long long)(int)count;  // `result.int_value = row_count` with an int row_count (aggregates.c:270)
+            } else if (F.agg_col[cell] < 0) {
+                // unknown column: NULL
+            } else if (f == CQG_AGG_SUM || f == CQG_AGG_AVG) {
+                const long long si = *(const long long*)(e + off);
+                const double sd = *(const double*)(e + off + 8);
+                n = (long long)*(const uint64_t*)(e + off + 16);
+                const long long s3 = *(const long long*)(e + off + 24);
+                // the same three IEEE operations as the host path, no contraction
+                sum = __dadd_rn(__dadd_rn(__ll2double_rn(si), sd), __ddiv_rn(__ll2double_rn(s3), 1000.0));
+                const double v = f == CQG_AGG_SUM ? sum : ((int)n > 0 ? __ddiv_rn(sum, (double)(int)n) : 0.0);
+                oc.type = T_DBL;
+                oc.payload = (uint64_t)__double_as_longlong(v);
+            } else {
+                const uint64_t* st = (const uint64_t*)(e + off);
+                const uint32_t cls = st[0] == ~0ull ? 0u : (uint32_t)(st[0] & 3u);
+                if (cls == 1u) {
+                    // type and bits of the extreme come from the row that holds it
+                    fetch_one(F.data, F.size, (st[3] >> 16) - F.global_base, F.delim, F.quote, F.agg_col[cell], false, oc, err);
+                } else if (cls == 3u) {
+                    oc.type = T_DATE;
+                    oc.payload = st[1] - 1ull;
+                } else if (cls == 2u) {
+                    oc.type = T_STR;
+                    oc.len = (uint32_t)(st[4] & 0x3ffffu);
+                    oc.payload = (st[4] & (1ull << 63)) | ((st[4] >> 18) & 0x1fffffffffffull);
+                }
+            }
+            F.sum[i] = sum;
+            F.ncount[i] = n;
+        } else if (first != ~0ull) {
+            fetch_one(F.data, F.size, (first >> 16) - F.global_base, F.delim, F.quote, F.out_cols[cell - F.n_aggs], false, oc, err);
+        }
+        F.cells[i] = oc;
+        F.str_size[i] = oc.type == T_STR ? (uint64_t)oc.len + 1ull : 0ull;
+    }
+    if (err) atomicOr(F.errflags, err);
+}
+
+// cells -> cqg_value_t (24 bytes: type, reserved, 16-byte union) in the device copy of the host block; strings are
+// copied behind the arrays, NUL-terminated, and pointed to by the address they will have ON THE HOST.
+__global__ void finish_values_kernel(const OutCell* cells, const uint64_t* str_off, uint64_t n, const uint8_t* data, uint8_t* values,
+                                     uint8_t* strings, uint64_t host_strings) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const OutCell oc = cells[i];
+        uint64_t w0 = 0, w1 = 0;
+        int32_t type = oc.type;
+        switch (oc.type) {
+            case T_INT:
+            case T_DBL: w0 = oc.payload; break;
+            case T_DATE:
+                w0 = ((oc.payload >> 16) & 0xffffffffull) | (((oc.payload >> 8) & 0xffull) << 32);  // year | month
+                w1 = oc.payload & 0xffull;                                                          // day
+                break;
+            case T_STR: {
+                const uint64_t so = str_off[i];
+                const uint8_t* src = data + (oc.payload & 0x7fffffffffffffffull);
+                uint8_t* d = strings + so;
+                for (uint32_t k = 0; k < oc.len; k++) d[k] = src[k];
+                d[oc.len] = 0;
+                w0 = host_strings + so;
+                break;
+            }
+            default: type = T_NULL; break;
+        }
+        uint8_t* v = values + 24ull * i;
+        *(uint64_t*)v = (uint64_t)(uint32_t)type;
+        *(uint64_t*)(v + 8) = w0;
+        *(uint64_t*)(v + 16) = w1;
+    }
 }
 
 // for aggregated joins: right row of the group's first joined row = the rank-th match of the left row
@@ -1628,7 +1757,7 @@ __host__ __device__ inline uint32_t gen_row(uint8_t* o, uint64_t seed, uint64_t 
 
 constexpr int kGenRowsPerBlock = 1024;
 // pass 1: bytes of each block of rows
-__global__ void gen_sizes_kernel(long long rows, uint64_t seed, long long key_card, unsigned long long* block_bytes) {
+__global__ void gen_sizes_kernel(long long row_start, long long rows, uint64_t seed, long long key_card, unsigned long long* block_bytes) {
     __shared__ unsigned int sum;
     if (threadIdx.x == 0) sum = 0;
     __syncthreads();
@@ -1636,20 +1765,20 @@ __global__ void gen_sizes_kernel(long long rows, uint64_t seed, long long key_ca
     unsigned my = 0;
     long long base = (long long)blockIdx.x * kGenRowsPerBlock;
     for (int k = threadIdx.x; k < kGenRowsPerBlock; k += blockDim.x)
-        if (base + k < rows) my += gen_row(tmp, seed, (uint64_t)(base + k), key_card);
+        if (base + k < rows) my += gen_row(tmp, seed, (uint64_t)(row_start + base + k), key_card);
     atomicAdd(&sum, my);
     __syncthreads();
     if (threadIdx.x == 0) block_bytes[blockIdx.x] = sum;
 }
 // pass 2: write the rows of block b at block_off[b]
-__global__ void gen_write_kernel(uint8_t* out, long long rows, uint64_t seed, long long key_card,
+__global__ void gen_write_kernel(uint8_t* out, long long row_start, long long rows, uint64_t seed, long long key_card,
                                  const unsigned long long* block_off) {
     __shared__ unsigned int lens[kGenRowsPerBlock];
     __shared__ unsigned int offs[kGenRowsPerBlock];
     uint8_t tmp[64];
     long long base = (long long)blockIdx.x * kGenRowsPerBlock;
     for (int k = threadIdx.x; k < kGenRowsPerBlock; k += blockDim.x)
-        lens[k] = (base + k < rows) ? gen_row(tmp, seed, (uint64_t)(base + k), key_card) : 0u;
+        lens[k] = (base + k < rows) ? gen_row(tmp, seed, (uint64_t)(row_start + base + k), key_card) : 0u;
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int o = 0;
@@ -1662,7 +1791,7 @@ __global__ void gen_write_kernel(uint8_t* out, long long rows, uint64_t seed, lo
     uint8_t* dst = out + block_off[blockIdx.x];
     for (int k = threadIdx.x; k < kGenRowsPerBlock; k += blockDim.x) {
         if (base + k < rows) {
-            uint32_t n = gen_row(tmp, seed, (uint64_t)(base + k), key_card);
+            uint32_t n = gen_row(tmp, seed, (uint64_t)(row_start + base + k), key_card);
             for (uint32_t j = 0; j < n; j++) dst[offs[k] + j] = tmp[j];
         }
     }

@@ -440,7 +440,9 @@ static ResultSet* run_on_backend(ASTNode* q, bool* fallback) {
     /* ---- open tables ---- */
     cqg_table_t* lt = NULL;
     cqg_table_t* rt = NULL;
-    if (BE(table_open)(from->from.table, current_cfg(), &lt) != CQG_OK) {
+    int orc = BE(table_open)(from->from.table, current_cfg(), &lt);
+    if (orc == CQG_ERR_UNSUPPORTED_PLAN) return NULL; /* a dialect the kernels do not cover: the reference's route */
+    if (orc != CQG_OK) {
         /* same messages as csv_load + load_from_table (src/csv_reader.c:382, joins.c:222) */
         *fallback = false;
         fprintf(stderr, "Error loading file: %s\n", BE(last_error)());
@@ -668,6 +670,12 @@ static ResultSet* run_on_backend(ASTNode* q, bool* fallback) {
     /* ---- run ---- */
     *fallback = false;
     int rc = BE(execute)(lt, &plan, &res);
+    if (rc == CQG_ERR_UNSUPPORTED_PLAN) {
+        /* declined at plan time (predicate depth, column count ...), before any table byte was uploaded: not an
+         * operator of this path, the reference evaluates it like every other unsupported shape */
+        *fallback = true;
+        goto done;
+    }
     if (rc == CQG_ERR_UNSUPPORTED) {
         /* The operators of this shape belong to the GPU path: there is no silent CPU route for
          * them. The statement fails with the reason, unless the operator explicitly opted into

@@ -19,10 +19,11 @@ from .engine import _check, decode_result
 
 
 def partition(lib, table, key_col, world):
-    """-> (int64 tensor of offsets on the device, list of per-owner counts) for the table's current shard."""
+    """-> (int64 tensor of offsets on the device, list of per-owner counts, key-class mask) for the table's current shard."""
     h = C.c_void_p()
     _check(lib, lib.partition_rows(table.handle, key_col, world, C.byref(h)))
     try:
+        classes = int(lib.rowlist_key_classes(h))
         counts = (C.c_int64 * world)()
         _check(lib, lib.rowlist_counts(h, world, counts))
         counts = [int(c) for c in counts]
@@ -30,7 +31,31 @@ def partition(lib, table, key_col, world):
         _check(lib, lib.rowlist_copy(h, rows.data_ptr(), rows.numel()))
     finally:
         lib.rowlist_free(h)
-    return rows[:sum(counts)], counts
+    return rows[:sum(counts)], counts, classes
+
+
+class MixedKeyClasses(RuntimeError):
+    """Join keys of more than one comparison class: the reference's cross-type "equal" is not reproduced."""
+
+
+def _check_classes(mask):
+    nonnull = mask & ~1
+    if nonnull & (nonnull - 1):
+        from . import _abi as A
+        from .engine import CqError
+        raise CqError(A.ERR_UNSUPPORTED, "join key columns mix comparison classes (cross-type value_compare)")
+
+
+def _agree(dist, err, what):
+    """Collective error check: every rank learns whether ANY rank failed, BEFORE the next collective - a rank
+    that raised on its own would leave the others blocked in NCCL until the watchdog fires. Re-raises the local
+    error, or a generic one on the ranks that were fine."""
+    flag = torch.tensor([1 if err is not None else 0], dtype=torch.int64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()) != 0:
+        if err is not None:
+            raise err
+        raise RuntimeError(f"another rank failed in {what}")
 
 
 def _all_to_all_rows(rows, counts, dist):
@@ -85,12 +110,24 @@ def join_aggregate(lib, left, right, plan, world=None, dist=None):
         world, rank = dist.get_world_size(), dist.get_rank()
         left.set_shard(rank, world)
         right.set_shard(rank, world)
+        err = None
+        lrows = rrows = None
+        lcounts = rcounts = None
         try:
-            lrows, lcounts = partition(lib, left, lcol, world)
-            rrows, rcounts = partition(lib, right, rcol, world)
+            lrows, lcounts, lcls = partition(lib, left, lcol, world)
+            rrows, rcounts, rcls = partition(lib, right, rcol, world)
+            classes = lcls | rcls
+        except Exception as e:  # a key this rank's shard holds and the kernels decline, out of memory, ...
+            err = e
+            classes = 0
         finally:
             left.set_shard(0, 1)
             right.set_shard(0, 1)
+        _agree(dist, err, "the partition scan")
+        # key classes over ALL ranks and both sides (per rank the mix can be invisible): every rank declines together
+        cm = torch.tensor([(classes >> b) & 1 for b in range(4)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+        _check_classes(sum(int(v) << b for b, v in enumerate(cm.tolist())))
         mine_l = _all_to_all_rows(lrows, lcounts, dist)
         mine_r = _all_to_all_rows(rrows, rcounts, dist)
         stats["rows_exchanged"] = int(lrows.numel() + rrows.numel())
@@ -107,7 +144,12 @@ def join_aggregate(lib, left, right, plan, world=None, dist=None):
             _check(lib, rc)
         try:
             stats["kernel_ms"] = lib.partial_kernel_ms(p)
-            buf, n, rec = _export(lib, p)
+            err, buf, n, rec = None, None, 0, 0
+            try:
+                buf, n, rec = _export(lib, p)
+            except Exception as e:
+                err = e
+            _agree(dist, err, "the export of the partial aggregates")
             ns = torch.empty(world, dtype=torch.int64, device="cuda")
             dist.all_gather_into_tensor(ns, torch.tensor([n], dtype=torch.int64, device="cuda"))
             ns = [int(x) for x in ns.tolist()]
@@ -117,7 +159,12 @@ def join_aggregate(lib, left, right, plan, world=None, dist=None):
             recv = torch.empty(world * nmax * rec, dtype=torch.uint8, device="cuda")
             dist.all_gather_into_tensor(recv, send)
             parts = [(recv[r * nmax * rec:(r + 1) * nmax * rec], ns[r]) for r in range(world)]
-            out = _merge_and_finish(lib, left, plan, parts, p)
+            err, out = None, None
+            try:
+                out = _merge_and_finish(lib, left, plan, parts, p)
+            except Exception as e:
+                err = e
+            _agree(dist, err, "the merge of the partial aggregates")  # (so that no rank runs ahead into a later collective)
         finally:
             lib.partial_free(p)
         out["stats"] = stats
@@ -125,13 +172,18 @@ def join_aggregate(lib, left, right, plan, world=None, dist=None):
     # one process, `world` simulated ranks
     world = world or 2
     lparts, rparts = [], []
+    classes = 0
     for r in range(world):
         left.set_shard(r, world)
         right.set_shard(r, world)
-        lparts.append(partition(lib, left, lcol, world))
-        rparts.append(partition(lib, right, rcol, world))
+        lr, lc, lk = partition(lib, left, lcol, world)
+        rr, rc_, rk = partition(lib, right, rcol, world)
+        lparts.append((lr, lc))
+        rparts.append((rr, rc_))
+        classes |= lk | rk
     left.set_shard(0, 1)
     right.set_shard(0, 1)
+    _check_classes(classes)
 
     def received(parts, owner):
         segs = []

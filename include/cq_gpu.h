@@ -69,8 +69,11 @@ enum {
     CQG_ERR_CUDA = 1,        /* no device, kernel image missing, CUDA runtime error */
     CQG_ERR_IO = 2,          /* open/fstat/mmap failed (src/mmap.c:78-108 returns NULL) */
     CQG_ERR_ARG = 3,         /* malformed plan */
-    CQG_ERR_UNSUPPORTED = 4, /* shape outside the GPU path; caller keeps the reference route */
-    CQG_ERR_NOMEM = 5
+    CQG_ERR_UNSUPPORTED = 4, /* input the kernels met and cannot reproduce exactly (data dependent) */
+    CQG_ERR_NOMEM = 5,
+    CQG_ERR_UNSUPPORTED_PLAN = 6 /* shape or dialect outside the GPU path, found at plan time before any table byte
+                                    was uploaded: the caller keeps the reference route, like for any other shape
+                                    that is not an operator of this path */
 };
 
 const char* cqg_last_error(void);
@@ -89,8 +92,10 @@ int cqg_abi_version(void);
 
 typedef struct cqg_table cqg_table_t;
 
-/* mmap `path` (src/mmap.c:78), stage the bytes into HBM with chunked async copies from a
- * pinned bounce buffer, split the header line (src/csv_reader.c:341-357). */
+/* mmap `path` (src/mmap.c:78) and split the header line (src/csv_reader.c:341-357). The bytes are staged into HBM
+ * when a query first needs them (parallel chunked async copies through page-locked bounce buffers), so a statement
+ * whose plan is declined never pays for the upload. A dialect the kernels do not cover fails with
+ * CQG_ERR_UNSUPPORTED_PLAN. */
 int cqg_table_open(const char* path, cqg_csv_config_t cfg, cqg_table_t** out);
 
 /* same, but the CSV bytes are already in host memory (`data` must stay valid until close).
@@ -324,6 +329,11 @@ typedef struct cqg_rowlist cqg_rowlist_t;
  * `world` dense segments in device memory, segment o = counts[o] offsets (uint64, global file offsets). */
 int cqg_partition_rows(const cqg_table_t* t, int key_col, int world, cqg_rowlist_t** out);
 uint64_t cqg_rowlist_device_ptr(const cqg_rowlist_t* rl);
+/* OR of (1 << comparison class) over the key values of the scanned shard: bit 0 NULL, 1 numeric, 2 text, 3 date
+ * (value_compare, src/csv_reader.c:98-130, is 0 - "equal" - across classes). The caller must OR the masks of all
+ * ranks and both sides and decline the join when more than one non-NULL class appears: a stray key of another
+ * class can land on a rank that owns no other key, where no single rank would see the mix. */
+unsigned cqg_rowlist_key_classes(const cqg_rowlist_t* rl);
 int cqg_rowlist_counts(const cqg_rowlist_t* rl, int world, int64_t* counts);
 /* all segments, in owner order, into caller-owned device memory (capacity in offsets) */
 int cqg_rowlist_copy(const cqg_rowlist_t* rl, uint64_t dst_device_ptr, int64_t capacity);
@@ -339,6 +349,10 @@ int cqg_execute_partial_rows(const cqg_table_t* t, const cqg_query_t* q, uint64_
  * Row i depends only on (seed, i), so CPU and GPU generators agree byte for byte. */
 int cqg_generate_bigdata(uint64_t device_ptr, size_t capacity, int64_t rows, uint64_t seed,
                          int64_t key_card, size_t* size_out);
+/* rows [row_start, row_start + rows) of the same file, with or without the header line: the slice of ONE seeded
+ * file a rank holds when the file is split over several GPUs (bench.py --gpus N) */
+int cqg_generate_bigdata_range(uint64_t device_ptr, size_t capacity, int64_t row_start, int64_t rows, uint64_t seed,
+                               int64_t key_card, int with_header, size_t* size_out);
 /* upper bound of the bytes cqg_generate_bigdata needs for `rows` */
 size_t cqg_generate_bigdata_bound(int64_t rows, int64_t key_card);
 

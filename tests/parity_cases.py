@@ -67,6 +67,12 @@ def plans_uid():
     P = {}
     P["group_uid"] = dict(group_by=[UID], out_cols=[UID],
                           aggs=[(A.AGG_SUM, AGE), (A.AGG_MIN, HEIGHT), (A.AGG_MAX, HEIGHT), (A.AGG_AVG, HEIGHT)])
+    # results of many groups are finished on the device: every cell kind (string / numeric MIN and MAX, COUNT(col),
+    # AVG, NULL for an unknown column, bare columns incl. text) and the general kernel's entries
+    P["group_uid_cell_kinds"] = dict(group_by=[UID], out_cols=[UID, NAME, HEIGHT, 11],
+                                     aggs=[(A.AGG_MIN, NAME), (A.AGG_MAX, SURNAME), (A.AGG_COUNT, GENDER), (A.AGG_MIN, AGE),
+                                           (A.AGG_AVG, HEIGHT), (A.AGG_SUM, 12), (A.AGG_MAX, HEIGHT)])
+    P["group_uid_keys_only"] = dict(where=("<", col(AGE), const(60)), group_by=[UID, GENDER], out_cols=[GENDER, UID])
     P["lean_group_uid_sum"] = dict(where=(">=", col(AGE), const(18)), group_by=[UID], out_cols=[UID],
                                    aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE), (A.AGG_AVG, HEIGHT)])
     return P

@@ -485,8 +485,9 @@ def test_hash_partitioned_join(world):
             got.pop("stats")
             pc.compare_results(got, want)
         # the lists partition the rows: every row on exactly one owner's list
-        rows, counts = pj.partition(lib_g, og, 4, world)
+        rows, counts, classes = pj.partition(lib_g, og, 4, world)
         assert sum(counts) == og.row_count() and len(set(rows.tolist())) == sum(counts)
+        assert classes == 0b011  # NULL keys and numbers
         # an unresolved key column never matches (evaluator_joins.c:54)
         got = pj.join_aggregate(lib_g, og, cg, pc.build(specs[0], join=(cg, -1, 0)), world=world)
         assert got["groups"][0]["count"] == 0
@@ -502,6 +503,24 @@ def test_join_keys_of_different_classes_are_declined():
         with pytest.raises(CqError) as ei:
             lg.execute(Plan(aggs=[(A.AGG_COUNT_STAR, -1)], join=(rg, 0, 0)))
         assert ei.value.code == A.ERR_UNSUPPORTED
+
+
+def test_partitioned_join_declines_a_stray_key_of_another_class():
+    """Left keys [1, 'x'], right keys [1]: the single-GPU join declines (the reference matches 'x' with 1 because
+    value_compare is 0 across classes). Hash-partitioned, the text key may land on a rank that owns no other key,
+    where no single rank sees the mix: the class masks of all ranks and both sides are ORed and every rank declines."""
+    from cq_b200 import partitioned_join as pj
+    left = b"k,v\n1,a\nx,b\n2,c\n3,d\n"
+    right = b"k,w\n1,10\n2,20\n"
+    spec = dict(aggs=[(A.AGG_COUNT_STAR, -1)])
+    with Table.from_bytes(left, lib=gpu()) as lg, Table.from_bytes(right, lib=gpu()) as rg:
+        with pytest.raises(CqError) as e1:
+            lg.execute(pc.build(spec, join=(rg, 0, 0)))
+        assert e1.value.code == A.ERR_UNSUPPORTED
+        for world in (2, 3, 5):
+            with pytest.raises(CqError) as e2:
+                pj.join_aggregate(gpu(), lg, rg, pc.build(spec, join=(rg, 0, 0)), world=world)
+            assert e2.value.code == A.ERR_UNSUPPORTED
 
 
 def test_ahead_of_time_lean_kernels_without_the_run_time_compiler():

@@ -25,12 +25,12 @@ SHAPE = """#define CQG_JIT 1
 #define CQG_JIT_GSLOT(i) ((i)==0?0:0)
 #define CQG_JIT_ASLOT(i) ((i)==0?2:(i)==1?1:0)
 #define CQG_JIT_AFUNC(i) ((i)==0?3:(i)==1?2:0)
-#define CQG_JIT_PKIDW 4
+#define CQG_JIT_PKIDW 3
 #define CQG_JIT_PKBYTES 64
-#define CQG_JIT_PKCOUNT 32
-#define CQG_JIT_PKKEYWORD(i) ((i)==0?2:0)
+#define CQG_JIT_PKCOUNT 24
+#define CQG_JIT_PKKEYWORD(i) ((i)==0?1:0)
 #define CQG_JIT_PKKEYWIDE(i) ((i)==0?1:0)
-#define CQG_JIT_PKAGGOFF(i) ((i)==0?40:(i)==1?-1:0)
+#define CQG_JIT_PKAGGOFF(i) ((i)==0?32:(i)==1?-1:0)
 #define CQG_JIT_PKAGGKEY(i) ((i)==0?-1:(i)==1?0:0)
 """
 
