@@ -309,6 +309,7 @@ def main():
             legs[leg] = {"query": sql, "value": nbytes / (ms / 1e3) / 1e9, "unit": UNIT, "ms_per_step": ms,
                          "rows_per_s": last["rows_scanned"] / (ms / 1e3), "groups": last["n_groups"],
                          "first_group_count": int(last["count0"]), "steps": args.steps, "warmup": args.warmup,
+                         "kernel_ms_per_step": [round(k, 3) for k in kms],
                          "roofline": roofline_of(nbytes, kernel_ms, kernel)}
         head = legs["groupby"]
 

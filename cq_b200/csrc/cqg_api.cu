@@ -142,6 +142,7 @@ struct cqg_table {
     mutable std::vector<uint8_t> sample;  // first bytes after the header (layout guesses only), fetched on first use
     mutable bool sample_ready = false;
     bool src_pinned = false;  // h_data is page-locked: DMA straight from it
+    int fd = -1;              // the mapped file, kept open: staging reads it with pread (no page faults on the mapping)
 };
 
 static inline bool host_is_space(unsigned c) { return c == 32u || (c - 9u) <= 4u; }
@@ -254,7 +255,7 @@ static int check_dialect(cqg_csv_config_t cfg) {
 // stream of its own, fault their chunks in and hand them to the copy engines, so that the host memcpy of one
 // chunk overlaps the DMA of others (one thread tops out far below what PCIe Gen5 takes).
 struct StagePool {
-    static constexpr int kThreads = 8;
+    static constexpr int kThreads = 16;
     static constexpr size_t kChunk = 8u << 20;
     uint8_t* bounce[kThreads][2] = {};
     cudaStream_t stream[kThreads] = {};
@@ -308,7 +309,17 @@ static int stage_to_device(cqg_table* t, const uint8_t* src, size_t size, bool p
         for (size_t c = (size_t)k; c < nchunks && !bad.load(); c += (size_t)T, b ^= 1) {
             const size_t off = c * chunk, n = std::min(chunk, size - off);
             if (cudaEventSynchronize(sp.ev[k][b]) != cudaSuccess) bad = 1;  // the copy that last used this buffer
-            memcpy(sp.bounce[k][b], src + off, n);
+            bool have = false;
+            if (t->fd >= 0) {  // page cache -> bounce buffer in the kernel: no per-page faults on the mapping
+                size_t got = 0;
+                while (got < n) {
+                    const ssize_t r = pread(t->fd, sp.bounce[k][b] + got, n - got, (off_t)(off + got));
+                    if (r <= 0) break;
+                    got += (size_t)r;
+                }
+                have = got == n;
+            }
+            if (!have) memcpy(sp.bounce[k][b], src + off, n);
             if (cudaMemcpyAsync(dst + off, sp.bounce[k][b], n, cudaMemcpyHostToDevice, sp.stream[k]) != cudaSuccess) bad = 1;
             cudaEventRecord(sp.ev[k][b], sp.stream[k]);
         }
@@ -366,10 +377,14 @@ CQG_API int cqg_table_open(const char* path, cqg_csv_config_t cfg, cqg_table_t**
         return fail(CQG_ERR_IO, "%s", sb.st_size == 0 ? "empty file" : strerror(e));
     }
     void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-    close(fd);
-    if (m == MAP_FAILED) return fail(CQG_ERR_IO, "mmap: %s", strerror(errno));
+    if (m == MAP_FAILED) {
+        int e = errno;
+        close(fd);
+        return fail(CQG_ERR_IO, "mmap: %s", strerror(e));
+    }
     madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
     cqg_table* t = new cqg_table();
+    t->fd = fd;
     t->cfg = cfg;
     t->size = (size_t)sb.st_size;
     t->map = m;
@@ -422,6 +437,7 @@ CQG_API void cqg_table_close(cqg_table_t* t) {
     if (!t) return;
     if (t->owns_device && t->d_data) cudaFreeAsync(t->d_data, 0);
     if (t->map) munmap(t->map, t->map_len);
+    if (t->fd >= 0) close(t->fd);
     delete t;
 }
 
