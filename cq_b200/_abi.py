@@ -15,6 +15,7 @@ OP_EQ, OP_NE, OP_GT, OP_LT, OP_GE, OP_LE, OP_IN, OP_NOT_IN, OP_LIKE, OP_ILIKE = 
 OP_AND, OP_OR, OP_NOT, OP_TRUE, OP_FALSE, OP_POP = range(50, 56)
 
 AGG_COUNT_STAR, AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX = range(6)
+JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_FULL = 0, 1, 2, 3
 MODE_AGGREGATE, MODE_SELECT = 0, 1
 MAX_GROUP_COLS, MAX_AGGS, MAX_OUT_COLS = 8, 16, 64
 
@@ -53,7 +54,8 @@ class Agg(C.Structure):
 
 
 class Join(C.Structure):
-    _fields_ = [("right", C.c_void_p), ("left_col", C.c_int32), ("right_col", C.c_int32)]
+    _fields_ = [("right", C.c_void_p), ("left_col", C.c_int32), ("right_col", C.c_int32), ("type", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Query(C.Structure):

@@ -1523,6 +1523,12 @@ static int build_plan(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, cu
         if (rt->cfg.delimiter != t->cfg.delimiter || rt->cfg.quote != t->cfg.quote)
             return fail(CQG_ERR_ARG, "joined tables must share one CSV dialect");
         P.join = 1;
+        if (q->join.type < CQG_JOIN_INNER || q->join.type > CQG_JOIN_FULL) return fail(CQG_ERR_ARG, "unknown join type %d", q->join.type);
+        P.join_type = q->join.type;
+        // with an unresolved key column no pair matches (joins.c:54): RIGHT / FULL would have to emit the whole right
+        // table, which the (empty) join table cannot enumerate
+        if (P.join_type >= CQG_JOIN_RIGHT && (q->join.left_col < 0 || q->join.right_col < 0))
+            return fail(CQG_ERR_UNSUPPORTED, "RIGHT / FULL JOIN on an unknown key column");
         P.rdata = rt->d_data;
         P.rsize = rt->size;
         P.jl_col = q->join.left_col;
@@ -2604,6 +2610,20 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     return CQG_OK;
 }
 
+// RIGHT / FULL joins: after the probe scan, the right rows no left row matched (general operators, global table)
+static int launch_unmatched_right(const DevPlan& P, cudaStream_t st) {
+    if (!P.join || P.join_type < CQG_JOIN_RIGHT || !P.jcap) return CQG_OK;
+    DevPlan R = P;
+    R.simple = 0;
+    R.scalar_regs = 0;
+    R.smem_cap = 0;
+    int grid = (int)std::min<uint64_t>((P.jcap + 127) / 128, 148 * 8);
+    join_unmatched_right_kernel<<<grid, 128, 0, st>>>(R);
+    g_launches++;
+    CU(cudaGetLastError());
+    return CQG_OK;
+}
+
 static int run_aggregate_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBlock& hs, float* ms_out) {
     DevPlan& P = hp.P;
     uint64_t cap = initial_group_cap(P);
@@ -2625,6 +2645,7 @@ static int run_aggregate_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, Sca
         cudaMemsetAsync(hp.d_scalars.p, 0, sizeof(ScalarBlock), st);
         cudaEventRecord(e0, st);
         if ((rc = launch_scan(P, hp.table_smem_bytes, st))) break;
+        if ((rc = launch_unmatched_right(P, st))) break;
         cudaEventRecord(e1, st);
         if ((rc = read_scalars(hp, hs, st))) break;
         float ms = 0;
@@ -2718,6 +2739,7 @@ static int execute_select(HostPlan& hp, const cqg_table* t, const cqg_table* rt,
         cudaMemsetAsync(P.sel_count, 0, 8, st);
         cudaEventRecord(e0, st);
         if ((rc = launch_scan(P, 0, st))) break;
+        if ((rc = launch_unmatched_right(P, st))) break;
         cudaEventRecord(e1, st);
         cudaError_t ce = cudaMemcpyAsync(&hs, hp.d_scalars.p, sizeof hs, cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
@@ -2919,7 +2941,10 @@ struct cqg_partial {
     double kernel_ms = 0;
 };
 
-static bool partial_query_ok(const cqg_query_t* q) { return q->mode == CQG_MODE_AGGREGATE; }
+// (RIGHT / FULL joins need every left row's matches before a right row is known to be without one: not per shard)
+static bool partial_query_ok(const cqg_query_t* q) {
+    return q->mode == CQG_MODE_AGGREGATE && !(q->join.right && q->join.type >= CQG_JOIN_RIGHT);
+}
 
 CQG_API int cqg_execute_partial(const cqg_table_t* t, const cqg_query_t* q, cqg_partial_t** out) {
     if (!t || !q || !out) return fail(CQG_ERR_ARG, "null argument");

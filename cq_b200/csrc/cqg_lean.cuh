@@ -1023,6 +1023,30 @@ __global__ void deferred_rows_kernel(const __grid_constant__ DevPlan P, const ui
     if (acc.err) atomicOr(P.errflags, acc.err);
 }
 
+// RIGHT / FULL joins: the right rows without a match (emit_right_only_row), one thread per slot of the join table
+__global__ void join_unmatched_right_kernel(const __grid_constant__ DevPlan P) {
+    CtaState cs;
+    cs.stab = nullptr;
+    cs.s_occ = nullptr;
+    ThreadAcc acc;
+    acc.rows = 0;
+    acc.count = 0;
+    acc.first = ~0ull;
+    acc.err = 0;
+    for (int a = 0; a < 4; a++) {
+        acc.si[a] = 0;
+        acc.sd[a] = 0.0;
+        acc.s3[a] = 0;
+        acc.sn[a] = 0;
+    }
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P.jcap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const JoinSlot* s = &P.jslots[i];
+        if (s->h == 0ull || (s->tag & kJoinMatched)) continue;
+        for (uint32_t it = s->head; it != 0u; it = P.jrow_next[it - 1]) emit_right_only_row(P, cs, P.jrow_off[it - 1], acc);
+    }
+    if (acc.err) atomicOr(P.errflags, acc.err);
+}
+
 // ---- packed table -> general entries ----
 // Every occupied line of the packed table becomes one general entry (DevPlan::entry_bytes, the image the host
 // finish path, the partial export and merge_entries_kernel read), written densely in arbitrary order; the

@@ -116,9 +116,13 @@ struct PackedLayout {
 struct JoinSlot {
     uint64_t h;  // 0 empty, bit 63 lock
     uint64_t w0, w1;
-    uint32_t tag;
+    uint32_t tag;   // key tag; bit 31 (kJoinMatched): a left row matched this key (RIGHT / FULL joins)
     uint32_t head;  // index of the most recently added right row + 1 (0: none)
 };
+constexpr uint32_t kJoinMatched = 0x80000000u;
+// okey of a right row without a match (RIGHT / FULL): behind every left row (their offsets stay below 2^45), in
+// right-file order; the row has no left row, its right row is the offset itself
+constexpr uint64_t kOkeyRightOnly = 1ull << 61;
 
 struct DevPlan {
     // ---- left file ----
@@ -199,6 +203,8 @@ struct DevPlan {
     const uint8_t* rdata;  // right file bytes
     uint64_t rsize;
     int32_t join;          // 0 none, 1 probe
+    int32_t join_type;     // cqg_join_type_t: LEFT / FULL emit left rows without a match, RIGHT / FULL right rows without one
+    int32_t join_pad;
     int32_t jl_col, jr_col;   // key columns (query column index; jr_col relative to the right table)
     JoinSlot* jslots;
     uint64_t jcap;

@@ -805,7 +805,8 @@ __device__ inline JoinSlot* join_find(const DevPlan& P, uint64_t h, uint32_t tag
         if ((cur & ~kLockBit) == h) {
             if (cur & kLockBit) continue;
             __threadfence();
-            if (*(volatile uint32_t*)&s->tag == tag && *(volatile uint64_t*)&s->w0 == w0 && *(volatile uint64_t*)&s->w1 == w1)
+            if ((*(volatile uint32_t*)&s->tag & ~kJoinMatched) == tag && *(volatile uint64_t*)&s->w0 == w0 &&
+                *(volatile uint64_t*)&s->w1 == w1)
                 return s;
         }
         i = (i + 1) & mask;
@@ -904,15 +905,32 @@ __device__ __noinline__ void process_row_slow(const DevPlan& P, const CtaState& 
         else select_row(P, okey, 0);
         return;
     }
-    // probe
-    if (P.jl_col < 0 || P.jr_col < 0) return;  // resolve_column -> NULL: condition false (joins.c:54)
-    DVal lk = row_value(rv, P.jl_col, acc.err);
-    atomicOr(&P.jclass[0], 1u << join_class(lk));
-    uint32_t tag;
-    uint64_t w0, w1, h;
-    join_key_of(lk, acc.err, tag, w0, w1, h);
-    JoinSlot* s = join_find(P, h, tag, w0, w1, false);
-    if (!s) return;
+    // probe (perform_join, evaluator_joins.c:96-139): every right row with an equal key, in right-file order; a left
+    // row without a match comes out once with NULL right columns in LEFT / FULL joins
+    const bool keep_unmatched_left = P.join_type == CQG_JOIN_LEFT || P.join_type == CQG_JOIN_FULL;
+    JoinSlot* s = nullptr;
+    if (P.jl_col >= 0 && P.jr_col >= 0) {  // else resolve_column -> NULL: the condition is false for every pair (joins.c:54)
+        DVal lk = row_value(rv, P.jl_col, acc.err);
+        atomicOr(&P.jclass[0], 1u << join_class(lk));
+        uint32_t tag;
+        uint64_t w0, w1, h;
+        join_key_of(lk, acc.err, tag, w0, w1, h);
+        s = join_find(P, h, tag, w0, w1, false);
+    }
+    if (!s || s->head == 0u) {
+        if (!keep_unmatched_left) return;
+        for (int k = 0; k < P.nwantR; k++) {  // every right column reads as NULL
+            foff[P.nwantL + k] = 0;
+            flen[P.nwantL + k] = 0;
+        }
+        rv.rbase = P.rdata;
+        bool pass = P.pred_kind == 0 ? true : (P.pred_kind == 1 ? eval_fused(P, row, acc.err) : eval_pred(P.pred, rv, acc.err));
+        if (!pass) return;
+        if (P.mode == SCAN_AGG) agg_row(P, cs, row, okey, acc);
+        else select_row(P, okey, ~0ull);
+        return;
+    }
+    if (P.join_type >= CQG_JOIN_RIGHT && !(*(volatile uint32_t*)&s->tag & kJoinMatched)) atomicOr(&s->tag, kJoinMatched);
     uint32_t head = s->head;
     for (uint32_t it = head; it != 0u; it = P.jrow_next[it - 1]) {
         uint64_t roff = P.jrow_off[it - 1];
@@ -934,6 +952,35 @@ __device__ __noinline__ void process_row_slow(const DevPlan& P, const CtaState& 
         if (P.mode == SCAN_AGG) agg_row(P, cs, row, okey | rank, acc);
         else select_row(P, okey | rank, roff);
     }
+}
+
+// RIGHT / FULL joins (evaluator_joins.c:142-171): behind the left-major rows, every right row whose key no left row
+// matched, in right-file order, joined to NULL left columns. A key's right rows hang off one slot of the join table;
+// the probe marked the slots it matched.
+__device__ __noinline__ void emit_right_only_row(const DevPlan& P, const CtaState& cs, uint64_t roff, ThreadAcc& acc) {
+    uint32_t foff[2 * kMaxSlots], flen[2 * kMaxSlots];
+    for (int k = 0; k < P.nwantL; k++) {
+        foff[k] = 0;
+        flen[k] = 0;
+    }
+    split_right_row(P, roff, foff, flen);
+    SlowRow row;
+    RowView& rv = row.rv;
+    rv.base = P.data;
+    rv.rbase = P.rdata + roff;
+    rv.lfile = P.data;
+    rv.rfile = P.rdata;
+    rv.foff = foff;
+    rv.flen = flen;
+    rv.colslot = P.colslot;
+    rv.ncols_total = P.n_cols_total;
+    rv.nleft_slots = P.nwantL;
+    if (roff >> 45) acc.err |= KERR_OFFSET_RANGE;
+    const uint64_t okey = kOkeyRightOnly | (roff << 16);
+    bool pass = P.pred_kind == 0 ? true : (P.pred_kind == 1 ? eval_fused(P, row, acc.err) : eval_pred(P.pred, rv, acc.err));
+    if (!pass) return;
+    if (P.mode == SCAN_AGG) agg_row(P, cs, row, okey, acc);
+    else select_row(P, okey, roff);
 }
 
 // a row that does not fit the staged window: found and split straight from HBM
@@ -1657,6 +1704,10 @@ __global__ void resolve_first_right_kernel(const __grid_constant__ DevPlan P, co
         uint64_t ok = first_okey[i];
         roff_out[i] = ~0ull;
         if (ok == ~0ull) continue;
+        if (ok & kOkeyRightOnly) {  // a right row without a match: the okey carries its offset
+            roff_out[i] = (ok >> 16) & ((1ull << 45) - 1ull);
+            continue;
+        }
         uint64_t loff = (ok >> 16) - P.global_base;
         uint32_t rank = (uint32_t)(ok & 0xffffu);
         const uint8_t* b = P.data + loff;

@@ -169,11 +169,12 @@ class Plan:
             q.out_cols[i] = c
         q.max_rows = max_rows
         if join is not None:
-            right, lcol, rcol = join
+            right, lcol, rcol = join[:3]
             self._keep.append(right)
             q.join.right = right.handle
             q.join.left_col = lcol
             q.join.right_col = rcol
+            q.join.type = join[3] if len(join) > 3 else A.JOIN_INNER
         self.q = q
 
 

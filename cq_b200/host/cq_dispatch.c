@@ -422,7 +422,10 @@ static ResultSet* run_on_backend(ASTNode* q, bool* fallback) {
     ASTNode* join = NULL;
     if (q->query.join_count == 1) {
         join = q->query.joins[0];
-        if (!join || join->type != NODE_TYPE_JOIN || join->join.join_type != JOIN_TYPE_INNER) return NULL;
+        if (!join || join->type != NODE_TYPE_JOIN) return NULL;
+        if (join->join.join_type != JOIN_TYPE_INNER && join->join.join_type != JOIN_TYPE_LEFT &&
+            join->join.join_type != JOIN_TYPE_RIGHT && join->join.join_type != JOIN_TYPE_FULL)
+            return NULL;
         ASTNode* on = join->join.condition;
         /* evaluate_join_condition (evaluator_joins.c:40-60) only ever matches `ident = ident` */
         if (!on || on->type != NODE_TYPE_CONDITION || !on->condition.operator ||
@@ -546,6 +549,13 @@ static ResultSet* run_on_backend(ASTNode* q, bool* fallback) {
         plan.join.right = rt;
         plan.join.left_col = cols[0];
         plan.join.right_col = cols[1];
+        /* perform_join's join_type (evaluator_joins.c:128-171): unmatched rows of the left / right / both tables */
+        plan.join.type = join->join.join_type == JOIN_TYPE_LEFT ? CQG_JOIN_LEFT
+                       : join->join.join_type == JOIN_TYPE_RIGHT ? CQG_JOIN_RIGHT
+                       : join->join.join_type == JOIN_TYPE_FULL ? CQG_JOIN_FULL : CQG_JOIN_INNER;
+        /* an unresolved key column matches nothing: RIGHT / FULL then return the whole right table, which the
+         * backend's (empty) join table cannot enumerate - the reference's route */
+        if (plan.join.type >= CQG_JOIN_RIGHT && (cols[0] < 0 || cols[1] < 0)) goto done_fallback;
     }
 
     /* ---- WHERE ---- */

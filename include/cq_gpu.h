@@ -200,10 +200,19 @@ typedef struct {
 
 /* ---- join: replaces perform_join for INNER `ident = ident` (evaluator_joins.c:40-140) ---- */
 
+typedef enum {
+    CQG_JOIN_INNER = 0,
+    CQG_JOIN_LEFT = 1,  /* + every left row without a match, right columns NULL (evaluator_joins.c:128-139) */
+    CQG_JOIN_RIGHT = 2, /* + behind all of those, every right row without a match, left columns NULL (:142-171) */
+    CQG_JOIN_FULL = 3
+} cqg_join_type_t;
+
 typedef struct {
     const cqg_table_t* right; /* NULL: no join */
     int32_t left_col;         /* key column in the left table; -1 = unresolved -> no row matches */
     int32_t right_col;        /* key column in the right table */
+    int32_t type;             /* cqg_join_type_t */
+    int32_t reserved;
 } cqg_join_t;
 
 /* ---- a query over one table (or one inner equi-join) ---- */
@@ -258,8 +267,10 @@ typedef struct {
     /* SELECT mode */
     int64_t n_selected;      /* rows passing WHERE (exact, even when truncated by max_rows) */
     int64_t n_rows_out;      /* rows materialised below */
-    uint64_t* row_offset;    /* [n_rows_out] byte offset of the row in the left file */
-    uint64_t* row_offset_right; /* [n_rows_out] byte offset in the right file (joins), else NULL */
+    uint64_t* row_offset;    /* [n_rows_out] byte offset of the row in the left file; outer joins: 2^45 | right
+                                offset for a right row without a match (it has no left row) */
+    uint64_t* row_offset_right; /* [n_rows_out] byte offset in the right file (joins), else NULL; ~0 for a left
+                                   row without a match */
     cqg_value_t* rows;       /* [n_rows_out][n_out_cols] row-major */
 
     /* bookkeeping */

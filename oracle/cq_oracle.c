@@ -943,7 +943,15 @@ typedef struct {
     long long* next;
     long long nbuckets;
     long long class_count[5];
+    unsigned char* matched; /* RIGHT / FULL joins: right row i matched some left row (evaluator_joins.c:146-157) */
 } run_t;
+
+/* offsets that stand for "no row on this side" in outer joins (include/cq_gpu.h, cqg_result_t::row_offset) */
+#define CQO_RIGHT_ONLY (1ULL << 45) /* | right offset: a right row without a match has no left row */
+#define CQO_NO_RIGHT (~0ULL)        /* a left row without a match */
+
+/* parse the row at `off`, or make the view an empty row (every column NULL) when that side has none */
+static void parse_side(rowview_t* rv, const cqo_table_t* t, uint64_t off, bool none);
 
 static int key_class(const val_t* v) {
     switch (v->type) {
@@ -1009,6 +1017,16 @@ static void right_row_cb(void* ctx, const char* ls, const char* le) {
     R->class_count[key_class(&rr->key)]++;
 }
 
+static const char* row_end(const cqo_table_t* t, const char* ls);
+static void parse_side(rowview_t* rv, const cqo_table_t* t, uint64_t off, bool none) {
+    if (none) {
+        rv->nf = 0;
+        return;
+    }
+    const char* ls = t->data + off;
+    row_parse(rv, ls, row_end(t, ls));
+}
+
 static int cmp_ll(const void* a, const void* b) {
     long long x = *(const long long*)a, y = *(const long long*)b;
     return x < y ? -1 : x > y;
@@ -1026,7 +1044,16 @@ static void left_row_cb(void* ctx, const char* ls, const char* le) {
     }
     /* perform_join's inner loop (evaluator_joins.c:96-126): all right rows r, in file
      * order, with value_compare(left_key, right_key) == 0 */
-    if (R->q->join.left_col < 0 || R->q->join.right_col < 0) return; /* resolve_column NULL -> false */
+    const int jtype = R->q->join.type;
+    const bool keep_left = jtype == CQG_JOIN_LEFT || jtype == CQG_JOIN_FULL;
+    if (R->q->join.left_col < 0 || R->q->join.right_col < 0) { /* resolve_column NULL -> false for every pair */
+        if (keep_left) { /* :128-139: the left row with NULL right columns */
+            R->rrow.nf = 0;
+            jrow_t jr = {&R->lrow, &R->rrow, R->lt->ncols};
+            emit_row(R, &jr, loff, CQO_NO_RIGHT);
+        }
+        return;
+    }
     val_t lk = row_col(&R->lrow, R->q->join.left_col);
     int lc = key_class(&lk);
     long long* matches = NULL;
@@ -1061,9 +1088,15 @@ static void left_row_cb(void* ctx, const char* ls, const char* le) {
     }
     for (long long k = 0; k < nm; k++) {
         rrow_t* rr = &R->right.rows[matches[k]];
+        if (R->matched) R->matched[matches[k]] = 1;
         row_parse(&R->rrow, R->rt->data + rr->off, R->rt->data + rr->off + rr->len);
         jrow_t jr = {&R->lrow, &R->rrow, R->lt->ncols};
         emit_row(R, &jr, loff, rr->off);
+    }
+    if (nm == 0 && keep_left) { /* :128-139 */
+        R->rrow.nf = 0;
+        jrow_t jr = {&R->lrow, &R->rrow, R->lt->ncols};
+        emit_row(R, &jr, loff, CQO_NO_RIGHT);
     }
     free(matches);
 }
@@ -1100,6 +1133,21 @@ CQO_EXPORT int cqo_execute(const cqg_table_t* tt, const cqg_query_t* q, cqg_resu
     cqg_result_t* res = calloc(1, sizeof *res);
     R.res = res;
 
+    if (R.rt && (q->join.type < CQG_JOIN_INNER || q->join.type > CQG_JOIN_FULL)) {
+        free(R.lrow.f);
+        free(R.rrow.f);
+        free(res);
+        set_err("unknown join type");
+        return CQG_ERR_ARG;
+    }
+    if (R.rt && q->join.type >= CQG_JOIN_RIGHT && (q->join.left_col < 0 || q->join.right_col < 0 || t->shard_count > 1)) {
+        /* the GPU library declines these too (empty join table / right rows are unmatched only over ALL left rows) */
+        free(R.lrow.f);
+        free(R.rrow.f);
+        free(res);
+        set_err("RIGHT / FULL JOIN on an unknown key column or on a shard");
+        return CQG_ERR_UNSUPPORTED;
+    }
     if (R.rt) {
         /* the right table is always read whole, whatever the left shard */
         cqo_table_t rt_all = *R.rt;
@@ -1118,7 +1166,21 @@ CQO_EXPORT int cqo_execute(const cqg_table_t* tt, const cqg_query_t* q, cqg_resu
         }
     }
 
+    if (R.rt && q->join.type >= CQG_JOIN_RIGHT) R.matched = calloc((size_t)(R.right.n + 1), 1);
     for_each_row(t, left_row_cb, &R);
+    if (R.matched) {
+        /* evaluator_joins.c:142-171: behind everything else, the right rows no left row matched, in file order,
+         * with NULL left columns */
+        for (long long i = 0; i < R.right.n; i++) {
+            if (R.matched[i]) continue;
+            rrow_t* rr = &R.right.rows[i];
+            row_parse(&R.rrow, R.rt->data + rr->off, R.rt->data + rr->off + rr->len);
+            R.lrow.nf = 0;
+            jrow_t jr = {&R.lrow, &R.rrow, R.lt->ncols};
+            emit_row(&R, &jr, CQO_RIGHT_ONLY | rr->off, rr->off);
+        }
+        free(R.matched);
+    }
 
     res->rows_scanned = R.rows_scanned;
     res->n_aggs = q->n_aggs;
@@ -1180,12 +1242,8 @@ CQO_EXPORT int cqo_execute(const cqg_table_t* tt, const cqg_query_t* q, cqg_resu
             /* bare columns: the group's first row (evaluator_aggregates.c:679-689) */
             if (q->n_out_cols > 0) {
                 if (g->count > 0) {
-                    const char* ls = t->data + g->first_off;
-                    row_parse(&R.lrow, ls, row_end(t, ls));
-                    if (R.rt) {
-                        const char* rs = R.rt->data + g->first_off_right;
-                        row_parse(&R.rrow, rs, row_end(R.rt, rs));
-                    }
+                    parse_side(&R.lrow, t, g->first_off, (g->first_off & CQO_RIGHT_ONLY) != 0);
+                    if (R.rt) parse_side(&R.rrow, R.rt, g->first_off_right, g->first_off_right == CQO_NO_RIGHT);
                     jrow_t jr = {&R.lrow, R.rt ? &R.rrow : NULL, t->ncols};
                     for (int c = 0; c < q->n_out_cols; c++) {
                         val_t v = jrow_col(&jr, q->out_cols[c]);
@@ -1206,12 +1264,8 @@ CQO_EXPORT int cqo_execute(const cqg_table_t* tt, const cqg_query_t* q, cqg_resu
         for (long long i = 0; i < nout; i++) {
             res->row_offset[i] = R.sel_off[i];
             if (R.rt) res->row_offset_right[i] = R.sel_off_r[i];
-            const char* ls = t->data + R.sel_off[i];
-            row_parse(&R.lrow, ls, row_end(t, ls));
-            if (R.rt) {
-                const char* rs = R.rt->data + R.sel_off_r[i];
-                row_parse(&R.rrow, rs, row_end(R.rt, rs));
-            }
+            parse_side(&R.lrow, t, R.sel_off[i], (R.sel_off[i] & CQO_RIGHT_ONLY) != 0);
+            if (R.rt) parse_side(&R.rrow, R.rt, R.sel_off_r[i], R.sel_off_r[i] == CQO_NO_RIGHT);
             jrow_t jr = {&R.lrow, R.rt ? &R.rrow : NULL, t->ncols};
             for (int c = 0; c < q->n_out_cols; c++) {
                 val_t v = jrow_col(&jr, q->out_cols[c]);

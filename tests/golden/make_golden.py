@@ -330,6 +330,18 @@ def make_queries():
     q("SELECT p.name, t.label FROM 'people.csv' AS p JOIN 'tags.csv' AS t ON p.role = t.code")
     q("SELECT t.label, COUNT(*), AVG(p.age) FROM 'people.csv' AS p JOIN 'tags.csv' AS t ON p.role = t.code GROUP BY t.label")
     q("SELECT p.name, t.label FROM 'people.csv' AS p JOIN 'tags.csv' AS t ON p.role = t.code WHERE p.age > 30 ORDER BY p.name")
+    # --- LEFT / RIGHT / FULL joins (evaluator_joins.c:128-171): unmatched rows of either side, NULL-extended ---
+    for jt in ("LEFT", "RIGHT", "FULL"):
+        JO = f"FROM 'orders.csv' AS o {jt} JOIN 'customers.csv' AS c ON o.customer_id = c.id"
+        q(f"SELECT o.id, o.customer_id, c.id, c.name {JO}")
+        q(f"SELECT COUNT(*), COUNT(c.name), SUM(o.price), MIN(c.name), MAX(o.id) {JO}")
+        q(f"SELECT c.name, COUNT(*), SUM(o.price) {JO} GROUP BY c.name")
+        q(f"SELECT o.customer_id, c.email, COUNT(*) {JO} GROUP BY o.customer_id")
+        q(f"SELECT o.id, c.name {JO} WHERE o.price > 20")
+        q(f"SELECT o.id, c.name {JO} WHERE c.name LIKE 'C%' ORDER BY o.id")
+        q(f"SELECT p.name, t.label FROM 'people.csv' AS p {jt} JOIN 'tags.csv' AS t ON p.role = t.code")
+        q(f"SELECT t.label, COUNT(*), AVG(p.age) FROM 'people.csv' AS p {jt} JOIN 'tags.csv' AS t ON p.role = t.code GROUP BY t.label")
+        q(f"SELECT COUNT(*) FROM 'orders.csv' AS o {jt} JOIN 'customers.csv' AS c ON o.nosuch = c.id")
     # --- shapes the GPU planner declines at plan time: they must come out of the drop-in binary all the same ---
     q(f"SELECT COUNT(*), SUM(age) FROM '{P}' WHERE age IN ({', '.join(str(k) for k in range(18, 48))})", route="any")
     q("SELECT COUNT(*), SUM(val) FROM 'alpha.csv' WHERE id > 1", args=["-s", "x"], route="any")

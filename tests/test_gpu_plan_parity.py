@@ -193,6 +193,44 @@ def test_join_parity():
         assert got["groups"][0]["count"] == 0
 
 
+@pytest.mark.parametrize("jtype", [A.JOIN_LEFT, A.JOIN_RIGHT, A.JOIN_FULL])
+def test_outer_join_parity(jtype):
+    """LEFT / RIGHT / FULL joins (evaluator_joins.c:128-171): left rows without a match once with NULL right columns, in
+    place; right rows without a match behind everything, in right-file order, with NULL left columns."""
+    od, cd = _join_tables(20000, 3000, 23)
+    # keys without a partner on either side, NULL keys on both sides (NULL = NULL matches), spellings the reference equates
+    od += b"90001,1.00,0.10,1,\n90002,2.00,0.20,2,7.0\n90003,3.00,0.30,3,0007\n90004,4.00,0.40,4,999999\n"
+    cd += b",nokey,none@example.com,1999\n7.00,seven,s@example.com,1998\n888888,lonely,l@example.com,1997\n888889,lonely2,l2@example.com,1997\n"
+    lib_g, lib_o = gpu(), oracle()
+    with Table.from_bytes(od, lib=lib_g) as og, Table.from_bytes(cd, lib=lib_g) as cg, \
+            Table.from_bytes(od, lib=lib_o) as oo, Table.from_bytes(cd, lib=lib_o) as co:
+        specs = [
+            dict(aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_COUNT, 6), (A.AGG_SUM, 1), (A.AGG_MIN, 6), (A.AGG_MAX, 0)]),
+            dict(group_by=[8], out_cols=[8, 6, 0], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, 1), (A.AGG_MAX, 7)]),
+            dict(group_by=[4], out_cols=[4, 5, 6], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_MIN, 0), (A.AGG_MIN, 8)]),
+            dict(group_by=[6], out_cols=[6], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_AVG, 3)],
+                 where=("or", ("like", ("col", 6), ("const", "cust1%")), (">", ("col", 1), ("const", 900)))),
+            dict(mode="select", where=("or", (">", ("col", 1), ("const", 990)), (">", ("col", 5), ("const", 2990))),
+                 out_cols=[0, 4, 5, 6, 8]),
+            dict(mode="select", out_cols=[0, 6], max_rows=40),
+            dict(mode="select", where=("=", ("col", 8), ("const", 1997)), out_cols=[0, 1, 5, 6]),
+        ]
+        for spec in specs:
+            got = og.execute(pc.build(spec, join=(cg, 4, 0, jtype)))
+            want = oo.execute(pc.build(spec, join=(co, 4, 0, jtype)))
+            pc.compare_results(got, want)
+        # an unresolved key column matches nothing: LEFT keeps every left row once
+        if jtype == A.JOIN_LEFT:
+            got = og.execute(pc.build(specs[0], join=(cg, -1, 0, jtype)))
+            want = oo.execute(pc.build(specs[0], join=(co, -1, 0, jtype)))
+            pc.compare_results(got, want)
+            assert got["groups"][0]["count"] == og.row_count()
+        else:
+            with pytest.raises(CqError) as ei:
+                og.execute(pc.build(specs[0], join=(cg, -1, 0, jtype)))
+            assert ei.value.code == A.ERR_UNSUPPORTED_PLAN
+
+
 def test_parse_value_matches_oracle():
     lib_g, lib_o = gpu(), oracle()
     samples = [b"", b"1", b"007", b"-5", b"+8", b"3.25", b".5", b"5.", b"-0.0", b"1e5", b"-", b"abc", b" 12 ", b"12 3",
