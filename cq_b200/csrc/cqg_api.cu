@@ -1016,10 +1016,11 @@ static void set_file(DevPlan& P, const cqg_table* t, bool whole) {
     P.global_base = t->global_base;
     P.delim = (uint8_t)t->cfg.delimiter;
     P.quote = (uint8_t)t->cfg.quote;
-    // the mask fast path needs: quote below 0x23 (so "careful tile" detection sees it), a
-    // delimiter that is neither blank nor below 0x23, delimiter != quote
+    // the mask fast paths need: a quote that is '"' or a control byte (so that the "special byte" tests see it:
+    // kLeanSpecialXor in cqg_lean.cuh, and the general kernel's test for bytes below 0x23), a delimiter that is
+    // neither blank nor below 0x23, delimiter != quote
     unsigned d = P.delim, q = P.quote;
-    P.exact_only = (q >= 0x23u || d < 0x23u || d == q || d >= 0x80u) ? 1 : 0;
+    P.exact_only = (!(q == 0x22u || q < 0x20u) || d < 0x23u || d == q || d >= 0x80u) ? 1 : 0;
     if (hi > lo) {
         P.first_tile = (int32_t)(lo / ScanGeo::TILE);
         P.n_tiles = (int32_t)((hi - 1) / ScanGeo::TILE) - P.first_tile + 1;

@@ -122,6 +122,9 @@ __device__ __forceinline__ bool lean_key_part(uint32_t fa, uint32_t len, uint32_
     const bool numeric_start = (c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.';
     if (!numeric_start) {
         if (len > 16u) return false;
+        // a blank is an ordinary byte of a clean tile, but the reference trims the value (src/csv_reader.c:195-240):
+        // a field that starts or ends with one is decoded by the general kernel
+        if (c0 == ' ' || lds8(fa + len - 1u) == ' ') return false;
         const uint32_t a = fa & ~3u, sh = (fa & 3u) * 8u;
         const uint32_t x0 = lds32(a), x1 = lds32(a + 4), x2 = lds32(a + 8), x3 = lds32(a + 12), x4 = lds32(a + 16);
         uint64_t lo = ((uint64_t)__funnelshift_r(x1, x2, sh) << 32) | __funnelshift_r(x0, x1, sh);
@@ -327,6 +330,14 @@ constexpr int kLeanDictEntry = 96;  // hash 8 | gid 4 | tags 4 | first okey 8 | 
 __host__ __device__ constexpr int lean_agg_block(bool minmax) { return kLeanGroups * (minmax ? 32 : 12); }
 __host__ __device__ constexpr int lean_warp_acc(bool minmax) { return kLeanGroups * 4 + 4 * lean_agg_block(minmax); }
 
+// The bytes a lean tile may not hold (other than '\n'): controls (< 0x20: CR, tab, NUL ...) and the quote '"' (0x22).
+// The blank (0x20) and '!' (0x21) are ordinary bytes: a file with `New York` in it stays on the lean kernels. One
+// test covers both ranges: b ^ 0x02 maps 0x22 -> 0x20 and 0x20, 0x21 -> 0x22, 0x23 and keeps every control below
+// 0x20, so "special" is (b ^ 0x02) < 0x21 (and bit 7 clear). Plans whose quote character is anything else than '"'
+// or a control take the general kernel (DevPlan::exact_only).
+constexpr uint32_t kLeanSpecialXor = 0x02020202u;
+constexpr uint32_t kLeanSpecialSub = 0xdededEdfu;  // -0x21212121
+
 // a + c issued as IMAD (a * 1 + c) so that it runs on the FMA pipe: LOP3/IADD3/SHF all share the ALU pipe,
 // which takes one warp instruction every two cycles; phase 1 is otherwise all-ALU (B300_MICROARCH: pipe rates)
 __device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t one, uint32_t c) {
@@ -485,9 +496,11 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                 const uint32_t d1 = ~(add_fma((v.y ^ patDv) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.y) & 0x80808080u;
                 const uint32_t d2 = ~(add_fma((v.z ^ patDv) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.z) & 0x80808080u;
                 const uint32_t d3 = ~(add_fma((v.w ^ patDv) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | v.w) & 0x80808080u;
-                const uint32_t x0 = v.x | f0, x1 = v.y | f1, x2 = v.z | f2, x3 = v.w | f3;
-                spec |= (add_fma(x0, one, 0xdcdcdcddu) & ~x0) | (add_fma(x1, one, 0xdcdcdcddu) & ~x1) |
-                        (add_fma(x2, one, 0xdcdcdcddu) & ~x2) | (add_fma(x3, one, 0xdcdcdcddu) & ~x3);  // x - 0x23232323
+                // "special" bytes (kLeanSpecialXor): controls and the quote, not the blank; '\n' is lifted out of the way first
+                const uint32_t x0 = (v.x | f0) ^ kLeanSpecialXor, x1 = (v.y | f1) ^ kLeanSpecialXor, x2 = (v.z | f2) ^ kLeanSpecialXor,
+                               x3 = (v.w | f3) ^ kLeanSpecialXor;
+                spec |= (add_fma(x0, one, kLeanSpecialSub) & ~x0) | (add_fma(x1, one, kLeanSpecialSub) & ~x1) |
+                        (add_fma(x2, one, kLeanSpecialSub) & ~x2) | (add_fma(x3, one, kLeanSpecialSub) & ~x3);  // x - 0x21212121
                 sts16(s_tm + 2 * c, flags_to_mask16b(f0, f1, f2, f3));
                 sts16(s_dm + 2 * c, flags_to_mask16b(d0, d1, d2, d3));
             }
@@ -655,7 +668,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean_kernel(const __grid_con
                                     } else if (l > 16u) {
                                         const uint32_t c0 = lds8(s_buf + o);
                                         const bool ns = (c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.';
-                                        if (ns) ok = false;
+                                        if (ns || c0 == ' ' || lds8(s_buf + o + l - 1u) == ' ') ok = false;  // (trimmed by the reference)
                                         bv = kind == 2;  // longer than the literal: different
                                     } else if (lean_key_part(s_buf + o, l, tag, w0, w1) && (tag == KT_STR || tag == KT_NULL)) {
                                         // (the text NULL packs as KT_NULL with zero words: compare its bytes directly)

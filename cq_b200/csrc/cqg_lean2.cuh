@@ -2,7 +2,8 @@
 // COUNT / SUM / AVG over short decimals, WHERE empty or a postfix program of `column <op> decimal
 // literal` / `column = | != 'text'` leaves. Same tile pipeline as cqg_lean.cuh (1-D TMA tile -> SWAR
 // masks -> thread-owned row walk) with half the instructions per byte:
-//   * two byte classes only: T = "byte < 0x23" (every terminator, quote and blank) and D = delimiter.
+//   * two byte classes only: T = "special" (every control, i.e. every terminator, and the quote - not the blank,
+//     see kLeanSpecialXor in cqg_lean.cuh) and D = delimiter.
 //     Whether a T byte really is '\n' is checked once per ROW (one byte load at the row's end), not
 //     once per byte; a tile where any row ends in something else, holds an empty line, or hands over
 //     too many rows is DIRTY and goes to the general kernel as a whole (src/csv_reader.c:404-427 row
@@ -194,16 +195,17 @@ __host__ __device__ __forceinline__ uint32_t l2_dp4a(uint32_t a, uint32_t b, uin
 #endif
 }
 
-// phase 1 of the scalar lean kernel on one 16-byte chunk: bit i of `t16` = byte i is below 0x23 (every terminator,
-// quote, blank, control byte), bit i of `d16` = byte i is the delimiter (patD = it, in every byte). Bytes with
+// phase 1 of the scalar lean kernel on one 16-byte chunk: bit i of `t16` = byte i is special (a control byte, so every
+// terminator, or the quote '"'; kLeanSpecialXor), bit i of `d16` = byte i is the delimiter (patD = it, in every byte). Bytes with
 // bit 7 set (UTF-8) are neither. 3 instructions per word and class, then the 0x80 flags become mask bits
 // through four dot products per class (weights 1,2,4,8 | 16..128 leave mask << 7).
+// `kx`: kLeanSpecialXor, handed in so that the kernel can pin it in a register ((v ^ kx) & 0x7f.. is then ONE LOP3).
 __host__ __device__ __forceinline__ void lean2_masks16(uint32_t vx, uint32_t vy, uint32_t vz, uint32_t vw, uint32_t patD, uint32_t one,
-                                                       uint32_t& t16, uint32_t& d16) {
-    const uint32_t a0 = ~(l2_add(vx & 0x7f7f7f7fu, one, 0x5d5d5d5du) | vx) & 0x80808080u;
-    const uint32_t a1 = ~(l2_add(vy & 0x7f7f7f7fu, one, 0x5d5d5d5du) | vy) & 0x80808080u;
-    const uint32_t a2 = ~(l2_add(vz & 0x7f7f7f7fu, one, 0x5d5d5d5du) | vz) & 0x80808080u;
-    const uint32_t a3 = ~(l2_add(vw & 0x7f7f7f7fu, one, 0x5d5d5d5du) | vw) & 0x80808080u;
+                                                       uint32_t& t16, uint32_t& d16, uint32_t kx = kLeanSpecialXor) {
+    const uint32_t a0 = ~(l2_add((vx ^ kx) & 0x7f7f7f7fu, one, 0x5f5f5f5fu) | vx) & 0x80808080u;
+    const uint32_t a1 = ~(l2_add((vy ^ kx) & 0x7f7f7f7fu, one, 0x5f5f5f5fu) | vy) & 0x80808080u;
+    const uint32_t a2 = ~(l2_add((vz ^ kx) & 0x7f7f7f7fu, one, 0x5f5f5f5fu) | vz) & 0x80808080u;
+    const uint32_t a3 = ~(l2_add((vw ^ kx) & 0x7f7f7f7fu, one, 0x5f5f5f5fu) | vw) & 0x80808080u;
     const uint32_t d0 = ~(l2_add((vx ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vx) & 0x80808080u;
     const uint32_t d1 = ~(l2_add((vy ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vy) & 0x80808080u;
     const uint32_t d2 = ~(l2_add((vz ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vz) & 0x80808080u;
@@ -450,6 +452,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
     const uint32_t one = (uint32_t)P.simple;  // == 1, but not to the compiler: a + c as IMAD (FMA pipe), see add_fma
+    uint32_t kxor;
+    asm volatile("mov.u32 %0, %1;" : "=r"(kxor) : "n"(kLeanSpecialXor));  // opaque: stays in a register
     const int nwant = CQG_SPEC(NWANT, P.nwantL);
     const int gap0 = GAP0 >= 0 ? GAP0 : CQG_SPEC(GAP0, P.gap[0]), gap1 = CQG_SPEC(GAP1, P.gap[1]), gap2 = CQG_SPEC(GAP2, P.gap[2]),
               gap3 = CQG_SPEC(GAP3, P.gap[3]);
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
             auto chunk = [&](uint32_t ca, uint32_t ma) {
                 const uint4 v = lds128(ca);
                 uint32_t ra, rd;
-                lean2_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd);
+                lean2_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd, kxor);
                 sts16(ma, ra);
                 sts16(ma + 4u, rd);
             };
@@ -687,7 +691,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                                         } else if (l > 16u) {
                                             const uint32_t c0 = lds8(rbase + o);
                                             const bool ns = (c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.';
-                                            if (ns) ok = false;
+                                            if (ns || c0 == ' ' || lds8(rbase + o + l - 1u) == ' ') ok = false;  // (trimmed by the reference)
                                             bv = kind == 2;
                                         } else if (lean_key_part(rbase + o, l, tag, w0, w1) && (tag == KT_STR || tag == KT_NULL)) {
                                             if (tag == KT_NULL) {

@@ -41,9 +41,10 @@ struct Lean2GLayout {
 __device__ __forceinline__ uint32_t l2g_hash_word(uint32_t h, uint32_t x) { return (h ^ x) * 0x9E3779B1u; }
 
 // phase 1 on one 16-byte chunk: bit i of `n16` = byte i is '\n', of `d16` = byte i is the delimiter; the return value
-// has a 0x80 bit set when the chunk holds any OTHER byte below 0x23 (CR, quote, blank, NUL ...: the tile is then left
-// to the general kernel). x - 0x23 per byte borrows into bit 7 exactly where the byte is below 0x23 and bit 7 clear
-// ('\n' bytes are lifted out of the way first); a borrow that crosses into the next byte can only ADD a flag.
+// has a 0x80 bit set when the chunk holds any OTHER special byte (a control - CR, tab, NUL ... - or the quote '"'; the
+// blank is an ordinary byte; kLeanSpecialXor in cqg_lean.cuh): the tile is then left to the general kernel.
+// (b ^ 0x02) - 0x21 per byte borrows into bit 7 exactly where the byte is special and bit 7 clear ('\n' bytes are
+// lifted out of the way first); a borrow that crosses into the next byte can only ADD a flag.
 __host__ __device__ __forceinline__ uint32_t l2g_masks16(uint32_t vx, uint32_t vy, uint32_t vz, uint32_t vw, uint32_t patD, uint32_t one,
                                                          uint32_t& n16, uint32_t& d16) {
     const uint32_t f0 = ~(l2_add((vx ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vx) & 0x80808080u;
@@ -54,9 +55,10 @@ __host__ __device__ __forceinline__ uint32_t l2g_masks16(uint32_t vx, uint32_t v
     const uint32_t d1 = ~(l2_add((vy ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vy) & 0x80808080u;
     const uint32_t d2 = ~(l2_add((vz ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vz) & 0x80808080u;
     const uint32_t d3 = ~(l2_add((vw ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vw) & 0x80808080u;
-    const uint32_t x0 = vx | f0, x1 = vy | f1, x2 = vz | f2, x3 = vw | f3;
-    const uint32_t spec = (l2_add(x0, one, 0xdcdcdcddu) & ~x0) | (l2_add(x1, one, 0xdcdcdcddu) & ~x1) |
-                          (l2_add(x2, one, 0xdcdcdcddu) & ~x2) | (l2_add(x3, one, 0xdcdcdcddu) & ~x3);
+    const uint32_t x0 = (vx | f0) ^ kLeanSpecialXor, x1 = (vy | f1) ^ kLeanSpecialXor, x2 = (vz | f2) ^ kLeanSpecialXor,
+                   x3 = (vw | f3) ^ kLeanSpecialXor;
+    const uint32_t spec = (l2_add(x0, one, kLeanSpecialSub) & ~x0) | (l2_add(x1, one, kLeanSpecialSub) & ~x1) |
+                          (l2_add(x2, one, kLeanSpecialSub) & ~x2) | (l2_add(x3, one, kLeanSpecialSub) & ~x3);
     uint32_t ra = l2_dp4a(f2, 0x08040201u, 0u);
     ra = l2_dp4a(f3, 0x80402010u, ra) * 256u;
     ra = l2_dp4a(f0, 0x08040201u, ra);
@@ -120,6 +122,7 @@ __device__ __forceinline__ bool l2g_key_part(uint32_t fa, uint32_t len, uint32_t
         return k.ok != 0u;
     }
     if (len > 16u) return false;
+    if (c0 == ' ' || lds8(fa + len - 1u) == ' ') return false;  // trimmed by the reference: the general kernel's business
     const uint32_t a = fa & ~3u, sh = fa << 3;
     const uint32_t x0 = lds32(a), x1 = lds32(a + 4), x2 = lds32(a + 8), x3 = lds32(a + 12), x4 = lds32(a + 16);
     const uint4 m = lds128(s_kmask + 16u * len);
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
                                 } else if (l > 16u) {
                                     const uint32_t c0 = lds8(rbase + o);
                                     const bool ns = (c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.';
-                                    if (ns) ok = false;
+                                    if (ns || c0 == ' ' || lds8(rbase + o + l - 1u) == ' ') ok = false;  // (trimmed by the reference)
                                     bv = kind == 2;
                                 } else if (l2g_key_part(rbase + o, l, sbase + LL::OFF_KMASK, tag, w0, w1) && (tag == KT_STR || tag == KT_NULL)) {
                                     if (tag == KT_NULL) {

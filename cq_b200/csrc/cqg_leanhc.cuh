@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) leanhc_kernel(const __grid_c
                                 } else if (l > 16u) {
                                     const uint32_t c0 = lds8(rbase + o);
                                     const bool ns = (c0 - 48u) <= 9u || c0 == '+' || c0 == '-' || c0 == '.';
-                                    if (ns) ok = false;
+                                    if (ns || c0 == ' ' || lds8(rbase + o + l - 1u) == ' ') ok = false;  // (trimmed by the reference)
                                     bv = kind == 2;
                                 } else if (l2g_key_part(rbase + o, l, sbase + LL::OFF_KMASK, tag, w0, w1) && (tag == KT_STR || tag == KT_NULL)) {
                                     if (tag == KT_NULL) {

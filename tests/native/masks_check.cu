@@ -27,7 +27,7 @@ static long long check(const unsigned char* b, unsigned char delim) {
     lean2_masks16(w[0], w[1], w[2], w[3], (uint32_t)delim * 0x01010101u, 1u, t16, d16);
     uint32_t et = 0, ed = 0;
     for (int i = 0; i < 16; i++) {
-        if (b[i] < 0x23) et |= 1u << i;
+        if (b[i] < 0x20 || b[i] == 0x22) et |= 1u << i;  // special: controls and the quote, not the blank
         if (b[i] == delim) ed |= 1u << i;
     }
     // the GROUP BY kernel's phase 1: exact '\n' class, delimiter class, and "any other byte below 0x23" (which may
@@ -37,7 +37,7 @@ static long long check(const unsigned char* b, unsigned char delim) {
     const uint32_t spec = l2g_masks16(w[0], w[1], w[2], w[3], (uint32_t)delim * 0x01010101u, 1u, n16, d16g) & 0x80808080u;
     for (int i = 0; i < 16; i++) {
         if (b[i] == '\n') en |= 1u << i;
-        if (b[i] < 0x23 && b[i] != '\n') dirty = true;
+        if ((b[i] < 0x20 || b[i] == 0x22) && b[i] != '\n') dirty = true;
     }
     if (n16 != en || d16g != ed || (dirty && spec == 0u)) {
         printf("MISMATCH (GROUP BY phase 1) delimiter %02x bytes", delim);

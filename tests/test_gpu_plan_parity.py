@@ -495,6 +495,45 @@ def test_scalar_lean_kernel_dirty_tiles(kind):
                 pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
 
 
+@pytest.mark.parametrize("dense", [True, False])
+def test_blanks_are_ordinary_bytes_on_the_lean_kernels(dense):
+    """Real CSV has blanks (`New York`, `2024-01-01 10:00`): a blank no longer sends a tile to the general kernel
+    (kLeanSpecialXor, cqg_lean.cuh). Interior blanks stay in keys and text literals as they are; a field that STARTS or
+    ENDS with one is trimmed by the reference (src/csv_reader.c:195-240) and must come out that way (those rows are
+    handed over). Every lean kernel: scalar, few groups, few groups with MIN/MAX, many groups."""
+    rnd = random.Random(9)
+    cities = ["New York", "San Jose", "Rio", "Los Angeles", " Lima", "Oslo ", "  ", "St. John s", "Quito"]
+    rows = ["city,zone,age,height"]
+    n = 60_000
+    for i in range(n):
+        city = rnd.choice(cities) if (dense or i % 211 == 3) else rnd.choice(["Rio", "Quito", "Bonn"])
+        zone = f"z{rnd.randint(0, 40 if dense else 3000)}"
+        age = str(rnd.randint(10, 80))
+        if i % 503 == 7:
+            age = " " + age
+        if i % 509 == 9:
+            age = age + " "
+        height = f"{rnd.randint(100, 200) / 100}"
+        rows.append(f"{city},{zone},{age},{height}")
+    data = ("\n".join(rows) + "\n").encode()
+    CITY, ZONE, AGE_, H = range(4)
+    specs = [
+        dict(where=(">", ("col", AGE_), ("const", 40)), aggs=[(A.AGG_COUNT_STAR, -1)]),
+        dict(where=("=", ("col", CITY), ("const", "New York")), aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE_)]),
+        dict(where=("!=", ("col", CITY), ("const", "Lima")), aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_AVG, H)]),
+        dict(where=("=", ("col", CITY), ("const", "Oslo")), aggs=[(A.AGG_COUNT_STAR, -1)]),
+        dict(where=(">", ("col", AGE_), ("const", 25)), group_by=[CITY], out_cols=[CITY],
+             aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_AVG, H), (A.AGG_SUM, AGE_)]),
+        dict(group_by=[CITY], out_cols=[CITY], aggs=[(A.AGG_MIN, H), (A.AGG_MAX, AGE_), (A.AGG_COUNT_STAR, -1)]),
+        dict(group_by=[CITY, ZONE], out_cols=[CITY, ZONE], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE_), (A.AGG_MAX, H)]),
+        dict(group_by=[CITY, ZONE, AGE_], out_cols=[CITY, ZONE, AGE_], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, AGE_)]),
+    ]
+    with Table.from_bytes(data, lib=gpu()) as tg, Table.from_bytes(data, lib=oracle()) as to:
+        assert tg.row_count() == to.row_count() == n
+        for spec in specs:
+            pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
+
+
 @pytest.mark.parametrize("world", [2, 5])
 def test_hash_partitioned_join(world):
     """BASELINE config 5 on one device: `world` simulated ranks split the row offsets of their shards by key
