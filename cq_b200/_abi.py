@@ -143,6 +143,7 @@ PROTOTYPES = {
                                          C.POINTER(C.c_size_t)]),
     "generate_bigdata_bound": (C.c_size_t, [C.c_int64, C.c_int64]),
     "total_kernel_launches": (C.c_int64, []),
+    "kernel_launches_named": (C.c_int64, [C.c_char_p]),
 }
 
 

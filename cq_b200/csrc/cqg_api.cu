@@ -25,6 +25,7 @@
 #include <thread>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -33,6 +34,7 @@
 #include "cqg_lean.cuh"
 #include "cqg_lean2.cuh"
 #include "cqg_lean2g.cuh"
+#include "cqg_lean2k.cuh"
 #include "cqg_leanhc.cuh"
 
 using namespace cqg;
@@ -62,6 +64,15 @@ static int fail(int code, const char* fmt, ...) {
 CQG_API const char* cqg_last_error(void) { return g_err; }
 CQG_API int cqg_abi_version(void) { return 1; }
 CQG_API int64_t cqg_total_kernel_launches(void) { return g_launches.load(); }
+// launches per scan kernel family (tests assert that the kernel a plan is meant for is the one that ran)
+enum { KF_SCAN = 0, KF_LEAN, KF_LEAN2, KF_LEAN2G, KF_LEAN2K, KF_LEANHC, KF_COUNT };
+static std::atomic<int64_t> g_family[KF_COUNT];
+static const char* const kFamilyName[KF_COUNT] = {"scan", "lean", "lean2", "lean2g", "lean2k", "leanhc"};
+CQG_API int64_t cqg_kernel_launches_named(const char* family) {
+    for (int k = 0; k < KF_COUNT; k++)
+        if (family && !strcmp(family, kFamilyName[k])) return g_family[k].load();
+    return -1;
+}
 
 CQG_API int cqg_device_count(void) {
     int n = 0;
@@ -143,6 +154,13 @@ struct cqg_table {
     mutable bool sample_ready = false;
     bool src_pinned = false;  // h_data is page-locked: DMA straight from it
     int fd = -1;              // the mapped file, kept open: staging reads it with pread (no page faults on the mapping)
+    // explicit ownership range of a scan (overrides the equal shards): the bytes one GPU of a multi-GPU table holds
+    uint64_t range_lo = 0, range_hi = 0;
+    // multi-GPU residency (CQ_GPUS, cqg_multi below): one virtual address range, slice d physically on device d
+    int ngpu = 0;
+    uint64_t va_size = 0;
+    std::vector<unsigned long long> vmm_handles;
+    std::vector<uint64_t> cuts;  // ngpu + 1 byte offsets: device d holds [cuts[d], cuts[d + 1])
 };
 
 static inline bool host_is_space(unsigned c) { return c == 32u || (c - 9u) <= 4u; }
@@ -280,46 +298,37 @@ struct StagePool {
 };
 static StagePool g_stage[64];
 
-static int stage_to_device(cqg_table* t, const uint8_t* src, size_t size, bool pinned) {
-    // stream-ordered allocation from the device pool (kept warm: release threshold is unlimited)
-    CU(cudaMallocAsync((void**)&t->d_data, size + kDevPad, 0));
-    t->owns_device = true;
-    CU(cudaMemsetAsync(t->d_data + size, '\n', kDevPad, 0));
-    if (pinned) {
-        CU(cudaMemcpyAsync(t->d_data, src, size, cudaMemcpyHostToDevice, 0));
-        CU(cudaStreamSynchronize(0));
-        return CQG_OK;
-    }
-    CU(cudaStreamSynchronize(0));  // the allocation is ordered on stream 0, the copies run on streams of their own
+// host bytes [off, off + n) of the table -> device memory at dst, on the CURRENT device (its own bounce buffers and
+// streams): several threads, each with two buffers
+static int copy_host_range(const cqg_table* t, const uint8_t* src, uint64_t off0, size_t n_total, uint8_t* dst) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
     StagePool& sp = g_stage[dev & 63];
     std::lock_guard<std::mutex> lock(sp.mu);
     constexpr size_t chunk = StagePool::kChunk;
-    const size_t nchunks = (size + chunk - 1) / chunk;
+    const size_t nchunks = (n_total + chunk - 1) / chunk;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     int want = (int)std::min<size_t>(std::min<size_t>(StagePool::kThreads, hw), std::max<size_t>(1, nchunks / 2));
     const int T = sp.prepare(want);
     if (T < 1) return fail(CQG_ERR_CUDA, "page-locked staging buffers: allocation failed");
     std::atomic<int> bad{0};
-    uint8_t* dst = t->d_data;
     auto work = [&](int k) {
         cudaSetDevice(dev);
         int b = 0;
         for (size_t c = (size_t)k; c < nchunks && !bad.load(); c += (size_t)T, b ^= 1) {
-            const size_t off = c * chunk, n = std::min(chunk, size - off);
+            const size_t off = c * chunk, n = std::min(chunk, n_total - off);
             if (cudaEventSynchronize(sp.ev[k][b]) != cudaSuccess) bad = 1;  // the copy that last used this buffer
             bool have = false;
             if (t->fd >= 0) {  // page cache -> bounce buffer in the kernel: no per-page faults on the mapping
                 size_t got = 0;
                 while (got < n) {
-                    const ssize_t r = pread(t->fd, sp.bounce[k][b] + got, n - got, (off_t)(off + got));
+                    const ssize_t r = pread(t->fd, sp.bounce[k][b] + got, n - got, (off_t)(off0 + off + got));
                     if (r <= 0) break;
                     got += (size_t)r;
                 }
                 have = got == n;
             }
-            if (!have) memcpy(sp.bounce[k][b], src + off, n);
+            if (!have) memcpy(sp.bounce[k][b], src + off0 + off, n);
             if (cudaMemcpyAsync(dst + off, sp.bounce[k][b], n, cudaMemcpyHostToDevice, sp.stream[k]) != cudaSuccess) bad = 1;
             cudaEventRecord(sp.ev[k][b], sp.stream[k]);
         }
@@ -334,6 +343,20 @@ static int stage_to_device(cqg_table* t, const uint8_t* src, size_t size, bool p
     }
     if (bad.load()) return fail(CQG_ERR_CUDA, "host to device staging: %s", cudaGetErrorString(cudaGetLastError()));
     return CQG_OK;
+}
+
+static int stage_to_device(cqg_table* t, const uint8_t* src, size_t size, bool pinned) {
+    // stream-ordered allocation from the device pool (kept warm: release threshold is unlimited)
+    CU(cudaMallocAsync((void**)&t->d_data, size + kDevPad, 0));
+    t->owns_device = true;
+    CU(cudaMemsetAsync(t->d_data + size, '\n', kDevPad, 0));
+    if (pinned) {
+        CU(cudaMemcpyAsync(t->d_data, src, size, cudaMemcpyHostToDevice, 0));
+        CU(cudaStreamSynchronize(0));
+        return CQG_OK;
+    }
+    CU(cudaStreamSynchronize(0));  // the allocation is ordered on stream 0, the copies run on streams of their own
+    return copy_host_range(t, src, 0, size, t->d_data);
 }
 
 // tables opened from host bytes are uploaded when a query first needs them: a statement whose shape is then
@@ -489,6 +512,7 @@ static int launch_scan_nw(const DevPlan& P, int smem, int dev, cudaStream_t st) 
     int grid = std::min(P.n_tiles, c.sms * per_sm);
     scan_kernel<ScanGeo, NW><<<grid, ScanGeo::THREADS, smem, st>>>(P);
     g_launches++;
+    g_family[KF_SCAN]++;
     CU(cudaGetLastError());
     return CQG_OK;
 }
@@ -704,6 +728,7 @@ static std::string lean_shape_defs(const cqg::DevPlan& P) {
     def("GAP2", P.gap[2]);
     def("GAP3", P.gap[3]);
     def("NPROG", P.l_nprog);
+    def("NLEAF", P.l_nleaf);
     def("NGC", P.ngc);
     def("NAGG", P.l_nagg);
     def_at("PROG", P.l_nprog, [&](int i) { return (int)P.l_prog[i]; });
@@ -761,6 +786,7 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
             if (cudaFuncSetAttribute((const void*)jk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
                 cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
                 g_launches++;
+    g_family[KF_LEAN]++;
                 return CQG_OK;
             }
             cudaGetLastError();
@@ -768,6 +794,7 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
     }
     lean_kernel<LG, MINB, GROUPED, ONELEAF, MINMAX><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
+    g_family[KF_LEAN]++;
     CU(cudaGetLastError());
     return CQG_OK;
 }
@@ -802,6 +829,7 @@ static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
             void* args[] = {(void*)&P};
             if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
                 g_launches++;
+    g_family[KF_LEAN2]++;
                 return CQG_OK;
             }
             cudaGetLastError();
@@ -809,6 +837,7 @@ static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
     }
     lean2_kernel<LG, MINB, ONELEAF, GAP0><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
+    g_family[KF_LEAN2]++;
     CU(cudaGetLastError());
     return CQG_OK;
 }
@@ -841,13 +870,59 @@ static int launch_lean2g_geo(const DevPlan& P0, cudaStream_t st) {
         void* args[] = {(void*)&P};
         if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
             g_launches++;
+    g_family[KF_LEAN2G]++;
             return CQG_OK;
         }
         cudaGetLastError();
     }
     lean2g_kernel<LG, MINB><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
+    g_family[KF_LEAN2G]++;
     CU(cudaGetLastError());
+    return CQG_OK;
+}
+
+// lean2k_kernel (cqg_lean2k.cuh) exists only compiled for the query's shape. *launched = 0: no run-time compiler (or the
+// shape does not compile): the caller runs lean2g_kernel instead.
+template <class LG, int MINB>
+static int launch_lean2k_geo(const DevPlan& P0, cudaStream_t st, int* launched) {
+    *launched = 0;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    DevPlan P = P0;
+    if (P.own_hi > P.own_lo) {
+        P.first_tile = (int32_t)(P.own_lo / LG::TILE);
+        P.n_tiles = (int32_t)((P.own_hi - 1) / LG::TILE) - P.first_tile + 1;
+    }
+    if (P.n_tiles <= 0) {
+        *launched = 1;
+        return CQG_OK;
+    }
+    const int smem = Lean2KLayout<LG>::TOTAL;  // tile + masks + dictionary + thread-private accumulators
+    LaunchCfg& c = g_cfg[dev & 63];
+    if (!c.ready) {
+        CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+        c.ready = true;
+    }
+    char name[160];
+    snprintf(name, sizeof name, "cqg::lean2k_kernel<cqg::Geo<%d, %d, %d, %d>, %d>", LG::THREADS, LG::TILE, LG::STAGES, LG::OVER, MINB);
+    cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean2k.cuh", name, P.own_hi - P.own_lo);
+    if (!jk) return CQG_OK;
+    int per_sm = 0;
+    if (cudaFuncSetAttribute((const void*)jk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)jk, LG::THREADS, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return CQG_OK;
+    }
+    const int grid = std::min(P.n_tiles, c.sms * per_sm);
+    void* args[] = {(void*)&P};
+    if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) != cudaSuccess) {
+        cudaGetLastError();
+        return CQG_OK;
+    }
+    g_launches++;
+    g_family[KF_LEAN2K]++;
+    *launched = 1;
     return CQG_OK;
 }
 
@@ -867,27 +942,25 @@ static int launch_leanhc_geo(const DevPlan& P0, cudaStream_t st) {
         CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
         c.ready = true;
     }
-    // the same kernel compiled for this query's shape, when the run-time compiler is there (else the generic one)
-    char name[160];
-    snprintf(name, sizeof name, "cqg::leanhc_kernel<cqg::Geo<%d, %d, %d, %d>, %d>", LG::THREADS, LG::TILE, LG::STAGES, LG::OVER, MINB);
-    if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_leanhc.cuh", name, P.own_hi - P.own_lo)) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)jk, LG::THREADS, smem) == cudaSuccess && per_sm >= 1) {
-            const int grid = std::min(P.n_tiles, c.sms * per_sm);
-            void* args[] = {(void*)&P};
-            if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
-                g_launches++;
-                return CQG_OK;
-            }
-        }
-        cudaGetLastError();
-    }
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leanhc_kernel<LG, MINB>, LG::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "leanhc kernel does not fit");
     const int grid = std::min(P.n_tiles, c.sms * per_sm);
+    // the same kernel compiled for this query's shape, when the run-time compiler is there (else the generic one)
+    char name[160];
+    snprintf(name, sizeof name, "cqg::leanhc_kernel<cqg::Geo<%d, %d, %d, %d>, %d>", LG::THREADS, LG::TILE, LG::STAGES, LG::OVER, MINB);
+    if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_leanhc.cuh", name, P.own_hi - P.own_lo)) {
+        void* args[] = {(void*)&P};
+        if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
+            g_launches++;
+    g_family[KF_LEANHC]++;
+            return CQG_OK;
+        }
+        cudaGetLastError();
+    }
     leanhc_kernel<LG, MINB><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
+    g_family[KF_LEANHC]++;
     CU(cudaGetLastError());
     return CQG_OK;
 }
@@ -904,7 +977,17 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
         for (int a = 0; a < P.l_nagg; a++) mm = mm || P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX;
         if (P.lean_global) return launch_leanhc_geo<Geo<128, 16384, 1, 224>, 6>(P, st);  // many groups: packed global table
         if (mm) return launch_lean_geo<Geo<128, 16384, 1>, 4, true, false, true>(P, st);
-        if (env_int("CQG_LEAN2", 1)) return launch_lean2g_geo<Geo<128, 16384, 1, 224>, 6>(P, st);  // few groups, COUNT/SUM/AVG
+        if (env_int("CQG_LEAN2", 1)) {  // few groups, COUNT/SUM/AVG
+            if (P.lean_k) {  // one text key, <= 16 groups: the written-out loop, compiled for the query
+                int launched = 0;
+                const int minb = env_int("CQG_L2K_MINB", 8);  // CTAs per SM the kernel is compiled for (A/B runs)
+                const int rc = minb == 6   ? launch_lean2k_geo<Geo<128, 16384, 1, 224>, 6>(P, st, &launched)
+                               : minb == 8 ? launch_lean2k_geo<Geo<128, 16384, 1, 224>, 8>(P, st, &launched)
+                                           : launch_lean2k_geo<Geo<128, 16384, 1, 224>, 7>(P, st, &launched);
+                if (rc || launched) return rc;
+            }
+            return launch_lean2g_geo<Geo<128, 16384, 1, 224>, 6>(P, st);
+        }
         return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false>(P, st);
     }
     const bool oneleaf = P.l_nprog == 1 && P.l_nleaf == 1 && P.l_leaf[0].kind == 0 && P.l_leaf[0].slot == 0 && P.l_nagg == 0 &&
@@ -984,6 +1067,7 @@ struct HostPlan {
     std::vector<uint8_t> packed_init;  // image of an empty packed line (lean GROUP BY, global mode)
     DevBuf d_packed_init;
     bool start_global = false;  // the sampled rows already hold more distinct keys than a CTA dictionary numbers
+    bool few_text_keys = false; // one key column, and the sampled rows hold <= 16 distinct keys, all of them plain text
 };
 
 struct ScalarBlock {
@@ -994,6 +1078,12 @@ struct ScalarBlock {
 };
 
 static void shard_range(const cqg_table* t, uint64_t& lo, uint64_t& hi) {
+    if (t->range_hi > t->range_lo) {
+        lo = std::max<uint64_t>(t->range_lo, t->data_start);
+        hi = std::min<uint64_t>(t->range_hi, t->size);
+        if (hi < lo) hi = lo;
+        return;
+    }
     unsigned __int128 sz = t->size;
     lo = (uint64_t)(sz * (unsigned)t->shard_index / (unsigned)t->shard_count);
     hi = (uint64_t)(sz * (unsigned)(t->shard_index + 1) / (unsigned)t->shard_count);
@@ -1454,7 +1544,19 @@ static void layout_packed(HostPlan& hp, const cqg_table* t) {
         // more distinct keys in the sample than a CTA dictionary numbers: start in global mode (a guess that costs
         // or saves one aborted launch, nothing else)
         std::sort(keys.begin(), keys.end());
-        hp.start_global = (size_t)(std::unique(keys.begin(), keys.end()) - keys.begin()) >= 48;
+        const size_t distinct = (size_t)(std::unique(keys.begin(), keys.end()) - keys.begin());
+        hp.start_global = distinct >= 48;
+        // lean2k_kernel: one key column of plain text (what cannot start a number, no blank at either end, <= 16 bytes)
+        // with few values. Again only a guess about where to start: the kernels check every row themselves.
+        bool plain = P.ngc == 1 && P.gslot[0] >= 0 && rows > 0 && distinct <= (size_t)kL2KGroups;
+        for (size_t k = 0; plain && k < distinct; k++) {
+            const std::string& key = keys[k];
+            const size_t n = key.size() ? key.size() - 1 : 0;  // (the trailing NUL of the key part)
+            if (n == 0) continue;
+            const unsigned char c0 = (unsigned char)key[0], c1 = (unsigned char)key[n - 1];
+            if (n > 16 || (c0 >= '0' && c0 <= '9') || c0 == '+' || c0 == '-' || c0 == '.' || c0 == ' ' || c1 == ' ') plain = false;
+        }
+        hp.few_text_keys = plain;
     }
     int w = 1;  // word 0: state / first okey | tags
     for (int g = 0; g < P.ngc; g++) {
@@ -2465,6 +2567,16 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     P.def_row_cap = row_cap;
     P.tile_list = nullptr;
     P.lean_global = (hp.start_global && P.pk.entry_bytes && env_int("CQG_START_GLOBAL", 1)) ? 1 : 0;
+    P.lean_k = 0;
+    if (!P.lean_global && hp.few_text_keys && P.ngc == 1 && P.l_nagg <= 3 && env_int("CQG_LEAN2K", 1)) {
+        bool fits = true;
+        for (int a = 0; a < P.l_nagg; a++) {
+            const int f = P.aggs[P.l_agg[a]].func;
+            fits = fits && (f == CQG_AGG_SUM || f == CQG_AGG_AVG);
+        }
+        for (int c = 0; c < P.l_nleaf; c++) fits = fits && P.l_leaf[c].kind == 0;
+        P.lean_k = fits ? 1 : 0;
+    }
     P.ptab = nullptr;
     P.pcap = 0;
     P.hc_debug = env_int("CQG_HC_DEBUG", 0);
@@ -2492,6 +2604,10 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         *ms_out += ms;
+        if (P.lean_k && (hs.errflags & (KERR_LEAN_GROUPS | KERR_LEAN_ABORT))) {
+            P.lean_k = 0;  // more than 16 groups in a CTA, or rows lean2k_kernel does not take: lean2g_kernel next
+            continue;
+        }
         if ((hs.errflags & KERR_LEAN_GROUPS) && !P.lean_global && P.pk.entry_bytes) {
             P.lean_global = 1;  // too many groups for per-CTA numbering
             cap = initial_group_cap(P);

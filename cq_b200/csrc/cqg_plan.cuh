@@ -156,7 +156,7 @@ struct DevPlan {
 
     // ---- lean kernel plans (cqg_lean.cuh): 1 = no GROUP BY, 2 = GROUP BY; 0 = general kernel only ----
     int32_t simple;
-    int32_t lean_pad;
+    int32_t lean_k;       // lean GROUP BY, few groups: try lean2k_kernel (cqg_lean2k.cuh) before lean2g_kernel
     // lean kernel WHERE: postfix program over up to kMaxLeanLeaf leaves. Leaf kinds:
     //   0  column <op> decimal literal   (mant * A[fd] vs LB[fd]; lop 0 >, 1 <, 2 ==, 3 !=)
     //   1  column =  'text'  /  2  column != 'text'   (text of 1..16 bytes, packed like a key part)

@@ -370,6 +370,9 @@ size_t cqg_generate_bigdata_bound(int64_t rows, int64_t key_card);
 /* ---- introspection for bench.py ---- */
 /* total kernels launched by this library in this process */
 int64_t cqg_total_kernel_launches(void);
+/* launches of one scan kernel family so far: "scan" (general), "lean", "lean2", "lean2g", "lean2k", "leanhc"
+ * (cq_b200/csrc/cqg_*.cuh); -1: no such family. Tests use it to assert which kernel a plan ran on. */
+int64_t cqg_kernel_launches_named(const char* family);
 
 #ifdef __cplusplus
 }

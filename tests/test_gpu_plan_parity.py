@@ -534,6 +534,74 @@ def test_blanks_are_ordinary_bytes_on_the_lean_kernels(dense):
             pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
 
 
+def _few_groups_table(n, seed, keys, odd_every=0):
+    """role-like key column (few values) + age / score / price columns; every `odd_every` rows one of the things the
+    written-out few-groups loop (cqg_lean2k.cuh) must hand over, count as NULL, or number as a group of its own."""
+    rnd = random.Random(seed)
+    rows = ["id,role,age,score,price,note"]
+    odd = ["", "NULL", " lead", "lead ", "7", "07", "7.0", "2024-01-05", "-3", "seventeen-bytes-xx", "sixteen-bytes-xxx", "new york"]
+    for i in range(n):
+        role = rnd.choice(keys)
+        age = str(rnd.randint(0, 99))
+        score = rnd.choice(["1.5", "2", "0.25", "10.5", "99", "7.", ".5", "100", "1234", "3.12"])
+        price = rnd.choice(["12345", "99999.9", "1234.56", "1000000", "5", "0.125"])
+        note = rnd.choice(["x", "yy", "a longer note that makes the row wide", "z" * 70])
+        if odd_every and i % odd_every == 3:
+            k = (i // odd_every) % 6
+            if k == 0:
+                role = odd[(i // odd_every // 6) % len(odd)]
+            elif k == 1:
+                age = rnd.choice(["", "NULL", "abc", "-5", "1e2"])
+            elif k == 2:
+                score = rnd.choice(["", "1.2345", "x"])
+            elif k == 3:
+                price = rnd.choice(["", "12345678", "1.5e3"])
+            elif k == 4:
+                rows.append(f"{i},{role}")  # ragged
+                continue
+            else:
+                rows.append("")  # empty line
+        rows.append(f"{i},{role},{age},{score},{price},{note}")
+    return ("\n".join(rows) + "\n").encode()
+
+
+@pytest.mark.parametrize("case", ["plain", "odd_rows", "seventeen_groups", "forty_groups"])
+def test_few_groups_written_out_loop(case):
+    """lean2k_kernel (cqg_lean2k.cuh): one text key, COUNT / SUM / AVG, decimal leaves. Keys are grouped by their raw bytes
+    per CTA and made canonical once per group: blanks at either end, the text NULL, empty keys, "7" / "07" / "7.0", dates
+    and 17-byte keys must come out as the reference groups them; NULL and 5..7-byte operands, wide and ragged rows; a 17th
+    group in a CTA moves the scan to lean2g_kernel, a 33rd to the global table."""
+    roles = ["admin", "user", "guest", "moderator"]
+    if case == "seventeen_groups":
+        roles = [f"role{k}" for k in range(17)]
+    elif case == "forty_groups":
+        roles = [f"r{k}" for k in range(40)]
+    data = _few_groups_table(120_000, 11, roles, odd_every=0 if case == "plain" else 97)
+    if case in ("seventeen_groups", "forty_groups"):
+        # the planner samples the head of the file: keep it to few keys so that the scan STARTS on lean2k_kernel
+        head = _few_groups_table(600, 12, ["admin", "user"])
+        data = head + data[data.index(b"\n") + 1:]
+    ID, ROLE, AGE_, SCORE, PRICE, NOTE = range(6)
+    specs = [
+        dict(where=(">", ("col", AGE_), ("const", 25)), group_by=[ROLE], out_cols=[ROLE],
+             aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_AVG, AGE_)]),
+        dict(group_by=[ROLE], out_cols=[ROLE, ID], aggs=[(A.AGG_COUNT_STAR, -1), (A.AGG_SUM, SCORE), (A.AGG_AVG, PRICE), (A.AGG_SUM, AGE_)]),
+        dict(where=("or", ("<", ("col", SCORE), ("const", 1)), ("not", (">=", ("col", AGE_), ("const", 50)))), group_by=[ROLE],
+             out_cols=[ROLE], aggs=[(A.AGG_SUM, PRICE), (A.AGG_COUNT, NOTE)]),
+        dict(where=("!=", ("col", AGE_), ("const", 33)), group_by=[ROLE], out_cols=[ROLE]),
+    ]
+    lib = gpu()
+    with Table.from_bytes(data, lib=lib) as tg, Table.from_bytes(data, lib=oracle()) as to:
+        before = lib.kernel_launches_named(b"lean2k")
+        for spec in specs:
+            pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
+        assert lib.kernel_launches_named(b"lean2k") >= before + len(specs)  # (needs libnvrtc: the kernel is compiled per query)
+        for i in range(3):
+            tg.set_shard(i, 3)
+            to.set_shard(i, 3)
+            pc.compare_results(tg.execute(pc.build(specs[1])), to.execute(pc.build(specs[1])))
+
+
 @pytest.mark.parametrize("world", [2, 5])
 def test_hash_partitioned_join(world):
     """BASELINE config 5 on one device: `world` simulated ranks split the row offsets of their shards by key
