@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
                             }
                         }
                     }
-                    // ---- WHERE ----
+                    // ---- WHERE and the SUM / AVG operands (value * 1000, exact), written for the common row: every operand
+                    // a decimal of <= 4 bytes (state 0). Anything else is put right in the cold block below. ----
                     bool pass = true;
                     if (nprog) {
                         uint32_t bs = 0;
@@ -345,7 +346,6 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
                             if (c >= 0) {
                                 const int sl = CQG_JIT_LEAFSLOT(c);
                                 const uint2 iv = lds64(s_cmp + 64u * (uint32_t)c + fd16[sl]);
-                                bad |= (state[sl] - 1u) < 2u ? 1u : 0u;  // NULL (1) or not a decimal (2): the general kernel's
                                 bs = (bs << 1) | (mant[sl] - iv.x <= iv.y ? 1u : 0u);
                             } else if (c == -1) {
                                 bs = ((bs >> 1) & ~1u) | ((bs >> 1) & bs & 1u);
@@ -357,22 +357,36 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
                         }
                         pass = (bs & 1u) != 0u;
                     }
-                    // ---- SUM / AVG operands: value * 1000, exact ----
                     uint32_t add[3] = {0u, 0u, 0u}, nulls = 0u, big = 0u;
 #pragma unroll
                     for (int a = 0; a < 3; a++) {
                         if (a < nagg) {
                             const int sl = CQG_JIT_ASLOT(a);
-                            const uint32_t sc = lds32(sbase + LL::OFF_SCALE + fd16[sl]);
-                            if (state[sl] == 0u) {
-                                add[a] = mant[sl] * sc;
-                            } else if (state[sl] == 1u) {
-                                if (nagg == 3) bad = 1u;  // (no room for NULL counts beside three sums)
-                                if (a < 2) nulls |= 1u << (16 * a);
-                            } else if (state[sl] == 3u) {
-                                big |= 1u << a;
-                            } else {
-                                bad = 1u;
+                            add[a] = mant[sl] * lds32(sbase + LL::OFF_SCALE + fd16[sl]);
+                        }
+                    }
+                    if (state[0] | state[1] | state[2] | state[3]) {
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            if (c < CQG_JIT_NLEAF) {
+                                const int sl = CQG_JIT_LEAFSLOT(c);
+                                if ((state[sl] - 1u) < 2u) bad = 1u;  // NULL (1) or not a decimal (2) in a comparison: the general kernel's
+                            }
+                        }
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            if (a < nagg) {
+                                const int sl = CQG_JIT_ASLOT(a);
+                                if (state[sl] == 1u) {
+                                    if (nagg == 3) bad = 1u;  // (no room for NULL counts beside three sums)
+                                    if (a < 2) nulls |= 1u << (16 * a);
+                                    add[a] = 0u;
+                                } else if (state[sl] == 3u) {
+                                    big |= 1u << a;
+                                    add[a] = 0u;
+                                } else if (state[sl] == 2u) {
+                                    bad = 1u;
+                                }
                             }
                         }
                     }
@@ -382,7 +396,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
                         const uint32_t fa = rbase + off[kslot], kl = len[kslot];
                         const uint32_t a = fa & ~3u, sh = fa << 3;
                         const uint32_t x0 = lds32(a), x1 = lds32(a + 4), x2 = lds32(a + 8), x3 = lds32(a + 12), x4 = lds32(a + 16);
-                        const uint4 m = lds128(sbase + LL::OFF_KMASK + 16u * (kl < 16u ? kl : 16u));
+                        const uint4 m = lds128(sbase + LL::OFF_KMASK + 16u * kl);  // (kl > 16: some other 16 bytes of this CTA's shared memory, and the row is handed over)
                         const uint32_t y0 = __funnelshift_r(x0, x1, sh) & m.x, y1 = __funnelshift_r(x1, x2, sh) & m.y;
                         const uint32_t y2 = __funnelshift_r(x2, x3, sh) & m.z, y3 = __funnelshift_r(x3, x4, sh) & m.w;
                         if (kl > 16u) bad = 1u;
@@ -405,18 +419,28 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
                         if (pass) {
                             const uint32_t aa = s_acc + (cur & 0x7cu);  // word [0][group]
                             reds32(aa, 1u);
+                            if ((big | nulls) == 0u) {
 #pragma unroll
-                            for (int a = 0; a < 3; a++) {
-                                if (a < nagg) {
-                                    const uint32_t lo_a = aa + (1 + a) * (kL2KGroups * 4), hi_a = aa + (4 + a) * (kL2KGroups * 4);
-                                    if ((big >> a) & 1u) {
-                                        const int sl = CQG_JIT_ASLOT(a);
-                                        l2k_add_big(lo_a, hi_a, mant[sl], lds32(sbase + LL::OFF_SCALE + fd16[sl]));
-                                    } else if (a < 2 && ((nulls >> (16 * a)) & 1u)) {
-                                        reds32(aa + (7 + a) * (kL2KGroups * 4), 1u);  // a NULL field: not a value of this aggregate
-                                    } else {
-                                        const uint32_t old = atoms32(lo_a, add[a]);
-                                        if (old + add[a] < old) reds32(hi_a, 1u);
+                                for (int a = 0; a < 3; a++) {
+                                    if (a < nagg) {
+                                        const uint32_t old = atoms32(aa + (1 + a) * (kL2KGroups * 4), add[a]);
+                                        if (old + add[a] < old) reds32(aa + (4 + a) * (kL2KGroups * 4), 1u);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int a = 0; a < 3; a++) {
+                                    if (a < nagg) {
+                                        const uint32_t lo_a = aa + (1 + a) * (kL2KGroups * 4), hi_a = aa + (4 + a) * (kL2KGroups * 4);
+                                        if ((big >> a) & 1u) {
+                                            const int sl = CQG_JIT_ASLOT(a);
+                                            l2k_add_big(lo_a, hi_a, mant[sl], lds32(sbase + LL::OFF_SCALE + fd16[sl]));
+                                        } else if (a < 2 && ((nulls >> (16 * a)) & 1u)) {
+                                            reds32(aa + (7 + a) * (kL2KGroups * 4), 1u);  // a NULL field: not a value of this aggregate
+                                        } else {
+                                            const uint32_t old = atoms32(lo_a, add[a]);
+                                            if (old + add[a] < old) reds32(hi_a, 1u);
+                                        }
                                     }
                                 }
                             }
