@@ -553,9 +553,20 @@ static Api& api() {
     static bool tried = false;
     if (tried) return a;
     tried = true;
-    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"}) {
-        a.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
-        if (a.h) break;
+    // the newest run-time compiler of those present: a process that loaded another CUDA's libnvrtc.so.12 first (PyTorch
+    // bundles its own) would otherwise compile with that one, and 256-bit loads (pk_load, cqg_lean.cuh) need 12.9
+    int best = -1;
+    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"}) {
+        void* h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+        if (!h) continue;
+        int major = 0, minor = 0;
+        typedef int (*nvrtcVersion_t)(int*, int*);
+        nvrtcVersion_t ver = (nvrtcVersion_t)dlsym(h, "nvrtcVersion");
+        if (ver) ver(&major, &minor);
+        if (major * 100 + minor > best) {
+            best = major * 100 + minor;
+            a.h = h;
+        }
     }
     if (!a.h) return a;
     a.create = (nvrtcCreateProgram_t)dlsym(a.h, "nvrtcCreateProgram");

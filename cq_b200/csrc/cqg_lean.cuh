@@ -172,7 +172,13 @@ struct PkChunk {
 };
 __device__ __forceinline__ PkChunk pk_load(const void* p) {
     PkChunk v;
+#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ < 1209)
+    // a run-time compiler older than CUDA 12.9 (PTX 8.8) has no 256-bit vector load: two 128-bit halves of the same sector
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.a), "=l"(v.b) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2+16];" : "=l"(v.c), "=l"(v.d) : "l"(p) : "memory");
+#else
     asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p) : "memory");
+#endif
     return v;
 }
 // word j (0..11) of a line read as three chunks; folds to one register when j is known at compile time

@@ -17,6 +17,7 @@ SHAPE = """#define CQG_JIT 1
 #define CQG_JIT_GAP2 2
 #define CQG_JIT_GAP3 0
 #define CQG_JIT_NPROG 3
+#define CQG_JIT_NLEAF 2
 #define CQG_JIT_NGC 1
 #define CQG_JIT_NAGG 2
 #define CQG_JIT_PROG(i) ((i)==0?0:(i)==1?1:(i)==2?-1:0)
@@ -37,32 +38,52 @@ SHAPE = """#define CQG_JIT 1
 KERNELS = [
     ("cqg_lean2.cuh", "cqg::lean2_kernel<cqg::Geo<128, 16384, 1, 224>, 8, false, -1>"),
     ("cqg_lean2g.cuh", "cqg::lean2g_kernel<cqg::Geo<128, 16384, 1, 224>, 6>"),
+    ("cqg_lean2k.cuh", "cqg::lean2k_kernel<cqg::Geo<128, 16384, 1, 224>, 8>"),
     ("cqg_leanhc.cuh", "cqg::leanhc_kernel<cqg::Geo<128, 16384, 1, 224>, 6>"),
     ("cqg_lean.cuh", "cqg::lean_kernel<cqg::Geo<128, 16384, 1, 992>, 5, true, false, false>"),
     ("cqg_lean.cuh", "cqg::lean_kernel<cqg::Geo<128, 16384, 1, 992>, 6, false, false, true>"),
 ]
 
 
-def _nvrtc():
-    for name in ("libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"):
+def _nvrtc_libs():
+    """Every run-time compiler a process might end up with: the toolkit's, and the one PyTorch bundles (an older CUDA:
+    a process that imported torch first resolves libnvrtc.so.12 to that one)."""
+    import glob
+    import sys
+    names = ["libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"]
+    for sp in sys.path:
+        names += glob.glob(os.path.join(sp, "nvidia", "cuda_nvrtc", "lib", "libnvrtc.so.*"))
+    libs, seen = [], set()
+    for name in names:
         try:
-            return C.CDLL(name)
+            lib = C.CDLL(name)
         except OSError:
             continue
-    return None
+        major, minor = C.c_int(), C.c_int()
+        lib.nvrtcVersion(C.byref(major), C.byref(minor))
+        if (major.value, minor.value) not in seen:
+            seen.add((major.value, minor.value))
+            libs.append(lib)
+    return libs
 
 
 @pytest.mark.parametrize("header,name", KERNELS)
 def test_lean_kernels_compile_at_run_time(header, name):
-    nv = _nvrtc()
-    if nv is None:
+    libs = _nvrtc_libs()
+    if not libs:
         pytest.skip("libnvrtc not found")
+    for nv in libs:
+        _compile(nv, header, name)
+
+
+def _compile(nv, header, name):
     src = (SHAPE + f'#include "{header}"\n').encode()
     prog = C.c_void_p()
     assert nv.nvrtcCreateProgram(C.byref(prog), src, b"cqg_jit.cu", 0, None, None) == 0
     try:
         assert nv.nvrtcAddNameExpression(prog, name.encode()) == 0
-        opts = [b"--gpu-architecture=sm_100a", b"--std=c++17", b"-default-device", f"-I{CSRC}".encode(), f"-I{INC}".encode()]
+        opts = [b"--gpu-architecture=sm_100a", b"--std=c++17", b"-default-device", f"-I{CSRC}".encode(), f"-I{INC}".encode(),
+                b"-I/usr/local/cuda/include"]
         rc = nv.nvrtcCompileProgram(prog, len(opts), (C.c_char_p * len(opts))(*opts))
         n = C.c_size_t()
         nv.nvrtcGetProgramLogSize(prog, C.byref(n))
