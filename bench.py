@@ -377,6 +377,54 @@ def main():
 
         extra = {}
         if not args.no_extra:
+            # ---- real-world bytes: the same two queries on 2 GB tables that hold a blank inside one field
+            # of every row / end every row in CR LF, beside the clean table of the same size; with the share of 16 KB tiles
+            # the lean kernels handed to the general kernel ----
+            def stats():
+                a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+                lib.last_scan_stats(C.byref(a), C.byref(b), C.byref(c))
+                return {"tiles": a.value, "handed_tiles": b.value, "handed_rows": c.value,
+                        "handed_tile_share": (b.value / a.value) if a.value else None}
+
+            def variant_legs(kind):
+                vt, vbuf, vn = make_slice(int(2e9 / 29.89), 1, 0)
+                view = vbuf[:vn]
+                if kind != "clean":
+                    nl = torch.nonzero(view == 10).flatten()
+                    if kind == "dirty_blank":      # `KKK KKKKKK,...`: a blank inside the first field of every data row
+                        view[nl[:-1] + 4] = 32
+                    elif kind == "crlf":           # every line ends in CR LF (the last digit of the row gives way to the CR)
+                        view[nl - 1] = 13
+                    del nl
+                out = {}
+                for leg in ("count_where", "groupby"):
+                    pl = pc.build(pc.plans()[LEGS[leg][0]])
+                    for _ in range(2):
+                        r = vt.execute_raw(pl)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    kms = []
+                    for _ in range(3):
+                        r = vt.execute_raw(pl)
+                        kms.append(r["kernel_ms"])
+                    torch.cuda.synchronize()
+                    dt = (time.perf_counter() - t0) / 3
+                    out[leg] = {"scan_kernel_gbs": vn / (sum(kms) / 3 / 1e3) / 1e9, "query_gbs": vn / dt / 1e9, "groups": r["n_groups"],
+                                "count0": int(r["count0"]), **stats()}
+                del vt, vbuf
+                torch.cuda.empty_cache()
+                return out
+
+            try:
+                clean = variant_legs("clean")
+                for kind in ("dirty_blank", "crlf"):
+                    v = variant_legs(kind)
+                    for leg in v:
+                        v[leg]["vs_clean"] = v[leg]["scan_kernel_gbs"] / clean[leg]["scan_kernel_gbs"]
+                    extra[kind] = v
+                extra["clean_2gb"] = clean
+            except Exception as ex:
+                extra["variants_error"] = repr(ex)
             for name in ["scalar_aggs", "lean_group_abort_many", "count_height_gt_1_5"]:
                 pl = pc.build(pc.plans()[name])
                 table.execute_raw(pl)

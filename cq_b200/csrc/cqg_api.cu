@@ -68,6 +68,13 @@ CQG_API int64_t cqg_total_kernel_launches(void) { return g_launches.load(); }
 enum { KF_SCAN = 0, KF_LEAN, KF_LEAN2, KF_LEAN2G, KF_LEAN2K, KF_LEANHC, KF_COUNT };
 static std::atomic<int64_t> g_family[KF_COUNT];
 static const char* const kFamilyName[KF_COUNT] = {"scan", "lean", "lean2", "lean2g", "lean2k", "leanhc"};
+// the last lean scan of this thread: tiles it covered, tiles and rows it handed to the general kernel
+static thread_local int64_t g_last_scan[3];
+CQG_API void cqg_last_scan_stats(int64_t* tiles, int64_t* handed_tiles, int64_t* handed_rows) {
+    if (tiles) *tiles = g_last_scan[0];
+    if (handed_tiles) *handed_tiles = g_last_scan[1];
+    if (handed_rows) *handed_rows = g_last_scan[2];
+}
 CQG_API int64_t cqg_kernel_launches_named(const char* family) {
     for (int k = 0; k < KF_COUNT; k++)
         if (family && !strcmp(family, kFamilyName[k])) return g_family[k].load();
@@ -156,11 +163,14 @@ struct cqg_table {
     int fd = -1;              // the mapped file, kept open: staging reads it with pread (no page faults on the mapping)
     // explicit ownership range of a scan (overrides the equal shards): the bytes one GPU of a multi-GPU table holds
     uint64_t range_lo = 0, range_hi = 0;
+    bool has_range = false;
     // multi-GPU residency (CQ_GPUS, cqg_multi below): one virtual address range, slice d physically on device d
     int ngpu = 0;
     uint64_t va_size = 0;
     std::vector<unsigned long long> vmm_handles;
     std::vector<uint64_t> cuts;  // ngpu + 1 byte offsets: device d holds [cuts[d], cuts[d + 1])
+    std::vector<int> devices;    // CUDA device of slice d
+    std::vector<cqg_table*> views;  // per slice: the same bytes (same address), scans own [cuts[d], cuts[d + 1])
 };
 
 static inline bool host_is_space(unsigned c) { return c == 32u || (c - 9u) <= 4u; }
@@ -359,11 +369,212 @@ static int stage_to_device(cqg_table* t, const uint8_t* src, size_t size, bool p
     return copy_host_range(t, src, 0, size, t->d_data);
 }
 
+// ------------------------------------------------------------------------------------------
+// multi-GPU tables (CQ_GPUS=N, cqg_table_open_multi): ONE virtual address range for the file, its 2 MB pages
+// physically on N devices (slice d = bytes [cuts[d], cuts[d + 1]) on device d), mapped readable and writable on
+// all of them (CUDA virtual memory management). Every device scans the rows that start in its own slice out of
+// its own HBM; a row reference (global offset) means the same on every device, so the merged result is finished
+// by device 0 reading the groups' representative rows over NVLink, and a query shape that does not shard (joins,
+// projections) simply runs on device 0 over the whole range. The driver entry points are looked up through the
+// runtime (cudaGetDriverEntryPoint): the library does not link libcuda.
+// ------------------------------------------------------------------------------------------
+namespace vmm {
+typedef CUresult (*GetGranularity_t)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+typedef CUresult (*AddressReserve_t)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+typedef CUresult (*AddressFree_t)(CUdeviceptr, size_t);
+typedef CUresult (*Create_t)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+typedef CUresult (*Release_t)(CUmemGenericAllocationHandle);
+typedef CUresult (*Map_t)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+typedef CUresult (*Unmap_t)(CUdeviceptr, size_t);
+typedef CUresult (*SetAccess_t)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+struct Api {
+    GetGranularity_t granularity = nullptr;
+    AddressReserve_t reserve = nullptr;
+    AddressFree_t addr_free = nullptr;
+    Create_t create = nullptr;
+    Release_t release = nullptr;
+    Map_t map = nullptr;
+    Unmap_t unmap = nullptr;
+    SetAccess_t set_access = nullptr;
+    bool ok = false;
+};
+static Api& api() {
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto get = [](const char* name) -> void* {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            return fn;
+        };
+        a.granularity = (GetGranularity_t)get("cuMemGetAllocationGranularity");
+        a.reserve = (AddressReserve_t)get("cuMemAddressReserve");
+        a.addr_free = (AddressFree_t)get("cuMemAddressFree");
+        a.create = (Create_t)get("cuMemCreate");
+        a.release = (Release_t)get("cuMemRelease");
+        a.map = (Map_t)get("cuMemMap");
+        a.unmap = (Unmap_t)get("cuMemUnmap");
+        a.set_access = (SetAccess_t)get("cuMemSetAccess");
+        a.ok = a.granularity && a.reserve && a.addr_free && a.create && a.release && a.map && a.unmap && a.set_access;
+    });
+    return a;
+}
+}  // namespace vmm
+
+static void release_multi(cqg_table* t) {
+    vmm::Api& v = vmm::api();
+    for (cqg_table* w : t->views) delete w;
+    t->views.clear();
+    if (!t->va_size || !v.ok) return;
+    for (int d : t->devices) {
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+    }
+    if (!t->devices.empty()) cudaSetDevice(t->devices[0]);
+    v.unmap((CUdeviceptr)(uintptr_t)t->d_data, t->va_size);
+    for (unsigned long long h : t->vmm_handles) v.release((CUmemGenericAllocationHandle)h);
+    v.addr_free((CUdeviceptr)(uintptr_t)t->d_data, t->va_size);
+    t->vmm_handles.clear();
+    t->d_data = nullptr;
+    t->va_size = 0;
+}
+
+// the host bytes of a multi-GPU table onto its devices: slices cut at 2 MB pages, one staging thread (with its own
+// bounce buffers and copy streams, copy_host_range) per device, so that N host-to-device links run at once
+static int stage_multi(cqg_table* t) {
+    vmm::Api& v = vmm::api();
+    if (!v.ok) return fail(CQG_ERR_CUDA, "multi-GPU tables need the CUDA virtual memory management entry points");
+    const int N = t->ngpu;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    const bool same = getenv("CQG_MULTI_SAME_DEVICE") != nullptr;  // (tests on a one-GPU box: every slice on device 0)
+    if (ndev < 1 || (!same && ndev < N)) return fail(CQG_ERR_CUDA, "CQ_GPUS=%d but %d CUDA device(s)", N, ndev);
+    int home = 0;
+    CU(cudaGetDevice(&home));
+    t->devices.resize(N);
+    for (int d = 0; d < N; d++) t->devices[d] = same ? home : d;
+    for (int d : t->devices) {  // (a context on every device before any driver call names it)
+        CU(cudaSetDevice(d));
+        CU(cudaFree(nullptr));
+        int rc = ensure_device();
+        if (rc) return rc;
+    }
+    CU(cudaSetDevice(t->devices[0]));
+    size_t gran = 2u << 20;
+    for (int d = 0; d < N; d++) {
+        CUmemAllocationProp prop{};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = t->devices[d];
+        size_t g = 0;
+        if (v.granularity(&g, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS) return fail(CQG_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+        gran = std::max(gran, g);
+    }
+    const uint64_t total = ((uint64_t)t->size + kDevPad + gran - 1) / gran * gran;
+    const uint64_t pages = total / gran;
+    t->cuts.assign(N + 1, 0);
+    for (int d = 0; d <= N; d++) t->cuts[d] = pages * (uint64_t)d / (uint64_t)N * gran;
+    CUdeviceptr va = 0;
+    if (v.reserve(&va, total, gran, 0, 0) != CUDA_SUCCESS) return fail(CQG_ERR_NOMEM, "cuMemAddressReserve of %llu bytes failed", (unsigned long long)total);
+    t->d_data = (uint8_t*)(uintptr_t)va;
+    t->va_size = total;
+    for (int d = 0; d < N; d++) {
+        const uint64_t len = t->cuts[d + 1] - t->cuts[d];
+        if (!len) continue;
+        CUmemAllocationProp prop{};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = t->devices[d];
+        CUmemGenericAllocationHandle h = 0;
+        if (v.create(&h, len, &prop, 0) != CUDA_SUCCESS) {
+            release_multi(t);
+            return fail(CQG_ERR_NOMEM, "cuMemCreate of %llu bytes on device %d failed", (unsigned long long)len, t->devices[d]);
+        }
+        t->vmm_handles.push_back((unsigned long long)h);
+        if (v.map(va + t->cuts[d], len, 0, h, 0) != CUDA_SUCCESS) {
+            release_multi(t);
+            return fail(CQG_ERR_CUDA, "cuMemMap failed");
+        }
+    }
+    {
+        std::vector<CUmemAccessDesc> acc;
+        for (int d = 0; d < N; d++) {
+            bool seen = false;
+            for (const CUmemAccessDesc& a : acc) seen = seen || a.location.id == t->devices[d];
+            if (seen) continue;
+            CUmemAccessDesc a{};
+            a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+            a.location.id = t->devices[d];
+            a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+            acc.push_back(a);
+        }
+        if (v.set_access(va, total, acc.data(), acc.size()) != CUDA_SUCCESS) {
+            release_multi(t);
+            return fail(CQG_ERR_CUDA, "cuMemSetAccess failed (no peer access between the devices of CQ_GPUS?)");
+        }
+    }
+    // the bytes: every device pulls its own slice
+    std::vector<int> rcs(N, CQG_OK);
+    std::vector<std::string> errs(N);
+    std::vector<std::thread> th;
+    for (int d = 0; d < N; d++) {
+        th.emplace_back([&, d] {
+            if (cudaSetDevice(t->devices[d]) != cudaSuccess) {
+                rcs[d] = CQG_ERR_CUDA;
+                return;
+            }
+            const uint64_t lo = std::min<uint64_t>(t->cuts[d], t->size), hi = std::min<uint64_t>(t->cuts[d + 1], t->size);
+            int rc = CQG_OK;
+            if (hi > lo) {
+                if (t->src_pinned) {
+                    if (cudaMemcpyAsync(t->d_data + lo, t->h_data + lo, hi - lo, cudaMemcpyHostToDevice, 0) != cudaSuccess) rc = CQG_ERR_CUDA;
+                } else {
+                    rc = copy_host_range(t, t->h_data, lo, hi - lo, t->d_data + lo);
+                }
+            }
+            if (rc == CQG_OK && t->cuts[d + 1] > t->size) {  // what lies behind the file on this device: newlines
+                const uint64_t from = std::max<uint64_t>(t->cuts[d], t->size);
+                if (cudaMemsetAsync(t->d_data + from, '\n', std::min<uint64_t>(t->cuts[d + 1], t->size + kDevPad) - from, 0) != cudaSuccess) rc = CQG_ERR_CUDA;
+            }
+            if (rc == CQG_OK && cudaStreamSynchronize(0) != cudaSuccess) rc = CQG_ERR_CUDA;
+            if (rc != CQG_OK) errs[d] = cqg_last_error();
+            rcs[d] = rc;
+        });
+    }
+    for (std::thread& x : th) x.join();
+    CU(cudaSetDevice(home));
+    for (int d = 0; d < N; d++)
+        if (rcs[d] != CQG_OK) {
+            release_multi(t);
+            return fail(rcs[d], "staging slice %d: %s", d, errs[d].empty() ? "CUDA error" : errs[d].c_str());
+        }
+    // per slice a view of the same address range that owns the rows starting in the slice
+    for (int d = 0; d < N; d++) {
+        cqg_table* w = new cqg_table();
+        w->d_data = t->d_data;
+        w->size = t->size;
+        w->cfg = t->cfg;
+        w->names = t->names;
+        w->data_start = t->data_start;
+        w->global_base = t->global_base;
+        w->range_lo = std::min<uint64_t>(t->cuts[d], t->size);
+        w->range_hi = d + 1 == N ? (uint64_t)t->size : std::min<uint64_t>(t->cuts[d + 1], t->size);
+        w->has_range = true;
+        t->views.push_back(w);
+    }
+    return CQG_OK;
+}
+
 // tables opened from host bytes are uploaded when a query first needs them: a statement whose shape is then
 // declined (plan-time checks) or routed elsewhere never pays for the copy
 static int ensure_staged(const cqg_table* tc) {
     cqg_table* t = const_cast<cqg_table*>(tc);
     if (!t || t->d_data || !t->h_data) return CQG_OK;
+    if (t->ngpu > 1) return stage_multi(t);
     return stage_to_device(t, t->h_data, t->size, t->src_pinned);
 }
 
@@ -418,9 +629,29 @@ CQG_API int cqg_table_open(const char* path, cqg_csv_config_t cfg, cqg_table_t**
         cqg_table_close(t);
         return rc;
     }
+    if (const char* e = getenv("CQ_GPUS")) {  // the drop-in CLI: CQ_GPUS=8 cq -q "SELECT ... FROM 'big.csv' ..."
+        const int n = atoi(e);
+        if (n > 1 && (rc = cqg_table_set_gpus(t, n)) != CQG_OK) {
+            cqg_table_close(t);
+            return rc;
+        }
+    }
     *out = t;
     return CQG_OK;
 }
+
+// Spread a table that still lives in host memory (opened from a path or a host buffer, no query run yet) over the first
+// `ngpu` devices. Files below CQG_MULTI_MIN_BYTES (default 64 MB) stay on one device: there is nothing to win.
+CQG_API int cqg_table_set_gpus(cqg_table_t* t, int ngpu) {
+    if (!t || ngpu < 1 || ngpu > 64) return fail(CQG_ERR_ARG, "bad argument");
+    if (t->d_data || !t->h_data) return fail(CQG_ERR_ARG, "the table is already resident on a device");
+    const char* e = getenv("CQG_MULTI_MIN_BYTES");
+    const uint64_t min_bytes = e ? strtoull(e, nullptr, 10) : (64ull << 20);
+    t->ngpu = (ngpu > 1 && t->size >= min_bytes) ? ngpu : 0;
+    return CQG_OK;
+}
+
+CQG_API int cqg_table_gpus(const cqg_table_t* t) { return t ? (t->ngpu > 1 ? t->ngpu : 1) : 0; }
 
 CQG_API int cqg_table_open_device(uint64_t device_ptr, size_t size, cqg_csv_config_t cfg, cqg_table_t** out) {
     if (!out || !device_ptr) return fail(CQG_ERR_ARG, "null argument");
@@ -458,7 +689,8 @@ CQG_API int cqg_table_set_global_offset(cqg_table_t* t, uint64_t offset) {
 
 CQG_API void cqg_table_close(cqg_table_t* t) {
     if (!t) return;
-    if (t->owns_device && t->d_data) cudaFreeAsync(t->d_data, 0);
+    if (t->ngpu > 1) release_multi(t);
+    else if (t->owns_device && t->d_data) cudaFreeAsync(t->d_data, 0);
     if (t->map) munmap(t->map, t->map_len);
     if (t->fd >= 0) close(t->fd);
     delete t;
@@ -811,7 +1043,7 @@ static int launch_lean_geo(const DevPlan& P0, cudaStream_t st) {
 }
 
 
-template <class LG, int MINB, bool ONELEAF, int GAP0>
+template <class LG, int MINB, bool ONELEAF, int GAP0, bool CRLF = false>
 static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
@@ -828,14 +1060,14 @@ static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
         c.ready = true;
     }
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2_kernel<LG, MINB, ONELEAF, GAP0>, LG::THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lean2_kernel<LG, MINB, ONELEAF, GAP0, CRLF>, LG::THREADS, smem));
     if (per_sm < 1) return fail(CQG_ERR_CUDA, "lean2 kernel does not fit");
     int grid = std::min(P.n_tiles, c.sms * per_sm);
     if (!ONELEAF) {
         // the general instantiation interprets the plan's shape per row: compiled for this query when possible
         char name[160];
-        snprintf(name, sizeof name, "cqg::lean2_kernel<cqg::Geo<%d, %d, %d, %d>, %d, false, -1>", LG::THREADS, LG::TILE, LG::STAGES,
-                 LG::OVER, MINB);
+        snprintf(name, sizeof name, "cqg::lean2_kernel<cqg::Geo<%d, %d, %d, %d>, %d, false, -1, %s>", LG::THREADS, LG::TILE, LG::STAGES,
+                 LG::OVER, MINB, CRLF ? "true" : "false");
         if (cudaKernel_t jk = cqg_jit::get(cqg_jit::lean_shape_defs(P), "cqg_lean2.cuh", name, P.own_hi - P.own_lo)) {
             void* args[] = {(void*)&P};
             if (cudaLaunchKernel((const void*)jk, dim3(grid), dim3(LG::THREADS), args, (size_t)smem, st) == cudaSuccess) {
@@ -846,7 +1078,7 @@ static int launch_lean2_geo(const DevPlan& P0, cudaStream_t st) {
             cudaGetLastError();
         }
     }
-    lean2_kernel<LG, MINB, ONELEAF, GAP0><<<grid, LG::THREADS, smem, st>>>(P);
+    lean2_kernel<LG, MINB, ONELEAF, GAP0, CRLF><<<grid, LG::THREADS, smem, st>>>(P);
     g_launches++;
     g_family[KF_LEAN2]++;
     CU(cudaGetLastError());
@@ -1008,6 +1240,7 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
     const int lean2 = env_int("CQG_LEAN2", 1);  // 0: the first lean kernel (A/B runs)
     if (lean2 && !mm0) {
         using LS = Geo<128, 16384, 1, 224>;  // rows of 64 bytes and more are handed over anyway: a short overlap
+        if (P.crlf) return oneleaf ? launch_lean2_geo<LS, 9, true, -1, true>(P, st) : launch_lean2_geo<LS, 8, false, -1, true>(P, st);
         if (oneleaf) {
             switch (P.gap[0]) {
                 case 0: return launch_lean2_geo<LS, 9, true, 0>(P, st);
@@ -1089,7 +1322,7 @@ struct ScalarBlock {
 };
 
 static void shard_range(const cqg_table* t, uint64_t& lo, uint64_t& hi) {
-    if (t->range_hi > t->range_lo) {
+    if (t->has_range) {
         lo = std::max<uint64_t>(t->range_lo, t->data_start);
         hi = std::min<uint64_t>(t->range_hi, t->size);
         if (hi < lo) hi = lo;
@@ -1683,6 +1916,13 @@ static int build_plan(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, cu
     }
     if ((rc = number_slots(P, hp.pool))) return rc;
     layout_packed(hp, t);
+    P.crlf = 0;
+    if (P.simple && env_int("CQG_CRLF", 1)) {
+        // a CR in the head of the file: the lean kernels then take '\r' as a terminator (CR LF files stay on them). A guess
+        // about the rest of the file that only costs speed: a CR they were not told about sends its tile to the general kernel
+        const std::vector<uint8_t>& sm = table_sample(t);
+        P.crlf = memchr(sm.data(), '\r', sm.size()) ? 1 : 0;
+    }
     P.need_right_fields = P.nwantR > 0;
     CU(hp.d_scalars.alloc(sizeof(ScalarBlock), st));
     CU(cudaMemsetAsync(hp.d_scalars.p, 0, sizeof(ScalarBlock), st));
@@ -2633,12 +2873,17 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     }
     if ((hs.errflags & (KERR_LEAN_ABORT | KERR_TABLE_FULL)) || hs.def_row_count > row_cap) {
         P.simple = 0;  // the data is not what the lean kernel is for
+        g_last_scan[0] = g_last_scan[1] = P.n_tiles;  // (everything goes to the general kernel)
+        g_last_scan[2] = 0;
         P.lean_global = 0;
         P.ptab = nullptr;
         P.pcap = 0;
         gt.packed.release();
         return CQG_OK;
     }
+    g_last_scan[0] = P.n_tiles;
+    g_last_scan[1] = (int64_t)hs.def_tile_count;
+    g_last_scan[2] = (int64_t)hs.def_row_count;
     const unsigned long long rows_after_lean = hs.rows_scanned;
     ScalarBlock h2{};
     if (hs.def_tile_count || hs.def_row_count) {
@@ -2943,11 +3188,27 @@ static int execute_select(HostPlan& hp, const cqg_table* t, const cqg_table* rt,
     return CQG_OK;
 }
 
+static bool partial_query_ok(const cqg_query_t* q);
+
+static int execute_multi(const cqg_table* t, const cqg_query_t* q, cqg_result_t** out);
+
 CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t** out) {
     if (!t || !q || !out) return fail(CQG_ERR_ARG, "null argument");
     int rc = ensure_device();
     if (rc) return rc;
     cudaStream_t st = 0;
+    if (t->ngpu > 1 || (q->join.right && q->join.right->ngpu > 1)) {
+        // a table spread over several devices: aggregates without a join run on all of them; every other shape runs on
+        // the first device of the table over the one address range (remote pages come over NVLink)
+        const cqg_table* mt = t->ngpu > 1 ? t : q->join.right;
+        {
+            HostPlan probe;  // (shape check from the header alone, as below: a declined shape costs no upload)
+            if ((rc = build_plan(probe, t, q, st))) return rc == CQG_ERR_UNSUPPORTED ? CQG_ERR_UNSUPPORTED_PLAN : rc;
+        }
+        if ((rc = ensure_staged(t)) || (rc = ensure_staged(q->join.right))) return rc;
+        if (t->ngpu > 1 && !q->join.right && partial_query_ok(q)) return execute_multi(t, q, out);
+        CU(cudaSetDevice(mt->devices[0]));
+    }
     HostPlan hp;
     PhaseTimer pt;
     // the plan is built from the header alone: a shape the planner declines costs no upload (the caller keeps its own
@@ -3439,6 +3700,100 @@ CQG_API int cqg_partial_finish(const cqg_partial_t* pc, const cqg_table_t* t, cq
 }
 
 CQG_API void cqg_partial_free(cqg_partial_t* p) { delete p; }
+
+// An aggregate over a multi-GPU table: every device scans the rows that start in its slice (cqg_execute_partial on the
+// slice's view, one host thread per device), the partial group records of devices 1.. cross NVLink into device 0
+// (cudaMemcpyPeer: one process, peer memory, no collective library needed), are merged there into one table and finished
+// there - the groups' first rows and MIN/MAX strings are read through the table's one address range wherever they live.
+static int execute_multi(const cqg_table* t, const cqg_query_t* q, cqg_result_t** out) {
+    const int N = t->ngpu;
+    int home = 0;
+    CU(cudaGetDevice(&home));
+    struct Slot {
+        int rc = CQG_OK;
+        std::string err;
+        cqg_partial_t* part = nullptr;
+        void* recs = nullptr;
+        int64_t n = 0;
+    };
+    std::vector<Slot> slots(N);
+    const long long launches0 = g_launches.load();
+    std::vector<std::thread> th;
+    for (int d = 0; d < N; d++) {
+        th.emplace_back([&, d] {
+            Slot& s = slots[d];
+            if (cudaSetDevice(t->devices[d]) != cudaSuccess) {
+                s.rc = CQG_ERR_CUDA;
+                s.err = "cudaSetDevice failed";
+                return;
+            }
+            s.rc = cqg_execute_partial(t->views[d], q, &s.part);
+            if (s.rc == CQG_OK) {
+                s.n = cqg_partial_count(s.part);
+                if (s.n < 0) s.rc = CQG_ERR_CUDA;
+            }
+            if (s.rc == CQG_OK && s.n > 0) {
+                const size_t rb = cqg_partial_record_size(s.part);
+                if (cudaMalloc(&s.recs, (size_t)s.n * rb) != cudaSuccess) {
+                    s.rc = fail(CQG_ERR_NOMEM, "records of %lld groups: out of device memory", (long long)s.n);
+                } else {
+                    int64_t got = 0;
+                    s.rc = cqg_partial_export(s.part, 0, 1, (uint64_t)(uintptr_t)s.recs, s.n, &got);
+                    s.n = got;
+                }
+            }
+            if (s.rc != CQG_OK) s.err = cqg_last_error();
+        });
+    }
+    for (std::thread& x : th) x.join();
+    cudaSetDevice(t->devices[0]);
+    int rc = CQG_OK;
+    cqg_partial_t* merged = nullptr;
+    for (int d = 0; d < N && rc == CQG_OK; d++)
+        if (slots[d].rc != CQG_OK) rc = fail(slots[d].rc, "%s", slots[d].err.c_str());
+    if (rc == CQG_OK) rc = cqg_partial_new_like(slots[0].part, &merged);
+    double kernel_ms = 0;
+    int64_t rows = 0;
+    for (int d = 0; d < N && rc == CQG_OK; d++) {
+        Slot& s = slots[d];
+        kernel_ms = std::max(kernel_ms, cqg_partial_kernel_ms(s.part));
+        rows += cqg_partial_rows_scanned(s.part);
+        if (s.n == 0) continue;
+        if (t->devices[d] == t->devices[0]) {
+            rc = cqg_partial_merge(merged, (uint64_t)(uintptr_t)s.recs, s.n);
+        } else {
+            const size_t bytes = (size_t)s.n * cqg_partial_record_size(s.part);
+            void* here = nullptr;
+            if (cudaMalloc(&here, bytes) != cudaSuccess) {
+                rc = fail(CQG_ERR_NOMEM, "records of %lld groups: out of device memory", (long long)s.n);
+                break;
+            }
+            if (cudaMemcpyPeer(here, t->devices[0], s.recs, t->devices[d], bytes) != cudaSuccess)
+                rc = fail(CQG_ERR_CUDA, "peer copy of partial records: %s", cudaGetErrorString(cudaGetLastError()));
+            else
+                rc = cqg_partial_merge(merged, (uint64_t)(uintptr_t)here, s.n);
+            cudaDeviceSynchronize();
+            cudaFree(here);
+        }
+    }
+    if (rc == CQG_OK) {
+        merged->rows_scanned = rows;
+        merged->kernel_ms = kernel_ms;
+        rc = cqg_partial_finish(merged, t, out);
+        if (rc == CQG_OK) (*out)->kernel_launches = (int32_t)(g_launches.load() - launches0);
+    }
+    std::string keep = rc != CQG_OK ? cqg_last_error() : "";
+    cqg_partial_free(merged);
+    for (int d = 0; d < N; d++) {
+        cudaSetDevice(t->devices[d]);
+        if (slots[d].recs) cudaFree(slots[d].recs);
+        cqg_partial_free(slots[d].part);
+    }
+    cudaSetDevice(home);
+    if (rc != CQG_OK) return fail(rc, "%s", keep.c_str());
+    return CQG_OK;
+}
+
 
 // ------------------------------------------------------------------------------------------
 // synthetic data

@@ -408,7 +408,11 @@ __device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
 #endif
 
 // GAP0: the wanted column index of ONELEAF plans when it is below 8 (the delimiter skips unroll), else -1
-template <class G, int MINB, bool ONELEAF, int GAP0>
+// CRLF (DevPlan::crlf: the head of the file holds a CR): every line ends in the two bytes CR LF. Both are `T` bytes; a row
+// is then clean when its first terminator is the '\r' and the byte behind it the '\n', and the next row starts two bytes
+// on. A line that ends in anything else makes the tile dirty as before (a bare '\n' included: the general kernel splits
+// such a file exactly as csv_load does, src/csv_reader.c:404-427).
+template <class G, int MINB, bool ONELEAF, int GAP0, bool CRLF = false>
 __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_constant__ DevPlan P) {
     extern __shared__ __align__(128) uint8_t smem[];
     static_assert(G::STAGES == 1 && G::TILE == G::THREADS * 128, "one stage, 128 bytes per thread");
@@ -544,8 +548,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                 e0 = fw != 0u ? q + ctz32(fw) : lean2_next_term(s_msk, q + 32u, (uint32_t)G::BUF);
             }
             uint32_t pos = e0 + 1u;
+            if (CRLF && pos < hi && lds8(s_buf + e0) == 0x0du) pos = e0 + 2u;  // (e0 is the CR of the pair, or its LF)
             if (pos < hi) {
-                dirty |= lds8(s_buf + e0) != 0x0au ? 1u : 0u;
+                if (CRLF) dirty |= (lds8(s_buf + pos - 2u) != 0x0du || lds8(s_buf + pos - 1u) != 0x0au) ? 1u : 0u;
+                else dirty |= lds8(s_buf + e0) != 0x0au ? 1u : 0u;
                 uint32_t ma = s_msk + ((pos >> 2) & ~7u);
                 uint2 m0 = lds64(ma), m1 = lds64(ma + 8u);
                 if constexpr (ONELEAF) {
@@ -568,13 +574,14 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                             dirty |= r >> 31;
                         }
                         const uint32_t rbase = s_buf + pos;
-                        const uint32_t npos = pos + et + 1u;
+                        const uint32_t npos = pos + et + (CRLF ? 2u : 1u);
                         const uint32_t nma = s_msk + ((npos >> 2) & ~7u);
                         uint2 n0, n1;
                         uint32_t lastb;
                         n0 = lds64(nma);  // (asked for before the decode, used after it)
                         n1 = lds64(nma + 8u);
                         lastb = lds8(rbase + et);
+                        if (CRLF) lastb = (lastb ^ 0x07u) | (lds8(rbase + et + 1u) ^ 0x0au) << 8;  // 0x0a when the line ends in CR LF
                         uint32_t val = 0, fd16 = 0, tab = 8u, bad = 1u;
                         if (flen - 1u < 4u) {
                             bad = lean2_dec4c(rbase + sp + flen, flen, kdot, val, fd16);
@@ -649,13 +656,14 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
                     }
                     const uint32_t rbase = s_buf + pos;
                     // the next row's mask words and this row's last byte: asked for now, used after the decode
-                    const uint32_t npos = pos + et + 1u;
+                    const uint32_t npos = pos + et + (CRLF ? 2u : 1u);
                     const uint32_t nma = s_msk + ((npos >> 2) & ~7u);
                     uint2 n0, n1;
                     uint32_t lastb;
                     n0 = lds64(nma);
                     n1 = lds64(nma + 8u);
                     lastb = lds8(rbase + et);
+                    if (CRLF) lastb = (lastb ^ 0x07u) | (lds8(rbase + et + 1u) ^ 0x0au) << 8;  // 0x0a when the line ends in CR LF
                     unsigned long long add0 = 0, add1 = 0, add2 = 0, add3 = 0;
                     uint32_t addmask = 0;
                     CQG_L2_DECODE_STATE

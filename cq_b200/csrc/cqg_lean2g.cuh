@@ -45,12 +45,21 @@ __device__ __forceinline__ uint32_t l2g_hash_word(uint32_t h, uint32_t x) { retu
 // blank is an ordinary byte; kLeanSpecialXor in cqg_lean.cuh): the tile is then left to the general kernel.
 // (b ^ 0x02) - 0x21 per byte borrows into bit 7 exactly where the byte is special and bit 7 clear ('\n' bytes are
 // lifted out of the way first); a borrow that crosses into the next byte can only ADD a flag.
+// `cr_too` (DevPlan::crlf: the head of the file holds a CR): '\r' is a line terminator like '\n' instead of a special byte,
+// exactly as csv_load splits lines (src/csv_reader.c:404-427: both end a line, empty lines are skipped) - a CR LF pair is
+// a terminator followed by an empty line, which the row walks skip. Four more instructions per word, only for such files.
 __host__ __device__ __forceinline__ uint32_t l2g_masks16(uint32_t vx, uint32_t vy, uint32_t vz, uint32_t vw, uint32_t patD, uint32_t one,
-                                                         uint32_t& n16, uint32_t& d16) {
-    const uint32_t f0 = ~(l2_add((vx ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vx) & 0x80808080u;
-    const uint32_t f1 = ~(l2_add((vy ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vy) & 0x80808080u;
-    const uint32_t f2 = ~(l2_add((vz ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vz) & 0x80808080u;
-    const uint32_t f3 = ~(l2_add((vw ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vw) & 0x80808080u;
+                                                         uint32_t& n16, uint32_t& d16, bool cr_too = false) {
+    uint32_t f0 = ~(l2_add((vx ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vx) & 0x80808080u;
+    uint32_t f1 = ~(l2_add((vy ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vy) & 0x80808080u;
+    uint32_t f2 = ~(l2_add((vz ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vz) & 0x80808080u;
+    uint32_t f3 = ~(l2_add((vw ^ 0x0a0a0a0au) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vw) & 0x80808080u;
+    if (cr_too) {
+        f0 |= ~(l2_add((vx ^ 0x0d0d0d0du) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vx) & 0x80808080u;
+        f1 |= ~(l2_add((vy ^ 0x0d0d0d0du) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vy) & 0x80808080u;
+        f2 |= ~(l2_add((vz ^ 0x0d0d0d0du) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vz) & 0x80808080u;
+        f3 |= ~(l2_add((vw ^ 0x0d0d0d0du) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vw) & 0x80808080u;
+    }
     const uint32_t d0 = ~(l2_add((vx ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vx) & 0x80808080u;
     const uint32_t d1 = ~(l2_add((vy ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vy) & 0x80808080u;
     const uint32_t d2 = ~(l2_add((vz ^ patD) & 0x7f7f7f7fu, one, 0x7f7f7f7fu) | vz) & 0x80808080u;
@@ -182,6 +191,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
     const uint32_t one = (uint32_t)P.simple >> 1;  // simple == 2 here: 1, but not to the compiler (IMAD adds)
+    const bool cr_too = P.crlf != 0;
     const int nwant = CQG_SPEC(NWANT, P.nwantL);
     const int gap0 = CQG_SPEC(GAP0, P.gap[0]), gap1 = CQG_SPEC(GAP1, P.gap[1]), gap2 = CQG_SPEC(GAP2, P.gap[2]),
               gap3 = CQG_SPEC(GAP3, P.gap[3]);
@@ -226,7 +236,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
             auto chunk = [&](uint32_t ca, uint32_t ma) {
                 const uint4 v = lds128(ca);
                 uint32_t ra, rd;
-                spec |= l2g_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd);
+                spec |= l2g_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd, cr_too);
                 sts16(ma, ra);
                 sts16(ma + 4u, rd);
             };
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
 #undef CQG_L2G_SUM
                     }
                 }
-                pos += et + 1u;
+                pos += et + 1u + (((tw >> 1) >> (et & 31u)) & 1u);  // (+1: the LF of a CR LF pair, an empty line)
             }
         }
         // too many rows outside this kernel's repertoire: let the general kernel do the whole scan.

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
     const uint32_t one = (uint32_t)P.simple >> 1;  // simple == 2 here: 1, but not to the compiler (IMAD adds)
+    const bool cr_too = P.crlf != 0;
 
     const int my_tiles = (P.n_tiles > (int)blockIdx.x) ? (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     for (int it = 0; it < my_tiles; it++) {
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
             auto chunk = [&](uint32_t ca, uint32_t ma) {
                 const uint4 v = lds128(ca);
                 uint32_t ra, rd;
-                spec |= l2g_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd);
+                spec |= l2g_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd, cr_too);
                 sts16(ma, ra);
                 sts16(ma + 4u, rd);
             };
@@ -315,7 +316,9 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
                     }
                     const uint32_t rbase = s_buf + pos;
                     // the next row's mask words: asked for now, used after the decode
-                    const uint32_t npos = pos + et + 1u;
+                    // (a second terminator right behind the first - the LF of a CR LF pair, an empty line - is skipped here
+                    // rather than by a trip through the loop)
+                    const uint32_t npos = pos + et + 1u + (((tw >> 1) >> (et & 31u)) & 1u);
                     const uint32_t nma = s_msk + ((npos >> 2) & ~7u);
                     const uint2 n0 = lds64(nma), n1 = lds64(nma + 8u);
                     myrows++;

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) leanhc_kernel(const __grid_c
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
     const uint32_t one = (uint32_t)P.simple >> 1;  // simple == 2 here: 1, but not to the compiler (IMAD adds)
+    const bool cr_too = P.crlf != 0;
     const int nwant = CQG_SPEC(NWANT, P.nwantL);
     const int gap0 = CQG_SPEC(GAP0, P.gap[0]), gap1 = CQG_SPEC(GAP1, P.gap[1]), gap2 = CQG_SPEC(GAP2, P.gap[2]),
               gap3 = CQG_SPEC(GAP3, P.gap[3]);
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) leanhc_kernel(const __grid_c
             auto chunk = [&](uint32_t ca, uint32_t ma) {
                 const uint4 v = lds128(ca);
                 uint32_t ra, rd;
-                spec |= l2g_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd);
+                spec |= l2g_masks16(v.x, v.y, v.z, v.w, patD, one, ra, rd, cr_too);
                 sts16(ma, ra);
                 sts16(ma + 4u, rd);
             };
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) leanhc_kernel(const __grid_c
 #undef CQG_HC_UPD
                     }
                 }
-                pos += et + 1u;
+                pos += et + 1u + (((tw >> 1) >> (et & 31u)) & 1u);  // (+1: the LF of a CR LF pair, an empty line)
             }
         }
         // too many rows outside this kernel's repertoire: let the general kernel do the whole scan.

@@ -167,7 +167,7 @@ struct DevPlan {
     int32_t lean_global;  // lean GROUP BY updates the packed global table directly (any number of groups)
     int32_t l_nagg;       // aggregates with a state (SUM/AVG/MIN/MAX over a known column): at most 4 on the lean kernel
     int32_t l_agg[4];     // their indices in aggs[]
-    int32_t l_pad;
+    int32_t crlf;         // the head of the file holds a CR: the lean kernels take '\r' as a line terminator (cqg_lean2g.cuh: l2g_masks16)
     const double* dec_table;  // [4][10000]: correctly rounded mant / 10^fd for mant < 10000 (lean MIN/MAX keys)
     // work the lean kernel hands to the general one
     int32_t* def_tiles;                 // tiles with bytes the lean kernel does not classify (CR, quotes, blanks, file edges)

@@ -229,6 +229,11 @@ class Table:
     def set_global_offset(self, off):
         _check(self.lib, self.lib.table_set_global_offset(self.handle, off))
 
+    def set_gpus(self, n):
+        """Spread the table over the first `n` devices of this process (cqg_table_set_gpus); before the first query."""
+        _check(self.lib, self.lib.table_set_gpus(self.handle, n))
+        return self.lib.table_gpus(self.handle)
+
     @property
     def columns(self):
         n = self.lib.table_column_count(self.handle)

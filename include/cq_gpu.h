@@ -109,6 +109,17 @@ int cqg_table_open_device(uint64_t device_ptr, size_t size, cqg_csv_config_t cfg
                           cqg_table_t** out);
 size_t cqg_device_padding(void);
 
+/* Multi-GPU residency in ONE process (the drop-in CLI: `CQ_GPUS=8 cq -q ...`; cqg_table_open reads CQ_GPUS itself). The
+ * file gets one virtual address range whose pages live on the first `ngpu` devices (slice d on device d, CUDA virtual
+ * memory management, every device mapped read/write); staging runs one copy thread per device. cqg_execute then runs
+ * aggregates without a join on all devices (each scans the rows starting in its slice, the partial group records cross
+ * NVLink to device 0, merge and finish there) and any other shape on device 0 over the whole range. Call before the
+ * first query; tables below CQG_MULTI_MIN_BYTES (64 MB) stay on one device. Replaces nothing in the reference (it has no
+ * threads): src/mmap.c:78-108 + src/csv_reader.c:375-465 are the single-core load it stands in for. */
+int cqg_table_set_gpus(cqg_table_t* t, int ngpu);
+/* devices the table is (or will be) resident on */
+int cqg_table_gpus(const cqg_table_t* t);
+
 /* restrict the table to the rows whose FIRST byte lies in the byte range of shard
  * `index` of `count` equal ranges (exact because row boundaries are not
  * quote-aware, src/csv_reader.c:407). Default is shard 0 of 1. The header is always
@@ -373,6 +384,10 @@ int64_t cqg_total_kernel_launches(void);
 /* launches of one scan kernel family so far: "scan" (general), "lean", "lean2", "lean2g", "lean2k", "leanhc"
  * (cq_b200/csrc/cqg_*.cuh); -1: no such family. Tests use it to assert which kernel a plan ran on. */
 int64_t cqg_kernel_launches_named(const char* family);
+/* the last scan of this thread that ran on a lean kernel: 16 KB tiles it covered, tiles and single rows it handed over to
+ * the general kernel (bytes the lean kernels do not classify: CR, quotes, controls; rows of 64 bytes and more, fields
+ * outside their repertoire). bench.py reports the shares. */
+void cqg_last_scan_stats(int64_t* tiles, int64_t* handed_tiles, int64_t* handed_rows);
 
 #ifdef __cplusplus
 }
