@@ -425,22 +425,51 @@ static Api& api() {
 }
 }  // namespace vmm
 
-static void release_multi(cqg_table* t) {
+// One released multi-GPU allocation is kept for the next table of the same size and devices (creating and mapping 10 GB
+// of physical memory costs 0.1-0.2 s; the single-GPU route keeps its stream-ordered pool warm in the same way).
+struct MultiAlloc {
+    uint8_t* va = nullptr;
+    uint64_t total = 0;
+    std::vector<int> devices;
+    std::vector<uint64_t> cuts;
+    std::vector<unsigned long long> handles;
+};
+static std::mutex g_multi_mu;
+static MultiAlloc g_multi_spare;
+
+static void release_multi(cqg_table* t, bool keep = true) {
     vmm::Api& v = vmm::api();
     for (cqg_table* w : t->views) delete w;
     t->views.clear();
     if (!t->va_size || !v.ok) return;
+    int home = 0;
+    cudaGetDevice(&home);
     for (int d : t->devices) {
         cudaSetDevice(d);
         cudaDeviceSynchronize();
     }
-    if (!t->devices.empty()) cudaSetDevice(t->devices[0]);
-    v.unmap((CUdeviceptr)(uintptr_t)t->d_data, t->va_size);
-    for (unsigned long long h : t->vmm_handles) v.release((CUmemGenericAllocationHandle)h);
-    v.addr_free((CUdeviceptr)(uintptr_t)t->d_data, t->va_size);
+    cudaSetDevice(home);
+    MultiAlloc old;
+    if (keep) {
+        std::lock_guard<std::mutex> lock(g_multi_mu);
+        old = g_multi_spare;
+        g_multi_spare.va = t->d_data;
+        g_multi_spare.total = t->va_size;
+        g_multi_spare.devices = t->devices;
+        g_multi_spare.cuts = t->cuts;
+        g_multi_spare.handles = t->vmm_handles;
+    } else {  // (a range that was never completely mapped: taken apart, not kept)
+        old.va = t->d_data;
+        old.total = t->va_size;
+        old.handles = t->vmm_handles;
+    }
     t->vmm_handles.clear();
     t->d_data = nullptr;
     t->va_size = 0;
+    if (!old.va) return;
+    v.unmap((CUdeviceptr)(uintptr_t)old.va, old.total);
+    for (unsigned long long h : old.handles) v.release((CUmemGenericAllocationHandle)h);
+    v.addr_free((CUdeviceptr)(uintptr_t)old.va, old.total);
 }
 
 // the host bytes of a multi-GPU table onto its devices: slices cut at 2 MB pages, one staging thread (with its own
@@ -474,15 +503,39 @@ static int stage_multi(cqg_table* t) {
         if (v.granularity(&g, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS) return fail(CQG_ERR_CUDA, "cuMemGetAllocationGranularity failed");
         gran = std::max(gran, g);
     }
+    const bool timing = getenv("CQG_TIMING") != nullptr;
+    auto now_ms = [] {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    double t_mark = now_ms();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const double t1 = now_ms();
+        fprintf(stderr, "[cqg timing] %-28s %9.3f ms\n", what, t1 - t_mark);
+        t_mark = t1;
+    };
     const uint64_t total = ((uint64_t)t->size + kDevPad + gran - 1) / gran * gran;
     const uint64_t pages = total / gran;
     t->cuts.assign(N + 1, 0);
     for (int d = 0; d <= N; d++) t->cuts[d] = pages * (uint64_t)d / (uint64_t)N * gran;
     CUdeviceptr va = 0;
-    if (v.reserve(&va, total, gran, 0, 0) != CUDA_SUCCESS) return fail(CQG_ERR_NOMEM, "cuMemAddressReserve of %llu bytes failed", (unsigned long long)total);
+    bool reused = false;
+    {
+        std::lock_guard<std::mutex> lock(g_multi_mu);
+        if (g_multi_spare.va && g_multi_spare.total == total && g_multi_spare.devices == t->devices && g_multi_spare.cuts == t->cuts) {
+            va = (CUdeviceptr)(uintptr_t)g_multi_spare.va;
+            t->vmm_handles = g_multi_spare.handles;
+            g_multi_spare = MultiAlloc();
+            reused = true;
+        }
+    }
+    if (!reused && v.reserve(&va, total, gran, 0, 0) != CUDA_SUCCESS)
+        return fail(CQG_ERR_NOMEM, "cuMemAddressReserve of %llu bytes failed", (unsigned long long)total);
     t->d_data = (uint8_t*)(uintptr_t)va;
     t->va_size = total;
-    for (int d = 0; d < N; d++) {
+    for (int d = 0; d < N && !reused; d++) {
         const uint64_t len = t->cuts[d + 1] - t->cuts[d];
         if (!len) continue;
         CUmemAllocationProp prop{};
@@ -491,16 +544,16 @@ static int stage_multi(cqg_table* t) {
         prop.location.id = t->devices[d];
         CUmemGenericAllocationHandle h = 0;
         if (v.create(&h, len, &prop, 0) != CUDA_SUCCESS) {
-            release_multi(t);
+            release_multi(t, false);
             return fail(CQG_ERR_NOMEM, "cuMemCreate of %llu bytes on device %d failed", (unsigned long long)len, t->devices[d]);
         }
         t->vmm_handles.push_back((unsigned long long)h);
         if (v.map(va + t->cuts[d], len, 0, h, 0) != CUDA_SUCCESS) {
-            release_multi(t);
+            release_multi(t, false);
             return fail(CQG_ERR_CUDA, "cuMemMap failed");
         }
     }
-    {
+    if (!reused) {
         std::vector<CUmemAccessDesc> acc;
         for (int d = 0; d < N; d++) {
             bool seen = false;
@@ -513,10 +566,11 @@ static int stage_multi(cqg_table* t) {
             acc.push_back(a);
         }
         if (v.set_access(va, total, acc.data(), acc.size()) != CUDA_SUCCESS) {
-            release_multi(t);
+            release_multi(t, false);
             return fail(CQG_ERR_CUDA, "cuMemSetAccess failed (no peer access between the devices of CQ_GPUS?)");
         }
     }
+    lap("multi: reserve, create, map");
     // the bytes: every device pulls its own slice
     std::vector<int> rcs(N, CQG_OK);
     std::vector<std::string> errs(N);
@@ -546,10 +600,11 @@ static int stage_multi(cqg_table* t) {
         });
     }
     for (std::thread& x : th) x.join();
+    lap("multi: slices staged");
     CU(cudaSetDevice(home));
     for (int d = 0; d < N; d++)
         if (rcs[d] != CQG_OK) {
-            release_multi(t);
+            release_multi(t, false);
             return fail(rcs[d], "staging slice %d: %s", d, errs[d].empty() ? "CUDA error" : errs[d].c_str());
         }
     // per slice a view of the same address range that owns the rows starting in the slice

@@ -46,6 +46,22 @@ static long long check(const unsigned char* b, unsigned char delim) {
         exit(1);
     }
     if (!dirty && spec != 0u) g_false_dirty++;
+    // the same with CR as a second line terminator (DevPlan::crlf): '\r' joins the terminator class and leaves "dirty"
+    {
+        uint32_t n16c = 0, d16c = 0, enc = 0;
+        bool dirtyc = false;
+        const uint32_t specc = l2g_masks16(w[0], w[1], w[2], w[3], (uint32_t)delim * 0x01010101u, 1u, n16c, d16c, true) & 0x80808080u;
+        for (int i = 0; i < 16; i++) {
+            if (b[i] == '\n' || b[i] == '\r') enc |= 1u << i;
+            if ((b[i] < 0x20 || b[i] == 0x22) && b[i] != '\n' && b[i] != '\r') dirtyc = true;
+        }
+        if (n16c != enc || d16c != ed || (dirtyc && specc == 0u)) {
+            printf("MISMATCH (GROUP BY phase 1, CR mode) delimiter %02x bytes", delim);
+            for (int i = 0; i < 16; i++) printf(" %02x", b[i]);
+            printf(": N %04x (expected %04x) D %04x (expected %04x) dirty %d spec %08x\n", n16c, enc, d16c, ed, (int)dirtyc, specc);
+            exit(1);
+        }
+    }
     if (t16 != et || d16 != ed) {
         printf("MISMATCH delimiter %02x bytes", delim);
         for (int i = 0; i < 16; i++) printf(" %02x", b[i]);
