@@ -425,6 +425,42 @@ def main():
                 extra["clean_2gb"] = clean
             except Exception as ex:
                 extra["variants_error"] = repr(ex)
+            # ---- BASELINE configs[4] at its stated size: 100 M x 10 M rows, equi-join on an integer key (the seeded
+            # generator's `uid` column on both sides: left `...,uid` ~ U{0..R-1}, right one row per draw of the same range),
+            # bytes(left) + bytes(right) read once ----
+            try:
+                scale = args.bytes / 1e10
+                Lr, Rr = int(100e6 * scale), int(10e6 * scale)
+
+                def gen(rows, seed):
+                    cap = lib.generate_bigdata_bound(rows, Rr) + lib.device_padding()
+                    b = torch.empty(cap, dtype=torch.uint8, device="cuda")
+                    sz = C.c_size_t()
+                    _check(lib, lib.generate_bigdata(b.data_ptr(), cap - lib.device_padding(), rows, seed, Rr, C.byref(sz)))
+                    return Table.from_device(b.data_ptr(), sz.value, lib=lib, keep=b), sz.value
+
+                lt, lbytes = gen(Lr, 11)
+                rt, rbytes = gen(Rr, 12)
+                UID, RIGHT = 5, 6
+                jspecs = {"count": dict(aggs=[(pc.A.AGG_COUNT_STAR, -1)]),
+                          "group_right_gender_sum_left_age": dict(group_by=[RIGHT + 3], out_cols=[RIGHT + 3],
+                                                                  aggs=[(pc.A.AGG_COUNT_STAR, -1), (pc.A.AGG_SUM, 2)])}
+                jl = {"left_rows": Lr, "right_rows": Rr, "bytes": lbytes + rbytes}
+                for jn, js in jspecs.items():
+                    pl = pc.build(js, join=(rt, UID, UID))
+                    lt.execute_raw(pl)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    r = lt.execute_raw(pl)
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    jl[jn] = {"query_gbs": (lbytes + rbytes) / dt / 1e9, "query_ms": dt * 1e3, "rows_per_s": (Lr + Rr) / dt,
+                              "groups": r["n_groups"], "count0": int(r["count0"]), "kernel_ms": r["kernel_ms"]}
+                extra["join_100m_x_10m"] = jl
+                del lt, rt
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                extra["join_error"] = repr(ex)
             for name in ["scalar_aggs", "lean_group_abort_many", "count_height_gt_1_5"]:
                 pl = pc.build(pc.plans()[name])
                 table.execute_raw(pl)

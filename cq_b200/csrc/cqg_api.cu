@@ -910,18 +910,50 @@ static bool worth_it(uint64_t scan_bytes) {
     return scan_bytes >= min_bytes;
 }
 
-// cubins persist across processes: $CQG_JIT_CACHE, else $HOME/.cache/cqg_jit, else /tmp/cqg_jit (best effort)
+// a hash of everything NVRTC will read (the kernel headers next to the library and cq_gpu.h): part of every cache key,
+// so that editing a header never reuses a cubin compiled from the old text
+static uint64_t sources_hash() {
+    static uint64_t h = 0;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::string csrc, inc;
+        source_dirs(csrc, inc);
+        uint64_t x = 1469598103934665603ull;
+        const char* files[] = {"cqg_rtc.h", "cqg_device.cuh", "cqg_plan.cuh", "cqg_scan.cuh", "cqg_lean.cuh", "cqg_lean2.cuh",
+                               "cqg_lean2g.cuh", "cqg_lean2k.cuh", "cqg_leanhc.cuh"};
+        auto eat = [&](const std::string& path) {
+            if (FILE* f = fopen(path.c_str(), "rb")) {
+                char buf[65536];
+                size_t n;
+                while ((n = fread(buf, 1, sizeof buf, f)) > 0)
+                    for (size_t i = 0; i < n; i++) x = (x ^ (unsigned char)buf[i]) * 1099511628211ull;
+                fclose(f);
+            }
+        };
+        for (const char* f : files) eat(csrc + "/" + f);
+        eat(inc + "/cq_gpu.h");
+        h = x;
+    });
+    return h;
+}
+
+// cubins persist across processes in $CQG_JIT_CACHE, else $HOME/.cache/cqg_jit; nowhere when neither is set. The
+// directory must belong to this user and be closed to everybody else (a cubin found there is loaded and launched).
+// "" : no disk cache.
 static std::string cache_path(const std::string& key) {
-    uint64_t h = 1469598103934665603ull;
-    for (unsigned char c : key) h = (h ^ c) * 1099511628211ull;
-    for (const char* c = "sm_100a|v1|" __DATE__ " " __TIME__; *c; c++) h = (h ^ (unsigned char)*c) * 1099511628211ull;
     const char* e = getenv("CQG_JIT_CACHE");
     std::string dir;
-    if (e) dir = e;
-    else if (const char* home = getenv("HOME")) dir = std::string(home) + "/.cache/cqg_jit";
-    else dir = "/tmp/cqg_jit";
-    mkdir(dir.substr(0, dir.rfind('/')).c_str(), 0700);
+    if (e && *e) dir = e;
+    else if (const char* home = getenv("HOME")) {
+        if (!*home) return "";
+        dir = std::string(home) + "/.cache/cqg_jit";
+        mkdir((std::string(home) + "/.cache").c_str(), 0700);
+    } else return "";
     mkdir(dir.c_str(), 0700);
+    struct stat sb;
+    if (lstat(dir.c_str(), &sb) != 0 || !S_ISDIR(sb.st_mode) || sb.st_uid != geteuid() || (sb.st_mode & 077) != 0) return "";
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : key) h = (h ^ c) * 1099511628211ull;
     char name[40];
     snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)h);
     return dir + name;
@@ -931,14 +963,17 @@ static std::string cache_path(const std::string& key) {
 static cudaKernel_t get(const std::string& defs, const char* header, const char* name, uint64_t scan_bytes) {
     if (!enabled() || !worth_it(scan_bytes)) return nullptr;
     std::lock_guard<std::mutex> lock(g_mu);
-    const std::string key = std::string(name) + "\n" + defs;
+    char sh[40];
+    snprintf(sh, sizeof sh, "sm_100a|v2|%016llx\n", (unsigned long long)sources_hash());
+    const std::string key = std::string(sh) + name + "\n" + defs;
     auto it = g_cache.find(key);
     if (it != g_cache.end()) return it->second.failed ? nullptr : it->second.fn;
     Kernel& k = g_cache[key];
     k.failed = true;
-    // a cubin of this shape from an earlier process? (file = lowered name, NUL, cubin)
+    // a cubin of this shape from an earlier process? (file = the whole key, NUL, lowered name, NUL, cubin: the key is
+    // compared, not just its hash in the file name)
     const std::string path = cache_path(key);
-    {
+    if (!path.empty()) {
         std::vector<char> blob;
         if (FILE* f = fopen(path.c_str(), "rb")) {
             char buf[65536];
@@ -946,15 +981,18 @@ static cudaKernel_t get(const std::string& defs, const char* header, const char*
             while ((n = fread(buf, 1, sizeof buf, f)) > 0) blob.insert(blob.end(), buf, buf + n);
             fclose(f);
         }
-        const void* nul = blob.empty() ? nullptr : memchr(blob.data(), 0, blob.size());
-        if (nul) {
-            const size_t off = (const char*)nul - blob.data() + 1;
-            if (off < blob.size() && cudaLibraryLoadData(&k.lib, blob.data() + off, nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
-                cudaLibraryGetKernel(&k.fn, k.lib, blob.data()) == cudaSuccess) {
-                k.failed = false;
-                return k.fn;
+        if (blob.size() > key.size() + 2 && memcmp(blob.data(), key.data(), key.size()) == 0 && blob[key.size()] == 0) {
+            const char* low0 = blob.data() + key.size() + 1;
+            const void* nul = memchr(low0, 0, blob.size() - key.size() - 1);
+            if (nul) {
+                const size_t off = (const char*)nul - blob.data() + 1;
+                if (off < blob.size() && cudaLibraryLoadData(&k.lib, blob.data() + off, nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+                    cudaLibraryGetKernel(&k.fn, k.lib, low0) == cudaSuccess) {
+                    k.failed = false;
+                    return k.fn;
+                }
+                cudaGetLastError();
             }
-            cudaGetLastError();
         }
     }
     Api& a = api();
@@ -993,10 +1031,11 @@ static cudaKernel_t get(const std::string& defs, const char* header, const char*
     }
     k.failed = false;
     if (getenv("CQG_JIT_VERBOSE")) fprintf(stderr, "[cqg jit] compiled %s (%zu bytes)\n", name, n);
-    {
+    if (!path.empty()) {
         const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
         if (FILE* f = fopen(tmp.c_str(), "wb")) {
-            const bool w = fwrite(lowered.c_str(), 1, lowered.size() + 1, f) == lowered.size() + 1 && fwrite(cubin.data(), 1, n, f) == n;
+            const bool w = fwrite(key.c_str(), 1, key.size() + 1, f) == key.size() + 1 &&
+                           fwrite(lowered.c_str(), 1, lowered.size() + 1, f) == lowered.size() + 1 && fwrite(cubin.data(), 1, n, f) == n;
             fclose(f);
             if (!w || rename(tmp.c_str(), path.c_str()) != 0) unlink(tmp.c_str());
         }
@@ -3147,7 +3186,7 @@ static int compact_groups(HostPlan& hp, GroupTable& gt, int owner, int world, De
 }
 
 static int execute_select(HostPlan& hp, const cqg_table* t, const cqg_table* rt, const cqg_query_t* q, cqg_result_t** out,
-                          cudaStream_t st, float* ms_total) {
+                          cudaStream_t st, float* ms_total, const JoinState* js = nullptr) {
     DevPlan& P = hp.P;
     uint64_t cap = 1 << 16;
     ScalarBlock hs{};
@@ -3187,6 +3226,10 @@ static int execute_select(HostPlan& hp, const cqg_table* t, const cqg_table* rt,
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (rc) return rc;
+    if (js) {  // what building the join table over the right file raised (a key beyond the decoders' range, ...)
+        hs.errflags |= js->flags;
+        hs.jclass[1] |= js->key_classes;
+    }
     if ((rc = check_flags(hs, P.join != 0))) return rc;
     uint64_t n = hs.sel_count;
     std::vector<uint64_t> ok(n), ro(rt ? n : 0);
@@ -3280,7 +3323,7 @@ CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t
     long long launches0 = g_launches.load();
     if (rt && (rc = build_join(hp, js, rt, q->join.right_col, st))) return rc;
     if (q->mode == CQG_MODE_SELECT) {
-        rc = execute_select(hp, t, rt, q, out, st, &ms);
+        rc = execute_select(hp, t, rt, q, out, st, &ms, &js);
     } else {
         GroupTable gt;
         ScalarBlock hs{};

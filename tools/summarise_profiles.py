@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Turn gpurun_out/<round>_* ncu outputs into the small text files committed under profiles/.
-usage: python tools/summarise_profiles.py r01"""
+"""Turn gpurun_out/<round>_* outputs of tools/collect_profiles.sh into the small text files committed under profiles/.
+usage: python tools/summarise_profiles.py r02"""
 import csv
 import json
 import os
@@ -8,10 +8,18 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 OUT = os.path.join(ROOT, "profiles")
 os.makedirs(OUT, exist_ok=True)
 G = os.path.join(ROOT, "gpurun_out")
+
+# 0. the bench line of the same run
+for src, dst in ((f"{R}_bench_plain.json", f"{R}_bench_line.json"),):
+    path = os.path.join(G, src)
+    if os.path.exists(path):
+        line = [ln for ln in open(path) if ln.startswith("{")][-1]
+        json.dump(json.loads(line), open(os.path.join(OUT, dst), "w"), indent=1)
+        print("wrote", dst)
 
 # 1. launch list: kernel name, count, total and share of device time
 path = os.path.join(G, f"{R}_launches.csv")
@@ -32,42 +40,36 @@ if os.path.exists(path):
         a[0] += 1
         a[1] += t
     with open(os.path.join(OUT, f"{R}_launch_list.txt"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-extra\n")
-        f.write(f"# {len(rows)} launches, {tot:.3f} ms of device time (cold-cache, serialised: compare shares)\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 600 : python bench.py --steps 2 --warmup 3 --no-extra\n")
+        f.write(f"# {len(rows)} launches, {tot:.3f} ms of device time (cold-cache, serialised: compare shares). The first launches are the\n")
+        f.write("# synthetic-data generator; then the three timed legs (lean2k, lean2<ONELEAF>, leanhc + expand + device-side finish) and the end-to-end legs (lean2k again)\n")
         f.write(f"{'kernel':90s} {'launches':>8s} {'ms':>10s} {'share':>7s}\n")
         for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{k:90s} {n:8d} {t:10.3f} {100 * t / tot:6.1f}%\n")
     print("wrote launch list:", len(rows), "launches")
 
-# 2. full capture of the headline kernel
-rep = os.path.join(G, f"{R}_lean_full.ncu-rep")
-if os.path.exists(rep):
+# 2. full captures
+KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_atom.sum",
+        "lts__t_sectors_srcunit_tex_op_red.sum", "sm__cycles_elapsed.avg.per_second"]
+for kern, plan in (("lean2k", "group_name"), ("lean2", "count_age_gt_40"), ("leanhc", "group_high_card")):
+    rep = os.path.join(G, f"{R}_{kern}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     h, u, v = r[0], r[1], r[2]
-    keep = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__cycles_active.avg",
-            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
-            "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
-            "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
-            "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-            "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
-    vals = {}
-    with open(os.path.join(OUT, f"{R}_lean_kernel_ncu.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:lean2_kernel : CQ_BENCH_BYTES=2e9 python bench.py --steps 2 --warmup 3 --no-extra\n")
+    with open(os.path.join(OUT, f"{R}_{kern}_ncu.txt"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kern} : python tools/run_plan.py {plan} 2e9 3\n")
+        f.write("# (one launch on a 2 GB table, kernel compiled for the query by cqg_jit where that applies; tools/collect_profiles.sh)\n")
         for i, k in enumerate(h):
-            if k in keep or (k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio")):
+            if k in KEEP or (k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio")):
                 f.write(f"{k} = {v[i]} {u[i]}\n")
-                vals[k] = v[i]
-    try:
-        rd = float(vals["dram__bytes_read.sum"].replace(",", ""))
-        wr = float(vals["dram__bytes_write.sum"].replace(",", ""))
-        bj = json.load(open(os.path.join(G, f"{R}_bench_plain.json")))
-        # the capture ran on a 2e9-byte input; units as ncu printed them
-        print("dram read/write as printed:", vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"])
-    except Exception as ex:
-        print("traffic:", ex)
-    lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "25"], capture_output=True, text=True).stdout
-    with open(os.path.join(OUT, f"{R}_lean_kernel_hot_lines.txt"), "w") as f:
-        f.write(lines)
-    print("wrote lean kernel summary")
+        f.write("\n")
+        f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "25"], capture_output=True, text=True).stdout)
+    print("wrote", f"{R}_{kern}_ncu.txt")
