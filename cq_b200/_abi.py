@@ -144,6 +144,7 @@ PROTOTYPES = {
     "generate_bigdata_bound": (C.c_size_t, [C.c_int64, C.c_int64]),
     "table_set_gpus": (C.c_int, [C.c_void_p, C.c_int]),
     "table_gpus": (C.c_int, [C.c_void_p]),
+    "table_field_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int64, C.POINTER(C.c_int32)]),
     "total_kernel_launches": (C.c_int64, []),
     "kernel_launches_named": (C.c_int64, [C.c_char_p]),
     "last_scan_stats": (None, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

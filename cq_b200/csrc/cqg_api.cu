@@ -3355,6 +3355,27 @@ CQG_API int cqg_execute(const cqg_table_t* t, const cqg_query_t* q, cqg_result_t
     return rc;
 }
 
+// csv_load's Row::column_count for the rows at `row_offsets` (host array, e.g. cqg_result_t::row_offset of a projection)
+CQG_API int cqg_table_field_counts(const cqg_table_t* t, const uint64_t* row_offsets, int64_t n, int32_t* counts) {
+    if (!t || n < 0 || (n && (!row_offsets || !counts))) return fail(CQG_ERR_ARG, "bad argument");
+    if (n == 0) return CQG_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = ensure_staged(t))) return rc;
+    if (t->ngpu > 1) CU(cudaSetDevice(t->devices[0]));
+    DevBuf d_off, d_cnt;
+    CU(d_off.alloc((size_t)n * 8, 0));
+    CU(d_cnt.alloc((size_t)n * 4, 0));
+    CU(cudaMemcpyAsync(d_off.p, row_offsets, (size_t)n * 8, cudaMemcpyHostToDevice, 0));
+    const int grid = (int)std::min<int64_t>((n + 127) / 128, 148 * 16);
+    field_count_kernel<<<grid, 128>>>(t->d_data, t->size, d_off.as<uint64_t>(), (uint64_t)n, (uint8_t)t->cfg.delimiter, (uint8_t)t->cfg.quote,
+                                      d_cnt.as<int32_t>());
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(counts, d_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return CQG_OK;
+}
+
 CQG_API int cqg_table_row_count(const cqg_table_t* t, int64_t* out) {
     if (!t || !out) return fail(CQG_ERR_ARG, "null argument");
     int rc = ensure_device();

@@ -1551,6 +1551,43 @@ __device__ inline void fetch_one(const uint8_t* file, uint64_t fsize, uint64_t o
     }
 }
 
+// Fields per row as parse_line counts them (src/csv_reader.c:278-338: leading whitespace skipped, quoted fields with doubled
+// quotes, a trailing delimiter opens no field, a line of blanks has none) for rows given by their byte offsets: csv_load's
+// Row::column_count (src/csv_reader.c:358-366), which a GPU-backed csv_load must hand to its callers.
+__global__ void field_count_kernel(const uint8_t* data, uint64_t size, const uint64_t* row_off, uint64_t n, uint8_t delim, uint8_t quote,
+                                   int32_t* out) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t ptr = row_off[r];
+        uint64_t re = ptr;
+        while (re < size && data[re] != '\n' && data[re] != '\r') re++;
+        int fc = 0;
+        while (ptr < re) {
+            while (ptr < re && is_space(data[ptr])) ptr++;
+            if (ptr >= re) break;
+            if (data[ptr] == quote) {
+                ptr++;
+                while (ptr < re) {
+                    if (data[ptr] == quote) {
+                        if (ptr + 1 < re && data[ptr + 1] == quote) {
+                            ptr += 2;
+                        } else {
+                            ptr++;
+                            break;
+                        }
+                    } else {
+                        ptr++;
+                    }
+                }
+            }
+            while (ptr < re && data[ptr] != delim) ptr++;
+            fc++;
+            if (ptr < re && data[ptr] == delim) ptr++;
+        }
+        out[r] = fc;
+    }
+}
+
+
 __global__ void fetch_kernel(const __grid_constant__ FetchParams F) {
     unsigned err = 0;
     const uint64_t total = F.n * (uint64_t)F.ncols;

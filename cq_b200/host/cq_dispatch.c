@@ -781,6 +781,108 @@ done:
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* csv_load for the callers that need the array of structs                  */
+/* ------------------------------------------------------------------------------------ */
+/* Every shape that keeps the reference's route (CASE, scalar functions, sub-queries, multi-join chains, window
+ * functions) and every DML statement starts with csv_load (evaluator_joins.c:219, :249; evaluator_statements.c), the
+ * single-threaded parse that dominates the reference's run time. src/csv_reader.c is compiled with that one
+ * name changed to cq_ref_csv_load and this csv_load stands in: split + typed decode on the GPU (a `SELECT *` projection
+ * and cqg_table_field_counts), then the same CsvTable csv_load builds - Row::column_count per row as parse_line counts
+ * fields, names and `$n` names, inferred types from the first 20 rows (src/csv_reader.c:429-462). Anything it cannot
+ * hand back identically goes to the reference's own csv_load: a file that does not open (so that the messages are the
+ * reference's), more columns than a projection carries, a row with MORE fields than the header (their values are not
+ * part of a projection), a dialect or datum the kernels decline. CQ_GPU=0 and CQ_GPU_LOAD=0 switch it off. */
+#ifndef CQ_BACKEND_ORACLE
+CsvTable* cq_ref_csv_load(const char* filename, CsvConfig config);
+
+static CsvTable* gpu_csv_load(const char* filename, CsvConfig config) {
+    cqg_csv_config_t cfg;
+    cfg.delimiter = config.delimiter;
+    cfg.quote = config.quote;
+    cfg.has_header = config.has_header ? 1 : 0;
+    cfg.reserved = 0;
+    cqg_table_t* t = NULL;
+    if (cqg_table_open(filename, cfg, &t) != CQG_OK) return NULL;
+    CsvTable* table = NULL;
+    cqg_result_t* res = NULL;
+    int32_t* fc = NULL;
+    int ncols = cqg_table_column_count(t);
+    if (ncols < 1 || ncols > CQG_MAX_OUT_COLS) goto out;
+    cqg_query_t q;
+    memset(&q, 0, sizeof q);
+    q.mode = CQG_MODE_SELECT;
+    q.n_out_cols = ncols;
+    for (int c = 0; c < ncols; c++) q.out_cols[c] = c;
+    q.max_rows = -1;
+    if (cqg_execute(t, &q, &res) != CQG_OK) goto out;
+    int64_t N = res->n_rows_out;
+    if (N > 0x7fffffff) goto out;
+    fc = malloc(sizeof(int32_t) * (size_t)(N > 0 ? N : 1));
+    if (!fc || cqg_table_field_counts(t, res->row_offset, N, fc) != CQG_OK) goto out;
+    for (int64_t i = 0; i < N; i++)
+        if (fc[i] > ncols) goto out; /* fields beyond the header: only the reference's loader keeps them */
+
+    table = calloc(1, sizeof(CsvTable));
+    table->filename = strdup(filename);
+    table->data = NULL; /* csv_free: nothing to unmap */
+    table->file_size = cqg_table_size(t);
+    table->fd = -1;
+    table->delimiter = config.delimiter;
+    table->quote = config.quote;
+    table->has_header = config.has_header;
+    table->column_count = ncols;
+    table->columns = malloc(sizeof(Column) * (size_t)ncols);
+    for (int c = 0; c < ncols; c++) {
+        table->columns[c].name = strdup(cqg_table_column_name(t, c));
+        table->columns[c].inferred_type = VALUE_TYPE_STRING;
+    }
+    table->row_count = (int)N;
+    table->row_capacity = (int)N;
+    table->rows = N > 0 ? malloc(sizeof(Row) * (size_t)N) : NULL;
+    for (int64_t i = 0; i < N; i++) {
+        const int n = fc[i];
+        table->rows[i].column_count = n;
+        table->rows[i].values = malloc(sizeof(Value) * (size_t)(n > 0 ? n : 1));
+        for (int c = 0; c < n; c++) table->rows[i].values[c] = to_value(&res->rows[(size_t)i * (size_t)ncols + (size_t)c]);
+    }
+    /* inferred column types: src/csv_reader.c:429-462 */
+    if (table->row_count > 0) {
+        const int sample = table->row_count < 20 ? table->row_count : 20;
+        for (int c = 0; c < ncols; c++) {
+            int counts[5] = {0, 0, 0, 0, 0};
+            for (int r = 0; r < sample; r++)
+                if (c < table->rows[r].column_count) {
+                    const ValueType ty = table->rows[r].values[c].type;
+                    if (ty >= 0 && ty < 5) counts[ty]++;
+                }
+            table->columns[c].inferred_type = counts[VALUE_TYPE_DATE] > 0      ? VALUE_TYPE_DATE
+                                              : counts[VALUE_TYPE_DOUBLE] > 0  ? VALUE_TYPE_DOUBLE
+                                              : counts[VALUE_TYPE_INTEGER] > 0 ? VALUE_TYPE_INTEGER
+                                                                               : VALUE_TYPE_STRING;
+        }
+    }
+out:
+    free(fc);
+    if (res) cqg_result_free(res);
+    cqg_table_close(t);
+    return table;
+}
+
+CsvTable* csv_load(const char* filename, CsvConfig config) {
+    const char* e = getenv("CQ_GPU_LOAD");
+    if (filename && gpu_enabled() && !(e && e[0] == '0')) {
+        CsvTable* table = gpu_csv_load(filename, config);
+        if (table) {
+            if (trace_enabled()) fprintf(stderr, "[cq-gpu] csv_load=gpu %s\n", filename);
+            return table;
+        }
+    }
+    if (trace_enabled()) fprintf(stderr, "[cq-gpu] csv_load=reference %s\n", filename ? filename : "(null)");
+    return cq_ref_csv_load(filename, config);
+}
+#endif
+
+/* ------------------------------------------------------------------------------------ */
 /* the two symbols cq binds to                                                          */
 /* ------------------------------------------------------------------------------------ */
 

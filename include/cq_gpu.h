@@ -365,6 +365,12 @@ void cqg_rowlist_free(cqg_rowlist_t* rl);
 int cqg_execute_partial_rows(const cqg_table_t* t, const cqg_query_t* q, uint64_t left_rows_device_ptr, int64_t n_left,
                              uint64_t right_rows_device_ptr, int64_t n_right, cqg_partial_t** out);
 
+/* ---- csv_load for callers that need the reference's array of structs (DML, the reference's own evaluator) ----
+ * Fields per row exactly as parse_line counts them (src/csv_reader.c:278-338) = Row::column_count (:358-366) for the rows
+ * at the given byte offsets (host array; cqg_result_t::row_offset of a `SELECT *` projection). Together with that
+ * projection it is everything csv_load (src/csv_reader.c:375-465) returns: cq_dispatch.c's csv_load is built from the two. */
+int cqg_table_field_counts(const cqg_table_t* t, const uint64_t* row_offsets, int64_t n, int32_t* counts);
+
 /* ---- synthetic data: seeded restatement of utils/generate_big_dataset.py:9-19 ----
  * Fills device memory with header + rows `name,surname,age,gender,height\n`; returns
  * the byte size. key_card>0 appends an integer column `uid` ~ U{0..key_card-1}.

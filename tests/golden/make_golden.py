@@ -162,6 +162,11 @@ NULL,16,2020-06-06
 123456.1234565,20,2020-06-06
 123456.1234575,21,2020-06-06
 """)
+    # rows with FEWER fields than the header (csv_load keeps Row::column_count per row; queries below touch column 0 only,
+    # which every row has: the reference reads out of bounds otherwise, SURVEY Q15) and a trailing delimiter (no field)
+    w("short.csv", "id,name,score\n1,ann,3.5\n2,bob\n3\n4,eve,5,\n5,\"q,x\",6\n")
+    # a row with MORE fields than the header: only the reference's own csv_load keeps the extra value
+    w("long.csv", "id,name,score\n1,ann,3.5\n2,bob,4,extra\n3,eve,5\n")
     w("mixed.csv", """g,v,z
 a,5,1
 a,3.5,1
@@ -190,10 +195,11 @@ P = "people.csv"
 QUERIES = []
 
 
-def q(sql, args=(), kind="fix", route=None):
+def q(sql, args=(), kind="fix", route=None, load=None):
     """route="any": the GPU planner may decline the shape at plan time (the reference then evaluates it); the
-    result must be the reference's either way."""
-    QUERIES.append({"sql": sql, "args": list(args), "kind": kind, "route": route})
+    result must be the reference's either way. load="gpu" / "reference": which csv_load the drop-in binary must have
+    used for a statement that keeps the reference's evaluator (cq_dispatch.c: csv_load)."""
+    QUERIES.append({"sql": sql, "args": list(args), "kind": kind, "route": route, "load": load})
 
 
 def make_queries():
@@ -345,6 +351,30 @@ def make_queries():
     # --- shapes the GPU planner declines at plan time: they must come out of the drop-in binary all the same ---
     q(f"SELECT COUNT(*), SUM(age) FROM '{P}' WHERE age IN ({', '.join(str(k) for k in range(18, 48))})", route="any")
     q("SELECT COUNT(*), SUM(val) FROM 'alpha.csv' WHERE id > 1", args=["-s", "x"], route="any")
+    # --- shapes that keep the reference's evaluator (scalar functions, CASE, STDDEV, sub-queries, expression GROUP BY):
+    # their csv_load is the GPU-backed one of cq_dispatch.c and must hand back the reference's own table ---
+    G = dict(route="reference", load="gpu")
+    q(f"SELECT name, UPPER(role), LENGTH(email) FROM '{P}' WHERE age > 30", **G)
+    q(f"SELECT name, CASE WHEN age > 30 THEN 'old' ELSE 'young' END FROM '{P}'", **G)
+    q(f"SELECT role, STDDEV(age), STDDEV(height) FROM '{P}' GROUP BY role", **G)
+    q(f"SELECT id, COALESCE(city, 'nowhere'), COALESCE(age, 0), joined FROM '{P}'", **G)
+    q(f"SELECT name FROM '{P}' WHERE age > (SELECT AVG(age) FROM '{P}')", route="any", load="gpu")
+    q(f"SELECT YEAR(joined), MONTH(joined), DAY(joined), name FROM '{P}' WHERE YEAR(joined) >= 2021", **G)
+    q(f"SELECT CONCAT(name, '-', role), ROUND(height, 1), ABS(age - 40), height * 2 FROM '{P}'", **G)
+    q("SELECT id, val, UPPER(tag), COALESCE(val, 'none') FROM 'types.csv'", **G)
+    q("SELECT id, LOWER(tag), val FROM 'types.csv' WHERE val > 3", **G)
+    q("SELECT id, UPPER(name), role, note FROM 'quoted.csv'", **G)
+    q("SELECT id, LENGTH(name), LENGTH(note) FROM 'quoted.csv' WHERE role = 'admin'", **G)
+    q("SELECT id, UPPER(role), age + 1 FROM 'crlf.csv'", **G)
+    q("SELECT id, UPPER(role), age FROM 'blank_lines.csv'", **G)
+    q("SELECT UPPER($1), $0, $2 FROM 'noheader.csv'", args=["-n"], **G)
+    q("SELECT id, UPPER(name), score FROM 'semi.csv'", args=["-s", ";"], **G)
+    q("SELECT id, UPPER(name), score FROM 'tabs.csv'", args=["-s", "\t"], **G)
+    q("SELECT g, STDDEV(v), COUNT(*) FROM 'mixed.csv' GROUP BY g", **G)
+    q("SELECT UPPER(k), v, d FROM 'keys.csv'", **G)
+    q("SELECT id, LENGTH(id) FROM 'short.csv'", **G)
+    q("SELECT id, LENGTH(id) FROM 'long.csv'", route="reference", load="reference")
+    q("SELECT o.id, UPPER(c.name) FROM 'orders.csv' AS o JOIN 'customers.csv' AS c ON o.customer_id = c.id", **G)
     # --- reference's own fixtures, in place ---
     q("SELECT role, COUNT(*), AVG(age) FROM 'data/users.csv' WHERE age > 25 GROUP BY role", kind="refdata")
     q("SELECT COUNT(*) FROM 'data/test_data.csv'", kind="refdata")
@@ -375,6 +405,8 @@ def main():
         route = item.get("route") or ("gpu" if "route=gpu" in err else "reference")
         out.append({"id": i, "kind": item["kind"], "args": item["args"], "sql": item["sql"], "rc": rc, "route": route,
                     "expected": text})
+        if item.get("load"):
+            out[-1]["load"] = item["load"]
     with open(os.path.join(ROOT, "tests", "golden", "sql_golden.json"), "w") as f:
         json.dump(out, f, indent=0)
     print(f"{len(out)} golden cases written")

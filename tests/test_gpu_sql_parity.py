@@ -23,3 +23,7 @@ def test_sql_matches_reference_golden(case):
     assert ok, f"{case['sql']}: {why}\n--- got\n{out}\n--- want\n{case['expected']}\n{err}"
     if case.get("route") == "gpu":
         assert "route=gpu" in err, f"{case['sql']} did not take the GPU route:\n{err}"
+    if case.get("load") == "gpu":  # a statement on the reference's evaluator: its tables came through the GPU-backed csv_load
+        assert "csv_load=gpu" in err and "csv_load=reference" not in err, f"{case['sql']}:\n{err}"
+    if case.get("load") == "reference":
+        assert "csv_load=reference" in err, f"{case['sql']}:\n{err}"
