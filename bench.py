@@ -43,7 +43,7 @@ QUERY = "SELECT name, COUNT(*), AVG(height), SUM(age) FROM f WHERE age > 25 GROU
 WORKLOAD = ("BASELINE configs[0] query shape (scan + filter + GROUP BY) on the 10 GB synthetic CSV of configs[1] "
             f"(seeded restatement of utils/generate_big_dataset.py): {QUERY}")
 LEGS = {  # name -> (plan in tests/parity_cases.py, SQL text, kernel)
-    "groupby": ("group_name", QUERY, "cqg::lean2g_kernel (per-CTA dictionary, per-warp shared-memory accumulators)"),
+    "groupby": ("group_name", QUERY, "cqg::lean2k_kernel (compiled for the query; two-word dictionary buckets, per-warp shared-memory accumulators)"),
     "count_where": ("count_age_gt_40", "SELECT COUNT(*) FROM f WHERE age > 40", "cqg::lean2_kernel<ONELEAF>"),
     "high_card": ("group_high_card",
                   "SELECT name, surname, age, height, COUNT(*), SUM(age), MIN(height), MAX(height), AVG(height) FROM f "
@@ -269,12 +269,27 @@ def main():
         t = Table.from_device(buf.data_ptr(), size.value, cfg=csv_config(has_header=(index == 0)), lib=lib, keep=buf)
         return t, buf, size.value
 
+    # DRAM bytes per CSV byte of each kernel, from THIS round's `ncu --set full` captures (profiles/r02_traffic.json, made by
+    # tools/summarise_profiles.py out of gpurun_out/r02_*.ncu-rep: one launch on a 2 GB table each). bench.py cannot run
+    # under ncu, so `traffic` is that measured ratio times this launch's algorithmic bytes, and says so.
+    traffic_ratio = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        traffic_ratio = {k: v["dram_bytes_per_csv_byte"] for k, v in tj.items()}
+    except Exception:
+        pass
+
     def roofline_of(nbytes, kernel_ms, kernel):
         ach = nbytes / (kernel_ms / 1e3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        key = "lean2k" if "lean2k" in kernel else "leanhc" if "leanhc" in kernel else "lean2" if "lean2_kernel" in kernel else None
+        ratio = traffic_ratio.get(key)
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": (ratio * nbytes) if ratio else None,
                 "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": ach / 8000.0,
-                "traffic_note": "dram__bytes per launch is in the ncu captures under profiles/ (r02_*), not re-measured here"}
+                "traffic_note": (f"dram__bytes_read + dram__bytes_write = {ratio:.4f} x the table's bytes in this round's ncu --set full capture "
+                                 f"of this kernel (profiles/r02_{key}_ncu.txt, one launch on a 2 GB table); scaled to this launch's bytes, "
+                                 "not re-measured here") if ratio else "no capture of this kernel under profiles/"}
 
     total_rows = int(args.bytes / 29.89)
 
@@ -293,6 +308,7 @@ def main():
             if sampler:
                 sampler.start()
             l0 = lib.total_kernel_launches()
+            k0 = lib.kernel_launches_named(b"lean2k")
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             kms = []
             e0.record()
@@ -301,6 +317,8 @@ def main():
                 kms.append(last["kernel_ms"])
             e1.record()
             torch.cuda.synchronize()
+            if leg == "groupby" and lib.kernel_launches_named(b"lean2k") == k0:
+                kernel = "cqg::lean2g_kernel (the run-time compiler was not available: lean2k_kernel exists only compiled per query)"
             if sampler:
                 clocks = sampler.stop()
                 launches = lib.total_kernel_launches() - l0

@@ -57,6 +57,8 @@ KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_atom.sum",
         "lts__t_sectors_srcunit_tex_op_red.sum", "sm__cycles_elapsed.avg.per_second"]
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+traffic = {}
 for kern, plan in (("lean2k", "group_name"), ("lean2", "count_age_gt_40"), ("leanhc", "group_high_card")):
     rep = os.path.join(G, f"{R}_{kern}.ncu-rep")
     if not os.path.exists(rep):
@@ -64,6 +66,17 @@ for kern, plan in (("lean2k", "group_name"), ("lean2", "count_age_gt_40"), ("lea
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     h, u, v = r[0], r[1], r[2]
+    try:  # DRAM bytes of the captured launch per byte of its table (tools/run_plan.py prints the table size: 2e9 / 29.89 rows)
+        rd = float(v[h.index("dram__bytes_read.sum")].replace(",", "")) * UNIT[u[h.index("dram__bytes_read.sum")]]
+        wr = float(v[h.index("dram__bytes_write.sum")].replace(",", "")) * UNIT[u[h.index("dram__bytes_write.sum")]]
+        plain = open(os.path.join(G, f"{R}_{kern}_plain.log")).read()
+        gbs = float(plain.strip().splitlines()[-1].split("GB/s")[1].split()[0])
+        kms = float(plain.strip().splitlines()[-1].split("kernel_ms")[1].split()[0])
+        table_bytes = gbs * 1e9 * kms / 1e3
+        traffic[kern] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "table_bytes": table_bytes,
+                         "dram_bytes_per_csv_byte": (rd + wr) / table_bytes, "capture": f"profiles/{R}_{kern}_ncu.txt"}
+    except Exception as ex:
+        print("traffic", kern, ex)
     with open(os.path.join(OUT, f"{R}_{kern}_ncu.txt"), "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kern} : python tools/run_plan.py {plan} 2e9 3\n")
         f.write("# (one launch on a 2 GB table, kernel compiled for the query by cqg_jit where that applies; tools/collect_profiles.sh)\n")
@@ -73,3 +86,6 @@ for kern, plan in (("lean2k", "group_name"), ("lean2", "count_age_gt_40"), ("lea
         f.write("\n")
         f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "25"], capture_output=True, text=True).stdout)
     print("wrote", f"{R}_{kern}_ncu.txt")
+if traffic:
+    json.dump(traffic, open(os.path.join(OUT, f"{R}_traffic.json"), "w"), indent=1)
+    print("wrote traffic ratios", {k: round(v["dram_bytes_per_csv_byte"], 4) for k, v in traffic.items()})
