@@ -2925,6 +2925,9 @@ static int run_lean_scan(HostPlan& hp, GroupTable& gt, cudaStream_t st, ScalarBl
     P.ptab = nullptr;
     P.pcap = 0;
     P.hc_debug = env_int("CQG_HC_DEBUG", 0);
+    // big scans: the two tiles at the file's edges stay on the lean kernel (no second launch, no second round trip); small
+    // files keep the general kernel for them (every tile of a file below 16 KB is an edge tile)
+    P.edge_in_kernel = (P.n_tiles >= env_int("CQG_EDGE_MIN_TILES", 64)) ? 1 : 0;
     {
         int dev = 0;
         CU(cudaGetDevice(&dev));

@@ -407,6 +407,33 @@ __device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
     }
 #endif
 
+// ---- tiles at the edges of the file (DevPlan::edge_in_kernel) ----
+// The first tile has no PRE bytes in front of it and the last ones run past the end of the file: the lean kernels used to
+// leave both to the general kernel (one more launch and one more host round trip per query: 0.06 ms, 2 % of a 10 GB
+// COUNT and 6 % of a 1.25 GB slice on 8 GPUs). With the flag set (scans of >= 64 tiles) the part of the tile that exists
+// is loaded - 16-byte multiples by the bulk copy, up to 15 bytes more one by one - and everything else reads as '\n',
+// which is how csv_load sees the edges too (a file starts at a line start; its last line needs no terminator,
+// src/csv_reader.c:404-427).
+struct LeanEdge {
+    uint32_t lo_b, hi_b, load16;  // buffer bytes [lo_b, hi_b) exist in the file; [lo_b, lo_b + load16) come by bulk copy
+};
+template <class G>
+__device__ __forceinline__ LeanEdge lean_edge_span(long long g0, uint64_t size) {
+    LeanEdge e;
+    e.lo_b = g0 < 0 ? (uint32_t)(-g0) : 0u;
+    const long long avail = (long long)size - g0;
+    e.hi_b = avail >= (long long)G::BUF ? (uint32_t)G::BUF : (avail > (long long)e.lo_b ? (uint32_t)avail : e.lo_b);
+    e.load16 = (e.hi_b - e.lo_b) & ~15u;
+    return e;
+}
+template <class G>
+__device__ __forceinline__ void lean_edge_fill(uint8_t* buf, const uint8_t* data, long long g0, const LeanEdge& e, int tid) {
+    for (uint32_t k = (uint32_t)tid; k < (uint32_t)G::BUF; k += (uint32_t)G::THREADS) {
+        if (k < e.lo_b || k >= e.hi_b) buf[k] = (uint8_t)'\n';
+        else if (k >= e.lo_b + e.load16) buf[k] = data[g0 + (long long)k];
+    }
+}
+
 // GAP0: the wanted column index of ONELEAF plans when it is below 8 (the delimiter skips unroll), else -1
 // CRLF (DevPlan::crlf: the head of the file holds a CR): every line ends in the two bytes CR LF. Both are `T` bytes; a row
 // is then clean when its first terminator is the '\r' and the byte behind it the '\n', and the next row starts two bytes
@@ -478,11 +505,16 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
     for (int it = 0; it < my_tiles; it++) {
         const long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
         const long long g0 = tile * (long long)G::TILE - G::PRE;
-        const bool edge = g0 < 0 || g0 + G::BUF > (long long)size;  // edge tiles are handed over, not loaded
+        const bool at_edge = g0 < 0 || g0 + G::BUF > (long long)size;
+        const bool edge = at_edge && !P.edge_in_kernel;  // handed over, not loaded
+        const LeanEdge es = lean_edge_span<G>(g0, size);
         if (tid == 0) {
-            if (!edge) {
+            if (!at_edge) {
                 mbar_expect_tx(&mbar[0], G::BUF);
                 tma_load_1d(smem + G::OFF_BUF, P.data + g0, G::BUF, &mbar[0]);
+            } else if (!edge && es.load16) {
+                mbar_expect_tx(&mbar[0], es.load16);
+                tma_load_1d(smem + G::OFF_BUF + es.lo_b, P.data + g0 + (long long)es.lo_b, es.load16, &mbar[0]);
             } else {
                 mbar_expect_tx(&mbar[0], 0);
             }
@@ -500,6 +532,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
             }
             __syncthreads();
             continue;
+        }
+        if (at_edge) {
+            lean_edge_fill<G>(smem + G::OFF_BUF, P.data, g0, es, tid);
+            __syncthreads();
         }
 
         // ---- phase 1: T ("< 0x23") and D (delimiter) masks, 16 bytes per thread and step ----

@@ -165,11 +165,16 @@ __global__ void __launch_bounds__(G::THREADS, MINB) leanhc_kernel(const __grid_c
     for (int it = 0; it < my_tiles; it++) {
         const long long tile = (long long)P.first_tile + blockIdx.x + (long long)it * gridDim.x;
         const long long g0 = tile * (long long)G::TILE - G::PRE;
-        const bool edge = g0 < 0 || g0 + G::BUF > (long long)size;
+        const bool at_edge = g0 < 0 || g0 + G::BUF > (long long)size;
+        const bool edge = at_edge && !P.edge_in_kernel;  // handed over, not loaded (cqg_lean2.cuh: LeanEdge)
+        const LeanEdge es = lean_edge_span<G>(g0, size);
         if (tid == 0) {
-            if (!edge) {
+            if (!at_edge) {
                 mbar_expect_tx(&mbar[0], G::BUF);
                 tma_load_1d(smem + G::OFF_BUF, P.data + g0, G::BUF, &mbar[0]);
+            } else if (!edge && es.load16) {
+                mbar_expect_tx(&mbar[0], es.load16);
+                tma_load_1d(smem + G::OFF_BUF + es.lo_b, P.data + g0 + (long long)es.lo_b, es.load16, &mbar[0]);
             } else {
                 mbar_expect_tx(&mbar[0], 0);
             }
@@ -179,6 +184,10 @@ __global__ void __launch_bounds__(G::THREADS, MINB) leanhc_kernel(const __grid_c
         }
         const unsigned abort_now = (*(volatile unsigned*)P.errflags) & (KERR_LEAN_ABORT | KERR_TABLE_FULL);
         mbar_wait(&mbar[0], (uint32_t)it & 1u);
+        if (at_edge && !edge) {
+            lean_edge_fill<G>(smem + G::OFF_BUF, P.data, g0, es, tid);
+            __syncthreads();
+        }
 
         // ---- phase 1: '\n' and delimiter masks, and "is the tile clean" (no other byte below 0x23) ----
         uint32_t spec = edge ? 0x80u : 0u;

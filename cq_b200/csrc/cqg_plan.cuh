@@ -182,7 +182,7 @@ struct DevPlan {
     uint64_t pcap;                      // power of two
     unsigned long long* pcount;         // occupied lines
     int32_t hc_debug;                   // CQG_HC_DEBUG (measurement only): 1 skip the updates, 2 skip the table altogether
-    int32_t hc_pad;
+    int32_t edge_in_kernel;             // the lean kernels process the tiles at the file's edges themselves (cqg_lean2.cuh: LeanEdge)
 
     // ---- aggregation ----
     int32_t ngc;

@@ -637,6 +637,39 @@ def test_cr_lf_files_stay_on_the_lean_kernels(kind):
                 pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
 
 
+@pytest.mark.parametrize("tail", ["newline", "none", "blank_lines", "crlf_none"])
+def test_edge_tiles_inside_the_lean_kernels(tail):
+    """Scans of >= 64 tiles keep the tiles at the file's edges on the lean kernel (DevPlan::edge_in_kernel, LeanEdge in
+    cqg_lean2.cuh): the first tile has nothing in front of it, the last one ends with the file - with or without a final
+    line terminator, or after trailing blank lines. Every lean kernel, whole file and shards; no tile may be handed over."""
+    data = generate_bigdata(90_000, seed=31)  # ~2.7 MB = 165 tiles
+    if tail == "none":
+        data = data[:-1]
+    elif tail == "blank_lines":
+        data = data + b"\n\n\n"
+    elif tail == "crlf_none":
+        data = b"\r\n".join(data.split(b"\n"))[:-2]
+    lib = gpu()
+    names = ["count_age_gt_40", "scalar_aggs", "group_name", "lean_group_two_keys", "group_high_card", "count_height_gt_1_5"]
+    with Table.from_bytes(data, lib=lib) as tg, Table.from_bytes(data, lib=oracle()) as to:
+        assert tg.row_count() == to.row_count() == 90_000
+        for name in names:
+            spec = pc.plans()[name]
+            pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
+            if name != "scalar_aggs":  # (MIN / MAX plans: the first lean kernel still hands its edge tiles over)
+                tiles, handed, rows = C.c_int64(), C.c_int64(), C.c_int64()
+                lib.last_scan_stats(C.byref(tiles), C.byref(handed), C.byref(rows))
+                # (the scalar kernel hands over a tile that holds an empty line, and in its CR LF mode one whose last line
+                # does not end in the pair: one tile at most, for what is IN the tile, not for being at the edge)
+                assert tiles.value >= 64 and handed.value <= (1 if tail in ("crlf_none", "blank_lines") else 0), (name, tiles.value, handed.value)
+        for i in range(3):
+            tg.set_shard(i, 3)
+            to.set_shard(i, 3)
+            for name in ("count_age_gt_40", "group_name", "group_high_card"):
+                spec = pc.plans()[name]
+                pc.compare_results(tg.execute(pc.build(spec)), to.execute(pc.build(spec)))
+
+
 @pytest.mark.parametrize("world", [2, 5])
 def test_hash_partitioned_join(world):
     """BASELINE config 5 on one device: `world` simulated ranks split the row offsets of their shards by key
