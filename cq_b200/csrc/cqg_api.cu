@@ -1328,7 +1328,7 @@ static int launch_lean(const DevPlan& P, cudaStream_t st) {
         return launch_lean_geo<Geo<128, 16384, 1>, 5, true, false, false>(P, st);
     }
     const bool oneleaf = P.l_nprog == 1 && P.l_nleaf == 1 && P.l_leaf[0].kind == 0 && P.l_leaf[0].slot == 0 && P.l_nagg == 0 &&
-                         P.nwantL == 1;
+                         P.nwantL == 1 && !P.signed_hint;
     bool mm0 = false;
     for (int a = 0; a < P.l_nagg; a++) mm0 = mm0 || P.aggs[P.l_agg[a]].func == CQG_AGG_MIN || P.aggs[P.l_agg[a]].func == CQG_AGG_MAX;
     const int lean2 = env_int("CQG_LEAN2", 1);  // 0: the first lean kernel (A/B runs)
@@ -2016,6 +2016,11 @@ static int build_plan(HostPlan& hp, const cqg_table* t, const cqg_query_t* q, cu
         // about the rest of the file that only costs speed: a CR they were not told about sends its tile to the general kernel
         const std::vector<uint8_t>& sm = table_sample(t);
         P.crlf = memchr(sm.data(), '\r', sm.size()) ? 1 : 0;
+        // a field that starts with '-' or '+': the written-out COUNT-WHERE loop (ONELEAF) hands such fields over row by row
+        // and gives the tile up after two; the general scalar loop decodes them (cqg_lean2.cuh: CQG_L2_SIGNED)
+        P.signed_hint = 0;
+        for (size_t k = 0; k + 1 < sm.size(); k++)
+            if ((sm[k] == (uint8_t)t->cfg.delimiter || sm[k] == '\n') && (sm[k + 1] == '-' || sm[k + 1] == '+')) P.signed_hint = 1;
     }
     P.need_right_fields = P.nwantR > 0;
     CU(hp.d_scalars.alloc(sizeof(ScalarBlock), st));

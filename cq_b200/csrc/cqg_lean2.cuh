@@ -160,6 +160,15 @@ __host__ __device__ inline void lean2_interval(const LeanLeaf& L, int fd, uint32
     }
 }
 
+// the same for a field with a leading '-': `-(mant / 10^fd) <op> literal` over mant, i.e. mant * A <op mirrored> -LB
+__host__ __device__ inline void lean2_interval_neg(const LeanLeaf& L, int fd, uint32_t& lo, uint32_t& width) {
+    LeanLeaf M = L;
+    M.LB[fd] = -L.LB[fd];
+    M.lop = L.lop == 0 ? 1 : L.lop == 1 ? 0 : L.lop;
+    uint32_t clo, cwidth;
+    lean2_interval(M, fd, lo, width, clo, cwidth);
+}
+
 // a + c as an IMAD on the device (add_fma, cqg_lean.cuh), plainly on the host
 __host__ __device__ __forceinline__ uint32_t l2_add(uint32_t a, uint32_t one, uint32_t c) {
 #ifdef __CUDA_ARCH__
@@ -365,6 +374,37 @@ __device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
     const bool ok = lean_decimal(fa, len, mant, fd, hd);
     return ok ? (0x80000000u | (fd << 28) | mant) : 0u;
 }
+// A decimal with a leading sign, 2..7 bytes in all ("-5", "+1.25", "-123.4"): shorter than the 8 bytes at which the
+// reference tries a date first (infer_type, src/csv_reader.c:137), typed and valued as strtoll / strtod do
+// (src/csv_reader.c:160-193, :195-240). Returns mant (< 10^6) | negative << 27 | fd << 28 | ok << 31. Out of line: a
+// field reaches it only after the unsigned decode said no.
+__device__ __noinline__ uint32_t lean2_signed(uint32_t fa, uint32_t len) {
+    if (len - 2u > 5u) return 0u;
+    const uint32_t c0 = lds8(fa);
+    if (c0 != '-' && c0 != '+') return 0u;
+    uint32_t mant, fd;
+    bool hd;
+    if (!lean_decimal(fa + 1u, len - 1u, mant, fd, hd)) return 0u;
+    return 0x80000000u | (fd << 28) | (c0 == '-' ? 0x08000000u : 0u) | mant;
+}
+// The sign travels in bit 3 of fd16 (fd16 = 16 * fraction digits | 8 * negative): a leaf's interval table holds, 8 bytes
+// behind the interval for `mant / 10^fd <op> literal`, the one for `-(mant / 10^fd) <op> literal` (lean2_interval_neg), so
+// a comparison costs a signed field nothing extra; sums mask the bit off and negate.
+#define CQG_L2_SIGNED(FA, LEN, DEC, MANT, FD16)                               \
+    if (!(DEC)) {                                                             \
+        const uint32_t rs_ = lean2_signed(FA, LEN);                           \
+        if (rs_ >> 31) {                                                      \
+            DEC = true;                                                       \
+            MANT = rs_ & 0x00ffffffu;                                         \
+            FD16 = (rs_ >> 24) & 0x38u;                                       \
+        }                                                                     \
+    }
+// value * 1000 of a decoded field as a two's-complement 64-bit integer
+__device__ __forceinline__ unsigned long long lean2_times_1000(uint32_t mant, uint32_t fd16) {
+    const uint32_t f = fd16 & 0x30u;
+    const unsigned long long v = (unsigned long long)mant * (f == 0u ? 1000u : f == 16u ? 100u : f == 32u ? 10u : 1u);
+    return (fd16 & 8u) ? 0ull - v : v;
+}
 #define CQG_L2_DEC7(FA, LEN, DEC, MANT, FD16)        \
     {                                                \
         const uint32_t r7 = lean2_dec7(FA, LEN);     \
@@ -390,6 +430,7 @@ __device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
             } else if ((L) - 1u < 7u) {                                                     \
                 CQG_L2_DEC7((RB) + (O), L, DEC, MANT, FD16)                                 \
             }                                                                               \
+            CQG_L2_SIGNED((RB) + (O), L, DEC, MANT, FD16)                                   \
             dcache_mant[SL] = MANT;                                                         \
             dcache_fd[SL] = FD16;                                                           \
             dcache_state |= (DEC ? 1u : 2u) << (2 * (SL));                                  \
@@ -404,6 +445,7 @@ __device__ __noinline__ uint32_t lean2_dec7(uint32_t fa, uint32_t len) {
         } else if ((L) - 1u < 7u) {                                                         \
             CQG_L2_DEC7((RB) + (O), L, DEC, MANT, FD16)                                     \
         }                                                                                   \
+        CQG_L2_SIGNED((RB) + (O), L, DEC, MANT, FD16)                                       \
     }
 #endif
 
@@ -464,6 +506,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
     if (tid < P.l_nleaf * 4 && P.l_leaf[tid >> 2].kind == 0) {
         uint32_t lo, width, clo, cwidth;
         lean2_interval(P.l_leaf[tid >> 2], tid & 3, lo, width, clo, cwidth);
+        if (!ONELEAF) lean2_interval_neg(P.l_leaf[tid >> 2], tid & 3, clo, cwidth);  // (ONELEAF: digit-code intervals there)
         sts64(s_cmp + 16 * tid, lo, width);
         sts64(s_cmp + 16 * tid + 8, clo, cwidth);
     }
@@ -768,7 +811,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
         bool dec = false;                                                                                \
         CQG_L2_DECODE(sl, rbase, o, l, dec, mant, fd16) \
         if (dec) {                                                                                       \
-            ADD = (unsigned long long)mant * (fd16 == 0u ? 1000u : fd16 == 16u ? 100u : fd16 == 32u ? 10u : 1u); \
+            ADD = lean2_times_1000(mant, fd16);                                                          \
             addmask |= 1u << A;                                                                          \
         } else if (l != 0u) {                                                                            \
             ok = false; /* a value this kernel does not decode (NULL is simply not summed) */           \

@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
         uint32_t lo, width, clo, cwidth;
         lean2_interval(P.l_leaf[tid >> 2], tid & 3, lo, width, clo, cwidth);
         sts64(s_cmp + 16 * tid, lo, width);
+        lean2_interval_neg(P.l_leaf[tid >> 2], tid & 3, clo, cwidth);  // fields with a leading '-' (cqg_lean2.cuh: CQG_L2_SIGNED)
+        sts64(s_cmp + 16 * tid + 8, clo, cwidth);
     }
     {
         const int words = (LL::TOTAL - LL::OFF_DICT) / 4;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2g_kernel(const __grid_c
         bool dec = false;                                                                                \
         CQG_L2_DECODE(sl, rbase, o, l, dec, mant, fd16) \
         if (dec) {                                                                                       \
-            ADD = (unsigned long long)mant * (fd16 == 0u ? 1000u : fd16 == 16u ? 100u : fd16 == 32u ? 10u : 1u); \
+            ADD = lean2_times_1000(mant, fd16);                                                          \
             addmask |= 1u << A;                                                                          \
         } else if (l != 0u) {                                                                            \
             ok = false;                                                                                  \

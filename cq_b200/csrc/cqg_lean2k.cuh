@@ -41,7 +41,7 @@ constexpr uint32_t kL2KLock = 2u, kL2KFresh = 2u;
 template <class G>
 struct Lean2KLayout {
     static constexpr int OFF_MSK = G::STAGES * G::BUF;
-    static constexpr int OFF_CMP = OFF_MSK + G::MASKW * 8;          // kMaxLeanLeaf x 4 fd x {lo, width}
+    static constexpr int OFF_CMP = OFF_MSK + G::MASKW * 8;          // kMaxLeanLeaf x 4 fd x {lo, width | lo, width for '-' fields}
     static constexpr int OFF_MBAR = OFF_CMP + kMaxLeanLeaf * 64;
     static constexpr int OFF_KMASK = (OFF_MBAR + G::STAGES * 8 + 15) / 16 * 16;  // [17][4] words: the first `len` bytes of 16
     static constexpr int OFF_SCALE = OFF_KMASK + 17 * 16;           // 10^(3 - fd) at byte offset fd16
@@ -61,22 +61,28 @@ __device__ __forceinline__ uint32_t atoms32(uint32_t a, uint32_t v) {
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
     return old;
 }
-// a decimal of 5..7 bytes (value * 1000 may not fit 32 bits) into the (lo, hi) words of a warp's sum
-__device__ __noinline__ void l2k_add_big(uint32_t lo_addr, uint32_t hi_addr, uint32_t mant, uint32_t scale) {
-    const unsigned long long v = (unsigned long long)mant * scale;
+// a decimal of 5..7 bytes (value * 1000 may not fit 32 bits) or one with a sign into the (lo, hi) words of a warp's sum
+__device__ __noinline__ void l2k_add_big(uint32_t lo_addr, uint32_t hi_addr, uint32_t mant, uint32_t scale, bool negative) {
+    unsigned long long v = (unsigned long long)mant * scale;
+    if (negative) v = 0ull - v;  // (two's complement: the (lo, hi) words add up modulo 2^64)
     const uint32_t vlo = (uint32_t)v, old = atoms32(lo_addr, vlo);
     const uint32_t up = (uint32_t)(v >> 32) + ((old + vlo) < old ? 1u : 0u);
     if (up) reds32(hi_addr, up);
 }
 
-// decimal field outside the 4-byte route: mant | fd16 << 24 | state << 30 (0 decimal of 5..7 bytes, 1 empty = NULL,
-// 2 anything else: the row is handed over)
+// decimal field outside the 4-byte route: mant | fd16 << 24 | state << 30 (0: a decimal of 5..7 bytes, or one with a
+// leading sign - fd16 then carries 8 for '-', cqg_lean2.cuh: CQG_L2_SIGNED -, 1 empty = NULL, 2 anything else: the row is
+// handed over)
 __device__ __noinline__ uint32_t l2k_decode_slow(uint32_t fa, uint32_t len) {
     if (len == 0u) return 1u << 30;
     if (len > 7u) return 2u << 30;
-    const uint32_t r7 = lean2_dec7(fa, len);
-    if ((r7 >> 31) == 0u) return 2u << 30;
-    return r7 & 0x3fffffffu;  // mant < 2^24, fd16 (0x00..0x30) << 24
+    if (len > 4u) {
+        const uint32_t r7 = lean2_dec7(fa, len);
+        if (r7 >> 31) return r7 & 0x3fffffffu;  // mant < 2^24, fd16 (0x00..0x30) << 24
+    }
+    const uint32_t rs = lean2_signed(fa, len);
+    if (rs >> 31) return rs & 0x3fffffffu;      // mant, fd16 | 8 * negative
+    return 2u << 30;
 }
 
 // the row that starts at `okey >> 16` belongs to a group numbered in this very tile: it may come before the row
@@ -173,6 +179,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
         uint32_t lo, width, clo, cwidth;
         lean2_interval(P.l_leaf[tid >> 2], tid & 3, lo, width, clo, cwidth);
         sts64(s_cmp + 16 * tid, lo, width);
+        lean2_interval_neg(P.l_leaf[tid >> 2], tid & 3, clo, cwidth);  // fields with a leading '-'
+        sts64(s_cmp + 16 * tid + 8, clo, cwidth);
     }
     for (int k = tid; k < (LL::TOTAL - LL::OFF_DICT) / 4; k += G::THREADS) ((uint32_t*)(smem + LL::OFF_DICT))[k] = 0u;
     if (tid < 17 * 4) {
@@ -337,13 +345,13 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
                         if (s < nwant && ((numslots >> s) & 1u)) {
-                            if (len[s] - 1u < 4u) {
-                                state[s] = lean2_dec4(rbase + off[s] + len[s], len[s], mant[s], fd16[s]) ? 0u : 2u;
-                            } else {
+                            state[s] = 2u;
+                            if (len[s] - 1u < 4u && lean2_dec4(rbase + off[s] + len[s], len[s], mant[s], fd16[s])) state[s] = 0u;
+                            if (state[s]) {
                                 const uint32_t r = l2k_decode_slow(rbase + off[s], len[s]);
                                 mant[s] = r & 0x00ffffffu;
-                                fd16[s] = (r >> 24) & 0x30u;
-                                state[s] = (r >> 30) == 0u ? 3u : (r >> 30);  // 3: a decimal of 5..7 bytes
+                                fd16[s] = (r >> 24) & 0x38u;
+                                state[s] = (r >> 30) == 0u ? 3u : (r >> 30);  // 3: a decimal of 5..7 bytes, or one with a sign
                             }
                         }
                     }
@@ -446,7 +454,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
                                         const uint32_t lo_a = aa + (1 + a) * (kL2KGroups * 4), hi_a = aa + (4 + a) * (kL2KGroups * 4);
                                         if ((big >> a) & 1u) {
                                             const int sl = CQG_JIT_ASLOT(a);
-                                            l2k_add_big(lo_a, hi_a, mant[sl], lds32(sbase + LL::OFF_SCALE + fd16[sl]));
+                                            l2k_add_big(lo_a, hi_a, mant[sl], lds32(sbase + LL::OFF_SCALE + (fd16[sl] & 0x30u)), (fd16[sl] & 8u) != 0u);
                                         } else if (a < 2 && ((nulls >> (16 * a)) & 1u)) {
                                             reds32(aa + (7 + a) * (kL2KGroups * 4), 1u);  // a NULL field: not a value of this aggregate
                                         } else {

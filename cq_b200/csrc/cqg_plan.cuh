@@ -133,7 +133,7 @@ struct DevPlan {
     uint64_t global_base; // offset of data[0] in the whole (multi-GPU) file: added to row offsets in okeys
     uint8_t delim, quote;
     uint8_t exact_only;   // dialect the mask fast path does not cover (whitespace delimiter, exotic quote)
-    uint8_t pad0;
+    uint8_t signed_hint;  // the head of the file holds a field that starts with a sign: COUNT-WHERE plans take the general scalar loop
     int32_t mode;         // ScanMode
     int32_t first_tile, n_tiles;
 

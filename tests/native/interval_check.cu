@@ -18,7 +18,8 @@ static long long p10(int k) {
 int main() {
     // literals as (mantissa, fraction digits); operators as in cq_gpu.h: compared through scaled integers
     const long long lits[][2] = {{0, 0}, {1, 0}, {25, 0}, {40, 0}, {80, 0}, {9999, 0}, {10000, 0}, {123456, 0}, {15, 1}, {5, 1},
-                                 {125, 2}, {184, 2}, {1, 3}, {999, 3}, {2500, 2}, {33500, 3}, {7, 0}, {70, 1}, {1000000000ll, 0}};
+                                 {125, 2}, {184, 2}, {1, 3}, {999, 3}, {2500, 2}, {33500, 3}, {7, 0}, {70, 1}, {1000000000ll, 0},
+                                 {-1, 0}, {-25, 0}, {-15, 1}, {-125, 2}, {-9999, 0}, {-1, 3}, {-123456, 0}};
     const char* opname[] = {">", ">=", "<", "<=", "==", "!="};
     long long checked = 0;
     for (auto& lit : lits) {
@@ -61,6 +62,24 @@ int main() {
                 for (uint32_t m = 0; m <= 12000u; m++) check(m);
                 for (uint32_t m = 12000u; m < 10000000u; m += 9973u) check(m);
                 check(9999999u);
+                // a field with a leading '-': value = -(mant / 10^fd), the interval 8 bytes behind (lean2_interval_neg)
+                uint32_t nlo, nwidth;
+                lean2_interval_neg(L, fd, nlo, nwidth);
+                auto check_neg = [&](uint32_t mant) {
+                    const long long lhs = -(long long)mant * p10(K - fd);
+                    const bool want = op == 0 ? lhs > rhs : op == 1 ? lhs >= rhs : op == 2 ? lhs < rhs : op == 3 ? lhs <= rhs
+                                    : op == 4 ? lhs == rhs : lhs != rhs;
+                    const bool got = (uint32_t)(mant - nlo) <= nwidth;
+                    if (got != want) {
+                        printf("MISMATCH negative value: -mant %u fd %d %s %lld/10^%d: want %d got %d (lo %u width %u)\n", mant, fd, opname[op],
+                               cm, cfd, (int)want, (int)got, nlo, nwidth);
+                        exit(1);
+                    }
+                    checked++;
+                };
+                for (uint32_t m = 0; m <= 12000u; m++) check_neg(m);
+                for (uint32_t m = 12000u; m < 1000000u; m += 997u) check_neg(m);
+                check_neg(999999u);
             }
         }
     }
