@@ -250,21 +250,33 @@ __device__ __forceinline__ bool packed_same_key(const DevPlan& P, int ngc, const
     if (idw > 4) c1 = pk_load(e + 32);
     if (idw > 8) c2 = pk_load(e + 64);
     word0 = c0.a;
-    bool same = (uint32_t)(c0.a & 0xffffull) == tags;
-    bool zero_miss = false, zero_image = false;
+    // all key words at once: XOR and OR (two LOP3 per word), one test. Which words read as 0 only matters when the
+    // outcome could rest on one: a mismatch (any of them unwritten yet?) or, for a match, a key image that is 0 itself
+    uint64_t diff = 0;
+    bool zero_image = false;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
         if (g < ngc) {
             const int j = CQG_PK_KEYWORD(g);
-            const uint64_t i0 = kw[2 * g] ^ kPkKeyMask, l0 = pk_word(c0, c1, c2, j);
-            same &= l0 == i0;
-            zero_miss |= (l0 == 0ull) & (i0 != 0ull);
+            const uint64_t i0 = kw[2 * g] ^ kPkKeyMask;
+            diff |= pk_word(c0, c1, c2, j) ^ i0;
             zero_image |= i0 == 0ull;
             if (CQG_PK_KEYWIDE(g)) {
-                const uint64_t i1 = kw[2 * g + 1] ^ kPkKeyMask, l1 = pk_word(c0, c1, c2, j + 1);
-                same &= l1 == i1;
-                zero_miss |= (l1 == 0ull) & (i1 != 0ull);
+                const uint64_t i1 = kw[2 * g + 1] ^ kPkKeyMask;
+                diff |= pk_word(c0, c1, c2, j + 1) ^ i1;
                 zero_image |= i1 == 0ull;
+            }
+        }
+    }
+    const bool same = (uint32_t)(c0.a & 0xffffull) == tags && diff == 0ull;
+    bool zero_miss = false;
+    if (!same) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if (g < ngc) {
+                const int j = CQG_PK_KEYWORD(g);
+                zero_miss |= (pk_word(c0, c1, c2, j) == 0ull) & ((kw[2 * g] ^ kPkKeyMask) != 0ull);
+                if (CQG_PK_KEYWIDE(g)) zero_miss |= (pk_word(c0, c1, c2, j + 1) == 0ull) & ((kw[2 * g + 1] ^ kPkKeyMask) != 0ull);
             }
         }
     }
