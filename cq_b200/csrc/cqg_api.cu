@@ -282,8 +282,13 @@ static int check_dialect(cqg_csv_config_t cfg) {
 // src/mmap.c:78-108) go through page-locked bounce buffers: several host threads, each with two buffers and a
 // stream of its own, fault their chunks in and hand them to the copy engines, so that the host memcpy of one
 // chunk overlaps the DMA of others (one thread tops out far below what PCIe Gen5 takes).
+static int env_int_early(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 struct StagePool {
-    static constexpr int kThreads = 16;
+    static constexpr int kThreads = 32;  // at most; copy_host_range uses min(kThreads, CQG_STAGE_THREADS (24), cores) of them
     static constexpr size_t kChunk = 8u << 20;
     uint8_t* bounce[kThreads][2] = {};
     cudaStream_t stream[kThreads] = {};
@@ -318,7 +323,8 @@ static int copy_host_range(const cqg_table* t, const uint8_t* src, uint64_t off0
     constexpr size_t chunk = StagePool::kChunk;
     const size_t nchunks = (n_total + chunk - 1) / chunk;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    int want = (int)std::min<size_t>(std::min<size_t>(StagePool::kThreads, hw), std::max<size_t>(1, nchunks / 2));
+    const int cap_threads = std::max(1, std::min(StagePool::kThreads, env_int_early("CQG_STAGE_THREADS", 24)));
+    int want = (int)std::min<size_t>(std::min<size_t>((size_t)cap_threads, hw), std::max<size_t>(1, nchunks / 2));
     const int T = sp.prepare(want);
     if (T < 1) return fail(CQG_ERR_CUDA, "page-locked staging buffers: allocation failed");
     std::atomic<int> bad{0};
@@ -3449,6 +3455,7 @@ CQG_API void cqg_value_release(cqg_value_t* v) {
 struct cqg_partial {
     HostPlan hp;
     GroupTable gt;
+    bool fresh = false;  // made by cqg_partial_new_like and nothing merged into it yet: it holds no groups
     JoinState js;  // build side of an equi-join (whole right table, or the rows this rank owns)
     JoinState js_finish;  // hash-partitioned joins: the whole right table again, built by the rank that finishes
     bool owned_rows_only = false;  // js covers only the keys one rank owns
@@ -3753,6 +3760,7 @@ CQG_API int cqg_partial_new_like(const cqg_partial_t* like, cqg_partial_t** out)
         delete p;
         return rc;
     }
+    p->fresh = true;
     *out = p;
     return CQG_OK;
 }
@@ -3764,7 +3772,8 @@ CQG_API int cqg_partial_merge(cqg_partial_t* p, uint64_t src_device_ptr, int64_t
     // room first: every record may be a new group, and a batch that overflowed half way could not be retried
     // (the records already folded in would be added twice)
     unsigned long long have = 0;
-    CU(cudaMemcpy(&have, P.gcount, 8, cudaMemcpyDeviceToHost));
+    if (!p->fresh) CU(cudaMemcpy(&have, P.gcount, 8, cudaMemcpyDeviceToHost));  // (a fresh table: no round trip for a 0)
+    p->fresh = false;
     while ((have + (unsigned long long)n) * 2ull > p->gt.cap) {
         if (p->gt.cap > (1ull << 32)) return fail(CQG_ERR_NOMEM, "merge table beyond 2^32 entries");
         DevBuf old_entries;
