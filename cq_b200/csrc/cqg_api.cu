@@ -708,6 +708,11 @@ CQG_API int cqg_table_set_gpus(cqg_table_t* t, int ngpu) {
     if (t->d_data || !t->h_data) return fail(CQG_ERR_ARG, "the table is already resident on a device");
     const char* e = getenv("CQG_MULTI_MIN_BYTES");
     const uint64_t min_bytes = e ? strtoull(e, nullptr, 10) : (64ull << 20);
+    if (!getenv("CQG_MULTI_SAME_DEVICE")) {  // no more slices than devices (CQ_GPUS=8 on a smaller box: what is there)
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess) ndev = 1;
+        ngpu = std::min(ngpu, std::max(ndev, 1));
+    }
     t->ngpu = (ngpu > 1 && t->size >= min_bytes) ? ngpu : 0;
     return CQG_OK;
 }
@@ -1073,6 +1078,7 @@ static std::string lean_shape_defs(const cqg::DevPlan& P) {
     def("NPROG", P.l_nprog);
     def("NLEAF", P.l_nleaf);
     def("NGC", P.ngc);
+    def("CRLF", P.crlf ? 1 : 0);  // (lean2k_kernel: CR as a terminator is part of the compiled shape)
     def("NAGG", P.l_nagg);
     def_at("PROG", P.l_nprog, [&](int i) { return (int)P.l_prog[i]; });
     def_at("LEAFSLOT", P.l_nleaf, [&](int i) { return P.l_leaf[i].slot; });

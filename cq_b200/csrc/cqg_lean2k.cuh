@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
     const uint64_t size = P.size;
     const uint32_t patD = (uint32_t)P.delim * 0x01010101u;
     const uint32_t one = (uint32_t)P.simple >> 1;  // simple == 2 here: 1, but not to the compiler (IMAD adds)
-    const bool cr_too = P.crlf != 0;
+    constexpr bool cr_too = CQG_JIT_CRLF != 0;  // CR is a line terminator too (DevPlan::crlf; part of the compiled shape here)
 
     const int my_tiles = (P.n_tiles > (int)blockIdx.x) ? (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     for (int it = 0; it < my_tiles; it++) {
@@ -333,9 +333,9 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
                     }
                     const uint32_t rbase = s_buf + pos;
                     // the next row's mask words: asked for now, used after the decode
-                    // (a second terminator right behind the first - the LF of a CR LF pair, an empty line - is skipped here
-                    // rather than by a trip through the loop)
-                    const uint32_t npos = pos + et + 1u + (((tw >> 1) >> (et & 31u)) & 1u);
+                    // (CR LF files: the LF right behind the CR is skipped here rather than by a trip through the loop as an
+                    // empty line)
+                    const uint32_t npos = pos + et + 1u + (cr_too ? (((tw >> 1) >> (et & 31u)) & 1u) : 0u);
                     const uint32_t nma = s_msk + ((npos >> 2) & ~7u);
                     const uint2 n0 = lds64(nma), n1 = lds64(nma + 8u);
                     myrows++;
@@ -435,7 +435,6 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
                         if (k < P.def_row_cap) P.def_rows[k] = (uint64_t)(g0 + (long long)pos);
                         handed++;
                     } else {
-                        rows++;
                         if (pass) {
                             const uint32_t aa = s_acc + (cur & 0x7cu);  // word [0][group]
                             reds32(aa, 1u);
@@ -477,6 +476,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
         }
         // too many rows outside this kernel's repertoire: let the general kernel do the whole scan.
         // The barrier also keeps the tile and its masks alive until every thread is done with them.
+        rows += myrows - handed;  // (rows this kernel took itself)
         const int many = __syncthreads_or((int)(handed * 8u > myrows + 8u));
         if (many && tid == 0) atomicOr(P.errflags, KERR_LEAN_ABORT);
     }

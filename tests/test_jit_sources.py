@@ -19,6 +19,7 @@ SHAPE = """#define CQG_JIT 1
 #define CQG_JIT_NPROG 3
 #define CQG_JIT_NLEAF 2
 #define CQG_JIT_NGC 1
+#define CQG_JIT_CRLF 0
 #define CQG_JIT_NAGG 2
 #define CQG_JIT_PROG(i) ((i)==0?0:(i)==1?1:(i)==2?-1:0)
 #define CQG_JIT_LEAFSLOT(i) ((i)==0?1:(i)==1?0:0)

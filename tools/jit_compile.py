@@ -32,6 +32,7 @@ SHAPES = {
 #define CQG_JIT_NPROG 1
 #define CQG_JIT_NLEAF 1
 #define CQG_JIT_NGC 1
+#define CQG_JIT_CRLF 0
 #define CQG_JIT_NAGG 2
 #define CQG_JIT_PROG(i) ((i)==0?0:0)
 #define CQG_JIT_LEAFSLOT(i) ((i)==0?1:0)
