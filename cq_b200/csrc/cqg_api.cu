@@ -2197,10 +2197,51 @@ struct Arena {
         return p;
     }
     void adopt(void* p) { blocks.push_back(p); }  // a malloc'ed block the arena frees with the rest
-    ~Arena() {
-        for (void* p : blocks) free(p);
-    }
+    // the one big block of a many-group result (finish_aggregate_device): handed back to big_block_put when the result
+    // is freed, so that the next such result writes into pages that are already there
+    void* big = nullptr;
+    size_t big_cap = 0;
+    ~Arena();
 };
+
+// One spare result block (hundreds of MB for ~10^6 groups): first touch of fresh pages is a third of the time the block
+// takes to reach the host. CQG_RESULT_CACHE=0: always malloc and free.
+static std::mutex g_big_mu;
+static void* g_big_spare = nullptr;
+static size_t g_big_spare_cap = 0;
+static void* big_block_get(size_t need, size_t* cap) {
+    {
+        std::lock_guard<std::mutex> lock(g_big_mu);
+        if (g_big_spare && g_big_spare_cap >= need) {
+            void* p = g_big_spare;
+            *cap = g_big_spare_cap;
+            g_big_spare = nullptr;
+            g_big_spare_cap = 0;
+            return p;
+        }
+    }
+    const size_t sz = (need + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    void* p = nullptr;
+    if (posix_memalign(&p, 2u << 20, sz) != 0) return nullptr;
+    madvise(p, sz, MADV_HUGEPAGE);  // (2 MB pages: ~10^5 first touches of small pages is what the copy would wait for)
+    *cap = sz;
+    return p;
+}
+static void big_block_put(void* p, size_t cap) {
+    const char* e = getenv("CQG_RESULT_CACHE");
+    if (!(e && e[0] == '0')) {
+        std::lock_guard<std::mutex> lock(g_big_mu);
+        if (!g_big_spare || g_big_spare_cap < cap) {
+            std::swap(p, g_big_spare);
+            std::swap(cap, g_big_spare_cap);
+        }
+    }
+    free(p);  // (the smaller of the two, or nullptr)
+}
+Arena::~Arena() {
+    for (void* p : blocks) free(p);
+    if (big) big_block_put(big, big_cap);
+}
 
 // CQG_TIMING=1: phase timings of the host side on stderr
 struct PhaseTimer {
@@ -2559,10 +2600,9 @@ static int finish_aggregate_device(HostPlan& hp, const cqg_table* t, const cqg_q
     CU(cudaStreamSynchronize(st));
     pt.lap("finish: sort, cells, string sizes");
     const size_t block_bytes = o_str + (size_t)str_total;
-    // 2 MB aligned and advised for huge pages: first touch of ~10^5 small pages is what the copy below would wait for
-    char* block = nullptr;
-    if (posix_memalign((void**)&block, 2u << 20, (block_bytes + 16 + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1)) != 0) block = nullptr;
-    if (block) madvise(block, block_bytes + 16, MADV_HUGEPAGE);
+    // 2 MB aligned and advised for huge pages, or the block of an earlier result of this size (big_block_get)
+    size_t block_cap = 0;
+    char* block = (char*)big_block_get(block_bytes + 16, &block_cap);
     if (!block) return fail(CQG_ERR_NOMEM, "result of %llu groups: out of host memory", (unsigned long long)G);
     DevBuf d_full;  // the arrays written so far and the strings in one piece
     CU(d_full.alloc(block_bytes + 16, st));
@@ -2581,13 +2621,14 @@ static int finish_aggregate_device(HostPlan& hp, const cqg_table* t, const cqg_q
     }
     int rc = copy_block_to_host(block, d_full.p, block_bytes, st);
     if (rc != CQG_OK) {
-        free(block);
+        big_block_put(block, block_cap);
         return rc;
     }
     pt.lap("finish: values, block to host");
     Arena* arena;
     cqg_result_t* r = new_result(&arena);
-    arena->adopt(block);
+    arena->big = block;
+    arena->big_cap = block_cap;
     r->n_groups = (int64_t)G;
     r->n_aggs = A;
     r->n_out_cols = O;
