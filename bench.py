@@ -479,6 +479,36 @@ def main():
                 torch.cuda.empty_cache()
             except Exception as ex:
                 extra["join_error"] = repr(ex)
+            # ---- BASELINE configs[3]: quoted / escaped-comma CSV with string predicates (the corpus of tools/bench_quoted.py and
+            # tests/test_gpu_large_parity.py: quoted names with embedded commas and doubled quotes; the general kernel) ----
+            try:
+                import random
+                rnd = random.Random(4)
+                first = ["Ada", "Brook", "Cyrus", "Dana", "Eli", "Fay", "Gus", "Hana", "Ivo", "Jude", "Max", "Xena", "Alex"]
+                lastn = ["Smith", "Jones", "Lee", "Fox", "Marx", "Nguyen", "O'Neil", "Baxter"]
+                block = []
+                for i in range(100_000):
+                    f, l = rnd.choice(first), rnd.choice(lastn)
+                    nm = f'"{l}, {f}"' if i % 3 else (f'"say ""{f}"""' if i % 2 else f + l)
+                    block.append(f"{nm},{rnd.choice(['admin', 'user', 'moderator'])},{rnd.randint(10, 80)},{rnd.randint(100, 200) / 100}")
+                qdata = b"name,role,age,height\n" + ("\n".join(block) + "\n").encode() * max(1, int(200 * args.bytes / 1e10))
+                ql = {"bytes": len(qdata)}
+                with Table.from_bytes(qdata, lib=lib) as qt:
+                    for qn, qs in {"role_eq_admin": dict(where=("=", ("col", 1), ("const", "admin")), aggs=[(pc.A.AGG_COUNT_STAR, -1)]),
+                                   "name_like_x": dict(where=("like", ("col", 0), ("const", "%x%")), aggs=[(pc.A.AGG_COUNT_STAR, -1)])}.items():
+                        pl = pc.build(qs)
+                        qt.execute_raw(pl)
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        r = qt.execute_raw(pl)
+                        torch.cuda.synchronize()
+                        dt = time.perf_counter() - t0
+                        ql[qn] = {"scan_kernel_gbs": len(qdata) / (r["kernel_ms"] / 1e3) / 1e9, "query_gbs": len(qdata) / dt / 1e9,
+                                  "count0": int(r["count0"])}
+                extra["quoted_csv"] = ql
+                del qdata
+            except Exception as ex:
+                extra["quoted_error"] = repr(ex)
             for name in ["scalar_aggs", "lean_group_abort_many", "count_height_gt_1_5"]:
                 pl = pc.build(pc.plans()[name])
                 table.execute_raw(pl)
