@@ -550,7 +550,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2_kernel(const __grid_co
         const long long g0 = tile * (long long)G::TILE - G::PRE;
         const bool at_edge = g0 < 0 || g0 + G::BUF > (long long)size;
         const bool edge = at_edge && !P.edge_in_kernel;  // handed over, not loaded
-        const LeanEdge es = lean_edge_span<G>(g0, size);
+        LeanEdge es{0u, 0u, 0u};
+        if (at_edge) es = lean_edge_span<G>(g0, size);  // (two tiles of a scan: not worth a dozen instructions on every tile)
         if (tid == 0) {
             if (!at_edge) {
                 mbar_expect_tx(&mbar[0], G::BUF);

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
         const long long g0 = tile * (long long)G::TILE - G::PRE;
         const bool at_edge = g0 < 0 || g0 + G::BUF > (long long)size;
         const bool edge = at_edge && !P.edge_in_kernel;  // handed over, not loaded (cqg_lean2.cuh: LeanEdge)
-        const LeanEdge es = lean_edge_span<G>(g0, size);
+        LeanEdge es{0u, 0u, 0u};
+        if (at_edge) es = lean_edge_span<G>(g0, size);  // (two tiles of a scan: not worth a dozen instructions on every tile)
         if (tid == 0) {
             if (!at_edge) {
                 mbar_expect_tx(&mbar[0], G::BUF);
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(G::THREADS, MINB) lean2k_kernel(const __grid_c
 
         // ---- phase 2: every thread walks the rows that START in its own 128 bytes ----
         uint32_t lo = (uint32_t)G::PRE + 128u * (uint32_t)tid, hi = lo + 128u;
-        {
+        if (it == 0 || it + 1 == my_tiles) {  // only the scan's first and last tile can hold an end of the ownership range
             const long long olo_l = (long long)P.own_lo - g0, ohi_l = (long long)P.own_hi - g0;
             if (olo_l > (long long)G::PRE || ohi_l < (long long)(G::PRE + G::TILE)) {
                 const uint32_t olo = (uint32_t)(olo_l < G::PRE ? G::PRE : (olo_l > G::PRE + G::TILE ? G::PRE + G::TILE : olo_l));
